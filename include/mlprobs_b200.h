@@ -1,0 +1,122 @@
+/* mlprobs_b200 -- C ABI of the B200-native all-pairs posterior + consistency engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of kuangmeng/MLProbs' two aligners: every entry point
+ * below replaces a reference call site (cited per function; cpnp = baseMSA/C_P_NP_Aln,
+ * QP = realign/QuickProbs/src/Alignment).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions: every function returns 0 on success or a negative MLP_E_* code and never throws;
+ * nothing is printed to stdout/stderr (the callers capture both streams); the caller owns
+ * host buffers, the library owns device memory; one context per process/GPU, calls serialised by the caller.
+ * There is NO CPU fallback: without a CUDA device mlp_create fails with MLP_E_NO_DEVICE.
+ */
+#ifndef MLPROBS_B200_H
+#define MLPROBS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlp_ctx mlp_ctx;
+
+enum { MLP_OK = 0, MLP_E_NO_DEVICE = -1, MLP_E_CUDA = -2, MLP_E_ARG = -3, MLP_E_STATE = -4,
+       MLP_E_CAPACITY = -5, MLP_E_OVERFLOW = -6, MLP_E_UNSUPPORTED = -7, MLP_E_NCCL = -8 };
+
+/* flavour = whose arithmetic is reproduced */
+enum { MLP_QP = 0,        /* quickprobs: PosteriorStage.cpp:58-196, ConsistencyStage.cpp:133-300            */
+       MLP_CPNP_P0 = 1,   /* c_p_np_aln -p 0: MSA.cpp:895-1051 (pdoAlign pair loop + DoRelaxation)          */
+       MLP_CPNP_P1 = 2 }; /* c_p_np_aln -p 1: MSA.cpp:1636-1765 (ArrangePosteriorProbs) + DoRelaxation      */
+/* model mask (cpnp: pid<=1 -> all three, pid==2 -> LOCAL, pid>=3 -> PART; QP: always HMM5|PART) */
+enum { MLP_M_HMM5 = 1, MLP_M_PART = 2, MLP_M_LOCAL = 4 };
+
+/* Log-space pair-HMM tables, index = letter - 'A'.
+ * cpnp ProbabilisticModel.h:42-47,58-135 ; QP ProbabilisticModel.h:43-46, ProbabilisticModel.cpp:15-56 */
+typedef struct {
+    float init[5];
+    float trans[5][5];
+    float match[26][26];
+    float ins[26];
+    float ltrans[3][3];   /* cpnp local model, ProbabilisticModel.h:46,103-127 */
+    float rtrans[2];      /* cpnp flanking random states, ProbabilisticModel.h:47,130-131 */
+} mlp_hmm_tables;
+
+/* Partition-function tables, index = letter - 'A' (NaN = letter the reference cannot score).
+ * cpnp MSAReadMatrix.cpp:85-116 + MSAPartProbs.cpp:698-709 ; QP ExpPartitionFunctionParams.h:17-49 */
+typedef struct {
+    double sub[26][26];
+    double go, ge, tgo, tge;
+} mlp_part_tables;
+
+/* Build the reference's default tables on the host with glibc logf/expf/exp.
+ * init_distrib2 is cpnp's identity-dependent initDistrib[2] (MSA.cpp:861-870); ignored for MLP_QP. */
+int mlp_default_tables(int flavour, float init_distrib2, mlp_hmm_tables* hmm, mlp_part_tables* part);
+
+/* Context on one CUDA device (replaces the OpenMP thread team of MSA.cpp:146-152 / PosteriorStage.cpp:67). */
+int mlp_create(int device, mlp_ctx** out);
+void mlp_destroy(mlp_ctx* ctx);
+const char* mlp_last_error(const mlp_ctx* ctx);
+/* scratch budget for dense DP layers in bytes (0 = 60 % of free device memory) and sparse pool capacity in cells (0 = auto) */
+int mlp_configure(mlp_ctx* ctx, int64_t scratch_bytes, int64_t cell_capacity);
+
+int mlp_set_tables(mlp_ctx* ctx, const mlp_hmm_tables* hmm, const mlp_part_tables* part);
+/* n sequences, upper-case letters 'A'..'Z', concatenated (what MultiSequence::LoadMFA leaves: cpnp
+ * MultiSequence.h:98-111 / Sequence.h:96-112; QP SequenceIO.cpp:98-155). */
+int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* residues);
+/* Restrict the posterior / relax stages of THIS context to pairs p with p % world == rank of the
+ * cost-sorted pair list (multi-GPU sharding). Default rank 0 of 1. */
+int mlp_set_shard(mlp_ctx* ctx, int rank, int world);
+
+/* All-pairs posterior stage: for every owned pair a<b -> dense posteriors of the selected models, merge,
+ * MEA score -> distance, threshold to CSR (both orientations).
+ * Replaces cpnp MSA.cpp:927-1031 (and :1652-1765 for -p 1) / QP PosteriorStage::run PosteriorStage.cpp:58-121. */
+int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model_mask, float cutoff);
+
+/* n*n float distances (row-major, symmetric, 0 diagonal): cpnp MSA.cpp:1019 / QP PosteriorStage.cpp:107,113 */
+int mlp_get_distances(mlp_ctx* ctx, float* nxn);
+
+/* One consistency repetition over all owned pairs.
+ * cpnp: MSA::DoRelaxation MSA.cpp:1172-1281 (weights/seldist NULL, unweighted, /N).
+ * QP:   ConsistencyStage::doRelaxation ConsistencyStage.cpp:133-266 with the default Max/Deterministic
+ *       selectivity (accept z iff max(seldist[i][z], seldist[j][z]) <= selectivity), weights from the guide tree. */
+int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
+              float selectivity, float selfweight, float cutoff);
+
+/* Sparse posterior read-back. Ordered pair (a,b), a != b; rows 1..len[a]; row_ptr has len[a]+2 entries
+ * (row_ptr[i]..row_ptr[i+1] = row i, row 0 empty).  val is the dequantised value for MLP_QP
+ * (SparseEntry.h:31-32).  Pass NULL col/val to query *nnz only. */
+int mlp_get_csr(mlp_ctx* ctx, int a, int b, int32_t* row_ptr, int32_t* col, float* val, int64_t* nnz);
+/* total cells currently stored over all ordered pairs */
+int mlp_total_cells(mlp_ctx* ctx, int64_t* cells);
+/* bulk read-back of the a<b orientation in pair order (p = row-major index of a<b): nnz[p], then concatenated
+ * col/val; row_ptr concatenated with len[a]+2 entries per pair. Any pointer may be NULL. */
+int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* row_ptr, int32_t* col, float* val);
+
+/* Dense per-pair debug read-back (tests): runs one pair and returns the merged dense posterior
+ * (len[a]+1 x len[b]+1) and, if non-NULL, each model's posterior. */
+int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_mask, int a, int b,
+                         float* merged, float* p_hmm5, float* p_part, float* p_local, float* distance);
+
+/* Multi-GPU exchange (one process per GPU): all-gather the sparse posteriors + distances of every rank's
+ * shard so that each context holds the complete set (needed before mlp_relax and by the host tail).
+ * unique_id is the 128-byte ncclUniqueId from mlp_nccl_unique_id on rank 0, distributed by the caller. */
+int mlp_nccl_unique_id(uint8_t id128[128]);
+int mlp_comm_init(mlp_ctx* ctx, const uint8_t id128[128], int rank, int world);
+int mlp_exchange(mlp_ctx* ctx);
+
+/* timing / accounting of the last stage call, measured with CUDA events on the library's stream */
+typedef struct {
+    double ms_total;        /* whole stage on the device                         */
+    double ms_kernel[8];    /* per kernel family, see MLP_K_*                    */
+    int64_t launches;       /* kernels launched                                  */
+    int64_t cells;          /* DP cells (L1+1)*(L2+1) summed over pairs processed */
+    int64_t pairs;
+    int64_t nnz;            /* sparse cells produced (a<b orientation)           */
+    int64_t h2d_bytes, d2h_bytes;
+} mlp_stage_stats;
+enum { MLP_K_PART_FWD = 0, MLP_K_PART_REV = 1, MLP_K_HMM_FWD = 2, MLP_K_HMM_BWD = 3, MLP_K_LOCAL_FWD = 4,
+       MLP_K_LOCAL_BWD = 5, MLP_K_FINAL = 6, MLP_K_RELAX = 7 };
+int mlp_last_stats(mlp_ctx* ctx, mlp_stage_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

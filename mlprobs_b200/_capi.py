@@ -1,0 +1,193 @@
+"""ctypes binding of libmlprobs_b200.so (include/mlprobs_b200.h).
+
+The library is the product; this module only marshals numpy arrays across the C ABI.  There is no CPU
+fallback: if the shared library is missing, or no CUDA device is visible, the calls raise.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmlprobs_b200.so")
+
+QP, CPNP_P0, CPNP_P1 = 0, 1, 2
+M_HMM5, M_PART, M_LOCAL = 1, 2, 4
+K_NAMES = ["part_fwd", "part_rev", "hmm_fwd", "hmm_bwd", "local_fwd", "local_bwd", "final", "relax"]
+
+ERRORS = {0: "ok", -1: "no CUDA device", -2: "CUDA error", -3: "bad argument", -4: "bad state",
+          -5: "capacity exhausted", -6: "partition function overflow", -7: "unsupported", -8: "NCCL error"}
+
+EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", "mlp_configure", "mlp_set_tables",
+           "mlp_set_sequences", "mlp_set_shard", "mlp_posterior_all_pairs", "mlp_get_distances", "mlp_relax",
+           "mlp_get_csr", "mlp_total_cells", "mlp_get_csr_bulk", "mlp_debug_pair_dense", "mlp_nccl_unique_id",
+           "mlp_comm_init", "mlp_exchange", "mlp_last_stats"]
+
+
+class HmmTables(C.Structure):
+    _fields_ = [("init", C.c_float * 5), ("trans", (C.c_float * 5) * 5), ("match", (C.c_float * 26) * 26),
+                ("ins", C.c_float * 26), ("ltrans", (C.c_float * 3) * 3), ("rtrans", C.c_float * 2)]
+
+
+class PartTables(C.Structure):
+    _fields_ = [("sub", (C.c_double * 26) * 26), ("go", C.c_double), ("ge", C.c_double),
+                ("tgo", C.c_double), ("tge", C.c_double)]
+
+
+class StageStats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_kernel", C.c_double * 8), ("launches", C.c_int64),
+                ("cells", C.c_int64), ("pairs", C.c_int64), ("nnz", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+class MlpError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("mlprobs_b200: %s (%d)%s" % (ERRORS.get(code, "error"), code, (": " + detail) if detail else ""))
+
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libmlprobs_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(LIB_PATH)
+        lib.mlp_last_error.restype = C.c_char_p
+        lib.mlp_last_error.argtypes = [C.c_void_p]
+        lib.mlp_destroy.restype = None
+        lib.mlp_destroy.argtypes = [C.c_void_p]
+        lib.mlp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.mlp_default_tables.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        lib.mlp_configure.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        lib.mlp_set_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_set_sequences.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_char_p]
+        lib.mlp_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.mlp_posterior_all_pairs.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_float]
+        lib.mlp_get_distances.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mlp_relax.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float]
+        lib.mlp_get_csr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        lib.mlp_total_cells.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        lib.mlp_get_csr_bulk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_debug_pair_dense.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        lib.mlp_nccl_unique_id.argtypes = [C.c_void_p]
+        lib.mlp_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.mlp_exchange.argtypes = [C.c_void_p]
+        lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def default_tables(flavour, init_distrib2=0.700645):
+    h, p = HmmTables(), PartTables()
+    rc = load().mlp_default_tables(flavour, C.c_float(init_distrib2), C.byref(h), C.byref(p))
+    if rc:
+        raise MlpError(rc)
+    return h, p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Engine:
+    """One GPU context (mlp_ctx)."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.mlp_create(device, C.byref(self._ctx))
+        if rc:
+            raise MlpError(rc)
+        self.n = 0
+        self.lens = None
+
+    def close(self):
+        if self._ctx:
+            self._lib.mlp_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise MlpError(rc, (self._lib.mlp_last_error(self._ctx) or b"").decode())
+
+    def configure(self, scratch_bytes=0, cell_capacity=0):
+        self._ck(self._lib.mlp_configure(self._ctx, scratch_bytes, cell_capacity))
+
+    def set_tables(self, hmm, part):
+        self._hmm, self._part = hmm, part
+        self._ck(self._lib.mlp_set_tables(self._ctx, C.byref(hmm), C.byref(part)))
+
+    def set_sequences(self, seqs):
+        """seqs: list of bytes, upper-case letters."""
+        self.lens = np.array([len(s) for s in seqs], np.int32)
+        self.n = len(seqs)
+        cat = b"".join(seqs)
+        self._ck(self._lib.mlp_set_sequences(self._ctx, self.n, _ptr(self.lens), cat))
+
+    def set_shard(self, rank, world):
+        self._ck(self._lib.mlp_set_shard(self._ctx, rank, world))
+
+    def posterior_all_pairs(self, flavour, mask, cutoff=0.01):
+        self._ck(self._lib.mlp_posterior_all_pairs(self._ctx, flavour, mask, C.c_float(cutoff)))
+
+    def distances(self):
+        d = np.zeros((self.n, self.n), np.float32)
+        self._ck(self._lib.mlp_get_distances(self._ctx, _ptr(d)))
+        return d
+
+    def relax(self, flavour, weights=None, seldist=None, selectivity=200.0, selfweight=3.0, cutoff=0.01):
+        w = np.ascontiguousarray(weights, np.float32) if weights is not None else None
+        sd = np.ascontiguousarray(seldist, np.float32) if seldist is not None else None
+        self._ck(self._lib.mlp_relax(self._ctx, flavour, _ptr(w), _ptr(sd), C.c_float(selectivity),
+                                     C.c_float(selfweight), C.c_float(cutoff)))
+
+    def csr(self, a, b):
+        nnz = C.c_int64(0)
+        rp = np.zeros(int(self.lens[a]) + 2, np.int32)
+        self._ck(self._lib.mlp_get_csr(self._ctx, a, b, _ptr(rp), None, None, C.byref(nnz)))
+        col = np.zeros(nnz.value, np.int32)
+        val = np.zeros(nnz.value, np.float32)
+        if nnz.value:
+            self._ck(self._lib.mlp_get_csr(self._ctx, a, b, None, _ptr(col), _ptr(val), C.byref(nnz)))
+        return rp, col, val
+
+    def csr_bulk(self):
+        npairs = self.n * (self.n - 1) // 2
+        nnz = np.zeros(npairs, np.int64)
+        self._ck(self._lib.mlp_get_csr_bulk(self._ctx, _ptr(nnz), None, None, None))
+        rows = int(sum(int(self.lens[a]) + 2 for a in range(self.n) for _ in range(a + 1, self.n)))
+        rp = np.zeros(rows, np.int32)
+        col = np.zeros(int(nnz.sum()), np.int32)
+        val = np.zeros(int(nnz.sum()), np.float32)
+        self._ck(self._lib.mlp_get_csr_bulk(self._ctx, None, _ptr(rp), _ptr(col), _ptr(val)))
+        return nnz, rp, col, val
+
+    def total_cells(self):
+        c = C.c_int64(0)
+        self._ck(self._lib.mlp_total_cells(self._ctx, C.byref(c)))
+        return c.value
+
+    def debug_pair_dense(self, flavour, mask, a, b):
+        L1, L2 = int(self.lens[a]), int(self.lens[b])
+        outs = [np.zeros((L1 + 1, L2 + 1), np.float32) for _ in range(4)]
+        dist = C.c_float(0)
+        self._ck(self._lib.mlp_debug_pair_dense(self._ctx, flavour, mask, a, b, _ptr(outs[0]), _ptr(outs[1]),
+                                                _ptr(outs[2]), _ptr(outs[3]), C.byref(dist)))
+        return {"merged": outs[0], "hmm5": outs[1], "part": outs[2], "local": outs[3], "dist": dist.value}
+
+    def stats(self):
+        s = StageStats()
+        self._ck(self._lib.mlp_last_stats(self._ctx, C.byref(s)))
+        return {"ms_total": s.ms_total, "ms_kernel": {K_NAMES[i]: s.ms_kernel[i] for i in range(8)},
+                "launches": s.launches, "cells": s.cells, "pairs": s.pairs, "nnz": s.nnz,
+                "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}

@@ -1,0 +1,690 @@
+// C ABI implementation (include/mlprobs_b200.h): host driver of the posterior and consistency stages.
+// One context = one GPU + one stream.  Pairs are cost-sorted, sharded (rank/world) and processed in batches
+// whose dense DP layers fit the scratch budget; every batch runs the sweep kernels back to back on the stream.
+#include "../../include/mlprobs_b200.h"
+#include "posterior.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return MLP_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static const int kCmaxLimit = 16;   // columns per lane; 32*16 = 512 columns per column block
+
+struct mlp_ctx {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // configuration
+    int64_t scratch_budget = 0, cell_capacity_req = 0;
+    // sequences
+    int n = 0;
+    std::vector<int> len;
+    std::vector<long long> seq_off;
+    long long total_res = 0;
+    std::vector<uint8_t> codes_h;
+    uint8_t* d_res = nullptr;
+    long long* d_seq_off = nullptr;
+    // tables
+    bool have_tables = false;
+    mlp_hmm_tables hmm;
+    mlp_part_tables part;
+    float* d_match = nullptr; float* d_ins = nullptr; double* d_sub = nullptr;
+    // pairs
+    std::vector<PairTask> all_pairs;     // cost-sorted (descending)
+    std::vector<PairTask> owned;         // this shard
+    int rank = 0, world = 1;
+    // sparse sets (double buffered for relax)
+    std::vector<long long> rp_off_h;
+    long long rp_total = 0;
+    long long* d_rp_off = nullptr;
+    CsrSetDev set[2] = {};
+    int cur = 0;
+    bool have_sets = false;
+    int flavour_of_set = -1;
+    float* d_dist = nullptr;
+    // per-launch scratch
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    PairTask* d_tasks = nullptr; PairOut* d_pout = nullptr; size_t tasks_cap = 0;
+    int* d_counter = nullptr; int* d_err = nullptr;
+    int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
+    int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
+    void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
+    float* d_wk = nullptr; long long wk_warps = 0;
+    float* d_weights = nullptr; float* d_seldist = nullptr;
+    // nccl
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+    // stats
+    mlp_stage_stats stats = {};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+static void free_dev(void* p) { if (p) cudaFree(p); }
+
+static void release_sets(mlp_ctx* ctx) {
+    for (int s = 0; s < 2; ++s) {
+        free_dev(ctx->set[s].rp_pool); free_dev(ctx->set[s].nz_off); free_dev(ctx->set[s].nz_cnt);
+        free_dev(ctx->set[s].cells); free_dev(ctx->set[s].cursor);
+        ctx->set[s] = CsrSetDev{};
+    }
+    free_dev(ctx->d_rp_off); ctx->d_rp_off = nullptr;
+    free_dev(ctx->d_dist); ctx->d_dist = nullptr;
+    ctx->have_sets = false;
+}
+
+static void release_launch_scratch(mlp_ctx* ctx) {
+    free_dev(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    free_dev(ctx->d_tasks); ctx->d_tasks = nullptr; free_dev(ctx->d_pout); ctx->d_pout = nullptr; ctx->tasks_cap = 0;
+    free_dev(ctx->d_stage); ctx->d_stage = nullptr; ctx->stage_warps = 0; ctx->stage_cap = 0;
+    free_dev(ctx->d_tfill); ctx->d_tfill = nullptr; ctx->tfill_warps = 0;
+    free_dev(ctx->d_edge); ctx->d_edge = nullptr; ctx->edge_warps = 0;
+    free_dev(ctx->d_wk); ctx->d_wk = nullptr; ctx->wk_warps = 0;
+}
+
+extern "C" int mlp_create(int device, mlp_ctx** out) {
+    if (!out) return MLP_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return MLP_E_NO_DEVICE;
+    if (device < 0 || device >= count) return MLP_E_ARG;
+    mlp_ctx* ctx = new mlp_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
+    cudaEventCreate(&ctx->ev[0]); cudaEventCreate(&ctx->ev[1]);
+    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess || cudaMalloc(&ctx->d_err, sizeof(int)) != cudaSuccess) {
+        delete ctx; return MLP_E_CUDA;
+    }
+    cudaMemset(ctx->d_err, 0, sizeof(int));
+    *out = ctx;
+    return MLP_OK;
+}
+
+extern "C" void mlp_destroy(mlp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    release_sets(ctx);
+    release_launch_scratch(ctx);
+    free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
+    free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
+    free_dev(ctx->d_counter); free_dev(ctx->d_err);
+    free_dev(ctx->d_weights); free_dev(ctx->d_seldist);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* mlp_last_error(const mlp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int mlp_configure(mlp_ctx* ctx, int64_t scratch_bytes, int64_t cell_capacity) {
+    if (!ctx || scratch_bytes < 0 || cell_capacity < 0) return MLP_E_ARG;
+    ctx->scratch_budget = scratch_bytes;
+    ctx->cell_capacity_req = cell_capacity;
+    return MLP_OK;
+}
+
+extern "C" int mlp_set_tables(mlp_ctx* ctx, const mlp_hmm_tables* hmm, const mlp_part_tables* part) {
+    if (!ctx || !hmm || !part) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (!(part->tgo == 1.0 && part->tge == 1.0)) {
+        ctx->err = "terminal gap terms other than exp(0)=1 are not supported (both references hard-code them)";
+        return MLP_E_UNSUPPORTED;
+    }
+    ctx->hmm = *hmm; ctx->part = *part;
+    if (!ctx->d_match) {
+        CK(cudaMalloc(&ctx->d_match, 676 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_ins, 32 * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_sub, 676 * sizeof(double)));
+    }
+    CK(cudaMemcpyAsync(ctx->d_match, &hmm->match[0][0], 676 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ins, hmm->ins, 26 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sub, &part->sub[0][0], 676 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DevScalars s;
+    for (int q = 0; q < 5; ++q) {
+        s.init[q] = hmm->init[q];
+        s.t0q[q] = hmm->trans[0][q];
+        s.tqq[q] = hmm->trans[q][q];
+        s.tq0[q] = hmm->trans[q][0];
+    }
+    s.lt00 = hmm->ltrans[0][0]; s.lt01 = hmm->ltrans[0][1]; s.lt02 = hmm->ltrans[0][2];
+    s.lt10 = hmm->ltrans[1][0]; s.lt11 = hmm->ltrans[1][1];
+    s.lt20 = hmm->ltrans[2][0]; s.lt22 = hmm->ltrans[2][2];
+    s.r = hmm->rtrans[1];
+    s.r2 = 2 * hmm->rtrans[1];
+    s.go = part->go; s.ge = part->ge;
+    CK(posterior_set_scalars(s, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_tables = true;
+    ctx->stats.h2d_bytes += 676 * 4 + 26 * 4 + 676 * 8 + (int64_t)sizeof(DevScalars);
+    return MLP_OK;
+}
+
+static void pair_geometry(int L2, int& C, int& nb) {
+    const int cols = L2 + 2;   // columns 0..L2 plus the virtual column L2+1 of the reverse sweeps
+    nb = (cols + 32 * kCmaxLimit - 1) / (32 * kCmaxLimit);
+    C = (cols + 32 * nb - 1) / (32 * nb);
+}
+
+extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* residues) {
+    if (!ctx || n < 2 || !len || !residues) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    release_sets(ctx);
+    ctx->n = n;
+    ctx->len.assign(len, len + n);
+    ctx->seq_off.resize(n);
+    long long tot = 0;
+    for (int i = 0; i < n; ++i) {
+        if (len[i] < 1 || len[i] > 65535) { ctx->err = "sequence length must be in 1..65535"; return MLP_E_ARG; }
+        ctx->seq_off[i] = tot; tot += len[i];
+    }
+    ctx->total_res = tot;
+    std::vector<uint8_t> codes(tot + 16, 0);
+    for (long long k = 0; k < tot; ++k) {
+        const uint8_t ch = residues[k];
+        if (ch < 'A' || ch > 'Z') { ctx->err = "residues must be upper-case letters"; return MLP_E_ARG; }
+        codes[k] = (uint8_t)(ch - 'A');
+    }
+    ctx->codes_h = codes;
+    free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
+    CK(cudaMalloc(&ctx->d_res, tot + 16));
+    CK(cudaMalloc(&ctx->d_seq_off, n * sizeof(long long)));
+    CK(cudaMemcpy(ctx->d_res, codes.data(), tot + 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_seq_off, ctx->seq_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
+    ctx->stats.h2d_bytes += tot + 16 + n * (int64_t)sizeof(long long);
+    // all pairs, cost-sorted (largest first) for load balance
+    ctx->all_pairs.clear();
+    ctx->all_pairs.reserve((size_t)n * (n - 1) / 2);
+    int pidx = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = a + 1; b < n; ++b) {
+            PairTask t;
+            t.a = a; t.b = b; t.L1 = len[a]; t.L2 = len[b];
+            pair_geometry(t.L2, t.C, t.nb);
+            t.pidx = pidx++; t.flags = 0; t.off = 0;
+            ctx->all_pairs.push_back(t);
+        }
+    std::stable_sort(ctx->all_pairs.begin(), ctx->all_pairs.end(), [](const PairTask& x, const PairTask& y) {
+        const long long cx = (long long)x.nb * (x.L1 + 32) * x.C, cy = (long long)y.nb * (y.L1 + 32) * y.C;
+        return cx > cy;
+    });
+    // fixed row-pointer layout: ordered pair (a,b) owns len[a]+2 ints
+    ctx->rp_off_h.assign((size_t)n * n, 0);
+    long long rp = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            ctx->rp_off_h[(size_t)a * n + b] = rp;
+            if (a != b) rp += len[a] + 2;
+        }
+    ctx->rp_total = rp;
+    ctx->rank = 0; ctx->world = 1;
+    ctx->owned = ctx->all_pairs;
+    return MLP_OK;
+}
+
+extern "C" int mlp_set_shard(mlp_ctx* ctx, int rank, int world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return MLP_E_ARG;
+    ctx->rank = rank; ctx->world = world;
+    ctx->owned.clear();
+    for (size_t k = 0; k < ctx->all_pairs.size(); ++k)
+        if ((int)(k % world) == rank) ctx->owned.push_back(ctx->all_pairs[k]);
+    return MLP_OK;
+}
+
+static int ensure_sets(mlp_ctx* ctx) {
+    if (ctx->have_sets) return MLP_OK;
+    const int n = ctx->n;
+    long long cap = ctx->cell_capacity_req;
+    if (cap <= 0) {
+        long long s = 0;
+        for (const PairTask& t : ctx->all_pairs) s += std::min(t.L1, t.L2);
+        cap = 16 * s + (1 << 20);   // both orientations, ~8 cells per row of head-room
+    }
+    CK(cudaMalloc(&ctx->d_rp_off, (size_t)n * n * sizeof(long long)));
+    CK(cudaMemcpy(ctx->d_rp_off, ctx->rp_off_h.data(), (size_t)n * n * sizeof(long long), cudaMemcpyHostToDevice));
+    ctx->stats.h2d_bytes += (int64_t)n * n * 8;
+    for (int s = 0; s < 2; ++s) {
+        CK(cudaMalloc(&ctx->set[s].rp_pool, (size_t)ctx->rp_total * sizeof(int)));
+        CK(cudaMalloc(&ctx->set[s].nz_off, (size_t)n * n * sizeof(long long)));
+        CK(cudaMalloc(&ctx->set[s].nz_cnt, (size_t)n * n * sizeof(int)));
+        CK(cudaMalloc(&ctx->set[s].cells, (size_t)cap * sizeof(int2)));
+        CK(cudaMalloc(&ctx->set[s].cursor, sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->set[s].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int)));
+        CK(cudaMemset(ctx->set[s].nz_off, 0, (size_t)n * n * sizeof(long long)));
+        CK(cudaMemset(ctx->set[s].nz_cnt, 0, (size_t)n * n * sizeof(int)));
+        CK(cudaMemset(ctx->set[s].cursor, 0, sizeof(unsigned long long)));
+        ctx->set[s].cap = cap;
+    }
+    CK(cudaMalloc(&ctx->d_dist, (size_t)n * n * sizeof(float)));
+    CK(cudaMemset(ctx->d_dist, 0, (size_t)n * n * sizeof(float)));
+    ctx->have_sets = true;
+    ctx->cur = 0;
+    return MLP_OK;
+}
+
+static int ensure_tasks(mlp_ctx* ctx, size_t ntasks) {
+    if (ntasks <= ctx->tasks_cap) return MLP_OK;
+    free_dev(ctx->d_tasks); free_dev(ctx->d_pout);
+    ctx->d_tasks = nullptr; ctx->d_pout = nullptr;
+    const size_t cap = ntasks + ntasks / 4 + 64;
+    CK(cudaMalloc(&ctx->d_tasks, cap * sizeof(PairTask)));
+    CK(cudaMalloc(&ctx->d_pout, cap * sizeof(PairOut)));
+    ctx->tasks_cap = cap;
+    return MLP_OK;
+}
+
+// per-warp buffers for `warps` resident warps
+static int ensure_warp_buffers(mlp_ctx* ctx, long long warps, int maxL1, int maxL2, bool need_edge, int stage_mult) {
+    const int want_stage = stage_mult * (maxL1 + 1);
+    if (warps > ctx->stage_warps || want_stage > ctx->stage_cap) {
+        free_dev(ctx->d_stage); ctx->d_stage = nullptr;
+        ctx->stage_cap = std::max(want_stage, ctx->stage_cap);
+        ctx->stage_warps = std::max(warps, ctx->stage_warps);
+        CK(cudaMalloc(&ctx->d_stage, (size_t)ctx->stage_warps * ctx->stage_cap * sizeof(int4)));
+    }
+    const long long want_fill = ((maxL2 + 2 + 31) / 32) * 32;
+    if (warps > ctx->tfill_warps || want_fill > ctx->tfill_stride) {
+        free_dev(ctx->d_tfill); ctx->d_tfill = nullptr;
+        ctx->tfill_stride = std::max(want_fill, ctx->tfill_stride);
+        ctx->tfill_warps = std::max(warps, ctx->tfill_warps);
+        CK(cudaMalloc(&ctx->d_tfill, (size_t)ctx->tfill_warps * ctx->tfill_stride * sizeof(int)));
+    }
+    if (need_edge) {
+        const long long want_edge = (long long)(maxL1 + 1) * 5;   // elements (of 8 bytes: doubles or padded floats)
+        if (warps > ctx->edge_warps || want_edge > ctx->edge_stride) {
+            free_dev(ctx->d_edge); ctx->d_edge = nullptr;
+            ctx->edge_stride = std::max(want_edge, ctx->edge_stride);
+            ctx->edge_warps = std::max(warps, ctx->edge_warps);
+            CK(cudaMalloc(&ctx->d_edge, (size_t)ctx->edge_warps * ctx->edge_stride * sizeof(double)));
+        }
+    }
+    return MLP_OK;
+}
+
+struct KernelTimer {
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    void begin(int k, cudaStream_t st) {
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st); spans.push_back({k, {a, b}});
+    }
+    void end(cudaStream_t st) { cudaEventRecord(spans.back().second.second, st); }
+    void collect(mlp_stage_stats& s) {
+        for (auto& sp : spans) {
+            float ms = 0; cudaEventElapsedTime(&ms, sp.second.first, sp.second.second);
+            if (sp.first >= 0 && sp.first < 8) s.ms_kernel[sp.first] += ms;
+            cudaEventDestroy(sp.second.first); cudaEventDestroy(sp.second.second);
+        }
+        spans.clear();
+    }
+};
+
+static int launch_one(mlp_ctx* ctx, int kernel, KArgs& a, int ntasks, KernelTimer& kt, int stat_slot) {
+    const int warps_per_cta = MLP_BLOCK / 32;
+    const size_t smem = posterior_smem_bytes(kernel, a.Cmax, warps_per_cta);
+    int bps = posterior_max_blocks_per_sm(kernel, smem);
+    bps = std::min(bps, 16);
+    int grid = ctx->num_sms * bps;
+    grid = std::min(grid, (ntasks + warps_per_cta - 1) / warps_per_cta);
+    grid = std::max(grid, 1);
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+    kt.begin(stat_slot, ctx->stream);
+    CK(posterior_launch(kernel, a, grid, smem, ctx->stream));
+    kt.end(ctx->stream);
+    ctx->stats.launches += 1;
+    return MLP_OK;
+}
+
+static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float cutoff, const std::vector<PairTask>& tasks_in,
+                               float* dense, float* dense5, float* denseP, float* denseL) {
+    if (tasks_in.empty()) return MLP_OK;
+    const bool useP = (mask & MLP_M_PART) != 0, use5 = (mask & MLP_M_HMM5) != 0, useL = (mask & MLP_M_LOCAL) != 0;
+    // bytes per dense element: Z(8)+P(4) | S5(4) | SL(4)+VB(4, aliases Z when the partition model is also run)
+    int bpe = 0;
+    if (useP) bpe += 12;
+    if (use5) bpe += 4;
+    if (useL) bpe += useP ? 4 : 8;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = ctx->scratch_budget > 0 ? (size_t)ctx->scratch_budget : (size_t)((free_b + ctx->scratch_bytes) * 0.6);
+    int maxL1 = 0, maxL2 = 0; bool need_edge = false; long long max_elems = 0;
+    for (const PairTask& t : tasks_in) {
+        maxL1 = std::max(maxL1, t.L1); maxL2 = std::max(maxL2, t.L2);
+        need_edge |= (t.nb > 1);
+        max_elems = std::max(max_elems, (long long)t.nb * (t.L1 + 32) * t.C * 32);
+    }
+    if ((size_t)max_elems * bpe > budget) budget = (size_t)max_elems * bpe;   // a single pair must fit
+    const long long max_warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
+    {
+        int rc = ensure_warp_buffers(ctx, max_warps, maxL1, maxL2, need_edge, 32);
+        if (rc != MLP_OK) return rc;
+    }
+    KernelTimer kt;
+    size_t pos = 0;
+    std::vector<PairTask> batch;
+    while (pos < tasks_in.size()) {
+        batch.clear();
+        long long elems = 0; int Cmax = 1;
+        while (pos < tasks_in.size()) {
+            PairTask t = tasks_in[pos];
+            const long long e = (long long)t.nb * (t.L1 + 32) * t.C * 32;
+            if (!batch.empty() && (size_t)(elems + e) * bpe > budget) break;
+            t.off = elems; elems += e; Cmax = std::max(Cmax, t.C);
+            batch.push_back(t); ++pos;
+        }
+        const size_t need = (size_t)elems * bpe + 256;
+        if (need > ctx->scratch_bytes) {
+            free_dev(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+            CK(cudaMalloc(&ctx->d_scratch, need));
+            ctx->scratch_bytes = need;
+        }
+        { int rc = ensure_tasks(ctx, batch.size()); if (rc != MLP_OK) return rc; }
+        CK(cudaMemcpyAsync(ctx->d_tasks, batch.data(), batch.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (int64_t)(batch.size() * sizeof(PairTask));
+        CK(cudaMemsetAsync(ctx->d_pout, 0, batch.size() * sizeof(PairOut), ctx->stream));
+
+        KArgs a = {};
+        a.tasks = ctx->d_tasks; a.ntasks = (int)batch.size(); a.counter = ctx->d_counter; a.pout = ctx->d_pout;
+        a.residues = ctx->d_res; a.seq_off = ctx->d_seq_off; a.n = ctx->n;
+        a.flavour = flavour; a.mask = mask; a.cutoff = cutoff; a.Cmax = Cmax;
+        a.match = ctx->d_match; a.ins = ctx->d_ins; a.sub = ctx->d_sub;
+        unsigned char* p = (unsigned char*)ctx->d_scratch;
+        if (useP) { a.layerZ = (double*)p; p += (size_t)elems * 8; a.layerP = (float*)p; p += (size_t)elems * 4; }
+        if (use5) { a.layerS5 = (float*)p; p += (size_t)elems * 4; }
+        if (useL) {
+            a.layerSL = (float*)p; p += (size_t)elems * 4;
+            if (useP) a.layerVB = (float*)a.layerZ; else { a.layerVB = (float*)p; p += (size_t)elems * 4; }
+        }
+        a.edge_f = need_edge ? (float*)ctx->d_edge : nullptr;
+        a.edge_d = need_edge ? (double*)ctx->d_edge : nullptr;
+        a.edge_stride = ctx->edge_stride;   // in elements of the kernel's own type; the buffer is sized for doubles
+        a.rp_off = ctx->d_rp_off; a.out = ctx->set[ctx->cur]; a.in = CsrSetDev{};
+        a.stage = ctx->d_stage; a.stage_cap = ctx->stage_cap;
+        a.tfill = ctx->d_tfill; a.tfill_stride = ctx->tfill_stride;
+        a.dist = ctx->d_dist; a.err = ctx->d_err;
+        a.dense = dense; a.dense5 = dense5; a.denseP = denseP; a.denseL = denseL;
+
+        const int nt = (int)batch.size();
+        int rc;
+        if (useP) {
+            if ((rc = launch_one(ctx, MLP_K_PART_FWD, a, nt, kt, MLP_K_PART_FWD)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_PART_REV, a, nt, kt, MLP_K_PART_REV)) != MLP_OK) return rc;
+        }
+        if (useL) {
+            if ((rc = launch_one(ctx, MLP_K_LOCAL_FWD, a, nt, kt, MLP_K_LOCAL_FWD)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_LOCAL_BWD, a, nt, kt, MLP_K_LOCAL_BWD)) != MLP_OK) return rc;
+        }
+        if (use5) {
+            if ((rc = launch_one(ctx, MLP_K_HMM_FWD, a, nt, kt, MLP_K_HMM_FWD)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_HMM_BWD, a, nt, kt, MLP_K_HMM_BWD)) != MLP_OK) return rc;
+        }
+        if ((rc = launch_one(ctx, MLP_K_FINAL, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
+        if ((rc = launch_one(ctx, MLP_K_TRANSPOSE, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        int err = 0;
+        CK(cudaMemcpy(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) {
+            cudaMemset(ctx->d_err, 0, sizeof(int));
+            ctx->err = (err & 2) ? "sparse cell pool exhausted: raise cell_capacity via mlp_configure"
+                                 : "per-pair staging buffer exhausted (more than 32 kept cells per row on average)";
+            return MLP_E_CAPACITY;
+        }
+        if (useP && flavour != MLP_QP) {
+            // cpnp runs the partition function in 80-bit long double; this FP64 kernel cannot represent Z beyond 1e308
+            std::vector<PairOut> po(batch.size());
+            CK(cudaMemcpy(po.data(), ctx->d_pout, batch.size() * sizeof(PairOut), cudaMemcpyDeviceToHost));
+            for (const PairOut& o : po)
+                if (!std::isfinite(o.Zpart) || o.Zpart == 0.0) {
+                    ctx->err = "partition function left the FP64 range for at least one pair (cpnp uses long double)";
+                    return MLP_E_OVERFLOW;
+                }
+        }
+        for (const PairTask& t : batch) { ctx->stats.cells += (int64_t)(t.L1 + 1) * (t.L2 + 1); }
+        ctx->stats.pairs += (int64_t)batch.size();
+    }
+    kt.collect(ctx->stats);
+    return MLP_OK;
+}
+
+extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model_mask, float cutoff) {
+    if (!ctx) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
+    if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
+    if (flavour == MLP_QP) model_mask = MLP_M_HMM5 | MLP_M_PART;
+    if (flavour == MLP_CPNP_P1) { ctx->err = "MLP_CPNP_P1 distance (MEA traceback match count) is not implemented yet"; return MLP_E_UNSUPPORTED; }
+    if ((model_mask & MLP_M_PART) && flavour != MLP_QP) {
+        // letters J, O, U index sub_matrix[-1] in the reference: refuse instead of guessing
+        for (long long k = 0; k < ctx->total_res; ++k) {
+            const int c = ctx->codes_h[k];
+            if (std::isnan(ctx->part.sub[c][c])) { ctx->err = "sequence contains a letter the reference partition table cannot score (J/O/U)"; return MLP_E_UNSUPPORTED; }
+        }
+    }
+    int rc = ensure_sets(ctx);
+    if (rc != MLP_OK) return rc;
+    ctx->stats = mlp_stage_stats{};
+    ctx->cur = 0;
+    CK(cudaMemsetAsync(ctx->set[0].cursor, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->set[0].nz_cnt, 0, (size_t)ctx->n * ctx->n * sizeof(int), ctx->stream));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = run_posterior_tasks(ctx, flavour, model_mask, cutoff, ctx->owned, nullptr, nullptr, nullptr, nullptr);
+    if (rc != MLP_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_total = ms;
+    unsigned long long cur = 0;
+    CK(cudaMemcpy(&cur, ctx->set[0].cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+    ctx->stats.nnz = (int64_t)(cur / 2);
+    ctx->flavour_of_set = flavour;
+    return MLP_OK;
+}
+
+extern "C" int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_mask, int a, int b,
+                                    float* merged, float* p_hmm5, float* p_part, float* p_local, float* distance) {
+    if (!ctx || !merged) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (!ctx->have_tables || ctx->n < 2) return MLP_E_STATE;
+    if (a < 0 || b <= a || b >= ctx->n) return MLP_E_ARG;
+    if (flavour == MLP_QP) model_mask = MLP_M_HMM5 | MLP_M_PART;
+    int rc = ensure_sets(ctx);
+    if (rc != MLP_OK) return rc;
+    const int L1 = ctx->len[a], L2 = ctx->len[b];
+    const size_t cells = (size_t)(L1 + 1) * (L2 + 1);
+    float* d = nullptr;
+    CK(cudaMalloc(&d, cells * 4 * sizeof(float)));
+    CK(cudaMemset(d, 0, cells * 4 * sizeof(float)));
+    std::vector<PairTask> one;
+    for (const PairTask& t : ctx->all_pairs) if (t.a == a && t.b == b) one.push_back(t);
+    unsigned long long cursor_save = 0;
+    CK(cudaMemcpy(&cursor_save, ctx->set[ctx->cur].cursor, sizeof(cursor_save), cudaMemcpyDeviceToHost));
+    mlp_stage_stats keep = ctx->stats;
+    rc = run_posterior_tasks(ctx, flavour == MLP_CPNP_P1 ? MLP_CPNP_P1 : flavour, model_mask, 0.01f, one, d, d + cells, d + 2 * cells, d + 3 * cells);
+    ctx->stats = keep;
+    if (rc == MLP_OK) {
+        cudaMemcpy(merged, d, cells * sizeof(float), cudaMemcpyDeviceToHost);
+        if (p_hmm5) cudaMemcpy(p_hmm5, d + cells, cells * sizeof(float), cudaMemcpyDeviceToHost);
+        if (p_part) cudaMemcpy(p_part, d + 2 * cells, cells * sizeof(float), cudaMemcpyDeviceToHost);
+        if (p_local) cudaMemcpy(p_local, d + 3 * cells, cells * sizeof(float), cudaMemcpyDeviceToHost);
+        if (distance) cudaMemcpy(distance, ctx->d_dist + (size_t)a * ctx->n + b, sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int mlp_get_distances(mlp_ctx* ctx, float* nxn) {
+    if (!ctx || !nxn) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpy(nxn, ctx->d_dist, (size_t)ctx->n * ctx->n * sizeof(float), cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += (int64_t)ctx->n * ctx->n * 4;
+    return MLP_OK;
+}
+
+extern "C" int mlp_get_csr(mlp_ctx* ctx, int a, int b, int32_t* row_ptr, int32_t* col, float* val, int64_t* nnz) {
+    if (!ctx || a < 0 || b < 0 || a >= ctx->n || b >= ctx->n || a == b) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    const CsrSetDev& s = ctx->set[ctx->cur];
+    const size_t slot = (size_t)a * ctx->n + b;
+    int cnt = 0; long long off = 0;
+    CK(cudaMemcpy(&cnt, s.nz_cnt + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&off, s.nz_off + slot, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (nnz) *nnz = cnt;
+    if (row_ptr) CK(cudaMemcpy(row_ptr, s.rp_pool + ctx->rp_off_h[slot], (size_t)(ctx->len[a] + 2) * sizeof(int), cudaMemcpyDeviceToHost));
+    if ((col || val) && cnt > 0) {
+        std::vector<int2> cells(cnt);
+        CK(cudaMemcpy(cells.data(), s.cells + off, (size_t)cnt * sizeof(int2), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < cnt; ++k) {
+            if (col) col[k] = cells[k].x;
+            if (val) std::memcpy(&val[k], &cells[k].y, 4);
+        }
+    }
+    return MLP_OK;
+}
+
+extern "C" int mlp_total_cells(mlp_ctx* ctx, int64_t* cells) {
+    if (!ctx || !cells) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    std::vector<int> cnt((size_t)ctx->n * ctx->n);
+    CK(cudaMemcpy(cnt.data(), ctx->set[ctx->cur].nz_cnt, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int64_t s = 0;
+    for (int c : cnt) s += c;
+    *cells = s;
+    return MLP_OK;
+}
+
+extern "C" int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* row_ptr, int32_t* col, float* val) {
+    if (!ctx) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    const int n = ctx->n;
+    const CsrSetDev& s = ctx->set[ctx->cur];
+    std::vector<int> cnt((size_t)n * n);
+    std::vector<long long> off((size_t)n * n);
+    CK(cudaMemcpy(cnt.data(), s.nz_cnt, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(off.data(), s.nz_off, off.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += (int64_t)n * n * 12;
+    std::vector<int> rp_all;
+    if (row_ptr) {
+        rp_all.resize(ctx->rp_total);
+        CK(cudaMemcpy(rp_all.data(), s.rp_pool, (size_t)ctx->rp_total * sizeof(int), cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += ctx->rp_total * 4;
+    }
+    std::vector<int2> cells;
+    unsigned long long used = 0;
+    if (col || val) {
+        CK(cudaMemcpy(&used, s.cursor, sizeof(used), cudaMemcpyDeviceToHost));
+        used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
+        cells.resize(used);
+        if (used) CK(cudaMemcpy(cells.data(), s.cells, used * sizeof(int2), cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += (int64_t)used * 8;
+    }
+    int64_t p = 0, rpos = 0, cpos = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = a + 1; b < n; ++b, ++p) {
+            const size_t slot = (size_t)a * n + b;
+            if (nnz_per_pair) nnz_per_pair[p] = cnt[slot];
+            if (row_ptr) { std::memcpy(row_ptr + rpos, rp_all.data() + ctx->rp_off_h[slot], (size_t)(ctx->len[a] + 2) * sizeof(int)); rpos += ctx->len[a] + 2; }
+            if (col || val)
+                for (int k = 0; k < cnt[slot]; ++k) {
+                    const int2 c = cells[off[slot] + k];
+                    if (col) col[cpos] = c.x;
+                    if (val) std::memcpy(&val[cpos], &c.y, 4);
+                    ++cpos;
+                }
+        }
+    return MLP_OK;
+}
+
+extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
+                         float selectivity, float selfweight, float cutoff) {
+    if (!ctx) return MLP_E_ARG;
+    if (!ctx->have_sets || ctx->flavour_of_set < 0) { ctx->err = "run mlp_posterior_all_pairs first"; return MLP_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const int n = ctx->n;
+    if (flavour == MLP_QP && (!weights || !seldist_nxn || !(selectivity > 0))) return MLP_E_ARG;
+    const int in = ctx->cur, out = 1 - ctx->cur;
+    ctx->stats = mlp_stage_stats{};
+    if (flavour == MLP_QP) {
+        if (!ctx->d_weights) { CK(cudaMalloc(&ctx->d_weights, n * sizeof(float))); CK(cudaMalloc(&ctx->d_seldist, (size_t)n * n * sizeof(float))); }
+        CK(cudaMemcpyAsync(ctx->d_weights, weights, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_seldist, seldist_nxn, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (int64_t)n * 4 + (int64_t)n * n * 4;
+    }
+    // tasks in row-major pair order: warps resident together share S_x* rows in L2
+    std::vector<PairTask> tasks = ctx->owned;
+    std::sort(tasks.begin(), tasks.end(), [](const PairTask& x, const PairTask& y) { return x.pidx < y.pidx; });
+    int rc = ensure_tasks(ctx, tasks.size());
+    if (rc != MLP_OK) return rc;
+    int maxL1 = 0, maxL2 = 0;
+    for (const PairTask& t : tasks) { maxL1 = std::max(maxL1, t.L1); maxL2 = std::max(maxL2, t.L2); }
+    int bps = std::min(relax_max_blocks_per_sm(), 16);
+    int grid = std::max(1, std::min(ctx->num_sms * bps, (int)((tasks.size() + 3) / 4)));
+    const long long warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
+    rc = ensure_warp_buffers(ctx, warps, maxL1, maxL2, false, 1);
+    if (rc != MLP_OK) return rc;
+    if (flavour == MLP_QP && warps > ctx->wk_warps) {
+        free_dev(ctx->d_wk); ctx->d_wk = nullptr;
+        CK(cudaMalloc(&ctx->d_wk, (size_t)warps * n * sizeof(float)));
+        ctx->wk_warps = warps;
+    }
+    CK(cudaMemcpyAsync(ctx->d_tasks, tasks.data(), tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += (int64_t)(tasks.size() * sizeof(PairTask));
+    CK(cudaMemsetAsync(ctx->set[out].cursor, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->set[out].nz_cnt, 0, (size_t)n * n * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+    RelaxArgs ra = {};
+    ra.tasks = ctx->d_tasks; ra.ntasks = (int)tasks.size(); ra.counter = ctx->d_counter;
+    ra.n = n; ra.flavour = flavour; ra.cutoff = cutoff; ra.rp_off = ctx->d_rp_off;
+    ra.in = ctx->set[in]; ra.out = ctx->set[out];
+    ra.weights = ctx->d_weights; ra.seldist = ctx->d_seldist; ra.selectivity = selectivity; ra.selfweight = selfweight;
+    ra.wk_scratch = ctx->d_wk; ra.wk_stride = n; ra.err = ctx->d_err;
+    KernelTimer kt;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    kt.begin(MLP_K_RELAX_ID, ctx->stream);
+    CK(relax_launch(ra, grid, ctx->stream));
+    kt.end(ctx->stream);
+    ctx->stats.launches += 1;
+    // second orientation of every new matrix
+    KArgs a = {};
+    a.tasks = ctx->d_tasks; a.ntasks = (int)tasks.size(); a.counter = ctx->d_counter; a.n = n; a.flavour = flavour;
+    a.rp_off = ctx->d_rp_off; a.out = ctx->set[out]; a.tfill = ctx->d_tfill; a.tfill_stride = ctx->tfill_stride; a.err = ctx->d_err;
+    a.Cmax = 1;
+    rc = launch_one(ctx, MLP_K_TRANSPOSE, a, (int)tasks.size(), kt, MLP_K_RELAX_ID);
+    if (rc != MLP_OK) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_total = ms;
+    kt.collect(ctx->stats);
+    int err = 0;
+    CK(cudaMemcpy(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { cudaMemset(ctx->d_err, 0, sizeof(int)); ctx->err = "sparse cell pool exhausted during relaxation"; return MLP_E_CAPACITY; }
+    ctx->cur = out;
+    ctx->stats.pairs = (int64_t)tasks.size();
+    unsigned long long cur = 0;
+    CK(cudaMemcpy(&cur, ctx->set[out].cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+    ctx->stats.nnz = (int64_t)(cur / 2);
+    return MLP_OK;
+}
+
+extern "C" int mlp_last_stats(mlp_ctx* ctx, mlp_stage_stats* out) {
+    if (!ctx || !out) return MLP_E_ARG;
+    *out = ctx->stats;
+    return MLP_OK;
+}

@@ -1,0 +1,116 @@
+// Host-side construction of the reference's default model tables (product code; the oracle has its own copy).
+// Built with the same glibc calls the reference uses so the float tables are bit-identical
+// (logf for the HMM tables, expf for cpnp's substitution table, double exp for gap terms).
+#include "../../include/mlprobs_b200.h"
+#include "param_data.h"
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+// cpnp ProbabilisticModel.h:58-135 ; QP PairHmm.cpp:4-33 + ProbabilisticModel.cpp:15-56
+void build_hmm(float init_distrib2, mlp_hmm_tables* t) {
+    const float initD[5] = {0.6814756989f, 8.615339902e-05f, 8.615339902e-05f, 0.1591759622f, 0.1591759622f};
+    const float gapOpen[2] = {0.0119511066f, 0.008008334786f};
+    const float gapExt[2] = {0.3965826333f, 0.8988758326f};
+    const float lgo = 0.01993141696f, lge = 0.7943345308f;
+    float tm[5][5];
+    std::memset(tm, 0, sizeof tm);
+    tm[0][0] = 1;
+    for (int i = 0; i < 2; i++) {
+        const int x = 2 * i + 1, y = 2 * i + 2;
+        tm[0][x] = gapOpen[i];
+        tm[0][y] = gapOpen[i];
+        tm[0][0] -= (gapOpen[i] + gapOpen[i]);
+        tm[x][x] = gapExt[i];
+        tm[y][y] = gapExt[i];
+        tm[x][0] = 1 - gapExt[i];
+        tm[y][0] = 1 - gapExt[i];
+    }
+    for (int i = 0; i < 5; i++) {
+        t->init[i] = logf(initD[i]);
+        for (int j = 0; j < 5; j++) t->trans[i][j] = logf(tm[i][j]);
+    }
+    const float unknown_single = 1e-5, unknown_pair = 1e-10;   // MSA.cpp:46-47 / ProbabilisticModel.cpp:36-39
+    for (int a = 0; a < 26; a++) {
+        t->ins[a] = logf(unknown_single);
+        for (int b = 0; b < 26; b++) t->match[a][b] = logf(unknown_pair);
+    }
+    const char* al = MLP_HMM_ALPHABET;
+    for (int i = 0; i < 20; i++) {
+        t->ins[al[i] - 'A'] = logf(MLP_EMIT_SINGLE[i]);
+        for (int j = 0; j <= i; j++) {
+            const float v = logf(MLP_EMIT_PAIRS_TRI[i * (i + 1) / 2 + j]);
+            t->match[al[i] - 'A'][al[j] - 'A'] = v;
+            t->match[al[j] - 'A'][al[i] - 'A'] = v;
+        }
+    }
+    float lt[3][3];
+    std::memset(lt, 0, sizeof lt);
+    lt[0][0] = 1;
+    lt[0][1] = lgo;
+    lt[0][2] = lgo;
+    lt[0][0] -= (lgo + lgo);
+    lt[1][1] = lge;
+    lt[2][2] = lge;
+    lt[1][0] = 1 - lge;
+    lt[2][0] = 1 - lge;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t->ltrans[i][j] = logf(lt[i][j]);
+    t->rtrans[0] = logf(init_distrib2);
+    t->rtrans[1] = logf(1 - init_distrib2);
+}
+
+// MSAReadMatrix.cpp:85-116,158-210 ; MSAPartProbs.cpp:698-709
+void build_part_cpnp(mlp_part_tables* t) {
+    const float temperature = 5;
+    const float beta = (float)(1.0 / temperature);
+    for (int a = 0; a < 26; a++)
+        for (int b = 0; b < 26; b++) t->sub[a][b] = NAN;
+    const char* al = MLP_GONNET160_ALPHABET;
+    const int n = (int)std::strlen(al);
+    int pos = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            const double v = expf(beta * MLP_GONNET160_TRI[pos++]);
+            t->sub[al[i] - 'A'][al[j] - 'A'] = v;
+            t->sub[al[j] - 'A'][al[i] - 'A'] = v;
+        }
+    const float gapopen = -22, gapext = -1;
+    const double b = beta;
+    t->tgo = std::exp(b * 0.0);
+    t->tge = std::exp(b * 0.0);
+    t->go = std::exp(b * (double)gapopen);
+    t->ge = std::exp(b * (double)gapext);
+}
+
+// ExpPartitionFunctionParams.h:30-49 ; Configuration.cpp:330-332
+void build_part_qp(mlp_part_tables* t) {
+    const double temperature = 5.6007, gi = -25.3549, ge = -1.30113;
+    const double beta = 1.0 / temperature;
+    std::memset(t->sub, 0, sizeof t->sub);
+    const char* al = MLP_VTML200_ALPHABET;
+    const int n = (int)std::strlen(al);
+    for (int i = 0; i < n - 1; i++)
+        for (int j = 0; j <= i; j++) {
+            const double v = std::exp(beta * MLP_VTML200[i * n + j]);
+            t->sub[al[i] - 'A'][al[j] - 'A'] = v;
+            t->sub[al[j] - 'A'][al[i] - 'A'] = v;
+        }
+    t->go = std::exp(beta * gi);
+    t->ge = std::exp(beta * ge);
+    t->tgo = std::exp(beta * 0);
+    t->tge = std::exp(beta * 0);
+}
+
+}  // namespace
+
+extern "C" int mlp_default_tables(int flavour, float init_distrib2, mlp_hmm_tables* hmm, mlp_part_tables* part) {
+    if (flavour < MLP_QP || flavour > MLP_CPNP_P1) return MLP_E_ARG;
+    if (hmm) build_hmm(flavour == MLP_QP ? 0.700645f : init_distrib2, hmm);
+    if (part) {
+        if (flavour == MLP_QP) build_part_qp(part);
+        else build_part_cpnp(part);
+    }
+    return MLP_OK;
+}

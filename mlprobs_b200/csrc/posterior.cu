@@ -1,0 +1,764 @@
+// Pair-DP kernels of the posterior stage (one warp per sequence pair, striped wavefront: sweep.cuh).
+//   k_part_fwd / k_part_rev   partition-function posterior   (QP PartitionFunction.cpp:71-291, cpnp MSAPartProbs.cpp:78-660)
+//   k_hmm_fwd  / k_hmm_bwd    5-state pair-HMM               (cpnp ProbabilisticModel.h:153-493 flag=true, QP ParallelProbabilisticModel.cpp:40-269)
+//   k_loc_fwd  / k_loc_bwd    3-state local pair-HMM + row-major Z replay (cpnp ProbabilisticModel.h flag=false)
+//   k_final                   merge + MEA score + threshold to CSR (PosteriorStage.cpp:156-196, MSA.cpp:992-1023, SparseMatrix.h:55-98)
+//   k_transpose               second orientation of each CSR matrix (PackedSparseMatrix.cpp:93-140, SparseMatrix.h:205-248)
+#include "posterior.cuh"
+#include "sweep.cuh"
+
+__constant__ DevScalars c_sc;
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ int next_task(int* counter, int lane) {
+    int ti = 0;
+    if (lane == 0) ti = atomicAdd(counter, 1);
+    return __shfl_sync(MLP_FULL, ti, 0);
+}
+
+__device__ __forceinline__ SweepCtx make_ctx(const PairTask& t, const KArgs& a, int lane) {
+    SweepCtx cx;
+    cx.task = &t;
+    cx.s1 = a.residues + a.seq_off[t.a];
+    cx.s2 = a.residues + a.seq_off[t.b];
+    cx.lane = lane;
+    cx.L1 = t.L1; cx.L2 = t.L2; cx.C = t.C; cx.nb = t.nb; cx.T = t.L1 + 32;
+    cx.off = t.off;
+    return cx;
+}
+
+// per-warp shared-memory carve-up: [tables (CTA)] [warp0: band | colres | cap] [warp1: ...]
+template <class T, int NS>
+__device__ __forceinline__ void warp_smem(unsigned char* base, int tables_bytes, int Cmax, int warp,
+                                          T*& band, uint8_t*& colres, float*& cap) {
+    const int band_bytes = NS * Cmax * 32 * (int)sizeof(T);
+    const int per_warp = band_bytes + Cmax * 32 + 64;
+    unsigned char* p = base + tables_bytes + (size_t)warp * ((per_warp + 15) & ~15);
+    band = reinterpret_cast<T*>(p);
+    colres = p + band_bytes;
+    cap = reinterpret_cast<float*>(p + band_bytes + Cmax * 32);
+}
+
+// ------------------------------------------------------------------------------------------------ 5-state HMM
+// state order (reference numbering): 0 = M, 1 = X1, 2 = Y1, 3 = X2, 4 = Y2
+struct HmmFwd {
+    typedef float T;
+    enum { NS = 5, REV = 0, COLMASK = 0x1f };
+    const float* match; const float* ins;
+    float* F;
+    int L1, L2;
+    float ins1; const float* mrow;
+    float fin[5]; bool has_fin;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st[s] = MLP_LOG_ZERO;
+    }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) e[s] = MLP_LOG_ZERO;
+    }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j; }
+    __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
+    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        // ProbabilisticModel.h:213-245 / ParallelProbabilisticModel.cpp:91-113
+        float m = __fadd_rn(diag[0], c_sc.tq0[0]);
+        m = dev_log_add(m, __fadd_rn(diag[1], c_sc.tq0[1]));
+        m = dev_log_add(m, __fadd_rn(diag[2], c_sc.tq0[2]));
+        m = dev_log_add(m, __fadd_rn(diag[3], c_sc.tq0[3]));
+        m = dev_log_add(m, __fadd_rn(diag[4], c_sc.tq0[4]));
+        m = __fadd_rn(m, mrow[r2]);
+        const float ins2 = ins[r2];
+        float x1 = __fadd_rn(ins1, dev_log_add(__fadd_rn(old[0], c_sc.t0q[1]), __fadd_rn(old[1], c_sc.tqq[1])));
+        float x2 = __fadd_rn(ins1, dev_log_add(__fadd_rn(old[0], c_sc.t0q[3]), __fadd_rn(old[3], c_sc.tqq[3])));
+        float y1 = __fadd_rn(ins2, dev_log_add(__fadd_rn(carry[0], c_sc.t0q[2]), __fadd_rn(carry[2], c_sc.tqq[2])));
+        float y2 = __fadd_rn(ins2, dev_log_add(__fadd_rn(carry[0], c_sc.t0q[4]), __fadd_rn(carry[4], c_sc.tqq[4])));
+        if (i <= 1 && j <= 1) {   // initialisation cells, ProbabilisticModel.h:173-184 (the recurrence is skipped there)
+            m = (i == 1 && j == 1) ? __fadd_rn(c_sc.init[0], mrow[r2]) : MLP_LOG_ZERO;
+            x1 = (i == 1 && j == 0) ? __fadd_rn(c_sc.init[1], ins1) : MLP_LOG_ZERO;
+            x2 = (i == 1 && j == 0) ? __fadd_rn(c_sc.init[3], ins1) : MLP_LOG_ZERO;
+            y1 = (i == 0 && j == 1) ? __fadd_rn(c_sc.init[2], ins2) : MLP_LOG_ZERO;
+            y2 = (i == 0 && j == 1) ? __fadd_rn(c_sc.init[4], ins2) : MLP_LOG_ZERO;
+        }
+        nw[0] = m; nw[1] = x1; nw[2] = y1; nw[3] = x2; nw[4] = y2;
+        F[slot] = m;
+        if (i == L1 && j == L2) { has_fin = true; fin[0] = m; fin[1] = x1; fin[2] = y1; fin[3] = x2; fin[4] = y2; }
+    }
+};
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* match = reinterpret_cast<float*>(smem);
+    float* ins = match + 676;
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
+    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* band; uint8_t* colres; float* cap;
+    warp_smem<float, 5>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        HmmFwd m;
+        m.match = match; m.ins = ins; m.F = a.layerS5; m.L1 = t.L1; m.L2 = t.L2; m.has_fin = false;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        if (m.has_fin) {   // total forward probability, ProbabilisticModel.h:415-419
+            float tF = MLP_LOG_ZERO;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) tF = dev_log_add(tF, __fadd_rn(m.fin[k], c_sc.init[k]));
+            a.pout[ti].tF5 = tF;
+        }
+    }
+}
+
+struct HmmBwd {
+    typedef float T;
+    enum { NS = 5, REV = 1, COLMASK = 0x0b };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
+    const float* match; const float* ins;
+    float* F;      // in: forward M, out: F + B (ProbabilisticModel.h:483 evaluates (F+B)-total)
+    float* cap;    // [0]=B_M(1,1) [1]=B_X1(1,0) [2]=B_Y1(0,1) [3]=B_X2(1,0) [4]=B_Y2(0,1)
+    int L1, L2;
+    float ins1; const float* mrow;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st[s] = MLP_LOG_ZERO;
+    }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) e[s] = MLP_LOG_ZERO;
+    }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i + 1; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j + 1; }
+    __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
+    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        if (j > L2) {   // virtual column L2+1 (and padding): nothing flows in from the right
+#pragma unroll
+            for (int s = 0; s < NS; ++s) nw[s] = MLP_LOG_ZERO;
+            return;
+        }
+        // ProbabilisticModel.h:340-379 / ParallelProbabilisticModel.cpp:196-218, same LOG_PLUS_EQUALS order
+        const float ins2 = ins[r2];
+        const float pxy = __fadd_rn(diag[0], mrow[r2]);
+        float bm = __fadd_rn(pxy, c_sc.tq0[0]);
+        float x1 = __fadd_rn(pxy, c_sc.tq0[1]);
+        float y1 = __fadd_rn(pxy, c_sc.tq0[2]);
+        float x2 = __fadd_rn(pxy, c_sc.tq0[3]);
+        float y2 = __fadd_rn(pxy, c_sc.tq0[4]);
+        const float a1 = __fadd_rn(old[1], ins1);
+        bm = dev_log_add(bm, __fadd_rn(a1, c_sc.t0q[1]));
+        x1 = dev_log_add(x1, __fadd_rn(a1, c_sc.tqq[1]));
+        const float a2 = __fadd_rn(old[3], ins1);
+        bm = dev_log_add(bm, __fadd_rn(a2, c_sc.t0q[3]));
+        x2 = dev_log_add(x2, __fadd_rn(a2, c_sc.tqq[3]));
+        const float b1 = __fadd_rn(carry[2], ins2);
+        bm = dev_log_add(bm, __fadd_rn(b1, c_sc.t0q[2]));
+        y1 = dev_log_add(y1, __fadd_rn(b1, c_sc.tqq[2]));
+        const float b2 = __fadd_rn(carry[4], ins2);
+        bm = dev_log_add(bm, __fadd_rn(b2, c_sc.t0q[4]));
+        y2 = dev_log_add(y2, __fadd_rn(b2, c_sc.tqq[4]));
+        if (i == L1 && j == L2) { bm = c_sc.init[0]; x1 = c_sc.init[1]; y1 = c_sc.init[2]; x2 = c_sc.init[3]; y2 = c_sc.init[4]; }
+        nw[0] = bm; nw[1] = x1; nw[2] = y1; nw[3] = x2; nw[4] = y2;
+        F[slot] = __fadd_rn(F[slot], bm);
+        if (i <= 1 && j <= 1) {
+            if (i == 1 && j == 1) cap[0] = bm;
+            if (i == 1 && j == 0) { cap[1] = x1; cap[3] = x2; }
+            if (i == 0 && j == 1) { cap[2] = y1; cap[4] = y2; }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* match = reinterpret_cast<float*>(smem);
+    float* ins = match + 676;
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
+    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* band; uint8_t* colres; float* cap;
+    warp_smem<float, 5>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        HmmBwd m;
+        m.match = match; m.ins = ins; m.F = a.layerS5; m.cap = cap; m.L1 = t.L1; m.L2 = t.L2;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        __syncwarp();
+        if (lane == 0) {   // ProbabilisticModel.h:421-432 / ParallelProbabilisticModel.cpp:226-231, then :453 and PosteriorStage.cpp:142
+            const int r1 = cx.s1[0], r2 = cx.s2[0];
+            float tB = __fadd_rn(__fadd_rn(c_sc.init[0], match[r1 * 26 + r2]), cap[0]);
+            tB = dev_log_add(tB, __fadd_rn(__fadd_rn(c_sc.init[1], ins[r1]), cap[1]));
+            tB = dev_log_add(tB, __fadd_rn(__fadd_rn(c_sc.init[2], ins[r2]), cap[2]));
+            tB = dev_log_add(tB, __fadd_rn(__fadd_rn(c_sc.init[3], ins[r1]), cap[3]));
+            tB = dev_log_add(tB, __fadd_rn(__fadd_rn(c_sc.init[4], ins[r2]), cap[4]));
+            float total = __fdiv_rn(__fadd_rn(a.pout[ti].tF5, tB), 2.0f);
+            if (a.flavour == 0 && total == 0.0f) total = 1.0f;   // ParallelProbabilisticModel.cpp:252-254
+            a.pout[ti].total5 = total;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ partition function
+// states: 0 = Zm, 1 = H (gap run along the row: Ze in QP, Zf in cpnp), 2 = V (gap run down the column)
+// The 3-term sums are (Zm+H)+V or (Zm+V)+H depending on which reference statement is reproduced:
+//   forward Zm and zz: QP (Zm+H)+V  PartitionFunction.cpp:137,139 ; cpnp (Zm+V)+H  MSAPartProbs.cpp:583,589
+//   reverse Zm:        QP (Zm+V)+H  PartitionFunction.cpp:257     ; cpnp (Zm+H)+V  MSAPartProbs.cpp:283
+__device__ __forceinline__ double sum3(double zm, double h, double v, bool h_first) {
+    return h_first ? __dadd_rn(__dadd_rn(zm, h), v) : __dadd_rn(__dadd_rn(zm, v), h);
+}
+
+struct PartFwd {
+    typedef double T;
+    enum { NS = 3, REV = 0, COLMASK = 0x7 };
+    const double* sub; double* Z; int L1, L2; bool qp;
+    const double* srow; double zz; bool has_zz;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0; st[1] = 0; st[2] = 0; }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0; e[1] = 0; e[2] = 0; }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j; }
+    __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
+    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        if (i == 0 || j == 0 || j > L2) {   // boundary: Zm(0,0)=1, H(0,j>=1)=1, V(i>=1,0)=1 (terminal gaps are exp(0))
+            nw[0] = (i == 0 && j == 0) ? 1.0 : 0.0;
+            nw[1] = (i == 0 && j >= 1 && j <= L2) ? 1.0 : 0.0;
+            nw[2] = (j == 0 && i >= 1) ? 1.0 : 0.0;
+            Z[slot] = nw[0];
+            return;
+        }
+        const double score = srow[r2];
+        const double o0 = (i == L1) ? 1.0 : c_sc.go, e0 = (i == L1) ? 1.0 : c_sc.ge;
+        const double o1 = (j == L2) ? 1.0 : c_sc.go, e1 = (j == L2) ? 1.0 : c_sc.ge;
+        const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
+        const double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
+        const double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], qp), score);
+        nw[0] = zm; nw[1] = h; nw[2] = v;
+        Z[slot] = zm;
+        if (i == L1 && j == L2) { has_zz = true; zz = sum3(zm, h, v, qp); }
+    }
+};
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* sub = reinterpret_cast<double*>(smem);
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* band; uint8_t* colres; float* cap;
+    warp_smem<double, 3>(smem, MLP_PART_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    double* edge = a.edge_d ? a.edge_d + gw * a.edge_stride : nullptr;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        PartFwd m;
+        m.sub = sub; m.Z = a.layerZ; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0); m.has_zz = false; m.zz = 0;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        if (m.has_zz) a.pout[ti].Zpart = m.zz;
+    }
+}
+
+struct PartRev {
+    typedef double T;
+    enum { NS = 3, REV = 1, COLMASK = 0x7 };
+    const double* sub; const double* Z; float* P; int L1, L2; bool qp; double Ztot;
+    const double* srow;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int j) const {   // virtual row L1+1
+        st[0] = (j == L2 + 1) ? 1.0 : 0.0;
+        st[1] = (j >= 1 && j <= L2) ? 1.0 : 0.0;
+        st[2] = 0.0;
+    }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int i) const {    // virtual column L2+1
+        e[0] = 0.0; e[1] = 0.0; e[2] = (i >= 1 && i <= L1) ? 1.0 : 0.0;
+    }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j; }
+    __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
+    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        if (j > L2) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = (j == L2 + 1 && i >= 1) ? 1.0 : 0.0; return; }
+        if (i == 0 || j == 0) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = 0.0; P[slot] = 0.0f; return; }
+        const double score = srow[r2];
+        const double o1 = (j == 1) ? 1.0 : c_sc.go, e1 = (j == 1) ? 1.0 : c_sc.ge;   // V-type terminal at the first column
+        const double o0 = (i == 1) ? 1.0 : c_sc.go, e0 = (i == 1) ? 1.0 : c_sc.ge;   // H-type terminal at the first row
+        const double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
+        const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
+        const double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], !qp), score);
+        nw[0] = zm; nw[1] = h; nw[2] = v;
+        // PartitionFunction.cpp:259-270 / MSAPartProbs.cpp:286-297
+        double tmp = __dmul_rn(Z[slot], zm);
+        tmp = __ddiv_rn(tmp, __dmul_rn(score, Ztot));
+        float p = (float)tmp;
+        if (qp && !(p <= 1.0f && (double)p >= 0.001)) p = 0.0f;
+        P[slot] = p;
+    }
+};
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* sub = reinterpret_cast<double*>(smem);
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* band; uint8_t* colres; float* cap;
+    warp_smem<double, 3>(smem, MLP_PART_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    double* edge = a.edge_d ? a.edge_d + gw * a.edge_stride : nullptr;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        PartRev m;
+        m.sub = sub; m.Z = a.layerZ; m.P = a.layerP; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
+        m.Ztot = a.pout[ti].Zpart;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ local 3-state HMM
+// states: 0 = M, 1 = X, 2 = Y  (ProbabilisticModel.h flag=false branches)
+struct LocFwd {
+    typedef float T;
+    enum { NS = 3, REV = 0, COLMASK = 0x7 };
+    const float* match; const float* ins; float* F; int L1, L2;
+    float ins1; const float* mrow;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = st[1] = st[2] = MLP_LOG_ZERO; }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = e[1] = e[2] = MLP_LOG_ZERO; }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j; }
+    __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
+    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        // ProbabilisticModel.h:210-211,222-227: base = ((m - a) - b); M = (base - 2r) (+) sum_k ((base + F_k) + lt[k][0]) - 2r
+        const float base = __fsub_rn(__fsub_rn(mrow[r2], ins1), ins[r2]);
+        float m = __fsub_rn(base, c_sc.r2);
+        m = dev_log_add(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[0]), c_sc.lt00), c_sc.r2));
+        m = dev_log_add(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[1]), c_sc.lt10), c_sc.r2));
+        m = dev_log_add(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[2]), c_sc.lt20), c_sc.r2));
+        // :238-241, :252-255
+        float x = dev_log_add(__fsub_rn(__fadd_rn(old[0], c_sc.lt01), c_sc.r), __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r));
+        float y = dev_log_add(__fsub_rn(__fadd_rn(carry[0], c_sc.lt02), c_sc.r), __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r));
+        if (i == 0 || j == 0) m = MLP_LOG_ZERO;
+        if (i == 0) x = MLP_LOG_ZERO;
+        if (j == 0) y = MLP_LOG_ZERO;
+        if (i <= 1 && j <= 1) {
+            m = (i == 1 && j == 1) ? __fsub_rn(base, c_sc.r2) : MLP_LOG_ZERO;
+            x = MLP_LOG_ZERO; y = MLP_LOG_ZERO;
+        }
+        nw[0] = m; nw[1] = x; nw[2] = y;
+        F[slot] = m;
+    }
+};
+
+struct LocBwd {
+    typedef float T;
+    enum { NS = 3, REV = 1, COLMASK = 0x3 };   // keep B_M and X of row i+1; Y travels along the row
+    const float* match; const float* ins; float* F; float* VB; int L1, L2;
+    float ins1n; const float* mrown;   // residue i+1 (transition out of the cell)
+    float ins1c; const float* mrowc;   // residue i   (the cell's own emission, for the Z term)
+    const uint8_t* s1; const uint8_t* s2;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = st[1] = st[2] = MLP_LOG_ZERO; }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = e[1] = e[2] = MLP_LOG_ZERO; }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i + 1; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j + 1; }
+    __device__ __forceinline__ void begin_row(int i, int r1) {
+        ins1n = ins[r1]; mrown = match + r1 * 26;
+        const int rc = (i >= 1) ? s1[i - 1] : 0;
+        ins1c = ins[rc]; mrowc = match + rc * 26;
+    }
+    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        if (j > L2) { nw[0] = nw[1] = nw[2] = MLP_LOG_ZERO; return; }
+        // ProbabilisticModel.h:339-379 flag=false.  B_M starts at LOG_ONE in every cell.
+        float bm = 0.0f, x = MLP_LOG_ZERO, y = MLP_LOG_ZERO;
+        if (i < L1 && j < L2) {
+            const float pxy = __fsub_rn(__fsub_rn(__fadd_rn(diag[0], mrown[r2]), ins1n), ins[r2]);
+            bm = dev_log_add(bm, __fsub_rn(__fadd_rn(pxy, c_sc.lt00), c_sc.r2));
+            x = __fsub_rn(__fadd_rn(pxy, c_sc.lt10), c_sc.r2);
+            y = __fsub_rn(__fadd_rn(pxy, c_sc.lt20), c_sc.r2);
+        }
+        if (i < L1) {
+            bm = dev_log_add(bm, __fsub_rn(__fadd_rn(old[1], c_sc.lt01), c_sc.r));
+            x = dev_log_add(x, __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r));
+        }
+        if (j < L2) {
+            bm = dev_log_add(bm, __fsub_rn(__fadd_rn(carry[2], c_sc.lt02), c_sc.r));
+            y = dev_log_add(y, __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r));
+        }
+        nw[0] = bm; nw[1] = x; nw[2] = y;
+        // Z term of this cell, ProbabilisticModel.h:445-446: (((B_M + m) - a) - b) - 2r with the cell's own residues
+        float vb = MLP_LOG_ZERO;
+        if (i >= 1 && j >= 1) {
+            const int rj = s2[j - 1];
+            vb = __fsub_rn(__fsub_rn(__fsub_rn(__fadd_rn(bm, mrowc[rj]), ins1c), ins[rj]), c_sc.r2);
+        }
+        VB[slot] = vb;
+        F[slot] = __fadd_rn(F[slot], bm);
+    }
+};
+
+// Exact replay of the reference's sequential row-major LOG_PLUS_EQUALS chain over a dense slot-layout layer
+// (ProbabilisticModel.h:434-451).  The running sum is monotone (LOOKUP(d) > d's loss), so a
+// cell more than 7.5 below the sum can never change it: a warp tests 32 cells at once and applies only the
+// cells that fire, in order -- bit-identical to the serial chain.
+__device__ float replay_rowmajor(const float* layer, const SweepCtx& cx) {
+    float sum = MLP_LOG_ZERO;
+    const int lane = cx.lane;
+    const int W = 32 * cx.C;
+    for (int i = 1; i <= cx.L1; ++i) {
+        for (int j0 = 0; j0 <= cx.L2; j0 += 32) {
+            const int j = j0 + lane;
+            float v = MLP_LOG_ZERO;
+            if (j >= 1 && j <= cx.L2) {
+                const int cb = j / W, rem = j - cb * W;
+                const int l = rem / cx.C, c = rem - l * cx.C;
+                v = layer[cx.off + ((long long)(cb * cx.T + i + l) * cx.C + c) * 32 + l];
+            }
+            int pos = 0;
+            for (;;) {
+                // the cell changes the sum unless sum >= v and (v == LOG_ZERO or sum - v >= 7.5)
+                const bool fires = (lane >= pos) && (j >= 1 && j <= cx.L2) &&
+                                   !(sum >= v && (v == MLP_LOG_ZERO || __fsub_rn(sum, v) >= 7.5f));
+                const unsigned mask = __ballot_sync(MLP_FULL, fires);
+                if (mask == 0) break;
+                const int l0 = __ffs(mask) - 1;
+                const float vv = __shfl_sync(MLP_FULL, v, l0);
+                sum = dev_log_add(sum, vv);
+                pos = l0 + 1;
+            }
+        }
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* match = reinterpret_cast<float*>(smem);
+    float* ins = match + 676;
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
+    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* band; uint8_t* colres; float* cap;
+    warp_smem<float, 3>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        LocFwd m;
+        m.match = match; m.ins = ins; m.F = a.layerSL; m.L1 = t.L1; m.L2 = t.L2;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        __syncwarp();
+        __threadfence_block();
+        const float tF = replay_rowmajor(a.layerSL, cx);
+        if (lane == 0) a.pout[ti].tFL = tF;
+    }
+}
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* match = reinterpret_cast<float*>(smem);
+    float* ins = match + 676;
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
+    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* band; uint8_t* colres; float* cap;
+    warp_smem<float, 3>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        LocBwd m;
+        m.match = match; m.ins = ins; m.F = a.layerSL; m.VB = a.layerVB; m.L1 = t.L1; m.L2 = t.L2; m.s1 = cx.s1; m.s2 = cx.s2;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        __syncwarp();
+        __threadfence_block();
+        const float tB = replay_rowmajor(a.layerVB, cx);
+        if (lane == 0) a.pout[ti].totalL = __fdiv_rn(__fadd_rn(a.pout[ti].tFL, tB), 2.0f);   // ProbabilisticModel.h:453
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ merge + MEA + sparsify
+// states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
+struct FinalSweep {
+    typedef float T;
+    enum { NS = 2, REV = 0, COLMASK = 0x1 };
+    const float* S5; const float* P; const float* SL;
+    float total5, totalL;
+    int flavour; unsigned mask; float cutoff;
+    int L1, L2;
+    int* rowcnt;            // [L1+2] in the row-pointer pool (counts first, scanned later)
+    int4* stage; int stage_cap; int* stage_n;   // per-warp staging of kept cells
+    float* dense;           // optional dense dump (debug), row-major (L1+1)x(L2+1)
+    float* dense5; float* denseP; float* denseL;
+    float score; bool has_score;
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0.0f; st[1] = 0.0f; }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0.0f; e[1] = 0.0f; }
+    __device__ __forceinline__ int row_residue_index(int) const { return 0; }
+    __device__ __forceinline__ int col_residue_index(int) const { return 0; }
+    __device__ __forceinline__ void begin_row(int, int) {}
+    __device__ __forceinline__ void cell(int i, int j, int, long long slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        if (j > L2) { nw[0] = carry[0]; nw[1] = carry[1]; return; }
+        float v5 = 0.0f, vp = 0.0f, vl = 0.0f, p;
+        if (mask & 1u) v5 = dev_posterior_from_sum(S5[slot], total5);
+        if (mask & 2u) vp = P[slot];
+        if (mask & 4u) vl = dev_posterior_from_sum(SL[slot], totalL);
+        if (i == 0 && j == 0) { v5 = 0.0f; vl = 0.0f; }   // posterior[0] = 0, ProbabilisticModel.h:490
+        if (flavour == 0) {
+            // PosteriorStage.cpp:169-177: borders forced to 0, sqrt((v1^2+v2^2)*0.5)
+            p = (i == 0 || j == 0) ? 0.0f : __fsqrt_rn(__fmul_rn(__fadd_rn(__fmul_rn(v5, v5), __fmul_rn(vp, vp)), 0.5f));
+        } else if (mask == 7u) {
+            // MSA.cpp:1001 ((dbl^2+glob^2)+loc^2)/3 ; MSA.cpp:1708 ((glob^2+loc^2)+dbl^2)/3
+            const float q5 = __fmul_rn(v5, v5), qp = __fmul_rn(vp, vp), ql = __fmul_rn(vl, vl);
+            const float s = (flavour == 2) ? __fadd_rn(__fadd_rn(qp, ql), q5) : __fadd_rn(__fadd_rn(q5, qp), ql);
+            p = __fsqrt_rn(__fdiv_rn(s, 3.0f));
+        } else {
+            p = (mask & 1u) ? v5 : ((mask & 2u) ? vp : vl);
+        }
+        if (dense) {
+            const long long d = (long long)i * (L2 + 1) + j;
+            dense[d] = p;
+            if (dense5) dense5[d] = v5;
+            if (denseP) denseP[d] = vp;
+            if (denseL) denseL[d] = vl;
+        }
+        // MEA row DP: ProbabilisticModel.h:834-836 / PosteriorStage.cpp:177 (row 0 / column 0 stay 0)
+        float sc = 0.0f;
+        if (i >= 1 && j >= 1) sc = fmaxf(fmaxf(__fadd_rn(p, diag[0]), carry[0]), old[0]);
+        float cnt = (j == 0) ? 0.0f : carry[1];
+        if (i >= 1 && j >= 1 && p >= cutoff) {   // SparseMatrix.h:89 / PackedSparseMatrix.cpp:68
+            const int k = atomicAdd(stage_n, 1);
+            if (k < stage_cap) stage[k] = make_int4(i, (int)cnt, j, __float_as_int(p));
+            cnt += 1.0f;
+        }
+        nw[0] = sc; nw[1] = cnt;
+        if (j == L2) {
+            rowcnt[i + 1] = (int)cnt;
+            if (i == L1) { has_score = true; score = sc; }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_final(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* band; uint8_t* colres; float* cap;
+    warp_smem<float, 2>(smem, 0, a.Cmax, warp, band, colres, cap);
+    int* stage_n = reinterpret_cast<int*>(cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    int4* stage = a.stage + gw * a.stage_cap;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        const long long slotAB = (long long)t.a * a.n + t.b;
+        int* rowptr = a.out.rp_pool + a.rp_off[slotAB];
+        if (lane == 0) { *stage_n = 0; rowptr[0] = 0; rowptr[1] = 0; }
+        __syncwarp();
+        FinalSweep m;
+        m.S5 = a.layerS5; m.P = a.layerP; m.SL = a.layerSL;
+        m.total5 = a.pout[ti].total5; m.totalL = a.pout[ti].totalL;
+        m.flavour = a.flavour; m.mask = a.mask; m.cutoff = a.cutoff;
+        m.L1 = t.L1; m.L2 = t.L2; m.rowcnt = rowptr; m.stage = stage; m.stage_cap = a.stage_cap; m.stage_n = stage_n;
+        m.dense = a.dense; m.dense5 = a.dense5; m.denseP = a.denseP; m.denseL = a.denseL;
+        m.has_score = false; m.score = 0.0f;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        if (m.has_score) {   // distance: MSA.cpp:1019 / PosteriorStage.cpp:194
+            const float dist = __fsub_rn(1.0f, __fdiv_rn(m.score, (float)min(t.L1, t.L2)));
+            a.dist[(long long)t.a * a.n + t.b] = dist;
+            a.dist[(long long)t.b * a.n + t.a] = dist;
+            a.pout[ti].mea = m.score;
+        }
+        __syncwarp();
+        __threadfence_block();
+        // exclusive scan of the per-row counts -> row pointers (row i occupies rowptr[i]..rowptr[i+1])
+        int run = 0;
+        for (int base = 1; base <= t.L1; base += 32) {
+            const int i = base + lane;
+            int v = (i <= t.L1) ? rowptr[i + 1] : 0;
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(MLP_FULL, inc, d); if (lane >= d) inc += o; }
+            if (i <= t.L1) rowptr[i + 1] = run + inc;
+            run += __shfl_sync(MLP_FULL, inc, 31);
+        }
+        const int nnz = run;
+        const int staged = *stage_n;
+        long long basecell = 0;
+        if (lane == 0) {
+            basecell = (long long)atomicAdd(a.out.cursor, (unsigned long long)nnz);
+            a.out.nz_off[slotAB] = basecell;
+            a.out.nz_cnt[slotAB] = nnz;
+            if (staged > a.stage_cap) atomicOr(a.err, 1);
+            if (basecell + nnz > a.out.cap) atomicOr(a.err, 2);
+        }
+        basecell = __shfl_sync(MLP_FULL, basecell, 0);
+        __syncwarp();
+        if (staged <= a.stage_cap && basecell + nnz <= a.out.cap) {
+            for (int k = lane; k < staged; k += 32) {
+                const int4 r = stage[k];
+                const long long d = basecell + rowptr[r.x] + r.y;
+                const float v = __int_as_float(r.w);
+                a.out.cells[d] = make_int2(r.z, __float_as_int(a.flavour == 0 ? dev_quantize_u16(v) : v));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ transpose
+// Stable counting-sort transpose, one warp per pair.  Cells are visited in row-major order 32 at a time; lanes
+// that hit the same column are ranked with __match_any_sync so the row order inside each transposed row is
+// the reference's (PackedSparseMatrix.cpp:119-134 / SparseMatrix.h:226-244).
+__global__ void __launch_bounds__(MLP_BLOCK) k_transpose(KArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long ti = gw; ti < a.ntasks; ti += nw) {
+        const PairTask t = a.tasks[ti];
+        const long long sAB = (long long)t.a * a.n + t.b, sBA = (long long)t.b * a.n + t.a;
+        const int* rp = a.out.rp_pool + a.rp_off[sAB];
+        int* trp = a.out.rp_pool + a.rp_off[sBA];
+        const int nnz = a.out.nz_cnt[sAB];
+        const long long src = a.out.nz_off[sAB];
+        long long dst = 0;
+        if (lane == 0) {
+            dst = (long long)atomicAdd(a.out.cursor, (unsigned long long)nnz);
+            a.out.nz_off[sBA] = dst; a.out.nz_cnt[sBA] = nnz;
+            if (dst + nnz > a.out.cap) atomicOr(a.err, 2);
+        }
+        dst = __shfl_sync(MLP_FULL, dst, 0);
+        if (dst + nnz > a.out.cap || src + nnz > a.out.cap) continue;
+        // 1. column histogram into trp[j+1]
+        for (int j = lane; j <= t.L2 + 1; j += 32) trp[j] = 0;
+        __syncwarp();
+        for (int k = lane; k < nnz; k += 32) {
+            atomicAdd(&trp[a.out.cells[src + k].x + 1], 1);
+        }
+        __syncwarp();
+        // 2. inclusive scan over trp[2..L2+1] -> trp[j+1] = end of row j ; trp[j] = start of row j
+        int run = 0;
+        for (int base = 1; base <= t.L2; base += 32) {
+            const int j = base + lane;
+            int inc = (j <= t.L2) ? trp[j + 1] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(MLP_FULL, inc, d); if (lane >= d) inc += o; }
+            if (j <= t.L2) trp[j + 1] = run + inc;
+            run += __shfl_sync(MLP_FULL, inc, 31);
+        }
+        __syncwarp();
+        // 3. stable placement; fill counters live in a.tfill (per warp, L2max+2 ints)
+        int* fill = a.tfill + gw * a.tfill_stride;
+        for (int j = lane; j <= t.L2 + 1; j += 32) fill[j] = 0;
+        __syncwarp();
+        // row of cell k: walk rows with a moving pointer
+        int row = 1;
+        for (int k0 = 0; k0 < nnz; k0 += 32) {
+            const int k = k0 + lane;
+            const bool ok = k < nnz;
+            int col = 0, r = 0; int2 cf = make_int2(0, 0);
+            if (ok) {
+                cf = a.out.cells[src + k]; col = cf.x;
+                // binary search the row containing k: largest r with rp[r] <= k
+                int lo = row, hi = t.L1;
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp[mid] <= k) lo = mid; else hi = mid - 1; }
+                r = lo;
+            }
+            const unsigned peers = __match_any_sync(MLP_FULL, ok ? col : -1 - lane);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (ok) {
+                const long long d = dst + trp[col] + fill[col] + rank;
+                a.out.cells[d] = make_int2(r, cf.y);
+            }
+            __syncwarp();
+            if (ok && (lane == 31 || (peers >> (lane + 1)) == 0)) fill[col] += __popc(peers);   // highest lane of each group
+            __syncwarp();
+            row = __shfl_sync(MLP_FULL, r, 31);
+            if (row < 1) row = 1;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+size_t posterior_smem_bytes(int kernel, int Cmax, int warps) {
+    size_t tables = 0, per = 0;
+    switch (kernel) {
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: tables = MLP_PART_TABLE_BYTES; per = 3 * Cmax * 32 * 8; break;
+        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: tables = MLP_HMM_TABLE_BYTES; per = 5 * Cmax * 32 * 4; break;
+        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: tables = MLP_HMM_TABLE_BYTES; per = 3 * Cmax * 32 * 4; break;
+        case MLP_K_FINAL: tables = 0; per = 2 * Cmax * 32 * 4; break;
+        default: return 0;
+    }
+    per += Cmax * 32 + 64;
+    per = (per + 15) & ~(size_t)15;
+    return tables + per * warps;
+}
+
+cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
+    return cudaMemcpyToSymbolAsync(c_sc, &s, sizeof(DevScalars), 0, cudaMemcpyHostToDevice, st);
+}
+
+cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, cudaStream_t st) {
+    void (*fn)(KArgs) = nullptr;
+    switch (kernel) {
+        case MLP_K_PART_FWD: fn = k_part_fwd; break;
+        case MLP_K_PART_REV: fn = k_part_rev; break;
+        case MLP_K_HMM_FWD: fn = k_hmm_fwd; break;
+        case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
+        case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
+        case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
+        case MLP_K_FINAL: fn = k_final; break;
+        case MLP_K_TRANSPOSE: fn = k_transpose; break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fn<<<grid, MLP_BLOCK, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+int posterior_max_blocks_per_sm(int kernel, size_t smem) {
+    void (*fn)(KArgs) = nullptr;
+    switch (kernel) {
+        case MLP_K_PART_FWD: fn = k_part_fwd; break;
+        case MLP_K_PART_REV: fn = k_part_rev; break;
+        case MLP_K_HMM_FWD: fn = k_hmm_fwd; break;
+        case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
+        case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
+        case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
+        case MLP_K_FINAL: fn = k_final; break;
+        case MLP_K_TRANSPOSE: fn = k_transpose; break;
+        default: return 1;
+    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, MLP_BLOCK, smem) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}

@@ -1,0 +1,66 @@
+// Shared between posterior.cu (kernels), relax.cu and capi.cu (host driver).
+#pragma once
+#include "dev_common.cuh"
+#include "../../include/mlprobs_b200.h"   // MLP_K_* kernel ids
+
+#define MLP_BLOCK 128                  // 4 warps per CTA, one pair per warp
+#define MLP_HMM_TABLE_BYTES 2816       // 676 match + 26 ins floats, padded to 16 B
+#define MLP_PART_TABLE_BYTES 5408      // 676 doubles
+#define MLP_K_TRANSPOSE 8              // extends the MLP_K_* kernel ids of mlprobs_b200.h
+#define MLP_K_RELAX_ID 7
+
+
+// per-pair scalars handed from one sweep kernel to the next
+struct PairOut {
+    double Zpart;          // partition function Z (Zfm[0][0])
+    float tF5, total5;     // 5-state: forward total, (forward+backward)/2
+    float tFL, totalL;     // local model
+    float mea;             // MEA score
+    float pad;
+};
+
+// Device view of a sparse-posterior set: every ordered pair (a,b) owns len[a]+2 row pointers at rp_off[a*n+b]
+// inside rp_pool and nz_cnt cells {column, float bits} at nz_off[a*n+b] inside `cells` (bump-allocated).
+struct CsrSetDev {
+    int* rp_pool; long long* nz_off; int* nz_cnt; int2* cells; unsigned long long* cursor; long long cap;
+};
+
+struct KArgs {
+    const PairTask* tasks; int ntasks; int* counter;
+    PairOut* pout;
+    const uint8_t* residues; const long long* seq_off; int n;
+    int flavour; unsigned mask; float cutoff;
+    int Cmax;
+    // tables in global memory (staged into shared memory by each CTA)
+    const float* match; const float* ins; const double* sub;
+    // dense layers (slot layout)
+    double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
+    // boundary-column hand-off between column blocks (only when some pair has nb > 1)
+    float* edge_f; double* edge_d; long long edge_stride;
+    // sparse sets: rp_off (fixed layout, shared), `out` is written, `in` is read (relax only)
+    const long long* rp_off; CsrSetDev out; CsrSetDev in;
+    int4* stage; int stage_cap;
+    int* tfill; long long tfill_stride;
+    float* dist; int* err;
+    // optional dense dumps (debug / tests), row-major
+    float* dense; float* dense5; float* denseP; float* denseL;
+};
+
+// relax.cu
+struct RelaxArgs {
+    const PairTask* tasks; int ntasks; int* counter;
+    int n; int flavour; float cutoff;
+    const long long* rp_off;
+    CsrSetDev in, out;
+    // QP only
+    const float* weights; const float* seldist; float selectivity, selfweight;
+    float* wk_scratch; long long wk_stride;   // per warp: n floats (weight of z for this pair, < 0 = z not accepted)
+    int* err;
+};
+cudaError_t relax_launch(const RelaxArgs& a, int grid, cudaStream_t st);
+int relax_max_blocks_per_sm();
+
+size_t posterior_smem_bytes(int kernel, int Cmax, int warps);
+cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st);
+cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, cudaStream_t st);
+int posterior_max_blocks_per_sm(int kernel, size_t smem);

@@ -1,0 +1,55 @@
+"""Synthetic protein families (SURVEY.md 8d generator; the reference ships none).
+
+Root sequence: L iid draws from the 20-letter ProbCons background (Defaults.h:30-34); every member copies the
+root with per-site substitution / deletion / insertion.  Deterministic for a given seed.
+"""
+import numpy as np
+
+ALPHABET = b"ARNDCQEGHILKMFPSTWYV"
+BACKGROUND = np.array([0.07831005, 0.05246024, 0.04433257, 0.05130349, 0.02189704, 0.03585766, 0.05615771,
+                       0.07783433, 0.02601093, 0.06511648, 0.09716489, 0.05877077, 0.02438117, 0.04463228,
+                       0.03940142, 0.05849916, 0.05115306, 0.01203523, 0.03124726, 0.07343426])
+
+
+def family(n, length, seed=20220148, p_sub=0.65, p_del=0.02, p_ins=0.02):
+    rng = np.random.default_rng(seed)
+    bg = BACKGROUND / BACKGROUND.sum()
+    root = rng.choice(20, size=length, p=bg)
+    seqs = []
+    for _ in range(n):
+        out = []
+        for r in root:
+            u = rng.random()
+            if u < p_del:
+                continue
+            out.append(int(rng.choice(20, p=bg)) if rng.random() < p_sub else int(r))
+            if rng.random() < p_ins:
+                for _ in range(int(rng.geometric(0.5))):
+                    out.append(int(rng.choice(20, p=bg)))
+        if not out:
+            out = [int(root[0])]
+        seqs.append(bytes(ALPHABET[k] for k in out))
+    return seqs
+
+
+def family_fast(n, length, seed=20220148, p_sub=0.65, p_del=0.02, p_ins=0.02):
+    """Vectorised variant for large n (same distribution, different stream than family())."""
+    rng = np.random.default_rng(seed)
+    bg = BACKGROUND / BACKGROUND.sum()
+    root = rng.choice(20, size=length, p=bg)
+    al = np.frombuffer(ALPHABET, np.uint8)
+    seqs = []
+    for _ in range(n):
+        keep = rng.random(length) >= p_del
+        sub = rng.random(length) < p_sub
+        res = np.where(sub, rng.choice(20, size=length, p=bg), root)
+        ins = (rng.random(length) < p_ins) & keep
+        nins = np.where(ins, rng.geometric(0.5, size=length), 0)
+        reps = keep.astype(np.int64) + nins
+        idx = np.repeat(np.arange(length), reps)
+        first = np.r_[True, idx[1:] != idx[:-1]] if len(idx) else np.zeros(0, bool)
+        vals = np.where(first & keep[idx], res[idx], rng.choice(20, size=len(idx), p=bg))
+        if len(vals) == 0:
+            vals = root[:1]
+        seqs.append(al[vals].tobytes())
+    return seqs
