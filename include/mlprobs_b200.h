@@ -65,6 +65,10 @@ int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* re
  * cost-sorted pair list (multi-GPU sharding). Default rank 0 of 1. */
 int mlp_set_shard(mlp_ctx* ctx, int rank, int world);
 
+/* Host-only helper (no GPU): the pairs a shard owns, in the order the device processes them. pairs_out receives
+ * 2*count ints (a0,b0,a1,b1,...); pass NULL to query *count. Same rule as mlp_set_shard. */
+int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, int32_t* pairs_out, int64_t* count);
+
 /* All-pairs posterior stage: for every owned pair a<b -> dense posteriors of the selected models, merge,
  * MEA score -> distance, threshold to CSR (both orientations).
  * Replaces cpnp MSA.cpp:927-1031 (and :1652-1765 for -p 1) / QP PosteriorStage::run PosteriorStage.cpp:58-121. */
@@ -79,6 +83,12 @@ int mlp_get_distances(mlp_ctx* ctx, float* nxn);
  *       selectivity (accept z iff max(seldist[i][z], seldist[j][z]) <= selectivity), weights from the guide tree. */
 int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
               float selectivity, float selfweight, float cutoff);
+
+/* Host utility of the QuickProbs flavour (no GPU work): UPGMA guide tree on the n*n distances (updated IN PLACE, as the
+ * reference does), normalised sequence weights and subtree-size selectivity distances for mlp_relax.
+ * Replaces ClusterTree::build ClusterTree.cpp:17-124, GuideTree::calculateSeqsWeights GuideTree.cpp:114-154 and
+ * GuideTree::calculateSubtreeDistances GuideTree.cpp:189-221.  parent_out (2n-1 ints, -1 = root) may be NULL. */
+int mlp_qp_guide_tree(int n, float* dist_nxn_inout, float* weights_out, float* subtree_dist_nxn_out, int32_t* parent_out);
 
 /* Sparse posterior read-back. Ordered pair (a,b), a != b; rows 1..len[a]; row_ptr has len[a]+2 entries
  * (row_ptr[i]..row_ptr[i+1] = row i, row 0 empty).  val is the dequantised value for MLP_QP

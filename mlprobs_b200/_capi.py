@@ -20,7 +20,7 @@ ERRORS = {0: "ok", -1: "no CUDA device", -2: "CUDA error", -3: "bad argument", -
 EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", "mlp_configure", "mlp_set_tables",
            "mlp_set_sequences", "mlp_set_shard", "mlp_posterior_all_pairs", "mlp_get_distances", "mlp_relax",
            "mlp_get_csr", "mlp_total_cells", "mlp_get_csr_bulk", "mlp_debug_pair_dense", "mlp_nccl_unique_id",
-           "mlp_comm_init", "mlp_exchange", "mlp_last_stats"]
+           "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs"]
 
 
 class HmmTables(C.Structure):
@@ -77,6 +77,7 @@ def load():
         lib.mlp_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.mlp_exchange.argtypes = [C.c_void_p]
         lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mlp_qp_guide_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -87,6 +88,36 @@ def default_tables(flavour, init_distrib2=0.700645):
     if rc:
         raise MlpError(rc)
     return h, p
+
+
+def qp_guide_tree(distances):
+    """UPGMA tree -> (weights, subtree distances, parent array, distances after the in-place update)."""
+    d = np.array(distances, np.float32, copy=True, order="C")
+    n = d.shape[0]
+    w = np.zeros(n, np.float32)
+    sd = np.zeros((n, n), np.float32)
+    par = np.zeros(2 * n - 1, np.int32)
+    rc = load().mlp_qp_guide_tree(n, d.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                                  sd.ctypes.data_as(C.c_void_p), par.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise MlpError(rc)
+    return w, sd, par, d
+
+
+def shard_pairs(lens, rank, world):
+    """Pairs (a,b) owned by `rank` of `world`, in device processing order (host-only, no GPU needed)."""
+    lens = np.ascontiguousarray(lens, np.int32)
+    lib = load()
+    lib.mlp_shard_pairs.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
+    cnt = C.c_int64(0)
+    rc = lib.mlp_shard_pairs(len(lens), lens.ctypes.data_as(C.c_void_p), rank, world, None, C.byref(cnt))
+    if rc:
+        raise MlpError(rc)
+    out = np.zeros((cnt.value, 2), np.int32)
+    rc = lib.mlp_shard_pairs(len(lens), lens.ctypes.data_as(C.c_void_p), rank, world, out.ctypes.data_as(C.c_void_p), C.byref(cnt))
+    if rc:
+        raise MlpError(rc)
+    return out
 
 
 def _ptr(a):

@@ -180,6 +180,39 @@ static void pair_geometry(int L2, int& C, int& nb) {
     C = (cols + 32 * nb - 1) / (32 * nb);
 }
 
+static void build_sorted_pairs(int n, const int32_t* len, std::vector<PairTask>& out) {
+    out.clear();
+    out.reserve((size_t)n * (n - 1) / 2);
+    int pidx = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = a + 1; b < n; ++b) {
+            PairTask t;
+            t.a = a; t.b = b; t.L1 = len[a]; t.L2 = len[b];
+            pair_geometry(t.L2, t.C, t.nb);
+            t.pidx = pidx++; t.flags = 0; t.off = 0;
+            out.push_back(t);
+        }
+    // cost-sorted (largest first) for load balance; stable, so ties keep row-major pair order
+    std::stable_sort(out.begin(), out.end(), [](const PairTask& x, const PairTask& y) {
+        const long long cx = (long long)x.nb * (x.L1 + 32) * x.C, cy = (long long)y.nb * (y.L1 + 32) * y.C;
+        return cx > cy;
+    });
+}
+
+extern "C" int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, int32_t* pairs_out, int64_t* count) {
+    if (n < 2 || !len || world < 1 || rank < 0 || rank >= world || !count) return MLP_E_ARG;
+    std::vector<PairTask> all;
+    build_sorted_pairs(n, len, all);
+    int64_t c = 0;
+    for (size_t k = 0; k < all.size(); ++k)
+        if ((int)(k % world) == rank) {
+            if (pairs_out) { pairs_out[2 * c] = all[k].a; pairs_out[2 * c + 1] = all[k].b; }
+            ++c;
+        }
+    *count = c;
+    return MLP_OK;
+}
+
 extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* residues) {
     if (!ctx || n < 2 || !len || !residues) return MLP_E_ARG;
     cudaSetDevice(ctx->device);
@@ -206,22 +239,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     CK(cudaMemcpy(ctx->d_res, codes.data(), tot + 16, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_seq_off, ctx->seq_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
     ctx->stats.h2d_bytes += tot + 16 + n * (int64_t)sizeof(long long);
-    // all pairs, cost-sorted (largest first) for load balance
-    ctx->all_pairs.clear();
-    ctx->all_pairs.reserve((size_t)n * (n - 1) / 2);
-    int pidx = 0;
-    for (int a = 0; a < n; ++a)
-        for (int b = a + 1; b < n; ++b) {
-            PairTask t;
-            t.a = a; t.b = b; t.L1 = len[a]; t.L2 = len[b];
-            pair_geometry(t.L2, t.C, t.nb);
-            t.pidx = pidx++; t.flags = 0; t.off = 0;
-            ctx->all_pairs.push_back(t);
-        }
-    std::stable_sort(ctx->all_pairs.begin(), ctx->all_pairs.end(), [](const PairTask& x, const PairTask& y) {
-        const long long cx = (long long)x.nb * (x.L1 + 32) * x.C, cy = (long long)y.nb * (y.L1 + 32) * y.C;
-        return cx > cy;
-    });
+    build_sorted_pairs(n, len, ctx->all_pairs);
     // fixed row-pointer layout: ordered pair (a,b) owns len[a]+2 ints
     ctx->rp_off_h.assign((size_t)n * n, 0);
     long long rp = 0;

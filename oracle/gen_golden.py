@@ -1,0 +1,97 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the COMPILED REFERENCE (oracle/_ref/ref_cpnp, oracle/_ref/ref_qp).
+
+Runs only in the build container (needs /root/reference for the input families and oracle/_ref built by
+`make -C oracle ref`).  Two fixture kinds:
+  full   : sequences, tables, distances, every CSR matrix (and dense posteriors when small) -- tiny families
+  digest : sequences, distances, tree weights, and per-pair nnz + CRC32 of the column / value arrays -- mid-size
+           families (a checksum of checksums keeps N>200 cases a few hundred KB)
+"""
+import os, subprocess, sys, zlib, tempfile
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from _dumpfmt import read_dump
+
+REF = "/root/reference/TEST"
+OUT = os.path.join(ROOT, "tests", "golden")
+CPNP = os.path.join(ROOT, "oracle", "_ref", "ref_cpnp")
+QP = os.path.join(ROOT, "oracle", "_ref", "ref_qp")
+
+
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xffffffff
+
+
+def pairs(n):
+    return [(a, b) for a in range(n) for b in range(a + 1, n)]
+
+
+def pack(d, tags, full, dense):
+    n = int(d["n"][0])
+    out = {"n": d["n"], "lens": d["lens"], "residues": d["residues"], "distances": d["distances"]}
+    for k in ("pid", "pid_ref", "initDistrib2", "weights", "seldist", "distances_after_tree", "cons.iterations",
+              "cons.selfweight", "reps", "p1"):
+        if k in d:
+            out[k] = d[k]
+    for k in d:
+        if k.startswith("hmm.") or k.startswith("part."):
+            out[k] = d[k]
+    for tag in tags:
+        nnz = np.zeros(len(pairs(n)), np.int32); ccrc = np.zeros_like(nnz, dtype=np.uint32); vcrc = np.zeros_like(ccrc)
+        rcrc = np.zeros_like(ccrc)
+        for p, (a, b) in enumerate(pairs(n)):
+            t = "pair.%d.%d.%s" % (a, b, tag)
+            nnz[p] = len(d[t + ".col"]); ccrc[p] = crc(d[t + ".col"].astype(np.int32)); vcrc[p] = crc(d[t + ".val"])
+            rcrc[p] = crc(d[t + ".rowptr"])
+            if full:
+                out[t + ".rowptr"] = d[t + ".rowptr"]; out[t + ".col"] = d[t + ".col"].astype(np.int32); out[t + ".val"] = d[t + ".val"]
+        out["digest.%s.nnz" % tag] = nnz; out["digest.%s.col_crc" % tag] = ccrc; out["digest.%s.val_crc" % tag] = vcrc
+        out["digest.%s.rowptr_crc" % tag] = rcrc
+    if dense:
+        for k in d:
+            if k.endswith((".post", ".post5", ".postP", ".postL")):
+                out[k] = d[k]
+    return out
+
+
+def run_cpnp(name, fasta, full, dense, pid=None, p1=False, reps=2):
+    with tempfile.TemporaryDirectory() as td:
+        dump = os.path.join(td, "d.bin")
+        cmd = ["taskset", "-c", "0", CPNP, "dump", fasta, dump, "--reps", str(reps)]
+        if pid is not None: cmd += ["--pid", str(pid)]
+        if p1: cmd += ["--p1"]
+        if not dense: cmd += ["--nodense"]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        d = read_dump(dump)
+    tags = ["s%d" % r for r in range(reps + 1)]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(d, tags, full, dense))
+    print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
+def run_qp(name, fasta, full, dense):
+    with tempfile.TemporaryDirectory() as td:
+        dump = os.path.join(td, "d.bin")
+        cmd = [QP, "dump", fasta, dump, "--threads", "8"]   # quickprobs is thread-count independent
+        if not dense: cmd += ["--nodense"]
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+        d = read_dump(dump)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(d, ["s0", "t0", "sF", "tF"], full, dense))
+    print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    f = lambda b, x: os.path.join(REF, b, "in", x)
+    # tiny, everything stored (dense posteriors of all three models)
+    run_cpnp("cpnp_sup139_mix", f("sabre", "sup_139"), True, True, pid=0)
+    run_cpnp("cpnp_sup139_local", f("sabre", "sup_139"), True, True, pid=2)
+    run_cpnp("cpnp_sup139_part", f("sabre", "sup_139"), True, True, pid=3)
+    run_cpnp("cpnp_sup139_p1mix", f("sabre", "sup_139"), True, False, pid=0, p1=True)
+    run_cpnp("cpnp_sup002_ref", f("sabre", "sup_002"), True, False)           # model chosen by the reference itself
+    run_qp("qp_sup139", f("sabre", "sup_139"), True, True)
+    run_qp("qp_sup002", f("sabre", "sup_002"), True, False)
+    # mid-size, digests only
+    run_cpnp("cpnp_676s4_ref", f("oxx", "_676s4"), False, False)
+    run_qp("qp_676s4", f("oxx", "_676s4"), False, False)                       # N=51 -> 1 consistency iteration, cutoff 1e-5
+    run_qp("qp_75t2", f("oxx", "__75t2"), False, False)                        # N=204 -> selectivity excludes some z

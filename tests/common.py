@@ -1,0 +1,52 @@
+"""Shared helpers for the test-suite (fixtures under tests/golden were written by oracle/gen_golden.py from the compiled reference)."""
+import os
+import zlib
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def split_seqs(d):
+    res = d["residues"].tobytes()
+    out, p = [], 0
+    for L in d["lens"]:
+        out.append(res[p:p + int(L)])
+        p += int(L)
+    return out
+
+
+def pairs(n):
+    return [(a, b) for a in range(n) for b in range(a + 1, n)]
+
+
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xffffffff
+
+
+def digest_of(getter, n, transposed=False):
+    """getter(a, b) -> (rowptr, col, val). Returns (nnz, rowptr_crc, col_crc, val_crc) arrays in pair order."""
+    P = pairs(n)
+    nnz = np.zeros(len(P), np.int32)
+    rc = np.zeros(len(P), np.uint32); cc = np.zeros(len(P), np.uint32); vc = np.zeros(len(P), np.uint32)
+    for p, (a, b) in enumerate(P):
+        rp, c, v = getter(b, a) if transposed else getter(a, b)
+        nnz[p] = len(c); rc[p] = crc(rp.astype(np.int32)); cc[p] = crc(c.astype(np.int32)); vc[p] = crc(v.astype(np.float32))
+    return nnz, rc, cc, vc
+
+
+def assert_digest(d, tag, getter, n, transposed=False):
+    nnz, rc, cc, vc = digest_of(getter, n, transposed)
+    np.testing.assert_array_equal(nnz, d["digest.%s.nnz" % tag], err_msg="nnz per pair (%s)" % tag)
+    np.testing.assert_array_equal(rc, d["digest.%s.rowptr_crc" % tag], err_msg="row pointers (%s)" % tag)
+    np.testing.assert_array_equal(cc, d["digest.%s.col_crc" % tag], err_msg="column index sets (%s)" % tag)
+    np.testing.assert_array_equal(vc, d["digest.%s.val_crc" % tag], err_msg="values (%s)" % tag)
+
+
+def cpnp_mask(pid):
+    pid = int(pid) % 10
+    return 7 if pid <= 1 else (4 if pid == 2 else 2)

@@ -1,0 +1,80 @@
+"""CPU: host-side logic of the product library and the C-ABI surface (no compute kernels are launched)."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+import mlprobs_b200 as M
+from mlprobs_b200 import _capi
+import oracle_lib as O
+from common import load_golden, HERE
+
+ROOT = os.path.dirname(HERE)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mlprobs_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mlp_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(M.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "symbol %s declared in include/mlprobs_b200.h is not exported" % name
+    assert set(_capi.EXPORTS) <= set(declared)
+
+
+def test_default_tables_equal_oracle_tables():
+    for flav, oflav, i2 in [(M.QP, O.QP, 0.700645), (M.CPNP_P0, O.CPNP_P0, 0.170705), (M.CPNP_P0, O.CPNP_P0, 0.100675)]:
+        h, p = M.default_tables(flav, i2)
+        oh = O.hmm_tables(i2 if flav != M.QP else 0.700645); op = O.part_tables(oflav)
+        assert bytes(h) == bytes(oh)
+        assert bytes(p) == bytes(op)
+
+
+def test_default_tables_equal_reference_dump():
+    d = load_golden("qp_sup139")
+    h, p = M.default_tables(M.QP)
+    np.testing.assert_array_equal(np.ctypeslib.as_array(h.match), d["hmm.match"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(p.sub), d["part.sub"])
+
+
+@pytest.mark.parametrize("name", ["qp_sup139", "qp_sup002", "qp_676s4", "qp_75t2"])
+def test_guide_tree_weights_and_subtree_distances(name):
+    d = load_golden(name)
+    w, sd, par, after = M.qp_guide_tree(d["distances"])
+    np.testing.assert_array_equal(np.maximum(w, np.float32(1e-6)), d["weights"])   # saturation, ExtendedMSA.cpp:169
+    np.testing.assert_array_equal(sd, d["seldist"])
+    np.testing.assert_array_equal(after, d["distances_after_tree"])
+    assert (par >= -1).all() and (par == -1).sum() == 1
+
+
+def test_shard_pairs_partition_is_a_disjoint_cover():
+    rng = np.random.default_rng(3)
+    lens = rng.integers(20, 700, size=37)
+    allp = set()
+    sizes = []
+    for r in range(4):
+        p = M.shard_pairs(lens, r, 4)
+        s = set(map(tuple, p.tolist()))
+        assert not (s & allp)
+        allp |= s
+        sizes.append(sum(int(lens[a] + 1) * int(lens[b] + 1) for a, b in s))
+    assert allp == {(a, b) for a in range(37) for b in range(a + 1, 37)}
+    assert max(sizes) / min(sizes) < 1.15          # cost-balanced
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(M.MlpError) as e:
+        M.Engine(0)
+    assert e.value.code == -1
+
+
+def test_argument_errors_are_reported_not_thrown():
+    lib = M.load()
+    assert lib.mlp_default_tables(9, C.c_float(0.5), None, None) == -3
+    cnt = C.c_int64(0)
+    lens = np.array([5], np.int32)
+    lib.mlp_shard_pairs.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
+    assert lib.mlp_shard_pairs(1, lens.ctypes.data_as(C.c_void_p), 0, 1, None, C.byref(cnt)) == -3

@@ -1,0 +1,129 @@
+"""CPU: the oracle (oracle/mlp_oracle.c) against golden vectors dumped from the compiled reference.
+
+This is what pins the oracle: every table, dense posterior, distance and CSR matrix the two
+reference programs produced for the fixture families must be reproduced bit for bit.
+"""
+import numpy as np
+import pytest
+import oracle_lib as O
+from common import load_golden, split_seqs, pairs, assert_digest, cpnp_mask
+
+USED_TRANS = [(0, 0), (0, 1), (0, 2), (0, 3), (0, 4), (1, 1), (2, 2), (3, 3), (4, 4), (1, 0), (2, 0), (3, 0), (4, 0)]
+
+
+def test_log_add_and_exp_known_answers():
+    lib = O.lib()
+    assert lib.orc_log_add(-2e20, -3.0) == np.float32(-3.0)
+    assert lib.orc_log_add(-1.0, -9.0) == np.float32(-1.0)            # gap >= 7.5: smaller operand dropped
+    x = np.float32(-1.0); y = np.float32(-2.0)
+    d = np.float32(1.0)
+    want = np.float32(np.float32(np.float32(np.float32(np.float32(np.float32(-0.009350833524763) * d) + np.float32(0.130659527668286)) * d
+                                            + np.float32(0.498799810682272)) * d) + np.float32(0.693203116424741)) + y
+    assert lib.orc_log_add(x, y) == want
+    assert lib.orc_exp(0.0) == np.float32(0.99999925508501600000)    # EXP(0) != 1
+    assert lib.orc_exp(-16.0) == 0.0 and lib.orc_exp(-20.0) == 0.0
+
+
+@pytest.mark.parametrize("name", ["cpnp_sup139_mix", "cpnp_sup139_local", "cpnp_sup139_part", "cpnp_sup002_ref"])
+def test_cpnp_tables(name):
+    d = load_golden(name)
+    ht = O.hmm_tables(float(d["initDistrib2"][0]))
+    pt = O.part_tables(O.CPNP_P0)
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.match), d["hmm.match"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.ins), d["hmm.ins"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.init), d["hmm.init"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.ltrans), d["hmm.ltrans"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.rtrans), d["hmm.rtrans"])
+    tr = np.ctypeslib.as_array(ht.trans)
+    for a, b in USED_TRANS:
+        assert tr[a, b] == d["hmm.trans"][a, b]
+    sub = np.ctypeslib.as_array(pt.sub); si = d["part.subst_index"]; raw = d["part.sub_raw"]
+    for a in range(26):
+        for b in range(26):
+            if si[a] >= 0 and si[b] >= 0:
+                assert raw[si[a], si[b]] == sub[a, b]
+
+
+def test_qp_tables():
+    d = load_golden("qp_sup139")
+    ht = O.hmm_tables(); pt = O.part_tables(O.QP)
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.match), d["hmm.match"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.ins), d["hmm.ins"])
+    np.testing.assert_array_equal(np.ctypeslib.as_array(ht.init), d["hmm.init"])
+    tr = np.ctypeslib.as_array(ht.trans)
+    for a, b in USED_TRANS:
+        assert tr[a, b] == d["hmm.trans"][a, b]
+    np.testing.assert_array_equal(np.ctypeslib.as_array(pt.sub), d["part.sub"])
+    assert [pt.tgo, pt.tge, pt.go, pt.ge] == list(d["part.gaps"])
+
+
+@pytest.mark.parametrize("name", ["cpnp_sup139_mix", "cpnp_sup139_local", "cpnp_sup139_part"])
+def test_cpnp_dense_posteriors(name):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    ht = O.hmm_tables(float(d["initDistrib2"][0])); pt = O.part_tables(O.CPNP_P0)
+    mask = cpnp_mask(d["pid"][0])
+    for a, b in pairs(n):
+        t = "pair.%d.%d" % (a, b)
+        if mask & 1:
+            np.testing.assert_array_equal(O.model_posterior("hmm5", ht, pt, seqs[a], seqs[b])[0], d[t + ".post5"])
+        if mask & 2:
+            np.testing.assert_array_equal(O.model_posterior("part_cpnp", ht, pt, seqs[a], seqs[b])[0], d[t + ".postP"])
+        if mask & 4:
+            np.testing.assert_array_equal(O.model_posterior("local", ht, pt, seqs[a], seqs[b])[0], d[t + ".postL"])
+        post, dist, rc = O.pair_posterior(O.CPNP_P0, mask, ht, pt, seqs[a], seqs[b])
+        assert rc == 0
+        np.testing.assert_array_equal(post, d[t + ".post"])
+
+
+def test_qp_dense_posteriors():
+    d = load_golden("qp_sup139")
+    seqs = split_seqs(d); n = len(seqs)
+    ht = O.hmm_tables(); pt = O.part_tables(O.QP)
+    for a, b in pairs(n):
+        t = "pair.%d.%d" % (a, b)
+        np.testing.assert_array_equal(O.model_posterior("hmm5", ht, pt, seqs[a], seqs[b], 1)[0], d[t + ".post5"])
+        np.testing.assert_array_equal(O.model_posterior("part_qp", ht, pt, seqs[a], seqs[b])[0], d[t + ".postP"])
+        post, dist, rc = O.pair_posterior(O.QP, 3, ht, pt, seqs[a], seqs[b])
+        np.testing.assert_array_equal(post, d[t + ".post"])
+
+
+@pytest.mark.parametrize("name,flav", [("cpnp_sup139_mix", O.CPNP_P0), ("cpnp_sup139_local", O.CPNP_P0),
+                                       ("cpnp_sup139_part", O.CPNP_P0), ("cpnp_sup139_p1mix", O.CPNP_P1),
+                                       ("cpnp_sup002_ref", O.CPNP_P0), ("cpnp_676s4_ref", O.CPNP_P0)])
+def test_cpnp_stage_and_relaxation(name, flav):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    ht = O.hmm_tables(float(d["initDistrib2"][0])); pt = O.part_tables(O.CPNP_P0)
+    dist, S, rc = O.posterior_stage(flav, cpnp_mask(d["pid"][0]), ht, pt, seqs, threads=4)
+    assert rc == 0
+    np.testing.assert_array_equal(dist, d["distances"])
+    assert_digest(d, "s0", S.get, n)
+    for r in range(int(d["reps"][0])):
+        S = O.relax_cpnp(S, 0.01, threads=4)
+        assert_digest(d, "s%d" % (r + 1), S.get, n)
+
+
+@pytest.mark.parametrize("name", ["qp_sup139", "qp_sup002", "qp_676s4", "qp_75t2"])
+def test_qp_stage_and_consistency(name):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    ht = O.hmm_tables(); pt = O.part_tables(O.QP)
+    dist, S, rc = O.posterior_stage(O.QP, 3, ht, pt, seqs, threads=8)
+    np.testing.assert_array_equal(dist, d["distances"])
+    assert_digest(d, "s0", S.get, n)
+    assert_digest(d, "t0", S.get, n, transposed=True)
+    iters = int(d["cons.iterations"][0]); sw = float(d["cons.selfweight"][0])
+    assert iters == (1 if n > 50 else 2)
+    for it in range(iters):
+        cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))
+        S = O.relax_qp(S, d["weights"], d["seldist"], cutoff, 200.0, sw, threads=8)
+    assert_digest(d, "sF", S.get, n)
+    assert_digest(d, "tF", S.get, n, transposed=True)
+
+
+def test_full_fixture_matches_digest():
+    """The digest fixtures and the full fixtures agree with each other (guards the fixture writer)."""
+    d = load_golden("qp_sup139")
+    n = int(d["n"][0])
+    assert_digest(d, "s0", lambda a, b: (d["pair.%d.%d.s0.rowptr" % (a, b)], d["pair.%d.%d.s0.col" % (a, b)], d["pair.%d.%d.s0.val" % (a, b)]), n)
