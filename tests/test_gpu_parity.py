@@ -1,0 +1,204 @@
+"""GPU parity: the CUDA path (through the C ABI) against golden vectors of the compiled reference, against the
+oracle on seeded synthetic inputs, and through size-independent properties at larger sizes.
+Bit-exact for everything except cpnp's 80-bit partition function (FP64 on the device): tolerance 1e-5 relative
+(BASELINE.json north_star), index sets must still be identical on the fixtures."""
+import numpy as np
+import pytest
+import mlprobs_b200 as M
+from mlprobs_b200 import synth
+import oracle_lib as O
+from common import load_golden, split_seqs, pairs, assert_digest, cpnp_mask
+
+pytestmark = pytest.mark.gpu
+REL_TOL_PARTITION = 1e-5
+
+
+def engine(flavour, seqs, init2=0.700645):
+    eng = M.Engine(0)
+    h, p = M.default_tables(flavour, init2)
+    eng.set_tables(h, p)
+    eng.set_sequences(seqs)
+    return eng
+
+
+# ------------------------------------------------------------------ golden vectors (reference-produced)
+@pytest.mark.parametrize("name", ["qp_sup139", "qp_sup002", "qp_676s4", "qp_75t2"])
+def test_qp_against_reference_fixture(name):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    np.testing.assert_array_equal(eng.distances(), d["distances"])
+    assert_digest(d, "s0", eng.csr, n)
+    assert_digest(d, "t0", eng.csr, n, transposed=True)
+    w, sd, par, _ = M.qp_guide_tree(eng.distances())
+    w = np.maximum(w, np.float32(1e-6))
+    iters = 1 if n > 50 else 2
+    for it in range(iters):
+        cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))
+        eng.relax(M.QP, w, sd, 200.0, 3.0, cutoff)
+    assert_digest(d, "sF", eng.csr, n)
+    assert_digest(d, "tF", eng.csr, n, transposed=True)
+    eng.close()
+
+
+def test_qp_dense_posteriors_fixture():
+    d = load_golden("qp_sup139")
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.QP, seqs)
+    for a, b in pairs(n):
+        g = eng.debug_pair_dense(M.QP, 3, a, b)
+        t = "pair.%d.%d" % (a, b)
+        np.testing.assert_array_equal(g["hmm5"], d[t + ".post5"])
+        np.testing.assert_array_equal(g["part"], d[t + ".postP"])
+        np.testing.assert_array_equal(g["merged"], d[t + ".post"])
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["cpnp_sup139_local", "cpnp_sup139_mix", "cpnp_sup139_part", "cpnp_sup002_ref", "cpnp_676s4_ref"])
+def test_cpnp_against_reference_fixture(name):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    mask = cpnp_mask(d["pid"][0])
+    eng = engine(M.CPNP_P0, seqs, float(d["initDistrib2"][0]))
+    eng.posterior_all_pairs(M.CPNP_P0, mask, 0.01)
+    if mask & 2:
+        # FP64 partition function vs the reference's long double: values within 1e-5, index sets identical here
+        np.testing.assert_allclose(eng.distances(), d["distances"], rtol=REL_TOL_PARTITION, atol=1e-6)
+        np.testing.assert_array_equal([len(eng.csr(a, b)[1]) for a, b in pairs(n)], d["digest.s0.nnz"])
+        from common import digest_of
+        _, _, cc, _ = digest_of(eng.csr, n)
+        np.testing.assert_array_equal(cc, d["digest.s0.col_crc"])
+    else:
+        np.testing.assert_array_equal(eng.distances(), d["distances"])
+        assert_digest(d, "s0", eng.csr, n)
+        for r in range(int(d["reps"][0])):
+            eng.relax(M.CPNP_P0, cutoff=0.01)
+            assert_digest(d, "s%d" % (r + 1), eng.csr, n)
+    eng.close()
+
+
+def test_cpnp_dense_models_fixture():
+    d = load_golden("cpnp_sup139_mix")
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.CPNP_P0, seqs, float(d["initDistrib2"][0]))
+    for a, b in pairs(n):
+        g = eng.debug_pair_dense(M.CPNP_P0, 7, a, b)
+        t = "pair.%d.%d" % (a, b)
+        np.testing.assert_array_equal(g["hmm5"], d[t + ".post5"])
+        np.testing.assert_array_equal(g["local"], d[t + ".postL"])
+        ref = d[t + ".postP"]
+        np.testing.assert_allclose(g["part"], ref, rtol=REL_TOL_PARTITION, atol=1e-30)
+        np.testing.assert_allclose(g["merged"], d[t + ".post"], rtol=REL_TOL_PARTITION, atol=1e-30)
+    eng.close()
+
+
+# ------------------------------------------------------------------ oracle on seeded synthetic inputs
+def _cmp_sets(eng, S, n):
+    for a in range(n):
+        for b in range(n):
+            if a == b:
+                continue
+            rp, c, v = eng.csr(a, b)
+            orp, oc, ov = S.get(a, b)
+            np.testing.assert_array_equal(rp, orp)
+            np.testing.assert_array_equal(c, oc)
+            np.testing.assert_array_equal(v, ov)
+
+
+@pytest.mark.parametrize("lens", [(1, 1, 2, 3), (31, 32, 33, 63, 64, 65), (510, 511, 512, 513), (40, 700, 1100)])
+def test_qp_ragged_and_multiblock_vs_oracle(lens):
+    seqs = [synth.family(1, L, seed=100 + L)[0][:L].ljust(L, b"A") for L in lens]
+    n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    dist, S, _ = O.posterior_stage(O.QP, 3, O.hmm_tables(), O.part_tables(O.QP), seqs, threads=8)
+    np.testing.assert_array_equal(eng.distances(), dist)
+    _cmp_sets(eng, S, n)
+    eng.close()
+
+
+@pytest.mark.parametrize("mask", [1, 4])
+def test_cpnp_models_vs_oracle_family(mask):
+    seqs = synth.family(9, 150, seed=7)
+    n = len(seqs)
+    i2 = 0.100675
+    eng = engine(M.CPNP_P0, seqs, i2)
+    eng.posterior_all_pairs(M.CPNP_P0, mask, 0.01)
+    dist, S, _ = O.posterior_stage(O.CPNP_P0, mask, O.hmm_tables(i2), O.part_tables(O.CPNP_P0), seqs, threads=8)
+    np.testing.assert_array_equal(eng.distances(), dist)
+    _cmp_sets(eng, S, n)
+    for _ in range(2):
+        eng.relax(M.CPNP_P0, cutoff=0.01)
+        S = O.relax_cpnp(S, 0.01, threads=8)
+        _cmp_sets(eng, S, n)
+    eng.close()
+
+
+def test_unknown_letters_and_identical_sequences():
+    seqs = [b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"XXBZACDWWWWWYYHHKKLMNP", b"MKV"]
+    n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    dist, S, _ = O.posterior_stage(O.QP, 3, O.hmm_tables(), O.part_tables(O.QP), seqs, threads=4)
+    np.testing.assert_array_equal(eng.distances(), dist)
+    _cmp_sets(eng, S, n)
+    eng.close()
+
+
+def test_cpnp_rejects_letters_the_reference_cannot_score():
+    eng = engine(M.CPNP_P0, [b"ACDJKL", b"ACDKLM"], 0.17)
+    with pytest.raises(M.MlpError) as e:
+        eng.posterior_all_pairs(M.CPNP_P0, 2, 0.01)
+    assert e.value.code == -7
+    eng.close()
+
+
+# ------------------------------------------------------------------ size-independent properties at a larger size
+def test_properties_on_a_large_family():
+    seqs = synth.family_fast(120, 300, seed=11)
+    n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    d1 = eng.distances()
+    assert np.array_equal(d1, d1.T) and (np.diag(d1) == 0).all() and (d1[np.triu_indices(n, 1)] > 0).all()
+    nnz, rp, col, val = eng.csr_bulk()
+    # determinism: a second run gives the same bytes
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    nnz2, rp2, col2, val2 = eng.csr_bulk()
+    assert np.array_equal(nnz, nnz2) and np.array_equal(rp, rp2) and np.array_equal(col, col2) and np.array_equal(val, val2)
+    assert np.array_equal(d1, eng.distances())
+    # every stored value is a uint16 code / 65535 and >= the cut-off code
+    codes = np.round(val.astype(np.float64) * 65535).astype(np.int64)
+    assert np.array_equal((codes.astype(np.float32) / np.float32(65535)), val)
+    assert (val >= np.float32(0.01) - np.float32(1.6e-5)).all() and (val <= 1).all()
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        a, b = sorted(rng.choice(n, 2, replace=False))
+        rp_ab, c_ab, v_ab = eng.csr(a, b)
+        rp_ba, c_ba, v_ba = eng.csr(b, a)
+        La, Lb = len(seqs[a]), len(seqs[b])
+        dense = np.zeros((La + 1, Lb + 1), np.float32)
+        for i in range(1, La + 1):
+            cols = c_ab[rp_ab[i]:rp_ab[i + 1]]
+            assert (np.diff(cols) > 0).all() and (cols >= 1).all() and (cols <= Lb).all()      # sorted, in range
+            dense[i, cols] = v_ab[rp_ab[i]:rp_ab[i + 1]]
+        denseT = np.zeros((Lb + 1, La + 1), np.float32)
+        for j in range(1, Lb + 1):
+            denseT[j, c_ba[rp_ba[j]:rp_ba[j + 1]]] = v_ba[rp_ba[j]:rp_ba[j + 1]]
+        assert np.array_equal(dense.T, denseT)                                                  # stored transpose
+        assert dense.sum(axis=1).max() < 1.5
+    # oracle spot-check of a few pairs at this size
+    ht, pt = O.hmm_tables(), O.part_tables(O.QP)
+    for a, b in [(0, 1), (17, 93), (118, 119)]:
+        post, dist, _ = O.pair_posterior(O.QP, 3, ht, pt, seqs[a], seqs[b])
+        assert dist == d1[a, b]
+        rp_ab, c_ab, v_ab = eng.csr(a, b)
+        keep = np.argwhere(post >= np.float32(0.01))
+        assert len(keep) == len(c_ab) and np.array_equal(keep[:, 1], c_ab)
+    # relaxation: pattern can only shrink, result deterministic
+    w, sd, _, _ = M.qp_guide_tree(d1)
+    eng.relax(M.QP, np.maximum(w, np.float32(1e-6)), sd, 200.0, 3.0, float(np.float32(1e-5)))
+    nnz3, rp3, col3, val3 = eng.csr_bulk()
+    assert (nnz3 <= nnz).all() and nnz3.sum() > 0
+    eng.close()
