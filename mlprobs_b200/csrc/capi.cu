@@ -279,18 +279,30 @@ static int ensure_sets(mlp_ctx* ctx) {
         CK(cudaMalloc(&ctx->set[s].rp_pool, (size_t)ctx->rp_total * sizeof(int)));
         CK(cudaMalloc(&ctx->set[s].nz_off, (size_t)n * n * sizeof(long long)));
         CK(cudaMalloc(&ctx->set[s].nz_cnt, (size_t)n * n * sizeof(int)));
-        CK(cudaMalloc(&ctx->set[s].cells, (size_t)cap * sizeof(int2)));
+        const long long this_cap = (s == 0) ? cap : 1024;   // the relax output pool is sized when mlp_relax runs
+        CK(cudaMalloc(&ctx->set[s].cells, (size_t)this_cap * sizeof(int2)));
         CK(cudaMalloc(&ctx->set[s].cursor, sizeof(unsigned long long)));
         CK(cudaMemset(ctx->set[s].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int)));
         CK(cudaMemset(ctx->set[s].nz_off, 0, (size_t)n * n * sizeof(long long)));
         CK(cudaMemset(ctx->set[s].nz_cnt, 0, (size_t)n * n * sizeof(int)));
         CK(cudaMemset(ctx->set[s].cursor, 0, sizeof(unsigned long long)));
-        ctx->set[s].cap = cap;
+        ctx->set[s].cap = this_cap;
     }
     CK(cudaMalloc(&ctx->d_dist, (size_t)n * n * sizeof(float)));
     CK(cudaMemset(ctx->d_dist, 0, (size_t)n * n * sizeof(float)));
     ctx->have_sets = true;
     ctx->cur = 0;
+    return MLP_OK;
+}
+
+// Re-allocate the cell pool of one set to new_cap cells, keeping the first `keep` cells.
+static int grow_cells(mlp_ctx* ctx, int which, long long new_cap, unsigned long long keep) {
+    int2* fresh = nullptr;
+    CK(cudaMalloc(&fresh, (size_t)new_cap * sizeof(int2)));
+    if (keep) CK(cudaMemcpy(fresh, ctx->set[which].cells, (size_t)keep * sizeof(int2), cudaMemcpyDeviceToDevice));
+    cudaFree(ctx->set[which].cells);
+    ctx->set[which].cells = fresh;
+    ctx->set[which].cap = new_cap;
     return MLP_OK;
 }
 
@@ -386,8 +398,9 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
     }
     if ((size_t)max_elems * bpe > budget) budget = (size_t)max_elems * bpe;   // a single pair must fit
     const long long max_warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
+    int stage_mult = 32;
     {
-        int rc = ensure_warp_buffers(ctx, max_warps, maxL1, maxL2, need_edge, 32);
+        int rc = ensure_warp_buffers(ctx, max_warps, maxL1, maxL2, need_edge, stage_mult);
         if (rc != MLP_OK) return rc;
     }
     KernelTimer kt;
@@ -414,6 +427,9 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         ctx->stats.h2d_bytes += (int64_t)(batch.size() * sizeof(PairTask));
         CK(cudaMemsetAsync(ctx->d_pout, 0, batch.size() * sizeof(PairOut), ctx->stream));
 
+        unsigned long long cursor_before = 0;
+        CK(cudaMemcpy(&cursor_before, ctx->set[ctx->cur].cursor, sizeof(cursor_before), cudaMemcpyDeviceToHost));
+        for (int attempt = 0;; ++attempt) {
         KArgs a = {};
         a.tasks = ctx->d_tasks; a.ntasks = (int)batch.size(); a.counter = ctx->d_counter; a.pout = ctx->d_pout;
         a.residues = ctx->d_res; a.seq_off = ctx->d_seq_off; a.n = ctx->n;
@@ -454,11 +470,35 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         CK(cudaStreamSynchronize(ctx->stream));
         int err = 0;
         CK(cudaMemcpy(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) {
-            cudaMemset(ctx->d_err, 0, sizeof(int));
-            ctx->err = (err & 2) ? "sparse cell pool exhausted: raise cell_capacity via mlp_configure"
-                                 : "per-pair staging buffer exhausted (more than 32 kept cells per row on average)";
-            return MLP_E_CAPACITY;
+        if (!err) break;
+        // capacity miss: grow what overflowed and redo this batch (batches are idempotent once the cursor is rewound)
+        cudaMemset(ctx->d_err, 0, sizeof(int));
+        if (attempt >= 6) { ctx->err = "sparse capacity still exhausted after 6 growth attempts"; return MLP_E_CAPACITY; }
+        if (err & 1) {
+            stage_mult *= 4;
+            int rc2 = ensure_warp_buffers(ctx, max_warps, maxL1, maxL2, need_edge, stage_mult);
+            if (rc2 != MLP_OK) return rc2;
+        }
+        if (err & 2) {
+            unsigned long long used = 0;
+            CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+            const double done_frac = (double)(pos) / (double)tasks_in.size();
+            long long want = (long long)((double)used / std::max(done_frac, 1e-3) * 1.15) + (1 << 20);
+            want = std::max(want, ctx->set[ctx->cur].cap * 2);
+            int rc2 = grow_cells(ctx, ctx->cur, want, cursor_before);
+            if (rc2 != MLP_OK) return rc2;
+        }
+        CK(cudaMemcpy(ctx->set[ctx->cur].cursor, &cursor_before, sizeof(cursor_before), cudaMemcpyHostToDevice));
+        }
+        {   // proactive growth: extrapolate the fill rate to the remaining pairs
+            unsigned long long used = 0;
+            CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+            const double done_frac = (double)pos / (double)tasks_in.size();
+            const long long want = (long long)((double)used / std::max(done_frac, 1e-3) * 1.10) + (1 << 20);
+            if (pos < tasks_in.size() && want > ctx->set[ctx->cur].cap) {
+                int rc2 = grow_cells(ctx, ctx->cur, want, used);
+                if (rc2 != MLP_OK) return rc2;
+            }
         }
         if (useP && flavour != MLP_QP) {
             // cpnp runs the partition function in 80-bit long double; this FP64 kernel cannot represent Z beyond 1e308
@@ -660,6 +700,11 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
         free_dev(ctx->d_wk); ctx->d_wk = nullptr;
         CK(cudaMalloc(&ctx->d_wk, (size_t)warps * n * sizeof(float)));
         ctx->wk_warps = warps;
+    }
+    {   // the relaxed set can only shrink: size the output pool to what the input set holds
+        unsigned long long used = 0;
+        CK(cudaMemcpy(&used, ctx->set[in].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+        if ((long long)used + 1024 > ctx->set[out].cap) { rc = grow_cells(ctx, out, (long long)used + 1024, 0); if (rc != MLP_OK) return rc; }
     }
     CK(cudaMemcpyAsync(ctx->d_tasks, tasks.data(), tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (int64_t)(tasks.size() * sizeof(PairTask));
