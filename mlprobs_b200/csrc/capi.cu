@@ -387,9 +387,15 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
     if (useP) bpe += 12;
     if (use5) bpe += 4;
     if (useL) bpe += useP ? 4 : 8;
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = ctx->scratch_budget > 0 ? (size_t)ctx->scratch_budget : (size_t)((free_b + ctx->scratch_bytes) * 0.6);
+    // Memory plan: the first batch is small and measures the sparse density; the cell pool is then grown once to the
+    // extrapolated size, the same amount is left free for the relaxation output set, and the rest goes to dense scratch.
+    size_t budget = (size_t)1 << 31;
+    bool planned = tasks_in.size() < 2048;
+    if (planned) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        budget = ctx->scratch_budget > 0 ? (size_t)ctx->scratch_budget : (size_t)((free_b + ctx->scratch_bytes) * 0.5);
+    }
     int maxL1 = 0, maxL2 = 0; bool need_edge = false; long long max_elems = 0;
     for (const PairTask& t : tasks_in) {
         maxL1 = std::max(maxL1, t.L1); maxL2 = std::max(maxL2, t.L2);
@@ -490,15 +496,21 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         }
         CK(cudaMemcpy(ctx->set[ctx->cur].cursor, &cursor_before, sizeof(cursor_before), cudaMemcpyHostToDevice));
         }
-        {   // proactive growth: extrapolate the fill rate to the remaining pairs
+        if (!planned && pos < tasks_in.size()) {
             unsigned long long used = 0;
             CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
-            const double done_frac = (double)pos / (double)tasks_in.size();
-            const long long want = (long long)((double)used / std::max(done_frac, 1e-3) * 1.10) + (1 << 20);
-            if (pos < tasks_in.size() && want > ctx->set[ctx->cur].cap) {
-                int rc2 = grow_cells(ctx, ctx->cur, want, used);
-                if (rc2 != MLP_OK) return rc2;
-            }
+            double done_cost = 0, all_cost = 0;
+            for (size_t k = 0; k < tasks_in.size(); ++k) { const double c = (double)std::min(tasks_in[k].L1, tasks_in[k].L2); all_cost += c; if (k < pos) done_cost += c; }   // kept cells scale with the shorter length
+            const long long want = (long long)((double)(used - cursor_before) * (all_cost / std::max(done_cost, 1.0)) * 1.25) + (long long)cursor_before + (1 << 20);
+            if (want > ctx->set[ctx->cur].cap) { int rc2 = grow_cells(ctx, ctx->cur, want, used); if (rc2 != MLP_OK) return rc2; }
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t reserve = (size_t)want * sizeof(int2) + ((size_t)2 << 30);   // relaxation output set + slack
+            const size_t avail = free_b + ctx->scratch_bytes;
+            size_t b2 = avail > reserve ? (size_t)((avail - reserve) * 0.9) : ((size_t)1 << 30);
+            if (ctx->scratch_budget > 0) b2 = std::min(b2, (size_t)ctx->scratch_budget);
+            budget = std::max(b2, (size_t)max_elems * bpe);
+            planned = true;
         }
         if (useP && flavour != MLP_QP) {
             // cpnp runs the partition function in 80-bit long double; this FP64 kernel cannot represent Z beyond 1e308
@@ -696,9 +708,9 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     const long long warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
     rc = ensure_warp_buffers(ctx, warps, maxL1, maxL2, false, 1);
     if (rc != MLP_OK) return rc;
-    if (flavour == MLP_QP && warps > ctx->wk_warps) {
+    if (warps > ctx->wk_warps) {
         free_dev(ctx->d_wk); ctx->d_wk = nullptr;
-        CK(cudaMalloc(&ctx->d_wk, (size_t)warps * n * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_wk, (size_t)warps * 2 * n * sizeof(float)));   // per warp: n weights + n indices
         ctx->wk_warps = warps;
     }
     {   // the relaxed set can only shrink: size the output pool to what the input set holds
@@ -716,7 +728,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     ra.n = n; ra.flavour = flavour; ra.cutoff = cutoff; ra.rp_off = ctx->d_rp_off;
     ra.in = ctx->set[in]; ra.out = ctx->set[out];
     ra.weights = ctx->d_weights; ra.seldist = ctx->d_seldist; ra.selectivity = selectivity; ra.selfweight = selfweight;
-    ra.wk_scratch = ctx->d_wk; ra.wk_stride = n; ra.err = ctx->d_err;
+    ra.wk_scratch = ctx->d_wk; ra.wk_stride = 2LL * n; ra.err = ctx->d_err;
     KernelTimer kt;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     kt.begin(MLP_K_RELAX_ID, ctx->stream);

@@ -11,11 +11,57 @@
 #include "posterior.cuh"
 
 
+// ---- chunked, shared-memory staged version -------------------------------------------------------------------
+// A chunk is RELAX_G*32 consecutive cells of S_xy (row-major), i.e. a handful of rows r0..r1 and a narrow column span
+// cmin..cmax.  For every third sequence z the warp stages, with coalesced loads, exactly the slices it needs:
+//   rows r0..r1   of S_xz  (one contiguous cell range)                      -> smem A
+//   rows cmin..cmax of S_yz (= columns cmin..cmax of S_zy; contiguous too)  -> smem B
+// and every lane then merge-joins row r of A with row c of B (both sorted by the z-residue q), which visits the
+// products S_xz[r][q] * S_zy[q][c] in ascending q -- the reference's accumulation order for that cell.
+#define RELAX_G 4
+#define RELAX_RMAX 64       // rows per chunk that fit the staged row-pointer slice
+#define RELAX_CWMAX 128     // column span per chunk
+#define RELAX_CAPA 384      // staged cells of S_xz
+#define RELAX_CAPB 768     // staged cells of S_yz
+struct RelaxSmem {
+    int2 A[RELAX_CAPA];
+    int2 B[RELAX_CAPB];
+    int rpA[RELAX_RMAX + 2];
+    int rpB[RELAX_CWMAX + 2];
+};
+
+__device__ __forceinline__ float merge_join(const int2* __restrict__ pa, const int2* __restrict__ ea,
+                                            const int2* __restrict__ pb, const int2* __restrict__ eb,
+                                            float acc, float w, bool weighted) {
+    if (pa >= ea || pb >= eb) return acc;
+    int2 x = *pa, y = *pb;
+    for (;;) {
+        if (x.x == y.x) {
+            const float v1 = __int_as_float(x.y), v2 = __int_as_float(y.y);
+            const float prod = weighted ? __fmul_rn(__fmul_rn(w, v1), v2) : __fmul_rn(v1, v2);   // ConsistencyStage.cpp:294 / MSA.cpp:1316
+            acc = __fadd_rn(acc, prod);
+            if (++pa >= ea || ++pb >= eb) break;
+            x = *pa; y = *pb;
+        } else if (x.x < y.x) {
+            if (++pa >= ea) break;
+            x = *pa;
+        } else {
+            if (++pb >= eb) break;
+            y = *pb;
+        }
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RelaxSmem& sm = reinterpret_cast<RelaxSmem*>(smem_raw)[warp];
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-    float* wk = a.wk_scratch ? a.wk_scratch + gw * a.wk_stride : nullptr;
+    float* wk = a.wk_scratch + gw * a.wk_stride;          // [n] weight of the m-th accepted z
+    int* kl = reinterpret_cast<int*>(wk + a.n);           // [n] index  of the m-th accepted z
     const int n = a.n;
+    const bool weighted = (a.flavour == 0);
     for (;;) {
         int ti = 0;
         if (lane == 0) ti = atomicAdd(a.counter, 1);
@@ -30,30 +76,36 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
         int* orp = a.out.rp_pool + a.rp_off[sIJ];
         for (int r = lane; r <= t.L1 + 1; r += 32) orp[r] = 0;
 
-        float norm;   // divisor applied before masking: N (cpnp, MSA.cpp:1234) or sumW (QP, ConsistencyStage.cpp:226)
-        if (a.flavour == 0) {
-            // ConsistencyStage.cpp:181-216: accepted z <=> max(d[i][z], d[j][z]) <= selectivity (Deterministic filter)
-            int acc_cnt = 0;
+        // ---- list of third sequences and the normaliser
+        int nk = 0;
+        float norm;
+        if (weighted) {
+            // ConsistencyStage.cpp:181-216: z accepted <=> max(d[x][z], d[y][z]) <= selectivity (Deterministic filter)
             for (int k0 = 0; k0 < n; k0 += 32) {
                 const int k = k0 + lane;
                 bool ok = false;
                 if (k < n && k != i && k != j) ok = fmaxf(a.seldist[(long long)i * n + k], a.seldist[(long long)j * n + k]) <= a.selectivity;
-                acc_cnt += __popc(__ballot_sync(MLP_FULL, ok));
-                if (k < n) wk[k] = ok ? 1.0f : -1.0f;
+                const unsigned m = __ballot_sync(MLP_FULL, ok);
+                if (ok) kl[nk + __popc(m & ((1u << lane) - 1u))] = k;
+                nk += __popc(m);
             }
-            float wi_wj = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(__fsub_rn(a.selfweight, 1.0f), (float)acc_cnt), a.selectivity));
+            float wi_wj = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(__fsub_rn(a.selfweight, 1.0f), (float)nk), a.selectivity));
             wi_wj = __fmul_rn(wi_wj, __fadd_rn(a.weights[i], a.weights[j]));
             __syncwarp();
-            for (int k0 = 0; k0 < n; k0 += 32) {
-                const int k = k0 + lane;
-                if (k < n && wk[k] > 0.0f) wk[k] = __fdiv_rn(a.weights[k], wi_wj);
-            }
+            for (int m = lane; m < nk; m += 32) wk[m] = __fdiv_rn(a.weights[kl[m]], wi_wj);
             __syncwarp();
-            float sumW = 1.0f;   // sequential float sum in z order
-            if (lane == 0) for (int k = 0; k < n; ++k) { const float w = wk[k]; if (w >= 0.0f) sumW = __fadd_rn(sumW, w); }
+            float sumW = 1.0f;   // ConsistencyStage.cpp:213: sequential float sum in z order
+            if (lane == 0) for (int m = 0; m < nk; ++m) sumW = __fadd_rn(sumW, wk[m]);
             norm = __shfl_sync(MLP_FULL, sumW, 0);
         } else {
-            norm = (float)n;
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + lane;
+                const bool ok = (k < n && k != i && k != j);
+                const unsigned m = __ballot_sync(MLP_FULL, ok);
+                if (ok) kl[nk + __popc(m & ((1u << lane) - 1u))] = k;
+                nk += __popc(m);
+            }
+            norm = (float)n;   // MSA.cpp:1234
         }
         __syncwarp();
 
@@ -67,59 +119,87 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
         const bool room = (obase + nnz <= a.out.cap);
         int kept_total = 0;
         int rowhint = 1;
-        for (int c0 = 0; c0 < nnz; c0 += 32) {
-            const int cidx = c0 + lane;
-            const bool ok = cidx < nnz;
-            int r = 1, y = 0;
-            float acc = 0.0f;
-            if (ok) {
-                const int2 cell = c_ij[cidx];
-                y = cell.x;
-                const float v0 = __int_as_float(cell.y);
-                acc = (a.flavour == 0) ? v0 : __fadd_rn(v0, v0);   // MSA.cpp:1211-1213 doubles the matrix first
-                int lo = rowhint, hi = t.L1;
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp_ij[mid] <= cidx) lo = mid; else hi = mid - 1; }
-                r = lo;
-            }
-            for (int k = 0; k < n; ++k) {
-                if (k == i || k == j) continue;
-                float w = 1.0f;
-                if (a.flavour == 0) { w = wk[k]; if (w < 0.0f) continue; }
-                const long long sIK = (long long)i * n + k, sKJ = (long long)k * n + j;
-                const int* rp_ik = a.in.rp_pool + a.rp_off[sIK];
-                const int2* c_ik = a.in.cells + a.in.nz_off[sIK];
-                const int* rp_kj = a.in.rp_pool + a.rp_off[sKJ];
-                const int2* c_kj = a.in.cells + a.in.nz_off[sKJ];
-                if (ok) {
-                    const int b = rp_ik[r], e = rp_ik[r + 1];
-                    for (int u = b; u < e; ++u) {
-                        const int2 xz = c_ik[u];
-                        const int b2 = rp_kj[xz.x], e2 = rp_kj[xz.x + 1];
-                        for (int q = b2; q < e2; ++q) {
-                            const int2 zy = c_kj[q];
-                            if (zy.x >= y) {
-                                if (zy.x == y) {
-                                    const float v1 = __int_as_float(xz.y), v2 = __int_as_float(zy.y);
-                                    const float prod = (a.flavour == 0) ? __fmul_rn(__fmul_rn(w, v1), v2) : __fmul_rn(v1, v2);
-                                    acc = __fadd_rn(acc, prod);
-                                }
-                                break;
-                            }
-                        }
-                    }
+        for (int c0 = 0; c0 < nnz; c0 += 32 * RELAX_G) {
+            int rr[RELAX_G], cc[RELAX_G];
+            float acc[RELAX_G];
+            bool okc[RELAX_G];
+            int cmin = 0x7fffffff, cmax = 0, rmin = 0x7fffffff, rmax = 0;
+#pragma unroll
+            for (int g = 0; g < RELAX_G; ++g) {
+                const int cidx = c0 + g * 32 + lane;
+                okc[g] = cidx < nnz;
+                rr[g] = 1; cc[g] = 0; acc[g] = 0.0f;
+                if (okc[g]) {
+                    const int2 cell = c_ij[cidx];
+                    cc[g] = cell.x;
+                    const float v0 = __int_as_float(cell.y);
+                    acc[g] = weighted ? v0 : __fadd_rn(v0, v0);   // MSA.cpp:1211-1213 doubles the matrix first
+                    int lo = rowhint, hi = t.L1;
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp_ij[mid] <= cidx) lo = mid; else hi = mid - 1; }
+                    rr[g] = lo;
+                    cmin = min(cmin, cc[g]); cmax = max(cmax, cc[g]); rmin = min(rmin, lo); rmax = max(rmax, lo);
                 }
             }
-            acc = __fdiv_rn(acc, norm);
-            const bool keep = ok && (acc >= a.cutoff);
-            const unsigned km = __ballot_sync(MLP_FULL, keep);
-            if (keep && room) {
-                const long long d = obase + kept_total + __popc(km & ((1u << lane) - 1u));
-                a.out.cells[d] = make_int2(y, __float_as_int(a.flavour == 0 ? dev_quantize_u16(acc) : acc));
-                atomicAdd(&orp[r + 1], 1);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                cmin = min(cmin, __shfl_xor_sync(MLP_FULL, cmin, d)); cmax = max(cmax, __shfl_xor_sync(MLP_FULL, cmax, d));
+                rmin = min(rmin, __shfl_xor_sync(MLP_FULL, rmin, d)); rmax = max(rmax, __shfl_xor_sync(MLP_FULL, rmax, d));
             }
-            kept_total += __popc(km);
-            rowhint = __shfl_sync(MLP_FULL, r, 31);
-            if (rowhint < 1) rowhint = 1;
+            const int R = rmax - rmin + 1, CW = cmax - cmin + 1;
+            const bool fits_idx = (R <= RELAX_RMAX && CW <= RELAX_CWMAX);
+            for (int m = 0; m < nk; ++m) {
+                const int k = kl[m];
+                const float w = weighted ? wk[m] : 1.0f;
+                const long long sIK = (long long)i * n + k, sJK = (long long)j * n + k;
+                const int* rp_ik = a.in.rp_pool + a.rp_off[sIK];
+                const int2* c_ik = a.in.cells + a.in.nz_off[sIK];
+                const int* rp_jk = a.in.rp_pool + a.rp_off[sJK];
+                const int2* c_jk = a.in.cells + a.in.nz_off[sJK];
+                bool staged = false;
+                int a0 = 0, b0 = 0;
+                if (fits_idx) {
+                    for (int x = lane; x <= R; x += 32) sm.rpA[x] = rp_ik[rmin + x];
+                    for (int x = lane; x <= CW; x += 32) sm.rpB[x] = rp_jk[cmin + x];
+                    __syncwarp();
+                    a0 = sm.rpA[0]; b0 = sm.rpB[0];
+                    const int na = sm.rpA[R] - a0, nb = sm.rpB[CW] - b0;
+                    staged = (na <= RELAX_CAPA && nb <= RELAX_CAPB);
+                    if (staged) {
+                        for (int x = lane; x < na; x += 32) sm.A[x] = c_ik[a0 + x];
+                        for (int x = lane; x < nb; x += 32) sm.B[x] = c_jk[b0 + x];
+                    }
+                    __syncwarp();
+                }
+                if (staged) {
+#pragma unroll
+                    for (int g = 0; g < RELAX_G; ++g)
+                        if (okc[g]) {
+                            const int ra = rr[g] - rmin, cb = cc[g] - cmin;
+                            acc[g] = merge_join(sm.A + (sm.rpA[ra] - a0), sm.A + (sm.rpA[ra + 1] - a0),
+                                                sm.B + (sm.rpB[cb] - b0), sm.B + (sm.rpB[cb + 1] - b0), acc[g], w, weighted);
+                        }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < RELAX_G; ++g)
+                        if (okc[g])
+                            acc[g] = merge_join(c_ik + rp_ik[rr[g]], c_ik + rp_ik[rr[g] + 1],
+                                                c_jk + rp_jk[cc[g]], c_jk + rp_jk[cc[g] + 1], acc[g], w, weighted);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int g = 0; g < RELAX_G; ++g) {
+                const float v = __fdiv_rn(acc[g], norm);
+                const bool keep = okc[g] && (v >= a.cutoff);
+                const unsigned km = __ballot_sync(MLP_FULL, keep);
+                if (keep && room) {
+                    const long long d = obase + kept_total + __popc(km & ((1u << lane) - 1u));
+                    a.out.cells[d] = make_int2(cc[g], __float_as_int(weighted ? dev_quantize_u16(v) : v));
+                    atomicAdd(&orp[rr[g] + 1], 1);
+                }
+                kept_total += __popc(km);
+            }
+            rowhint = max(rmax, 1);   // cells are row-major: the next chunk starts at or after this row
         }
         __syncwarp();
         __threadfence_block();
@@ -138,13 +218,18 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
     }
 }
 
+static size_t relax_smem() { return sizeof(RelaxSmem) * (MLP_BLOCK / 32); }
+
 cudaError_t relax_launch(const RelaxArgs& a, int grid, cudaStream_t st) {
-    k_relax<<<grid, MLP_BLOCK, 0, st>>>(a);
+    cudaError_t e = cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem());
+    if (e != cudaSuccess) return e;
+    k_relax<<<grid, MLP_BLOCK, relax_smem(), st>>>(a);
     return cudaGetLastError();
 }
 
 int relax_max_blocks_per_sm() {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_relax, MLP_BLOCK, 0) != cudaSuccess || nb < 1) nb = 1;
+    cudaFuncSetAttribute(k_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_smem());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_relax, MLP_BLOCK, relax_smem()) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
