@@ -13,21 +13,20 @@
 
 // ---- chunked, shared-memory staged version -------------------------------------------------------------------
 // A chunk is RELAX_G*32 consecutive cells of S_xy (row-major), i.e. a handful of rows r0..r1 and a narrow column span
-// cmin..cmax.  For every third sequence z the warp stages, with coalesced loads, exactly the slices it needs:
-//   rows r0..r1   of S_xz  (one contiguous cell range)                      -> smem A
-//   rows cmin..cmax of S_yz (= columns cmin..cmax of S_zy; contiguous too)  -> smem B
-// and every lane then merge-joins row r of A with row c of B (both sorted by the z-residue q), which visits the
-// products S_xz[r][q] * S_zy[q][c] in ascending q -- the reference's accumulation order for that cell.
+// cmin..cmax.  For every third sequence z the warp stages exactly the slices it needs:
+//   rows r0..r1 of S_xz (one contiguous cell range, coalesced)                         -> smem A (sparse, sorted by q)
+//   rows cmin..cmax of S_yz (= columns cmin..cmax of S_zy) restricted to q in [qmin,qmax] -> smem W, a DENSE window
+// and every lane walks row r of A in ascending q and adds [w*]S_xz[r][q]*W[c][q].  Absent entries of W are +0, and
+// acc + (+0) == acc exactly, so the result and the order of the non-zero adds are the reference's (q ascending).
+// Chunks whose slices do not fit fall back to a sorted merge-join straight from global memory.
 #define RELAX_G 4
 #define RELAX_RMAX 64       // rows per chunk that fit the staged row-pointer slice
-#define RELAX_CWMAX 128     // column span per chunk
 #define RELAX_CAPA 384      // staged cells of S_xz
-#define RELAX_CAPB 768     // staged cells of S_yz
+#define RELAX_WIN 2304      // floats in the dense (column x z-residue) window of S_zy
 struct RelaxSmem {
     int2 A[RELAX_CAPA];
-    int2 B[RELAX_CAPB];
+    float W[RELAX_WIN];
     int rpA[RELAX_RMAX + 2];
-    int rpB[RELAX_CWMAX + 2];
 };
 
 __device__ __forceinline__ float merge_join(const int2* __restrict__ pa, const int2* __restrict__ ea,
@@ -146,7 +145,6 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
                 rmin = min(rmin, __shfl_xor_sync(MLP_FULL, rmin, d)); rmax = max(rmax, __shfl_xor_sync(MLP_FULL, rmax, d));
             }
             const int R = rmax - rmin + 1, CW = cmax - cmin + 1;
-            const bool fits_idx = (R <= RELAX_RMAX && CW <= RELAX_CWMAX);
             for (int m = 0; m < nk; ++m) {
                 const int k = kl[m];
                 const float w = weighted ? wk[m] : 1.0f;
@@ -156,17 +154,33 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
                 const int* rp_jk = a.in.rp_pool + a.rp_off[sJK];
                 const int2* c_jk = a.in.cells + a.in.nz_off[sJK];
                 bool staged = false;
-                int a0 = 0, b0 = 0;
-                if (fits_idx) {
+                int a0 = 0, qmin = 0, QW = 1;
+                if (R <= RELAX_RMAX) {
                     for (int x = lane; x <= R; x += 32) sm.rpA[x] = rp_ik[rmin + x];
-                    for (int x = lane; x <= CW; x += 32) sm.rpB[x] = rp_jk[cmin + x];
                     __syncwarp();
-                    a0 = sm.rpA[0]; b0 = sm.rpB[0];
-                    const int na = sm.rpA[R] - a0, nb = sm.rpB[CW] - b0;
-                    staged = (na <= RELAX_CAPA && nb <= RELAX_CAPB);
-                    if (staged) {
-                        for (int x = lane; x < na; x += 32) sm.A[x] = c_ik[a0 + x];
-                        for (int x = lane; x < nb; x += 32) sm.B[x] = c_jk[b0 + x];
+                    a0 = sm.rpA[0];
+                    const int na = sm.rpA[R] - a0;
+                    if (na <= RELAX_CAPA) {
+                        int qlo = 0x7fffffff, qhi = -1;
+                        for (int x = lane; x < na; x += 32) { const int2 e = c_ik[a0 + x]; sm.A[x] = e; qlo = min(qlo, e.x); qhi = max(qhi, e.x); }
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) { qlo = min(qlo, __shfl_xor_sync(MLP_FULL, qlo, d)); qhi = max(qhi, __shfl_xor_sync(MLP_FULL, qhi, d)); }
+                        if (na == 0) { qlo = 1; qhi = 1; }
+                        qmin = qlo;
+                        QW = (qhi - qlo + 1) | 1;                  // odd stride: lanes on neighbouring columns hit different banks
+                        if (CW * QW <= RELAX_WIN) {
+                            staged = true;
+                            for (int x = lane; x < CW * QW; x += 32) sm.W[x] = 0.0f;
+                            __syncwarp();
+                            for (int c = cmin + lane; c <= cmax; c += 32) {   // one lane per row of S_yz
+                                const int b = rp_jk[c], e = rp_jk[c + 1];
+                                float* wrow = sm.W + (c - cmin) * QW - qlo;
+                                for (int x = b; x < e; ++x) {
+                                    const int2 cell = c_jk[x];
+                                    if (cell.x >= qlo && cell.x <= qhi) wrow[cell.x] = __int_as_float(cell.y);
+                                }
+                            }
+                        }
                     }
                     __syncwarp();
                 }
@@ -174,9 +188,18 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
 #pragma unroll
                     for (int g = 0; g < RELAX_G; ++g)
                         if (okc[g]) {
-                            const int ra = rr[g] - rmin, cb = cc[g] - cmin;
-                            acc[g] = merge_join(sm.A + (sm.rpA[ra] - a0), sm.A + (sm.rpA[ra + 1] - a0),
-                                                sm.B + (sm.rpB[cb] - b0), sm.B + (sm.rpB[cb + 1] - b0), acc[g], w, weighted);
+                            const int ra = rr[g] - rmin;
+                            const int2* pa = sm.A + (sm.rpA[ra] - a0);
+                            const int2* ea = sm.A + (sm.rpA[ra + 1] - a0);
+                            const float* wrow = sm.W + (cc[g] - cmin) * QW - qmin;
+                            float ac = acc[g];
+                            for (; pa < ea; ++pa) {
+                                const int2 e = *pa;
+                                const float v1 = __int_as_float(e.y), v2 = wrow[e.x];
+                                const float prod = weighted ? __fmul_rn(__fmul_rn(w, v1), v2) : __fmul_rn(v1, v2);   // ConsistencyStage.cpp:294 / MSA.cpp:1316
+                                ac = __fadd_rn(ac, prod);
+                            }
+                            acc[g] = ac;
                         }
                 } else {
 #pragma unroll
