@@ -696,9 +696,16 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
         CK(cudaMemcpyAsync(ctx->d_seldist, seldist_nxn, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += (int64_t)n * 4 + (int64_t)n * n * 4;
     }
-    // tasks in row-major pair order: warps resident together share S_x* rows in L2
+    // Task order = 2-D tiles of the pair grid: the ~2-5 k warps resident together then work on a TxT block of pairs and,
+    // for each third sequence z, touch only 2T matrices (S_x z for T values of x, S_y z for T values of y) -> L2 reuse.
     std::vector<PairTask> tasks = ctx->owned;
-    std::sort(tasks.begin(), tasks.end(), [](const PairTask& x, const PairTask& y) { return x.pidx < y.pidx; });
+    const int T = 48;
+    std::sort(tasks.begin(), tasks.end(), [T](const PairTask& x, const PairTask& y) {
+        const int xa = x.a / T, xb = x.b / T, ya = y.a / T, yb = y.b / T;
+        if (xa != ya) return xa < ya;
+        if (xb != yb) return xb < yb;
+        return x.pidx < y.pidx;
+    });
     int rc = ensure_tasks(ctx, tasks.size());
     if (rc != MLP_OK) return rc;
     int maxL1 = 0, maxL2 = 0;

@@ -23,10 +23,11 @@
 #define RELAX_RMAX 64       // rows per chunk that fit the staged row-pointer slice
 #define RELAX_CAPA 384      // staged cells of S_xz
 #define RELAX_WIN 2304      // floats in the dense (column x z-residue) window of S_zy
-struct RelaxSmem {
-    int2 A[RELAX_CAPA];
+struct __align__(16) RelaxSmem {
     float W[RELAX_WIN];
+    int2 A[RELAX_CAPA];
     int rpA[RELAX_RMAX + 2];
+    int pad[2];
 };
 
 __device__ __forceinline__ float merge_join(const int2* __restrict__ pa, const int2* __restrict__ ea,
@@ -170,7 +171,11 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_relax(RelaxArgs a) {
                         QW = (qhi - qlo + 1) | 1;                  // odd stride: lanes on neighbouring columns hit different banks
                         if (CW * QW <= RELAX_WIN) {
                             staged = true;
-                            for (int x = lane; x < CW * QW; x += 32) sm.W[x] = 0.0f;
+                            {
+                                float4* w4 = reinterpret_cast<float4*>(sm.W);
+                                const int n4 = (CW * QW + 3) >> 2;
+                                for (int x = lane; x < n4; x += 32) w4[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
                             __syncwarp();
                             for (int c = cmin + lane; c <= cmax; c += 32) {   // one lane per row of S_yz
                                 const int b = rp_jk[c], e = rp_jk[c + 1];
