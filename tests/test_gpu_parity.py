@@ -156,7 +156,7 @@ def test_cpnp_rejects_letters_the_reference_cannot_score():
 
 # ------------------------------------------------------------------ size-independent properties at a larger size
 def test_properties_on_a_large_family():
-    seqs = synth.family_fast(120, 300, seed=11)
+    seqs = synth.family_fast(120, 300, seed=11, p_sub=0.65)
     n = len(seqs)
     eng = engine(M.QP, seqs)
     eng.posterior_all_pairs(M.QP, 3, 0.01)
