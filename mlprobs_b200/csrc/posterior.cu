@@ -27,28 +27,47 @@ __device__ __forceinline__ SweepCtx make_ctx(const PairTask& t, const KArgs& a, 
     return cx;
 }
 
-// per-warp shared-memory carve-up: [tables (CTA)] [warp0: band | colres | cap] [warp1: ...]
-template <class T, int NS>
+// per-warp shared-memory carve-up: [tables (CTA)] [warp0: band | stage | colres | cap] [warp1: ...]
+// stage = NIN double-buffered wavefront slots of dense input (cp.async targets), element size sizeof(T)
+template <class T, int NS, int NIN>
 __device__ __forceinline__ void warp_smem(unsigned char* base, int tables_bytes, int Cmax, int warp,
-                                          T*& band, uint8_t*& colres, float*& cap) {
+                                          T*& band, T*& stage, uint8_t*& colres, float*& cap) {
     const int band_bytes = NS * Cmax * 32 * (int)sizeof(T);
-    const int per_warp = band_bytes + Cmax * 32 + 64;
+    const int stage_bytes = NIN * 2 * Cmax * 32 * (int)sizeof(T);
+    const int per_warp = band_bytes + stage_bytes + Cmax * 32 + 64;
     unsigned char* p = base + tables_bytes + (size_t)warp * ((per_warp + 15) & ~15);
     band = reinterpret_cast<T*>(p);
-    colres = p + band_bytes;
-    cap = reinterpret_cast<float*>(p + band_bytes + Cmax * 32);
+    stage = reinterpret_cast<T*>(p + band_bytes);
+    colres = p + band_bytes + stage_bytes;
+    cap = reinterpret_cast<float*>(p + band_bytes + stage_bytes + Cmax * 32);
+}
+
+// HMM kernels: CTA-shared tables = match[676] | ins[26] (+pad to 704 floats) | LogAddLut (256 B)
+__device__ __forceinline__ void load_hmm_tables(unsigned char* smem, const KArgs& a, float*& match, float*& ins, LogAddLut*& lut) {
+    match = reinterpret_cast<float*>(smem);
+    ins = match + 676;
+    lut = reinterpret_cast<LogAddLut*>(smem + 2816);
+    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
+    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
+    log_add_lut_fill(lut, threadIdx.x);
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------ 5-state HMM
 // state order (reference numbering): 0 = M, 1 = X1, 2 = Y1, 3 = X2, 4 = Y2
 struct HmmFwd {
     typedef float T;
-    enum { NS = 5, REV = 0, COLMASK = 0x1f };
-    const float* match; const float* ins;
+    enum { NS = 5, REV = 0, COLMASK = 0x1f, NIN = 0 };
+    const float* match; const float* ins; const LogAddLut* lut;
     float* F;
     int L1, L2;
     float ins1; const float* mrow;
     float fin[5]; bool has_fin;
+    float t0q[5], tqq[5], tq0[5];   // transitions hoisted out of constant memory into registers
+    __device__ __forceinline__ void load_consts() {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { t0q[q] = c_sc.t0q[q]; tqq[q] = c_sc.tqq[q]; tq0[q] = c_sc.tq0[q]; }
+    }
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const {
 #pragma unroll
         for (int s = 0; s < NS; ++s) st[s] = MLP_LOG_ZERO;
@@ -60,20 +79,21 @@ struct HmmFwd {
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void prefetch(long long, int, int) const {}
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         // ProbabilisticModel.h:213-245 / ParallelProbabilisticModel.cpp:91-113
-        float m = __fadd_rn(diag[0], c_sc.tq0[0]);
-        m = dev_log_add(m, __fadd_rn(diag[1], c_sc.tq0[1]));
-        m = dev_log_add(m, __fadd_rn(diag[2], c_sc.tq0[2]));
-        m = dev_log_add(m, __fadd_rn(diag[3], c_sc.tq0[3]));
-        m = dev_log_add(m, __fadd_rn(diag[4], c_sc.tq0[4]));
+        float m = __fadd_rn(diag[0], tq0[0]);
+        m = dev_log_add_lut(m, __fadd_rn(diag[1], tq0[1]), lut);
+        m = dev_log_add_lut(m, __fadd_rn(diag[2], tq0[2]), lut);
+        m = dev_log_add_lut(m, __fadd_rn(diag[3], tq0[3]), lut);
+        m = dev_log_add_lut(m, __fadd_rn(diag[4], tq0[4]), lut);
         m = __fadd_rn(m, mrow[r2]);
         const float ins2 = ins[r2];
-        float x1 = __fadd_rn(ins1, dev_log_add(__fadd_rn(old[0], c_sc.t0q[1]), __fadd_rn(old[1], c_sc.tqq[1])));
-        float x2 = __fadd_rn(ins1, dev_log_add(__fadd_rn(old[0], c_sc.t0q[3]), __fadd_rn(old[3], c_sc.tqq[3])));
-        float y1 = __fadd_rn(ins2, dev_log_add(__fadd_rn(carry[0], c_sc.t0q[2]), __fadd_rn(carry[2], c_sc.tqq[2])));
-        float y2 = __fadd_rn(ins2, dev_log_add(__fadd_rn(carry[0], c_sc.t0q[4]), __fadd_rn(carry[4], c_sc.tqq[4])));
+        float x1 = __fadd_rn(ins1, dev_log_add_lut(__fadd_rn(old[0], t0q[1]), __fadd_rn(old[1], tqq[1]), lut));
+        float x2 = __fadd_rn(ins1, dev_log_add_lut(__fadd_rn(old[0], t0q[3]), __fadd_rn(old[3], tqq[3]), lut));
+        float y1 = __fadd_rn(ins2, dev_log_add_lut(__fadd_rn(carry[0], t0q[2]), __fadd_rn(carry[2], tqq[2]), lut));
+        float y2 = __fadd_rn(ins2, dev_log_add_lut(__fadd_rn(carry[0], t0q[4]), __fadd_rn(carry[4], tqq[4]), lut));
         if (i <= 1 && j <= 1) {   // initialisation cells, ProbabilisticModel.h:173-184 (the recurrence is skipped there)
             m = (i == 1 && j == 1) ? __fadd_rn(c_sc.init[0], mrow[r2]) : MLP_LOG_ZERO;
             x1 = (i == 1 && j == 0) ? __fadd_rn(c_sc.init[1], ins1) : MLP_LOG_ZERO;
@@ -89,28 +109,27 @@ struct HmmFwd {
 
 __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float* match = reinterpret_cast<float*>(smem);
-    float* ins = match + 676;
-    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
-    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
-    __syncthreads();
+    float* match; float* ins; LogAddLut* lut;
+    load_hmm_tables(smem, a, match, ins, lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* band; uint8_t* colres; float* cap;
-    warp_smem<float, 5>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    float* band; float* stage; uint8_t* colres; float* cap;
+    warp_smem<float, 5, 0>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    HmmFwd m;
+    m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerS5;
+    m.load_consts();
     for (;;) {
         const int ti = next_task(a.counter, lane);
         if (ti >= a.ntasks) break;
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
-        HmmFwd m;
-        m.match = match; m.ins = ins; m.F = a.layerS5; m.L1 = t.L1; m.L2 = t.L2; m.has_fin = false;
+        m.L1 = t.L1; m.L2 = t.L2; m.has_fin = false;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         if (m.has_fin) {   // total forward probability, ProbabilisticModel.h:415-419
             float tF = MLP_LOG_ZERO;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) tF = dev_log_add(tF, __fadd_rn(m.fin[k], c_sc.init[k]));
+            for (int k = 0; k < 5; ++k) tF = dev_log_add(tF, __fadd_rn(m.fin[k], c_sc.init[k]));   // once per pair: plain version
             a.pout[ti].tF5 = tF;
         }
     }
@@ -118,12 +137,18 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
 
 struct HmmBwd {
     typedef float T;
-    enum { NS = 5, REV = 1, COLMASK = 0x0b };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
-    const float* match; const float* ins;
+    enum { NS = 5, REV = 1, COLMASK = 0x0b, NIN = 1 };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
+    const float* match; const float* ins; const LogAddLut* lut;
     float* F;      // in: forward M, out: F + B (ProbabilisticModel.h:483 evaluates (F+B)-total)
+    float* stage; int Cmax;
     float* cap;    // [0]=B_M(1,1) [1]=B_X1(1,0) [2]=B_Y1(0,1) [3]=B_X2(1,0) [4]=B_Y2(0,1)
-    int L1, L2;
+    int L1, L2, lane;
     float ins1; const float* mrow;
+    float t0q[5], tqq[5], tq0[5];
+    __device__ __forceinline__ void load_consts() {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { t0q[q] = c_sc.t0q[q]; tqq[q] = c_sc.tqq[q]; tq0[q] = c_sc.tq0[q]; }
+    }
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const {
 #pragma unroll
         for (int s = 0; s < NS; ++s) st[s] = MLP_LOG_ZERO;
@@ -135,7 +160,10 @@ struct HmmBwd {
     __device__ __forceinline__ int row_residue_index(int i) const { return i + 1; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j + 1; }
     __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + (long long)c * 32);
+    }
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) {   // virtual column L2+1 (and padding): nothing flows in from the right
 #pragma unroll
@@ -145,26 +173,26 @@ struct HmmBwd {
         // ProbabilisticModel.h:340-379 / ParallelProbabilisticModel.cpp:196-218, same LOG_PLUS_EQUALS order
         const float ins2 = ins[r2];
         const float pxy = __fadd_rn(diag[0], mrow[r2]);
-        float bm = __fadd_rn(pxy, c_sc.tq0[0]);
-        float x1 = __fadd_rn(pxy, c_sc.tq0[1]);
-        float y1 = __fadd_rn(pxy, c_sc.tq0[2]);
-        float x2 = __fadd_rn(pxy, c_sc.tq0[3]);
-        float y2 = __fadd_rn(pxy, c_sc.tq0[4]);
+        float bm = __fadd_rn(pxy, tq0[0]);
+        float x1 = __fadd_rn(pxy, tq0[1]);
+        float y1 = __fadd_rn(pxy, tq0[2]);
+        float x2 = __fadd_rn(pxy, tq0[3]);
+        float y2 = __fadd_rn(pxy, tq0[4]);
         const float a1 = __fadd_rn(old[1], ins1);
-        bm = dev_log_add(bm, __fadd_rn(a1, c_sc.t0q[1]));
-        x1 = dev_log_add(x1, __fadd_rn(a1, c_sc.tqq[1]));
+        bm = dev_log_add_lut(bm, __fadd_rn(a1, t0q[1]), lut);
+        x1 = dev_log_add_lut(x1, __fadd_rn(a1, tqq[1]), lut);
         const float a2 = __fadd_rn(old[3], ins1);
-        bm = dev_log_add(bm, __fadd_rn(a2, c_sc.t0q[3]));
-        x2 = dev_log_add(x2, __fadd_rn(a2, c_sc.tqq[3]));
+        bm = dev_log_add_lut(bm, __fadd_rn(a2, t0q[3]), lut);
+        x2 = dev_log_add_lut(x2, __fadd_rn(a2, tqq[3]), lut);
         const float b1 = __fadd_rn(carry[2], ins2);
-        bm = dev_log_add(bm, __fadd_rn(b1, c_sc.t0q[2]));
-        y1 = dev_log_add(y1, __fadd_rn(b1, c_sc.tqq[2]));
+        bm = dev_log_add_lut(bm, __fadd_rn(b1, t0q[2]), lut);
+        y1 = dev_log_add_lut(y1, __fadd_rn(b1, tqq[2]), lut);
         const float b2 = __fadd_rn(carry[4], ins2);
-        bm = dev_log_add(bm, __fadd_rn(b2, c_sc.t0q[4]));
-        y2 = dev_log_add(y2, __fadd_rn(b2, c_sc.tqq[4]));
+        bm = dev_log_add_lut(bm, __fadd_rn(b2, t0q[4]), lut);
+        y2 = dev_log_add_lut(y2, __fadd_rn(b2, tqq[4]), lut);
         if (i == L1 && j == L2) { bm = c_sc.init[0]; x1 = c_sc.init[1]; y1 = c_sc.init[2]; x2 = c_sc.init[3]; y2 = c_sc.init[4]; }
         nw[0] = bm; nw[1] = x1; nw[2] = y1; nw[3] = x2; nw[4] = y2;
-        F[slot] = __fadd_rn(F[slot], bm);
+        F[slot] = __fadd_rn(stage[(buf * Cmax + c) * 32 + lane], bm);
         if (i <= 1 && j <= 1) {
             if (i == 1 && j == 1) cap[0] = bm;
             if (i == 1 && j == 0) { cap[1] = x1; cap[3] = x2; }
@@ -175,23 +203,22 @@ struct HmmBwd {
 
 __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float* match = reinterpret_cast<float*>(smem);
-    float* ins = match + 676;
-    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
-    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
-    __syncthreads();
+    float* match; float* ins; LogAddLut* lut;
+    load_hmm_tables(smem, a, match, ins, lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* band; uint8_t* colres; float* cap;
-    warp_smem<float, 5>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    float* band; float* stage; uint8_t* colres; float* cap;
+    warp_smem<float, 5, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    HmmBwd m;
+    m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerS5; m.cap = cap; m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
+    m.load_consts();
     for (;;) {
         const int ti = next_task(a.counter, lane);
         if (ti >= a.ntasks) break;
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
-        HmmBwd m;
-        m.match = match; m.ins = ins; m.F = a.layerS5; m.cap = cap; m.L1 = t.L1; m.L2 = t.L2;
+        m.L1 = t.L1; m.L2 = t.L2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         if (lane == 0) {   // ProbabilisticModel.h:421-432 / ParallelProbabilisticModel.cpp:226-231, then :453 and PosteriorStage.cpp:142
@@ -220,15 +247,16 @@ __device__ __forceinline__ double sum3(double zm, double h, double v, bool h_fir
 
 struct PartFwd {
     typedef double T;
-    enum { NS = 3, REV = 0, COLMASK = 0x7 };
+    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
     const double* sub; double* Z; int L1, L2; bool qp;
     const double* srow; double zz; bool has_zz;
+    __device__ __forceinline__ void prefetch(long long, int, int) const {}
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0; st[1] = 0; st[2] = 0; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0; e[1] = 0; e[2] = 0; }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (i == 0 || j == 0 || j > L2) {   // boundary: Zm(0,0)=1, H(0,j>=1)=1, V(i>=1,0)=1 (terminal gaps are exp(0))
             nw[0] = (i == 0 && j == 0) ? 1.0 : 0.0;
@@ -255,8 +283,8 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd(KArgs a) {
     for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* band; uint8_t* colres; float* cap;
-    warp_smem<double, 3>(smem, MLP_PART_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    double* band; double* stage; uint8_t* colres; float* cap;
+    warp_smem<double, 3, 0>(smem, MLP_PART_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     double* edge = a.edge_d ? a.edge_d + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -273,9 +301,13 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd(KArgs a) {
 
 struct PartRev {
     typedef double T;
-    enum { NS = 3, REV = 1, COLMASK = 0x7 };
+    enum { NS = 3, REV = 1, COLMASK = 0x7, NIN = 1 };
     const double* sub; const double* Z; float* P; int L1, L2; bool qp; double Ztot;
     const double* srow;
+    double* stage; int Cmax, lane;
+    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) cp_async8(stage + (buf * Cmax + c) * 32 + lane, Z + slotbase + (long long)c * 32);
+    }
     __device__ __forceinline__ void band_init(T (&st)[NS], int j) const {   // virtual row L1+1
         st[0] = (j == L2 + 1) ? 1.0 : 0.0;
         st[1] = (j >= 1 && j <= L2) ? 1.0 : 0.0;
@@ -287,7 +319,7 @@ struct PartRev {
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = (j == L2 + 1 && i >= 1) ? 1.0 : 0.0; return; }
         if (i == 0 || j == 0) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = 0.0; P[slot] = 0.0f; return; }
@@ -299,7 +331,7 @@ struct PartRev {
         const double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], !qp), score);
         nw[0] = zm; nw[1] = h; nw[2] = v;
         // PartitionFunction.cpp:259-270 / MSAPartProbs.cpp:286-297
-        double tmp = __dmul_rn(Z[slot], zm);
+        double tmp = __dmul_rn(stage[(buf * Cmax + c) * 32 + lane], zm);
         tmp = __ddiv_rn(tmp, __dmul_rn(score, Ztot));
         float p = (float)tmp;
         if (qp && !(p <= 1.0f && (double)p >= 0.001)) p = 0.0f;
@@ -313,8 +345,8 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
     for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* band; uint8_t* colres; float* cap;
-    warp_smem<double, 3>(smem, MLP_PART_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    double* band; double* stage; uint8_t* colres; float* cap;
+    warp_smem<double, 3, 1>(smem, MLP_PART_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     double* edge = a.edge_d ? a.edge_d + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -323,6 +355,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         PartRev m;
+        m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
         m.sub = sub; m.Z = a.layerZ; m.P = a.layerP; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
         m.Ztot = a.pout[ti].Zpart;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
@@ -333,25 +366,26 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
 // states: 0 = M, 1 = X, 2 = Y  (ProbabilisticModel.h flag=false branches)
 struct LocFwd {
     typedef float T;
-    enum { NS = 3, REV = 0, COLMASK = 0x7 };
-    const float* match; const float* ins; float* F; int L1, L2;
+    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
+    const float* match; const float* ins; const LogAddLut* lut; float* F; int L1, L2;
     float ins1; const float* mrow;
+    __device__ __forceinline__ void prefetch(long long, int, int) const {}
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = st[1] = st[2] = MLP_LOG_ZERO; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = e[1] = e[2] = MLP_LOG_ZERO; }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         // ProbabilisticModel.h:210-211,222-227: base = ((m - a) - b); M = (base - 2r) (+) sum_k ((base + F_k) + lt[k][0]) - 2r
         const float base = __fsub_rn(__fsub_rn(mrow[r2], ins1), ins[r2]);
         float m = __fsub_rn(base, c_sc.r2);
-        m = dev_log_add(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[0]), c_sc.lt00), c_sc.r2));
-        m = dev_log_add(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[1]), c_sc.lt10), c_sc.r2));
-        m = dev_log_add(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[2]), c_sc.lt20), c_sc.r2));
+        m = dev_log_add_lut(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[0]), c_sc.lt00), c_sc.r2), lut);
+        m = dev_log_add_lut(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[1]), c_sc.lt10), c_sc.r2), lut);
+        m = dev_log_add_lut(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[2]), c_sc.lt20), c_sc.r2), lut);
         // :238-241, :252-255
-        float x = dev_log_add(__fsub_rn(__fadd_rn(old[0], c_sc.lt01), c_sc.r), __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r));
-        float y = dev_log_add(__fsub_rn(__fadd_rn(carry[0], c_sc.lt02), c_sc.r), __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r));
+        float x = dev_log_add_lut(__fsub_rn(__fadd_rn(old[0], c_sc.lt01), c_sc.r), __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r), lut);
+        float y = dev_log_add_lut(__fsub_rn(__fadd_rn(carry[0], c_sc.lt02), c_sc.r), __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r), lut);
         if (i == 0 || j == 0) m = MLP_LOG_ZERO;
         if (i == 0) x = MLP_LOG_ZERO;
         if (j == 0) y = MLP_LOG_ZERO;
@@ -366,8 +400,12 @@ struct LocFwd {
 
 struct LocBwd {
     typedef float T;
-    enum { NS = 3, REV = 1, COLMASK = 0x3 };   // keep B_M and X of row i+1; Y travels along the row
-    const float* match; const float* ins; float* F; float* VB; int L1, L2;
+    enum { NS = 3, REV = 1, COLMASK = 0x3, NIN = 1 };   // keep B_M and X of row i+1; Y travels along the row
+    const float* match; const float* ins; const LogAddLut* lut; float* F; float* VB; int L1, L2;
+    float* stage; int Cmax, lane;
+    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + (long long)c * 32);
+    }
     float ins1n; const float* mrown;   // residue i+1 (transition out of the cell)
     float ins1c; const float* mrowc;   // residue i   (the cell's own emission, for the Z term)
     const uint8_t* s1; const uint8_t* s2;
@@ -380,24 +418,24 @@ struct LocBwd {
         const int rc = (i >= 1) ? s1[i - 1] : 0;
         ins1c = ins[rc]; mrowc = match + rc * 26;
     }
-    __device__ __forceinline__ void cell(int i, int j, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = nw[1] = nw[2] = MLP_LOG_ZERO; return; }
         // ProbabilisticModel.h:339-379 flag=false.  B_M starts at LOG_ONE in every cell.
         float bm = 0.0f, x = MLP_LOG_ZERO, y = MLP_LOG_ZERO;
         if (i < L1 && j < L2) {
             const float pxy = __fsub_rn(__fsub_rn(__fadd_rn(diag[0], mrown[r2]), ins1n), ins[r2]);
-            bm = dev_log_add(bm, __fsub_rn(__fadd_rn(pxy, c_sc.lt00), c_sc.r2));
+            bm = dev_log_add_lut(bm, __fsub_rn(__fadd_rn(pxy, c_sc.lt00), c_sc.r2), lut);
             x = __fsub_rn(__fadd_rn(pxy, c_sc.lt10), c_sc.r2);
             y = __fsub_rn(__fadd_rn(pxy, c_sc.lt20), c_sc.r2);
         }
         if (i < L1) {
-            bm = dev_log_add(bm, __fsub_rn(__fadd_rn(old[1], c_sc.lt01), c_sc.r));
-            x = dev_log_add(x, __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r));
+            bm = dev_log_add_lut(bm, __fsub_rn(__fadd_rn(old[1], c_sc.lt01), c_sc.r), lut);
+            x = dev_log_add_lut(x, __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r), lut);
         }
         if (j < L2) {
-            bm = dev_log_add(bm, __fsub_rn(__fadd_rn(carry[2], c_sc.lt02), c_sc.r));
-            y = dev_log_add(y, __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r));
+            bm = dev_log_add_lut(bm, __fsub_rn(__fadd_rn(carry[2], c_sc.lt02), c_sc.r), lut);
+            y = dev_log_add_lut(y, __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r), lut);
         }
         nw[0] = bm; nw[1] = x; nw[2] = y;
         // Z term of this cell, ProbabilisticModel.h:445-446: (((B_M + m) - a) - b) - 2r with the cell's own residues
@@ -407,7 +445,7 @@ struct LocBwd {
             vb = __fsub_rn(__fsub_rn(__fsub_rn(__fadd_rn(bm, mrowc[rj]), ins1c), ins[rj]), c_sc.r2);
         }
         VB[slot] = vb;
-        F[slot] = __fadd_rn(F[slot], bm);
+        F[slot] = __fadd_rn(stage[(buf * Cmax + c) * 32 + lane], bm);
     }
 };
 
@@ -447,14 +485,11 @@ __device__ float replay_rowmajor(const float* layer, const SweepCtx& cx) {
 
 __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float* match = reinterpret_cast<float*>(smem);
-    float* ins = match + 676;
-    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
-    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
-    __syncthreads();
+    float* match; float* ins; LogAddLut* lut;
+    load_hmm_tables(smem, a, match, ins, lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* band; uint8_t* colres; float* cap;
-    warp_smem<float, 3>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    float* band; float* stage; uint8_t* colres; float* cap;
+    warp_smem<float, 3, 0>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -463,7 +498,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         LocFwd m;
-        m.match = match; m.ins = ins; m.F = a.layerSL; m.L1 = t.L1; m.L2 = t.L2;
+        m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerSL; m.L1 = t.L1; m.L2 = t.L2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         __threadfence_block();
@@ -474,14 +509,11 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
 
 __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float* match = reinterpret_cast<float*>(smem);
-    float* ins = match + 676;
-    for (int k = threadIdx.x; k < 676; k += blockDim.x) match[k] = a.match[k];
-    for (int k = threadIdx.x; k < 26; k += blockDim.x) ins[k] = a.ins[k];
-    __syncthreads();
+    float* match; float* ins; LogAddLut* lut;
+    load_hmm_tables(smem, a, match, ins, lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* band; uint8_t* colres; float* cap;
-    warp_smem<float, 3>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, colres, cap);
+    float* band; float* stage; uint8_t* colres; float* cap;
+    warp_smem<float, 3, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -490,6 +522,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         LocBwd m;
+        m.stage = stage; m.Cmax = a.Cmax; m.lane = lane; m.lut = lut;
         m.match = match; m.ins = ins; m.F = a.layerSL; m.VB = a.layerVB; m.L1 = t.L1; m.L2 = t.L2; m.s1 = cx.s1; m.s2 = cx.s2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
@@ -503,8 +536,18 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
 // states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
 struct FinalSweep {
     typedef float T;
-    enum { NS = 2, REV = 0, COLMASK = 0x1 };
+    enum { NS = 2, REV = 0, COLMASK = 0x1, NIN = 3 };
     const float* S5; const float* P; const float* SL;
+    float* dstage; int Cmax, lane;
+    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) {
+            const long long g = slotbase + (long long)c * 32;
+            float* d = dstage + ((buf * 3) * Cmax + c) * 32 + lane;
+            if (mask & 1u) cp_async4(d, S5 + g);
+            if (mask & 2u) cp_async4(d + Cmax * 32, P + g);
+            if (mask & 4u) cp_async4(d + 2 * Cmax * 32, SL + g);
+        }
+    }
     float total5, totalL;
     int flavour; unsigned mask; float cutoff;
     int L1, L2;
@@ -518,13 +561,14 @@ struct FinalSweep {
     __device__ __forceinline__ int row_residue_index(int) const { return 0; }
     __device__ __forceinline__ int col_residue_index(int) const { return 0; }
     __device__ __forceinline__ void begin_row(int, int) {}
-    __device__ __forceinline__ void cell(int i, int j, int, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, long long, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = carry[0]; nw[1] = carry[1]; return; }
         float v5 = 0.0f, vp = 0.0f, vl = 0.0f, p;
-        if (mask & 1u) v5 = dev_posterior_from_sum(S5[slot], total5);
-        if (mask & 2u) vp = P[slot];
-        if (mask & 4u) vl = dev_posterior_from_sum(SL[slot], totalL);
+        const float* sg = dstage + ((buf * 3) * Cmax + c) * 32 + lane;
+        if (mask & 1u) v5 = dev_posterior_from_sum(sg[0], total5);
+        if (mask & 2u) vp = sg[Cmax * 32];
+        if (mask & 4u) vl = dev_posterior_from_sum(sg[2 * Cmax * 32], totalL);
         if (i == 0 && j == 0) { v5 = 0.0f; vl = 0.0f; }   // posterior[0] = 0, ProbabilisticModel.h:490
         if (flavour == 0) {
             // PosteriorStage.cpp:169-177: borders forced to 0, sqrt((v1^2+v2^2)*0.5)
@@ -564,8 +608,8 @@ struct FinalSweep {
 __global__ void __launch_bounds__(MLP_BLOCK) k_final(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* band; uint8_t* colres; float* cap;
-    warp_smem<float, 2>(smem, 0, a.Cmax, warp, band, colres, cap);
+    float* band; float* stg; uint8_t* colres; float* cap;
+    warp_smem<float, 2, 3>(smem, 0, a.Cmax, warp, band, stg, colres, cap);
     int* stage_n = reinterpret_cast<int*>(cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
@@ -580,7 +624,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_final(KArgs a) {
         if (lane == 0) { *stage_n = 0; rowptr[0] = 0; rowptr[1] = 0; }
         __syncwarp();
         FinalSweep m;
-        m.S5 = a.layerS5; m.P = a.layerP; m.SL = a.layerSL;
+        m.S5 = a.layerS5; m.P = a.layerP; m.SL = a.layerSL; m.dstage = stg; m.Cmax = a.Cmax; m.lane = lane;
         m.total5 = a.pout[ti].total5; m.totalL = a.pout[ti].totalL;
         m.flavour = a.flavour; m.mask = a.mask; m.cutoff = a.cutoff;
         m.L1 = t.L1; m.L2 = t.L2; m.rowcnt = rowptr; m.stage = stage; m.stage_cap = a.stage_cap; m.stage_n = stage_n;
@@ -706,12 +750,15 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_transpose(KArgs a) {
 
 // ------------------------------------------------------------------------------------------------ launch helpers
 size_t posterior_smem_bytes(int kernel, int Cmax, int warps) {
-    size_t tables = 0, per = 0;
+    size_t tables = 0, per = 0;   // per = band + staging, must mirror warp_smem<T, NS, NIN>
     switch (kernel) {
-        case MLP_K_PART_FWD: case MLP_K_PART_REV: tables = MLP_PART_TABLE_BYTES; per = 3 * Cmax * 32 * 8; break;
-        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: tables = MLP_HMM_TABLE_BYTES; per = 5 * Cmax * 32 * 4; break;
-        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: tables = MLP_HMM_TABLE_BYTES; per = 3 * Cmax * 32 * 4; break;
-        case MLP_K_FINAL: tables = 0; per = 2 * Cmax * 32 * 4; break;
+        case MLP_K_PART_FWD: tables = MLP_PART_TABLE_BYTES; per = (size_t)3 * Cmax * 32 * 8; break;
+        case MLP_K_PART_REV: tables = MLP_PART_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 8; break;
+        case MLP_K_HMM_FWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)5 * Cmax * 32 * 4; break;
+        case MLP_K_HMM_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(5 + 2) * Cmax * 32 * 4; break;
+        case MLP_K_LOCAL_FWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)3 * Cmax * 32 * 4; break;
+        case MLP_K_LOCAL_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 4; break;
+        case MLP_K_FINAL: tables = 0; per = (size_t)(2 + 6) * Cmax * 32 * 4; break;
         default: return 0;
     }
     per += Cmax * 32 + 64;

@@ -4,7 +4,7 @@
 #include "../../include/mlprobs_b200.h"   // MLP_K_* kernel ids
 
 #define MLP_BLOCK 128                  // 4 warps per CTA, one pair per warp
-#define MLP_HMM_TABLE_BYTES 2816       // 676 match + 26 ins floats, padded to 16 B
+#define MLP_HMM_TABLE_BYTES 3072       // 676 match + 26 ins floats padded to 2816 B, then the 256-byte LogAddLut
 #define MLP_PART_TABLE_BYTES 5408      // 676 doubles
 #define MLP_K_TRANSPOSE 8              // extends the MLP_K_* kernel ids of mlprobs_b200.h
 #define MLP_K_RELAX_ID 7

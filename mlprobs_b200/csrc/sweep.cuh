@@ -38,6 +38,9 @@ struct SweepCtx {
 //   void begin_row(int i, int r1)                       per-row setup (r1 = residue the model needs for this row)
 //   void cell(int i, int j, int c, long long slotbase, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS], T (&nw)[NS])
 //   int row_residue_index(int i) / col_residue_index(int j)   1-based residue used at row i / column j (0 = none)
+//   void prefetch(long long slotbase, int C, int buf)   issue cp.async of the dense inputs of one wavefront slot into
+//                                                       staging buffer `buf` (models without dense inputs: no-op);
+//                                                       cell() receives `buf` and reads its inputs from there
 template <class M>
 __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::T* band /* [NS][Cmax][32] per warp */,
                                           uint8_t* colres /* [Cmax][32] per warp */, int Cmax,
@@ -69,11 +72,23 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
         T myout[NS], diag_in[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) { myout[s] = (T)0; diag_in[s] = (T)0; }
+        // software pipeline of the dense inputs: the slot of step t+1 is fetched (cp.async) while step t computes
+        {
+            const int i0 = M::REV ? (cx.L1 + 31 - lane) : (0 - lane);
+            if (lane_has_cols && i0 >= 0 && i0 <= cx.L1)
+                m.prefetch(cx.off + ((long long)(cb * cx.T + (M::REV ? (cx.L1 + 31) : 0)) * C) * 32 + lane, C, 0);
+        }
 
         for (int t = 0; t < cx.T; ++t) {
             const int i = M::REV ? (cx.L1 - t + 31 - lane) : (t - lane);
             const bool in_rows = (i >= 0 && i <= cx.L1);
             const bool active = in_rows && lane_has_cols;
+            if (M::NIN > 0) {
+                cp_async_wait_all();
+                const int inext = M::REV ? (i - 1) : (i + 1);
+                if (lane_has_cols && inext >= 0 && inext <= cx.L1 && t + 1 < cx.T)
+                    m.prefetch(cx.off + ((long long)(cb * cx.T + (M::REV ? (cx.L1 + 31 - (t + 1)) : (t + 1))) * C) * 32 + lane, C, (t + 1) & 1);
+            }
             T in[NS];
             shfl_vec<NS, T>(in, myout, src);
             if (first_lane && in_rows) {
@@ -106,7 +121,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
                         if ((M::COLMASK >> s) & 1) old[s] = band[(s * Cmax + c) * 32 + lane]; else old[s] = (T)0;
-                    m.cell(i, j, colres[c * 32 + lane], slotbase + (long long)c * 32, old, carry, diag, nw);
+                    m.cell(i, j, c, t & 1, colres[c * 32 + lane], slotbase + (long long)c * 32, old, carry, diag, nw);
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         if ((M::COLMASK >> s) & 1) band[(s * Cmax + c) * 32 + lane] = nw[s];
