@@ -109,25 +109,31 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
-def one_step(eng, M, n, e2e, seqs=None):
-    """posterior stage + tree + consistency. Returns (device_ms_posterior, device_ms_relax, stats)."""
+def one_step(eng, M, n, e2e, seqs=None, world=1, read_back=True):
+    """posterior stage [+ exchange] + host tree + consistency [+ exchange]. Returns the per-stage stats."""
     if e2e:
         eng.set_sequences(seqs)                       # host -> device copy of the family inside the timed region
+        if world > 1:
+            eng.set_shard(int(os.environ.get("RANK", "0")), world)
+    stats = []
     eng.posterior_all_pairs(M.QP, 3, 0.01)
-    st_p = eng.stats()
-    d = eng.distances()                               # tree needs the distances on the host (as in the reference)
+    stats.append(("posterior", eng.stats()))
+    if world > 1:
+        eng.exchange(); stats.append(("exchange", eng.stats()))
+    d = eng.distances()                               # the guide tree is host work between the stages, as in the reference
     w, sd, _, _ = M.qp_guide_tree(d)
     w = np.maximum(w, np.float32(1e-6))
     iters = 1 if n > 50 else 2
-    st_r = []
     for it in range(iters):
         cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))
         eng.relax(M.QP, w, sd, 200.0, 3.0, cutoff)
-        st_r.append(eng.stats())
+        stats.append(("relax", eng.stats()))
+        if world > 1:
+            eng.exchange(); stats.append(("exchange", eng.stats()))
     out = None
-    if e2e:
+    if e2e and read_back:
         out = eng.csr_bulk()                          # device -> host read of the step's result
-    return st_p, st_r, out
+    return stats, out
 
 
 def main():
@@ -150,11 +156,11 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    dev = local_rank
+    torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = local_rank
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     seqs = make_family(wl)
     n = len(seqs)
     eng = M.Engine(dev)
@@ -162,42 +168,46 @@ def main():
     eng.set_tables(h, p)
     eng.set_sequences(seqs)
     if world > 1:
-        eng.set_shard(rank, world)
+        uid = [M.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)            # also selects this rank's shard of the cost-sorted pair list
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    total_cells = sum((len(a) + 1) * (len(b) + 1) for i, a in enumerate(seqs) for b in seqs[i + 1:])
+    lens = np.array([len(s) for s in seqs], np.int64) + 1
+    total_cells = int((lens.sum() ** 2 - (lens ** 2).sum()) // 2)
     npairs = n * (n - 1) // 2
     sampler = ClockSampler(dev); sampler.start()
-    # ---- kernel-resident arm
+    # ---- kernel-resident arm (inputs already in HBM)
     for _ in range(args.warmup):
-        one_step(eng, M, n, False)
+        one_step(eng, M, n, False, world=world)
     barrier()
     ms_dev, launches, kms = [], 0, {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st_p, st_r, _ = one_step(eng, M, n, False)
-        ms = st_p["ms_total"] + sum(s["ms_total"] for s in st_r)
-        ms_dev.append(ms)
-        launches += st_p["launches"] + sum(s["launches"] for s in st_r)
-        for k, v in st_p["ms_kernel"].items():
-            kms[k] = kms.get(k, 0.0) + v
-        for s in st_r:
-            kms["relax"] = kms.get("relax", 0.0) + s["ms_kernel"]["relax"]
+        stats, _ = one_step(eng, M, n, False, world=world)
+        ms_dev.append(sum(s["ms_total"] for _, s in stats))
+        launches += sum(s["launches"] for _, s in stats)
+        for name, s_ in stats:
+            if name == "exchange":
+                kms["exchange"] = kms.get("exchange", 0.0) + s_["ms_total"]
+            else:
+                for k, v in s_["ms_kernel"].items():
+                    kms[k] = kms.get(k, 0.0) + v
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     dev_ms = float(np.mean(ms_dev))
-    # ---- end-to-end arm (host buffers in, host buffers out)
+    # ---- end-to-end arm (host buffers in, host buffers out through the C ABI)
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(args.steps):
-        st_p, st_r, out = one_step(eng, M, n, True, seqs)
-        h2d = st_p["h2d_bytes"] + sum(s["h2d_bytes"] for s in st_r) + sum(len(s) for s in seqs)
-        d2h = n * n * 4 + sum(a.nbytes for a in out)
+        stats, out = one_step(eng, M, n, True, seqs, world=world, read_back=(rank == 0))
+        h2d = sum(s["h2d_bytes"] for _, s in stats) + sum(len(s) for s in seqs)
+        d2h = n * n * 4 + (sum(a.nbytes for a in out) if out is not None else 0)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -205,31 +215,42 @@ def main():
         t = torch.tensor([wall_ms, e2e_ms, dev_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall_ms, e2e_ms, dev_ms = [float(x) for x in t.tolist()]
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     if rank == 0:
         models = 2
         value = total_cells * models / (wall_ms * 1e-3) / 1e9
         e2e = total_cells * models / (e2e_ms * 1e-3) / 1e9
         peaks = measured_peaks()
         per_kernel_ms = {k: v / args.steps for k, v in kms.items() if v}
-        # dominant kernel: 5-state forward+backward (FP32 issue bound); its algorithmic work is 358 slots per cell
+        # dominant kernels: 5-state forward + backward sweeps (FP32-issue bound). Algorithmic work 358 lane-ops per cell,
+        # algorithmic HBM bytes 12 per cell (forward layer written, read back, F+B written), see DESIGN.md.
         hmm_ms = per_kernel_ms.get("hmm_fwd", 0) + per_kernel_ms.get("hmm_bwd", 0)
-        slot_rate = (total_cells / max(world, 1)) * SLOTS_PER_CELL["hmm5"] / (hmm_ms * 1e-3) if hmm_ms else 0.0
-        hbm_bytes = (total_cells / max(world, 1)) * 12.0   # F write + F read + S write per cell
+        cells_rank = total_cells / max(world, 1)
+        slot_rate = cells_rank * SLOTS_PER_CELL["hmm5"] / (hmm_ms * 1e-3) if hmm_ms else 0.0
         line = {"metric": "pair_hmm_cell_updates_per_second", "value": value, "unit": "GCUPS", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-                "config": {"workload": wl["name"], "flavour": "quickprobs", "models_per_cell": models, "n": n, "pairs": npairs,
-                           "cells": total_cells, "l2_policy": "inputs larger than L2 (dense DP layers >> 126 MB per batch)"},
+                "config": {"workload": wl["name"], "flavour": "quickprobs (5-state pair-HMM f32 + partition function f64, 1 consistency rep)",
+                           "models_per_cell": models, "n": n, "pairs": npairs, "cells": total_cells,
+                           "generator": "mlprobs_b200.synth.family_fast(p_sub=0.5): expected pairwise identity ~0.29",
+                           "l2_policy": "inputs larger than L2: each batch streams >10 GB of dense DP layers (L2 = 126 MB)"},
                 "device_ms_per_step": dev_ms, "kernel_ms_per_step": per_kernel_ms,
                 "alignments_per_sec": npairs / (wall_ms * 1e-3),
+                "gcups_posterior_stage": total_cells * models / max(world, 1) / (sum(v for k, v in per_kernel_ms.items() if k not in ("relax", "exchange")) * 1e-3) / 1e9,
+                "gcups_hmm5_fwd_bwd_per_gpu": cells_rank / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
                 "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "fp32_issue", "kernel": "k_hmm_fwd+k_hmm_bwd", "achieved": slot_rate / 1e12, "peak": FP32_ISSUE_PEAK / 1e12,
-                             "unit": "Tlane-op/s", "frac": slot_rate / FP32_ISSUE_PEAK, "traffic": None,
-                             "hbm": {"achieved": hbm_bytes / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
+                             "unit": "Tlane-op/s", "frac": slot_rate / FP32_ISSUE_PEAK,
+                             "peak_source": "148 SMs x 128 FP32 lanes x 1.965 GHz (MEASURED_PEAKS.json sm_max_mhz); no measured FP32-issue peak exists in MEASURED_PEAKS.json",
+                             "algorithmic_ops_per_cell": SLOTS_PER_CELL["hmm5"], "traffic": None,
+                             "hbm": {"bound": "hbm", "achieved": cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
                                      "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
-                                     "peak_source": "measured" if peaks else "fallback"}}}
+                                     "frac": (cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9) / (peaks["hbm_gbs"] if peaks else 6650.0) if hmm_ms else None,
+                                     "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_cell": 12}}}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, seqs, args.ref_sample)
         print(json.dumps(line))

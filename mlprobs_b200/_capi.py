@@ -90,6 +90,14 @@ def default_tables(flavour, init_distrib2=0.700645):
     return h, p
 
 
+def nccl_unique_id():
+    buf = (C.c_uint8 * 128)()
+    rc = load().mlp_nccl_unique_id(buf)
+    if rc:
+        raise MlpError(rc)
+    return bytes(buf)
+
+
 def qp_guide_tree(distances):
     """UPGMA tree -> (weights, subtree distances, parent array, distances after the in-place update)."""
     d = np.array(distances, np.float32, copy=True, order="C")
@@ -181,6 +189,14 @@ class Engine:
         sd = np.ascontiguousarray(seldist, np.float32) if seldist is not None else None
         self._ck(self._lib.mlp_relax(self._ctx, flavour, _ptr(w), _ptr(sd), C.c_float(selectivity),
                                      C.c_float(selfweight), C.c_float(cutoff)))
+
+    def comm_init(self, id128: bytes, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self._ck(self._lib.mlp_comm_init(self._ctx, buf, rank, world))
+
+    def exchange(self):
+        """All-gather the sparse posteriors + distances of every rank's shard (NCCL)."""
+        self._ck(self._lib.mlp_exchange(self._ctx))
 
     def csr(self, a, b):
         nnz = C.c_int64(0)

@@ -10,66 +10,9 @@
 #include <string>
 #include <vector>
 
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess) {                                                                  \
-            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
-            return MLP_E_CUDA;                                                                     \
-        }                                                                                          \
-    } while (0)
+#include "ctx.h"
 
-static const int kCmaxLimit = 16;   // columns per lane; 32*16 = 512 columns per column block
-
-struct mlp_ctx {
-    int device = 0, num_sms = 0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    // configuration
-    int64_t scratch_budget = 0, cell_capacity_req = 0;
-    // sequences
-    int n = 0;
-    std::vector<int> len;
-    std::vector<long long> seq_off;
-    long long total_res = 0;
-    std::vector<uint8_t> codes_h;
-    uint8_t* d_res = nullptr;
-    long long* d_seq_off = nullptr;
-    // tables
-    bool have_tables = false;
-    mlp_hmm_tables hmm;
-    mlp_part_tables part;
-    float* d_match = nullptr; float* d_ins = nullptr; double* d_sub = nullptr;
-    // pairs
-    std::vector<PairTask> all_pairs;     // cost-sorted (descending)
-    std::vector<PairTask> owned;         // this shard
-    int rank = 0, world = 1;
-    // sparse sets (double buffered for relax)
-    std::vector<long long> rp_off_h;
-    long long rp_total = 0;
-    long long* d_rp_off = nullptr;
-    CsrSetDev set[2] = {};
-    int cur = 0;
-    bool have_sets = false;
-    int flavour_of_set = -1;
-    float* d_dist = nullptr;
-    // per-launch scratch
-    void* d_scratch = nullptr; size_t scratch_bytes = 0;
-    PairTask* d_tasks = nullptr; PairOut* d_pout = nullptr; size_t tasks_cap = 0;
-    int* d_counter = nullptr; int* d_err = nullptr;
-    int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
-    int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
-    void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
-    float* d_wk = nullptr; long long wk_warps = 0;
-    float* d_weights = nullptr; float* d_seldist = nullptr;
-    // nccl
-    void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
-    // stats
-    mlp_stage_stats stats = {};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-};
-
-static void free_dev(void* p) { if (p) cudaFree(p); }
+void free_dev(void* p) { if (p) cudaFree(p); }
 
 static void release_sets(mlp_ctx* ctx) {
     for (int s = 0; s < 2; ++s) {
@@ -296,7 +239,7 @@ static int ensure_sets(mlp_ctx* ctx) {
 }
 
 // Re-allocate the cell pool of one set to new_cap cells, keeping the first `keep` cells.
-static int grow_cells(mlp_ctx* ctx, int which, long long new_cap, unsigned long long keep) {
+int grow_cells(mlp_ctx* ctx, int which, long long new_cap, unsigned long long keep) {
     int2* fresh = nullptr;
     CK(cudaMalloc(&fresh, (size_t)new_cap * sizeof(int2)));
     if (keep) CK(cudaMemcpy(fresh, ctx->set[which].cells, (size_t)keep * sizeof(int2), cudaMemcpyDeviceToDevice));
@@ -549,6 +492,11 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     ctx->cur = 0;
     CK(cudaMemsetAsync(ctx->set[0].cursor, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->set[0].nz_cnt, 0, (size_t)ctx->n * ctx->n * sizeof(int), ctx->stream));
+    if (ctx->world > 1) {   // slots of pairs other shards own must read as zero for the sum-exchange (mlp_exchange)
+        CK(cudaMemsetAsync(ctx->set[0].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->set[0].nz_off, 0, (size_t)ctx->n * ctx->n * sizeof(long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_dist, 0, (size_t)ctx->n * ctx->n * sizeof(float), ctx->stream));
+    }
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = run_posterior_tasks(ctx, flavour, model_mask, cutoff, ctx->owned, nullptr, nullptr, nullptr, nullptr);
     if (rc != MLP_OK) return rc;
@@ -729,6 +677,10 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     ctx->stats.h2d_bytes += (int64_t)(tasks.size() * sizeof(PairTask));
     CK(cudaMemsetAsync(ctx->set[out].cursor, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->set[out].nz_cnt, 0, (size_t)n * n * sizeof(int), ctx->stream));
+    if (ctx->world > 1) {
+        CK(cudaMemsetAsync(ctx->set[out].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->set[out].nz_off, 0, (size_t)n * n * sizeof(long long), ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
     RelaxArgs ra = {};
     ra.tasks = ctx->d_tasks; ra.ntasks = (int)tasks.size(); ra.counter = ctx->d_counter;

@@ -1,0 +1,69 @@
+// Internal: the context object behind the opaque mlp_ctx handle (shared by capi.cu and exchange.cu).
+#pragma once
+#include "../../include/mlprobs_b200.h"
+#include "posterior.cuh"
+#include <string>
+#include <vector>
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return MLP_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static const int kCmaxLimit = 16;   // columns per lane; 32*16 = 512 columns per column block
+
+struct mlp_ctx {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // configuration
+    int64_t scratch_budget = 0, cell_capacity_req = 0;
+    // sequences
+    int n = 0;
+    std::vector<int> len;
+    std::vector<long long> seq_off;
+    long long total_res = 0;
+    std::vector<uint8_t> codes_h;
+    uint8_t* d_res = nullptr;
+    long long* d_seq_off = nullptr;
+    // tables
+    bool have_tables = false;
+    mlp_hmm_tables hmm;
+    mlp_part_tables part;
+    float* d_match = nullptr; float* d_ins = nullptr; double* d_sub = nullptr;
+    // pairs
+    std::vector<PairTask> all_pairs;     // cost-sorted (descending)
+    std::vector<PairTask> owned;         // this shard
+    int rank = 0, world = 1;
+    // sparse sets (double buffered for relax)
+    std::vector<long long> rp_off_h;
+    long long rp_total = 0;
+    long long* d_rp_off = nullptr;
+    CsrSetDev set[2] = {};
+    int cur = 0;
+    bool have_sets = false;
+    int flavour_of_set = -1;
+    float* d_dist = nullptr;
+    // per-launch scratch
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    PairTask* d_tasks = nullptr; PairOut* d_pout = nullptr; size_t tasks_cap = 0;
+    int* d_counter = nullptr; int* d_err = nullptr;
+    int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
+    int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
+    void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
+    float* d_wk = nullptr; long long wk_warps = 0;
+    float* d_weights = nullptr; float* d_seldist = nullptr;
+    // nccl
+    void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+    // stats
+    mlp_stage_stats stats = {};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+
+
+void free_dev(void* p);
+int grow_cells(mlp_ctx* ctx, int which, long long new_cap, unsigned long long keep);

@@ -1,5 +1,147 @@
-// Multi-GPU exchange of the sparse posteriors -- filled in by exchange step; see DESIGN.md.
-#include "../../include/mlprobs_b200.h"
-extern "C" int mlp_nccl_unique_id(uint8_t id128[128]) { (void)id128; return MLP_E_UNSUPPORTED; }
-extern "C" int mlp_comm_init(mlp_ctx* ctx, const uint8_t id128[128], int rank, int world) { (void)ctx; (void)id128; (void)rank; (void)world; return MLP_E_UNSUPPORTED; }
-extern "C" int mlp_exchange(mlp_ctx* ctx) { (void)ctx; return MLP_E_UNSUPPORTED; }
+// Multi-GPU exchange of the sparse posteriors: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// Every rank computes the pairs of its shard (mlp_set_shard).  Because the row-pointer pool and the per-pair tables
+// have the SAME fixed layout on every rank and slots of foreign pairs are kept zero, "gather" is a sum:
+//   distances, row pointers, cell counts, cell offsets -> ncclAllReduce(sum) in place (x + 0 == x, exact);
+//   cells (variable size, bump-allocated per rank)       -> one grouped ncclBroadcast per rank into a common pool, rank
+//                                                          q's cells landing at base_q = sum of the lower ranks' usage
+//                                                          (the cell offsets of owned pairs are shifted by base_q first).
+// NCCL is bound at run time (dlopen libnccl.so.2) so the library loads on machines without it; inside a torch process
+// the already-loaded torch-bundled NCCL is the one that resolves.
+#include "ctx.h"
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl() {
+    if (g_nccl.ok) return true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl.h = h;
+#define BIND(field, sym) *(void**)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) return false;
+    BIND(GetUniqueId, "ncclGetUniqueId") BIND(CommInitRank, "ncclCommInitRank") BIND(CommDestroy, "ncclCommDestroy")
+    BIND(AllReduce, "ncclAllReduce") BIND(AllGather, "ncclAllGather") BIND(Broadcast, "ncclBroadcast")
+    BIND(GroupStart, "ncclGroupStart") BIND(GroupEnd, "ncclGroupEnd") BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+    g_nccl.ok = true;
+    return true;
+}
+
+__global__ void k_shift_offsets(const PairTask* tasks, int ntasks, int n, long long* nz_off, long long base) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntasks) return;
+    const PairTask p = tasks[t];
+    nz_off[(long long)p.a * n + p.b] += base;
+    nz_off[(long long)p.b * n + p.a] += base;
+}
+}  // namespace
+
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r__ = (call);                                                            \
+        if (r__ != ncclSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(r__);                \
+            return MLP_E_NCCL;                                                                \
+        }                                                                                     \
+    } while (0)
+
+extern "C" int mlp_nccl_unique_id(uint8_t id128[128]) {
+    if (!id128) return MLP_E_ARG;
+    if (!load_nccl()) return MLP_E_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return MLP_E_NCCL;
+    memcpy(id128, &id, 128);
+    return MLP_OK;
+}
+
+extern "C" int mlp_comm_init(mlp_ctx* ctx, const uint8_t id128[128], int rank, int world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return MLP_E_ARG;
+    if (!load_nccl()) { ctx->err = "libnccl.so.2 could not be loaded"; return MLP_E_NCCL; }
+    cudaSetDevice(ctx->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    NK(g_nccl.CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm; ctx->comm_rank = rank; ctx->comm_world = world;
+    return mlp_set_shard(ctx, rank, world);
+}
+
+extern "C" int mlp_exchange(mlp_ctx* ctx) {
+    if (!ctx) return MLP_E_ARG;
+    if (ctx->comm_world <= 1) return MLP_OK;
+    if (!ctx->nccl_comm || !ctx->have_sets) { ctx->err = "mlp_comm_init and a posterior/relax stage must come first"; return MLP_E_STATE; }
+    cudaSetDevice(ctx->device);
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int W = ctx->comm_world, R = ctx->comm_rank, n = ctx->n;
+    const int cur = ctx->cur, oth = 1 - ctx->cur;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    // 1. how many cells does every rank hold?
+    unsigned long long* d_used = nullptr;
+    CK(cudaMalloc(&d_used, (size_t)W * sizeof(unsigned long long)));
+    NK(g_nccl.AllGather(ctx->set[cur].cursor, d_used, 1, ncclUint64, comm, st));
+    std::vector<unsigned long long> used(W);
+    CK(cudaMemcpyAsync(used.data(), d_used, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_used);
+    std::vector<long long> base(W + 1, 0);
+    for (int r = 0; r < W; ++r) base[r + 1] = base[r] + (long long)used[r];
+    const long long total = base[W];
+    if (total + 1024 > ctx->set[oth].cap) { int rc = grow_cells(ctx, oth, total + 1024, 0); if (rc != MLP_OK) return rc; }
+    // 2. shift the offsets of my pairs to their place in the common pool
+    if (!ctx->owned.empty()) {
+        int rc = MLP_OK;
+        if (ctx->owned.size() > ctx->tasks_cap) {
+            free_dev(ctx->d_tasks); free_dev(ctx->d_pout); ctx->d_tasks = nullptr; ctx->d_pout = nullptr;
+            const size_t cap = ctx->owned.size() + 64;
+            CK(cudaMalloc(&ctx->d_tasks, cap * sizeof(PairTask)));
+            CK(cudaMalloc(&ctx->d_pout, cap * sizeof(PairOut)));
+            ctx->tasks_cap = cap;
+        }
+        (void)rc;
+        CK(cudaMemcpyAsync(ctx->d_tasks, ctx->owned.data(), ctx->owned.size() * sizeof(PairTask), cudaMemcpyHostToDevice, st));
+        const int nt = (int)ctx->owned.size();
+        k_shift_offsets<<<(nt + 255) / 256, 256, 0, st>>>(ctx->d_tasks, nt, n, ctx->set[cur].nz_off, base[R]);
+        CK(cudaGetLastError());
+    }
+    // 3. fixed-layout tables: sum == union
+    NK(g_nccl.AllReduce(ctx->d_dist, ctx->d_dist, (size_t)n * n, ncclFloat32, ncclSum, comm, st));
+    NK(g_nccl.AllReduce(ctx->set[cur].rp_pool, ctx->set[cur].rp_pool, (size_t)ctx->rp_total, ncclInt32, ncclSum, comm, st));
+    NK(g_nccl.AllReduce(ctx->set[cur].nz_cnt, ctx->set[cur].nz_cnt, (size_t)n * n, ncclInt32, ncclSum, comm, st));
+    NK(g_nccl.AllReduce(ctx->set[cur].nz_off, ctx->set[cur].nz_off, (size_t)n * n, ncclInt64, ncclSum, comm, st));
+    // 4. cells: every rank broadcasts its slab into the common pool (8-byte cells sent as uint64)
+    NK(g_nccl.GroupStart());
+    for (int r = 0; r < W; ++r)
+        if (used[r])
+            NK(g_nccl.Broadcast(ctx->set[cur].cells, ctx->set[oth].cells + base[r], (size_t)used[r], ncclUint64, r, comm, st));
+    NK(g_nccl.GroupEnd());
+    const unsigned long long tot = (unsigned long long)total;
+    CK(cudaMemcpyAsync(ctx->set[cur].cursor, &tot, sizeof(tot), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    std::swap(ctx->set[cur].cells, ctx->set[oth].cells);
+    std::swap(ctx->set[cur].cap, ctx->set[oth].cap);
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats = mlp_stage_stats{};
+    ctx->stats.ms_total = ms;
+    ctx->stats.nnz = total / 2;
+    ctx->stats.launches = 1;
+    return MLP_OK;
+}

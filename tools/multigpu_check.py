@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""torchrun --nproc-per-node W tools/multigpu_check.py : sharded posterior + exchange + relax + exchange must give
+every rank the same bytes a single GPU produces (developer/CI check for the NCCL path)."""
+import os, sys, zlib
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import mlprobs_b200 as M
+from mlprobs_b200 import synth
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+seqs = synth.family_fast(int(sys.argv[1]) if len(sys.argv) > 1 else 60, 200, seed=5) + [synth.family(1, 700, seed=9)[0]]
+n = len(seqs)
+
+
+def run(sharded):
+    eng = M.Engine(lr)
+    h, p = M.default_tables(M.QP); eng.set_tables(h, p); eng.set_sequences(seqs)
+    if sharded:
+        uid = [M.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    if sharded: eng.exchange()
+    d = eng.distances()
+    w, sd, _, _ = M.qp_guide_tree(d)
+    eng.relax(M.QP, np.maximum(w, np.float32(1e-6)), sd, 200.0, 3.0, float(np.float32(1e-5)))
+    if sharded: eng.exchange()
+    nnz, rp, col, val = eng.csr_bulk()
+    tr = [eng.csr(b, a) for a, b in [(0, 1), (n - 2, n - 1), (3, n // 2)]]
+    sig = (zlib.crc32(d.tobytes()), zlib.crc32(nnz.tobytes()), zlib.crc32(rp.tobytes()), zlib.crc32(col.tobytes()), zlib.crc32(val.tobytes()),
+           tuple(zlib.crc32(x[1].tobytes()) ^ zlib.crc32(x[2].tobytes()) for x in tr))
+    eng.close()
+    return sig
+
+single = run(False)
+multi = run(True)
+ok = single == multi
+flags = [None] * world
+dist.all_gather_object(flags, ok)
+if rank == 0:
+    print("multi-GPU exchange parity (world=%d, n=%d):" % (world, n), "OK" if all(flags) else "MISMATCH %s" % flags, single[:2], multi[:2])
+dist.destroy_process_group()
+sys.exit(0 if all(flags) else 1)
