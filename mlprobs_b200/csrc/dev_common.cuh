@@ -112,6 +112,36 @@ __device__ __forceinline__ float dev_exp(float xf) {
     return (float)r;
 }
 
+// Table-driven EXP: the six ranges of ScoreType.h:36-68 are (-2^k, -2^(k-1)] for k = -1..4 plus (-0.5, 0], so the piece index
+// is the clamped binary exponent of |x| + 2 (x = -0.5 -> piece 1, x = -1 -> piece 2, ... exactly the reference's strict '>'
+// tests). Coefficients (doubles) come from shared memory; same double Horner chain, one rounding to float.
+struct ExpLut { double c[6][6]; };   // c[piece][0..4] = c4..c0, [5] pad
+__device__ __forceinline__ void exp_lut_fill(ExpLut* lut, int tid) {
+    if (tid < 6) {
+        const double t[6][5] = {
+            {0.03254409303190190000, 0.16280432765779600000, 0.49929760485974900000, 0.99995149601363700000, 0.99999925508501600000},
+            {0.01973899026052090000, 0.13822379685007000000, 0.48056651562365000000, 0.99326940370383500000, 0.99906756856399500000},
+            {0.00940528203591384000, 0.09414963667859410000, 0.40825793595877300000, 0.93933625499130400000, 0.98369508190545300000},
+            {0.00217245711583303000, 0.03484829428350620000, 0.22118199801337800000, 0.67049462206469500000, 0.83556950223398500000},
+            {0.00012398771025456900, 0.00349155785951272000, 0.03727721426017900000, 0.17974997741536900000, 0.33249299994217400000},
+            {0.00000051741713416603, 0.00002721456879608080, 0.00053418601865636800, 0.00464101989351936000, 0.01507447981459420000}};
+        for (int k = 0; k < 5; ++k) lut->c[tid][k] = t[tid][k];
+        lut->c[tid][5] = 0.0;
+    }
+}
+__device__ __forceinline__ float dev_exp_lut(float xf, const ExpLut* __restrict__ lut) {
+    // callers guarantee xf <= 0
+    const int e = (int)((__float_as_uint(xf) >> 23) & 0xffu) - 127;        // floor(log2|x|), -127 for 0/denormals
+    const int piece = min(max(e + 2, 0), 5);
+    const double* c = lut->c[piece];
+    const double x = (double)xf;
+    double r = __dadd_rn(__dmul_rn(c[0], x), c[1]);
+    r = __dadd_rn(__dmul_rn(r, x), c[2]);
+    r = __dadd_rn(__dmul_rn(r, x), c[3]);
+    r = __dadd_rn(__dmul_rn(r, x), c[4]);
+    return (xf > -16.0f) ? (float)r : 0.0f;
+}
+
 // posterior cell: EXP(min(LOG_ONE, F+B-total)) with s = F+B already rounded (ProbabilisticModel.h:483)
 __device__ __forceinline__ float dev_posterior_from_sum(float s, float total) {
     return dev_exp(fminf(0.0f, __fsub_rn(s, total)));

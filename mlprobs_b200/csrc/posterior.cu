@@ -29,10 +29,10 @@ __device__ __forceinline__ SweepCtx make_ctx(const PairTask& t, const KArgs& a, 
 
 // per-warp shared-memory carve-up: [tables (CTA)] [warp0: band | stage | colres | cap] [warp1: ...]
 // stage = NIN double-buffered wavefront slots of dense input (cp.async targets), element size sizeof(T)
-template <class T, int NS, int NIN>
+template <class T, int NSB /* states kept in the band */, int NIN>
 __device__ __forceinline__ void warp_smem(unsigned char* base, int tables_bytes, int Cmax, int warp,
                                           T*& band, T*& stage, uint8_t*& colres, float*& cap) {
-    const int band_bytes = NS * Cmax * 32 * (int)sizeof(T);
+    const int band_bytes = NSB * Cmax * 32 * (int)sizeof(T);
     const int stage_bytes = NIN * 2 * Cmax * 32 * (int)sizeof(T);
     const int per_warp = band_bytes + stage_bytes + Cmax * 32 + 64;
     unsigned char* p = base + tables_bytes + (size_t)warp * ((per_warp + 15) & ~15);
@@ -79,8 +79,8 @@ struct HmmFwd {
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
-    __device__ __forceinline__ void prefetch(long long, int, int) const {}
-    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         // ProbabilisticModel.h:213-245 / ParallelProbabilisticModel.cpp:91-113
         float m = __fadd_rn(diag[0], tq0[0]);
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
         if (ti >= a.ntasks) break;
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
-        m.L1 = t.L1; m.L2 = t.L2; m.has_fin = false;
+        m.F = a.layerS5 + t.off; m.L1 = t.L1; m.L2 = t.L2; m.has_fin = false;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         if (m.has_fin) {   // total forward probability, ProbabilisticModel.h:415-419
             float tF = MLP_LOG_ZERO;
@@ -160,10 +160,10 @@ struct HmmBwd {
     __device__ __forceinline__ int row_residue_index(int i) const { return i + 1; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j + 1; }
     __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
-    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
-        for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + (long long)c * 32);
+    __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + c * 32);
     }
-    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) {   // virtual column L2+1 (and padding): nothing flows in from the right
 #pragma unroll
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd(KArgs a) {
     load_hmm_tables(smem, a, match, ins, lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* band; float* stage; uint8_t* colres; float* cap;
-    warp_smem<float, 5, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
+    warp_smem<float, 3, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     HmmBwd m;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd(KArgs a) {
         if (ti >= a.ntasks) break;
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
-        m.L1 = t.L1; m.L2 = t.L2;
+        m.F = a.layerS5 + t.off; m.L1 = t.L1; m.L2 = t.L2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         if (lane == 0) {   // ProbabilisticModel.h:421-432 / ParallelProbabilisticModel.cpp:226-231, then :453 and PosteriorStage.cpp:142
@@ -250,13 +250,13 @@ struct PartFwd {
     enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
     const double* sub; double* Z; int L1, L2; bool qp;
     const double* srow; double zz; bool has_zz;
-    __device__ __forceinline__ void prefetch(long long, int, int) const {}
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0; st[1] = 0; st[2] = 0; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0; e[1] = 0; e[2] = 0; }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (i == 0 || j == 0 || j > L2) {   // boundary: Zm(0,0)=1, H(0,j>=1)=1, V(i>=1,0)=1 (terminal gaps are exp(0))
             nw[0] = (i == 0 && j == 0) ? 1.0 : 0.0;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         PartFwd m;
-        m.sub = sub; m.Z = a.layerZ; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0); m.has_zz = false; m.zz = 0;
+        m.sub = sub; m.Z = a.layerZ + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0); m.has_zz = false; m.zz = 0;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         if (m.has_zz) a.pout[ti].Zpart = m.zz;
     }
@@ -305,8 +305,8 @@ struct PartRev {
     const double* sub; const double* Z; float* P; int L1, L2; bool qp; double Ztot;
     const double* srow;
     double* stage; int Cmax, lane;
-    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
-        for (int c = 0; c < C; ++c) cp_async8(stage + (buf * Cmax + c) * 32 + lane, Z + slotbase + (long long)c * 32);
+    __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) cp_async8(stage + (buf * Cmax + c) * 32 + lane, Z + slotbase + c * 32);
     }
     __device__ __forceinline__ void band_init(T (&st)[NS], int j) const {   // virtual row L1+1
         st[0] = (j == L2 + 1) ? 1.0 : 0.0;
@@ -319,7 +319,7 @@ struct PartRev {
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = (j == L2 + 1 && i >= 1) ? 1.0 : 0.0; return; }
         if (i == 0 || j == 0) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = 0.0; P[slot] = 0.0f; return; }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
         SweepCtx cx = make_ctx(t, a, lane);
         PartRev m;
         m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
-        m.sub = sub; m.Z = a.layerZ; m.P = a.layerP; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
+        m.sub = sub; m.Z = a.layerZ + t.off; m.P = a.layerP + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
         m.Ztot = a.pout[ti].Zpart;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
     }
@@ -369,13 +369,13 @@ struct LocFwd {
     enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
     const float* match; const float* ins; const LogAddLut* lut; float* F; int L1, L2;
     float ins1; const float* mrow;
-    __device__ __forceinline__ void prefetch(long long, int, int) const {}
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = st[1] = st[2] = MLP_LOG_ZERO; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = e[1] = e[2] = MLP_LOG_ZERO; }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
-    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         // ProbabilisticModel.h:210-211,222-227: base = ((m - a) - b); M = (base - 2r) (+) sum_k ((base + F_k) + lt[k][0]) - 2r
         const float base = __fsub_rn(__fsub_rn(mrow[r2], ins1), ins[r2]);
@@ -403,8 +403,8 @@ struct LocBwd {
     enum { NS = 3, REV = 1, COLMASK = 0x3, NIN = 1 };   // keep B_M and X of row i+1; Y travels along the row
     const float* match; const float* ins; const LogAddLut* lut; float* F; float* VB; int L1, L2;
     float* stage; int Cmax, lane;
-    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
-        for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + (long long)c * 32);
+    __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
+        for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + c * 32);
     }
     float ins1n; const float* mrown;   // residue i+1 (transition out of the cell)
     float ins1c; const float* mrowc;   // residue i   (the cell's own emission, for the Z term)
@@ -418,7 +418,7 @@ struct LocBwd {
         const int rc = (i >= 1) ? s1[i - 1] : 0;
         ins1c = ins[rc]; mrowc = match + rc * 26;
     }
-    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, long long slot, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = nw[1] = nw[2] = MLP_LOG_ZERO; return; }
         // ProbabilisticModel.h:339-379 flag=false.  B_M starts at LOG_ONE in every cell.
@@ -464,7 +464,7 @@ __device__ float replay_rowmajor(const float* layer, const SweepCtx& cx) {
             if (j >= 1 && j <= cx.L2) {
                 const int cb = j / W, rem = j - cb * W;
                 const int l = rem / cx.C, c = rem - l * cx.C;
-                v = layer[cx.off + ((long long)(cb * cx.T + i + l) * cx.C + c) * 32 + l];
+                v = layer[cx.off + ((long long)(cb * cx.T + i + l) * cx.C + c) * 32 + l];   // layer = batch base here
             }
             int pos = 0;
             for (;;) {
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         LocFwd m;
-        m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerSL; m.L1 = t.L1; m.L2 = t.L2;
+        m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerSL + t.off; m.L1 = t.L1; m.L2 = t.L2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         __threadfence_block();
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
     load_hmm_tables(smem, a, match, ins, lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* band; float* stage; uint8_t* colres; float* cap;
-    warp_smem<float, 3, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
+    warp_smem<float, 2, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
         SweepCtx cx = make_ctx(t, a, lane);
         LocBwd m;
         m.stage = stage; m.Cmax = a.Cmax; m.lane = lane; m.lut = lut;
-        m.match = match; m.ins = ins; m.F = a.layerSL; m.VB = a.layerVB; m.L1 = t.L1; m.L2 = t.L2; m.s1 = cx.s1; m.s2 = cx.s2;
+        m.match = match; m.ins = ins; m.F = a.layerSL + t.off; m.VB = a.layerVB + t.off; m.L1 = t.L1; m.L2 = t.L2; m.s1 = cx.s1; m.s2 = cx.s2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         __threadfence_block();
@@ -534,14 +534,15 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
 
 // ------------------------------------------------------------------------------------------------ merge + MEA + sparsify
 // states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
+template <bool DENSE>
 struct FinalSweep {
     typedef float T;
     enum { NS = 2, REV = 0, COLMASK = 0x1, NIN = 3 };
     const float* S5; const float* P; const float* SL;
     float* dstage; int Cmax, lane;
-    __device__ __forceinline__ void prefetch(long long slotbase, int C, int buf) const {
+    __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
         for (int c = 0; c < C; ++c) {
-            const long long g = slotbase + (long long)c * 32;
+            const int g = slotbase + c * 32;
             float* d = dstage + ((buf * 3) * Cmax + c) * 32 + lane;
             if (mask & 1u) cp_async4(d, S5 + g);
             if (mask & 2u) cp_async4(d + Cmax * 32, P + g);
@@ -556,19 +557,20 @@ struct FinalSweep {
     float* dense;           // optional dense dump (debug), row-major (L1+1)x(L2+1)
     float* dense5; float* denseP; float* denseL;
     float score; bool has_score;
+    const ExpLut* elut;
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0.0f; st[1] = 0.0f; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0.0f; e[1] = 0.0f; }
     __device__ __forceinline__ int row_residue_index(int) const { return 0; }
     __device__ __forceinline__ int col_residue_index(int) const { return 0; }
     __device__ __forceinline__ void begin_row(int, int) {}
-    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, long long, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, int, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = carry[0]; nw[1] = carry[1]; return; }
         float v5 = 0.0f, vp = 0.0f, vl = 0.0f, p;
         const float* sg = dstage + ((buf * 3) * Cmax + c) * 32 + lane;
-        if (mask & 1u) v5 = dev_posterior_from_sum(sg[0], total5);
+        if (mask & 1u) v5 = dev_exp_lut(fminf(0.0f, __fsub_rn(sg[0], total5)), elut);
         if (mask & 2u) vp = sg[Cmax * 32];
-        if (mask & 4u) vl = dev_posterior_from_sum(sg[2 * Cmax * 32], totalL);
+        if (mask & 4u) vl = dev_exp_lut(fminf(0.0f, __fsub_rn(sg[2 * Cmax * 32], totalL)), elut);
         if (i == 0 && j == 0) { v5 = 0.0f; vl = 0.0f; }   // posterior[0] = 0, ProbabilisticModel.h:490
         if (flavour == 0) {
             // PosteriorStage.cpp:169-177: borders forced to 0, sqrt((v1^2+v2^2)*0.5)
@@ -581,7 +583,7 @@ struct FinalSweep {
         } else {
             p = (mask & 1u) ? v5 : ((mask & 2u) ? vp : vl);
         }
-        if (dense) {
+        if (DENSE) {
             const long long d = (long long)i * (L2 + 1) + j;
             dense[d] = p;
             if (dense5) dense5[d] = v5;
@@ -605,11 +607,15 @@ struct FinalSweep {
     }
 };
 
-__global__ void __launch_bounds__(MLP_BLOCK) k_final(KArgs a) {
+template <bool DENSE>
+__global__ void __launch_bounds__(MLP_BLOCK) k_final_t(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
+    ExpLut* elut = reinterpret_cast<ExpLut*>(smem);
+    exp_lut_fill(elut, threadIdx.x);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* band; float* stg; uint8_t* colres; float* cap;
-    warp_smem<float, 2, 3>(smem, 0, a.Cmax, warp, band, stg, colres, cap);
+    warp_smem<float, 1, 3>(smem, MLP_FINAL_TABLE_BYTES, a.Cmax, warp, band, stg, colres, cap);
     int* stage_n = reinterpret_cast<int*>(cap);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
@@ -623,8 +629,9 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_final(KArgs a) {
         int* rowptr = a.out.rp_pool + a.rp_off[slotAB];
         if (lane == 0) { *stage_n = 0; rowptr[0] = 0; rowptr[1] = 0; }
         __syncwarp();
-        FinalSweep m;
-        m.S5 = a.layerS5; m.P = a.layerP; m.SL = a.layerSL; m.dstage = stg; m.Cmax = a.Cmax; m.lane = lane;
+        FinalSweep<DENSE> m;
+        m.elut = elut;
+        m.S5 = a.layerS5 ? a.layerS5 + t.off : nullptr; m.P = a.layerP ? a.layerP + t.off : nullptr; m.SL = a.layerSL ? a.layerSL + t.off : nullptr; m.dstage = stg; m.Cmax = a.Cmax; m.lane = lane;
         m.total5 = a.pout[ti].total5; m.totalL = a.pout[ti].totalL;
         m.flavour = a.flavour; m.mask = a.mask; m.cutoff = a.cutoff;
         m.L1 = t.L1; m.L2 = t.L2; m.rowcnt = rowptr; m.stage = stage; m.stage_cap = a.stage_cap; m.stage_n = stage_n;
@@ -755,10 +762,10 @@ size_t posterior_smem_bytes(int kernel, int Cmax, int warps) {
         case MLP_K_PART_FWD: tables = MLP_PART_TABLE_BYTES; per = (size_t)3 * Cmax * 32 * 8; break;
         case MLP_K_PART_REV: tables = MLP_PART_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 8; break;
         case MLP_K_HMM_FWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)5 * Cmax * 32 * 4; break;
-        case MLP_K_HMM_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(5 + 2) * Cmax * 32 * 4; break;
+        case MLP_K_HMM_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 4; break;
         case MLP_K_LOCAL_FWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)3 * Cmax * 32 * 4; break;
-        case MLP_K_LOCAL_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 4; break;
-        case MLP_K_FINAL: tables = 0; per = (size_t)(2 + 6) * Cmax * 32 * 4; break;
+        case MLP_K_LOCAL_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(2 + 2) * Cmax * 32 * 4; break;
+        case MLP_K_FINAL: tables = MLP_FINAL_TABLE_BYTES; per = (size_t)(1 + 6) * Cmax * 32 * 4; break;
         default: return 0;
     }
     per += Cmax * 32 + 64;
@@ -772,6 +779,7 @@ cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
 
 cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, cudaStream_t st) {
     void (*fn)(KArgs) = nullptr;
+    const bool a_dense = a.dense != nullptr;
     switch (kernel) {
         case MLP_K_PART_FWD: fn = k_part_fwd; break;
         case MLP_K_PART_REV: fn = k_part_rev; break;
@@ -779,7 +787,7 @@ cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, 
         case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
         case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
         case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
-        case MLP_K_FINAL: fn = k_final; break;
+        case MLP_K_FINAL: fn = a_dense ? k_final_t<true> : k_final_t<false>; break;
         case MLP_K_TRANSPOSE: fn = k_transpose; break;
         default: return cudaErrorInvalidValue;
     }
@@ -793,6 +801,7 @@ cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, 
 
 int posterior_max_blocks_per_sm(int kernel, size_t smem) {
     void (*fn)(KArgs) = nullptr;
+    const bool a_dense = false;
     switch (kernel) {
         case MLP_K_PART_FWD: fn = k_part_fwd; break;
         case MLP_K_PART_REV: fn = k_part_rev; break;
@@ -800,7 +809,7 @@ int posterior_max_blocks_per_sm(int kernel, size_t smem) {
         case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
         case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
         case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
-        case MLP_K_FINAL: fn = k_final; break;
+        case MLP_K_FINAL: fn = a_dense ? k_final_t<true> : k_final_t<false>; break;
         case MLP_K_TRANSPOSE: fn = k_transpose; break;
         default: return 1;
     }

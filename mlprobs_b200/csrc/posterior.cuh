@@ -6,6 +6,7 @@
 #define MLP_BLOCK 128                  // 4 warps per CTA, one pair per warp
 #define MLP_HMM_TABLE_BYTES 3072       // 676 match + 26 ins floats padded to 2816 B, then the 256-byte LogAddLut
 #define MLP_PART_TABLE_BYTES 5408      // 676 doubles
+#define MLP_FINAL_TABLE_BYTES 288      // ExpLut: 6 pieces x 6 doubles
 #define MLP_K_TRANSPOSE 8              // extends the MLP_K_* kernel ids of mlprobs_b200.h
 #define MLP_K_RELAX_ID 7
 

@@ -36,11 +36,15 @@ struct SweepCtx {
 //   void band_init(T (&st)[NS], int j)                  value of the virtual row before the first (row -1 / L1+1)
 //   void edge_init(T (&e)[NS], int i)                   value of the virtual column before the first (col -1 / L2+1)
 //   void begin_row(int i, int r1)                       per-row setup (r1 = residue the model needs for this row)
-//   void cell(int i, int j, int c, long long slotbase, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS], T (&nw)[NS])
+//   void cell(int i, int j, int c, int buf, int r2, int slot /* element index inside the pair's dense layer */, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS], T (&nw)[NS])
 //   int row_residue_index(int i) / col_residue_index(int j)   1-based residue used at row i / column j (0 = none)
 //   void prefetch(long long slotbase, int C, int buf)   issue cp.async of the dense inputs of one wavefront slot into
 //                                                       staging buffer `buf` (models without dense inputs: no-op);
 //                                                       cell() receives `buf` and reads its inputs from there
+// rank of state s among the states kept in the row band (compile-time after unrolling)
+template <int COLMASK>
+__device__ __forceinline__ constexpr int band_rank(int s) { return __builtin_popcount(COLMASK & ((1 << s) - 1)); }
+
 template <class M>
 __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::T* band /* [NS][Cmax][32] per warp */,
                                           uint8_t* colres /* [Cmax][32] per warp */, int Cmax,
@@ -64,7 +68,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
             m.band_init(st, j);
 #pragma unroll
             for (int s = 0; s < NS; ++s)
-                if ((M::COLMASK >> s) & 1) band[(s * Cmax + c) * 32 + lane] = st[s];
+                if ((M::COLMASK >> s) & 1) band[(band_rank<M::COLMASK>(s) * Cmax + c) * 32 + lane] = st[s];
             const int rj = m.col_residue_index(j);
             colres[c * 32 + lane] = (rj >= 1 && rj <= cx.L2) ? cx.s2[rj - 1] : (uint8_t)0;
         }
@@ -76,7 +80,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
         {
             const int i0 = M::REV ? (cx.L1 + 31 - lane) : (0 - lane);
             if (lane_has_cols && i0 >= 0 && i0 <= cx.L1)
-                m.prefetch(cx.off + ((long long)(cb * cx.T + (M::REV ? (cx.L1 + 31) : 0)) * C) * 32 + lane, C, 0);
+                m.prefetch(((cb * cx.T + (M::REV ? (cx.L1 + 31) : 0)) * C) * 32 + lane, C, 0);
         }
 
         for (int t = 0; t < cx.T; ++t) {
@@ -87,7 +91,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                 cp_async_wait_all();
                 const int inext = M::REV ? (i - 1) : (i + 1);
                 if (lane_has_cols && inext >= 0 && inext <= cx.L1 && t + 1 < cx.T)
-                    m.prefetch(cx.off + ((long long)(cb * cx.T + (M::REV ? (cx.L1 + 31 - (t + 1)) : (t + 1))) * C) * 32 + lane, C, (t + 1) & 1);
+                    m.prefetch(((cb * cx.T + (M::REV ? (cx.L1 + 31 - (t + 1)) : (t + 1))) * C) * 32 + lane, C, (t + 1) & 1);
             }
             T in[NS];
             shfl_vec<NS, T>(in, myout, src);
@@ -113,18 +117,18 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                 const int ri = m.row_residue_index(i);
                 const int r1 = (ri >= 1 && ri <= cx.L1) ? cx.s1[ri - 1] : 0;
                 m.begin_row(i, r1);
-                const long long slotbase = cx.off + ((long long)(cb * cx.T + (M::REV ? (cx.L1 + 31 - t) : t)) * C) * 32 + lane;
+                const int slotbase = ((cb * cx.T + (M::REV ? (cx.L1 + 31 - t) : t)) * C) * 32 + lane;   // element index inside this pair's layer
                 for (int cc = 0; cc < C; ++cc) {
                     const int c = M::REV ? (C - 1 - cc) : cc;
                     const int j = jbase + c;
                     T old[NS], nw[NS];
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
-                        if ((M::COLMASK >> s) & 1) old[s] = band[(s * Cmax + c) * 32 + lane]; else old[s] = (T)0;
-                    m.cell(i, j, c, t & 1, colres[c * 32 + lane], slotbase + (long long)c * 32, old, carry, diag, nw);
+                        if ((M::COLMASK >> s) & 1) old[s] = band[(band_rank<M::COLMASK>(s) * Cmax + c) * 32 + lane]; else old[s] = (T)0;
+                    m.cell(i, j, c, t & 1, colres[c * 32 + lane], slotbase + c * 32, old, carry, diag, nw);
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        if ((M::COLMASK >> s) & 1) band[(s * Cmax + c) * 32 + lane] = nw[s];
+                        if ((M::COLMASK >> s) & 1) band[(band_rank<M::COLMASK>(s) * Cmax + c) * 32 + lane] = nw[s];
                         diag[s] = old[s];
                         carry[s] = nw[s];
                     }
