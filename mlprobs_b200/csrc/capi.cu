@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,8 +48,13 @@ extern "C" int mlp_create(int device, mlp_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
     cudaEventCreate(&ctx->ev[0]); cudaEventCreate(&ctx->ev[1]);
-    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess || cudaMalloc(&ctx->d_err, sizeof(int)) != cudaSuccess) {
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (const char* e = getenv("MLP_OVERLAP")) ctx->overlap = atoi(e);
+    if (const char* e = getenv("MLP_BPS_PART")) ctx->bps_part = atoi(e);
+    if (const char* e = getenv("MLP_BPS_HMM")) ctx->bps_hmm = atoi(e);
+    if (cudaMalloc(&ctx->d_counter, 16 * sizeof(int)) != cudaSuccess || cudaMalloc(&ctx->d_err, sizeof(int)) != cudaSuccess) {
         delete ctx; return MLP_E_CUDA;
     }
     cudaMemset(ctx->d_err, 0, sizeof(int));
@@ -69,6 +75,9 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 
@@ -305,18 +314,22 @@ struct KernelTimer {
     }
 };
 
-static int launch_one(mlp_ctx* ctx, int kernel, KArgs& a, int ntasks, KernelTimer& kt, int stat_slot) {
+static int launch_one(mlp_ctx* ctx, int kernel, KArgs a, int ntasks, KernelTimer& kt, int stat_slot,
+                      cudaStream_t st = nullptr, int bps_cap = 0) {
+    if (!st) st = ctx->stream;
     const int warps_per_cta = MLP_BLOCK / 32;
     const size_t smem = posterior_smem_bytes(kernel, a.Cmax, warps_per_cta);
     int bps = posterior_max_blocks_per_sm(kernel, smem);
     bps = std::min(bps, 16);
+    if (bps_cap > 0) bps = std::min(bps, bps_cap);
     int grid = ctx->num_sms * bps;
     grid = std::min(grid, (ntasks + warps_per_cta - 1) / warps_per_cta);
     grid = std::max(grid, 1);
-    CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-    kt.begin(stat_slot, ctx->stream);
-    CK(posterior_launch(kernel, a, grid, smem, ctx->stream));
-    kt.end(ctx->stream);
+    a.counter = ctx->d_counter + (kernel & 15);      // every kernel id has its own work-queue head (kernels may overlap)
+    CK(cudaMemsetAsync(a.counter, 0, sizeof(int), st));
+    kt.begin(stat_slot, st);
+    CK(posterior_launch(kernel, a, grid, smem, st));
+    kt.end(st);
     ctx->stats.launches += 1;
     return MLP_OK;
 }
@@ -402,18 +415,28 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
 
         const int nt = (int)batch.size();
         int rc;
+        // The FP64 partition sweeps and the FP32 HMM sweeps are independent until the merge: run them on two streams
+        // with capped residency so both kinds of warps share every SM (FP64 pipe + FP32/ALU pipes busy together).
+        const bool fork = ctx->overlap && useP && (use5 || useL);
+        cudaStream_t sp = fork ? ctx->stream2 : ctx->stream;
+        if (fork) { CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0)); }
+        const int capP = fork ? (ctx->bps_part > 0 ? ctx->bps_part : 2) : 0;
+        const int capH = fork ? (ctx->bps_hmm > 0 ? ctx->bps_hmm : 4) : 0;
         if (useP) {
-            if ((rc = launch_one(ctx, MLP_K_PART_FWD, a, nt, kt, MLP_K_PART_FWD)) != MLP_OK) return rc;
-            if ((rc = launch_one(ctx, MLP_K_PART_REV, a, nt, kt, MLP_K_PART_REV)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_PART_FWD, a, nt, kt, MLP_K_PART_FWD, sp, capP)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_PART_REV, a, nt, kt, MLP_K_PART_REV, sp, capP)) != MLP_OK) return rc;
         }
         if (useL) {
+            // the local model's Z terms alias the partition layer: it must wait for the partition posterior
+            if (fork) { CK(cudaEventRecord(ctx->ev_join, ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
             if ((rc = launch_one(ctx, MLP_K_LOCAL_FWD, a, nt, kt, MLP_K_LOCAL_FWD)) != MLP_OK) return rc;
             if ((rc = launch_one(ctx, MLP_K_LOCAL_BWD, a, nt, kt, MLP_K_LOCAL_BWD)) != MLP_OK) return rc;
         }
         if (use5) {
-            if ((rc = launch_one(ctx, MLP_K_HMM_FWD, a, nt, kt, MLP_K_HMM_FWD)) != MLP_OK) return rc;
-            if ((rc = launch_one(ctx, MLP_K_HMM_BWD, a, nt, kt, MLP_K_HMM_BWD)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_HMM_FWD, a, nt, kt, MLP_K_HMM_FWD, nullptr, useL ? 0 : capH)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_HMM_BWD, a, nt, kt, MLP_K_HMM_BWD, nullptr, useL ? 0 : capH)) != MLP_OK) return rc;
         }
+        if (fork && !useL) { CK(cudaEventRecord(ctx->ev_join, ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
         if ((rc = launch_one(ctx, MLP_K_FINAL, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
         if ((rc = launch_one(ctx, MLP_K_TRANSPOSE, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
         CK(cudaStreamSynchronize(ctx->stream));

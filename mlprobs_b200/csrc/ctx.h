@@ -18,7 +18,9 @@ static const int kCmaxLimit = 16;   // columns per lane; 32*16 = 512 columns per
 
 struct mlp_ctx {
     int device = 0, num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: partition-function sweeps, overlapped with the HMM sweeps
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap = 1, bps_part = 0, bps_hmm = 0;          // tuning knobs (MLP_OVERLAP, MLP_BPS_PART, MLP_BPS_HMM)
     std::string err;
     // configuration
     int64_t scratch_budget = 0, cell_capacity_req = 0;
@@ -51,7 +53,7 @@ struct mlp_ctx {
     // per-launch scratch
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
     PairTask* d_tasks = nullptr; PairOut* d_pout = nullptr; size_t tasks_cap = 0;
-    int* d_counter = nullptr; int* d_err = nullptr;
+    int* d_counter = nullptr; int* d_err = nullptr;   // d_counter: 16 work-queue heads, one per kernel id
     int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
     int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
     void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
