@@ -404,6 +404,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             a.layerSL = (float*)p; p += (size_t)elems * 4;
             if (useP) a.layerVB = (float*)a.layerZ; else { a.layerVB = (float*)p; p += (size_t)elems * 4; }
         }
+        a.layerTB = (int*)(a.layerS5 ? a.layerS5 : (a.layerP ? a.layerP : a.layerSL));
         a.edge_f = need_edge ? (float*)ctx->d_edge : nullptr;
         a.edge_d = need_edge ? (double*)ctx->d_edge : nullptr;
         a.edge_stride = ctx->edge_stride;   // in elements of the kernel's own type; the buffer is sized for doubles
@@ -501,7 +502,6 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
     if (flavour == MLP_QP) model_mask = MLP_M_HMM5 | MLP_M_PART;
-    if (flavour == MLP_CPNP_P1) { ctx->err = "MLP_CPNP_P1 distance (MEA traceback match count) is not implemented yet"; return MLP_E_UNSUPPORTED; }
     if ((model_mask & MLP_M_PART) && flavour != MLP_QP) {
         // letters J, O, U index sub_matrix[-1] in the reference: refuse instead of guessing
         for (long long k = 0; k < ctx->total_res; ++k) {

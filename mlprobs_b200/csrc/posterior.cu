@@ -558,12 +558,13 @@ struct FinalSweep {
     float* dense5; float* denseP; float* denseL;
     float score; bool has_score;
     const ExpLut* elut;
+    int* tb;                // traceback codes 0 = D, 1 = L, 2 = U (ProbabilisticModel.h:834-836), MLP_CPNP_P1 only
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0.0f; st[1] = 0.0f; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0.0f; e[1] = 0.0f; }
     __device__ __forceinline__ int row_residue_index(int) const { return 0; }
     __device__ __forceinline__ int col_residue_index(int) const { return 0; }
     __device__ __forceinline__ void begin_row(int, int) {}
-    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, int, const T (&old)[NS], const T (&carry)[NS],
+    __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = carry[0]; nw[1] = carry[1]; return; }
         float v5 = 0.0f, vp = 0.0f, vl = 0.0f, p;
@@ -593,6 +594,17 @@ struct FinalSweep {
         // MEA row DP: ProbabilisticModel.h:834-836 / PosteriorStage.cpp:177 (row 0 / column 0 stay 0)
         float sc = 0.0f;
         if (i >= 1 && j >= 1) sc = fmaxf(fmaxf(__fadd_rn(p, diag[0]), carry[0]), old[0]);
+        if (tb) {   // ChooseBestOfThree tie order D >= L >= U (ScoreType.h:347-366); row 0 = 'L', column 0 = 'U'
+            int code = 1;
+            if (i >= 1) {
+                code = 2;
+                if (j >= 1) {
+                    const float x1 = __fadd_rn(p, diag[0]), x2 = carry[0], x3 = old[0];
+                    code = (x1 >= x2) ? ((x1 >= x3) ? 0 : 2) : ((x2 >= x3) ? 1 : 2);
+                }
+            }
+            tb[slot] = code;
+        }
         float cnt = (j == 0) ? 0.0f : carry[1];
         if (i >= 1 && j >= 1 && p >= cutoff) {   // SparseMatrix.h:89 / PackedSparseMatrix.cpp:68
             const int k = atomicAdd(stage_n, 1);
@@ -637,12 +649,29 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_final_t(KArgs a) {
         m.L1 = t.L1; m.L2 = t.L2; m.rowcnt = rowptr; m.stage = stage; m.stage_cap = a.stage_cap; m.stage_n = stage_n;
         m.dense = a.dense; m.dense5 = a.dense5; m.denseP = a.denseP; m.denseL = a.denseL;
         m.has_score = false; m.score = 0.0f;
+        m.tb = (a.flavour == 2 && a.layerTB) ? a.layerTB + t.off : nullptr;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
-        if (m.has_score) {   // distance: MSA.cpp:1019 / PosteriorStage.cpp:194
-            const float dist = __fsub_rn(1.0f, __fdiv_rn(m.score, (float)min(t.L1, t.L2)));
+        if (m.has_score) a.pout[ti].mea = m.score;
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) {
+            const float score = a.pout[ti].mea;
+            float dist;
+            if (a.flavour == 2) {
+                // ArrangePosteriorProbs, MSA.cpp:1744-1752: distance = score / number of 'B' columns on the MEA traceback
+                int r = t.L1, c = t.L2, nb = 0;
+                const int W = 32 * t.C;
+                while (r != 0 || c != 0) {
+                    const int cb = c / W, rem = c - cb * W, l = rem / t.C, cc = rem - l * t.C;
+                    const int code = m.tb[((cb * cx.T + r + l) * t.C + cc) * 32 + l];
+                    if (code == 1) --c; else if (code == 2) --r; else { --r; --c; ++nb; }
+                }
+                dist = __fdiv_rn(score, (float)nb);
+            } else {
+                dist = __fsub_rn(1.0f, __fdiv_rn(score, (float)min(t.L1, t.L2)));   // MSA.cpp:1019 / PosteriorStage.cpp:194
+            }
             a.dist[(long long)t.a * a.n + t.b] = dist;
             a.dist[(long long)t.b * a.n + t.a] = dist;
-            a.pout[ti].mea = m.score;
         }
         __syncwarp();
         __threadfence_block();

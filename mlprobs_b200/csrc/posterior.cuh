@@ -36,6 +36,7 @@ struct KArgs {
     const float* match; const float* ins; const double* sub;
     // dense layers (slot layout)
     double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
+    int* layerTB;   // MEA traceback codes (MLP_CPNP_P1 only); aliases a dense layer whose slot has already been consumed
     // boundary-column hand-off between column blocks (only when some pair has nb > 1)
     float* edge_f; double* edge_d; long long edge_stride;
     // sparse sets: rp_off (fixed layout, shared), `out` is written, `in` is read (relax only)

@@ -135,6 +135,33 @@ def test_cpnp_models_vs_oracle_family(mask):
     eng.close()
 
 
+@pytest.mark.parametrize("mask", [1, 4])
+def test_cpnp_p1_distance_uses_the_traceback_match_count(mask):
+    # -p 1 (ArrangePosteriorProbs, MSA.cpp:1744-1752): distance = MEA score / number of matched columns
+    seqs = synth.family(7, 90, seed=31) + [synth.family(1, 600, seed=32)[0]]
+    n = len(seqs)
+    i2 = 0.170705
+    eng = engine(M.CPNP_P1, seqs, i2)
+    eng.posterior_all_pairs(M.CPNP_P1, mask, 0.01)
+    dist, S, _ = O.posterior_stage(O.CPNP_P1, mask, O.hmm_tables(i2), O.part_tables(O.CPNP_P0), seqs, threads=8)
+    np.testing.assert_array_equal(eng.distances(), dist)
+    _cmp_sets(eng, S, n)
+    eng.close()
+
+
+def test_cpnp_p1_mix_against_reference_fixture():
+    d = load_golden("cpnp_sup139_p1mix")
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.CPNP_P1, seqs, float(d["initDistrib2"][0]))
+    eng.posterior_all_pairs(M.CPNP_P1, 7, 0.01)
+    np.testing.assert_allclose(eng.distances(), d["distances"], rtol=REL_TOL_PARTITION, atol=1e-6)
+    from common import digest_of
+    nnz, _, cc, _ = digest_of(eng.csr, n)
+    np.testing.assert_array_equal(nnz, d["digest.s0.nnz"])
+    np.testing.assert_array_equal(cc, d["digest.s0.col_crc"])
+    eng.close()
+
+
 def test_unknown_letters_and_identical_sequences():
     seqs = [b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"XXBZACDWWWWWYYHHKKLMNP", b"MKV"]
     n = len(seqs)
