@@ -4,6 +4,7 @@
 // and GuideTree::calculateSubtreeDistances (GuideTree.cpp:189-221) with flat arrays instead of linked nodes:
 // same scan order, strict '<' minimum, first minimum wins, in-place update of the distance matrix.
 #include "../../include/mlprobs_b200.h"
+#include <algorithm>
 #include <vector>
 
 extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out) {
@@ -13,25 +14,33 @@ extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subt
     std::vector<float> branch(total, 0.0f), joins(n);
     alive.reserve(n);
     for (int i = 0; i < n; ++i) { alive.push_back(i); slot_node[i] = i; leaves[i] = 1; }
+    // Cached row minima: rowmin[i] / rowarg[i] = smallest d[i][j] over alive j < i and the smallest such j.  The reference scans
+    // (i ascending, j ascending, strict '<'), i.e. it takes the lexicographically first minimal pair; the cache reproduces
+    // exactly that choice while turning the O(N^3) scan into ~O(N^2).
+    std::vector<float> rowmin(n, 3.0f);
+    std::vector<int> rowarg(n, -1);
+    std::vector<char> is_alive(n, 1);
+    auto rescan = [&](int i) {
+        float best = 3.0f; int arg = -1;
+        const float* row = dist + (size_t)i * n;
+        for (int j : alive) { if (j >= i) break; if (row[j] < best) { best = row[j]; arg = j; } }
+        rowmin[i] = best; rowarg[i] = arg;
+    };
+    for (int i : alive) rescan(i);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) if (dist[(size_t)i * n + j] < 0) return MLP_E_ARG;
     for (int node = n; node < total; ++node) {
         float best = 2.0f;
-        int bi = -1, bj = -1;
-        for (size_t x = 0; x < alive.size(); ++x) {
-            const int mi = alive[x];
-            const float* row = dist + (size_t)mi * n;
-            for (size_t y = 0; y < x; ++y) {          // alive is kept ascending, so alive[y] < mi
-                const float d = row[alive[y]];
-                if (d < 0) return MLP_E_ARG;
-                if (d < best) { best = d; bi = (int)x; bj = (int)y; }
-            }
-        }
-        if (bi < 0) return MLP_E_ARG;
-        const int si = alive[bi], sj = alive[bj];
+        int si = -1;
+        for (int i : alive) if (rowarg[i] >= 0 && rowmin[i] < best) { best = rowmin[i]; si = i; }
+        if (si < 0) return MLP_E_ARG;
+        const int sj = rowarg[si];
         const int ni = slot_node[si], nj = slot_node[sj];
         const float half = best * 0.5f;
         parent[ni] = node; parent[nj] = node; branch[ni] = half; branch[nj] = half;
         leaves[node] = leaves[ni] + leaves[nj];
-        alive.erase(alive.begin() + bj);
+        alive.erase(std::lower_bound(alive.begin(), alive.end(), sj));
+        is_alive[sj] = 0;
         const unsigned isize = (unsigned)leaves[ni], jsize = (unsigned)leaves[nj];
         for (int idx : alive) {
             const float idist = dist[(size_t)si * n + idx], jdist = dist[(size_t)sj * n + idx];
@@ -39,6 +48,16 @@ extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subt
         }
         slot_node[si] = node;
         for (int idx : alive) { dist[(size_t)si * n + idx] = joins[idx]; dist[(size_t)idx * n + si] = joins[idx]; }
+        // repair the cache
+        rescan(si);
+        for (int i : alive) {
+            if (i <= sj || i == si) continue;
+            if (rowarg[i] == sj || rowarg[i] == si) { rescan(i); continue; }
+            if (i > si) {
+                const float d = dist[(size_t)i * n + si];
+                if (d < rowmin[i] || (d == rowmin[i] && si < rowarg[i])) { rowmin[i] = d; rowarg[i] = si; }
+            }
+        }
     }
     // weights: sum over the path to the root of branch / leaves-below, float accumulation from the leaf upwards
     float wsum = 0.0f;

@@ -368,6 +368,7 @@ struct LocFwd {
     typedef float T;
     enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
     const float* match; const float* ins; const LogAddLut* lut; float* F; int L1, L2;
+    float* RM;   // row-major copy of F_M for the sequential Z replay (lives in the not-yet-used Z-term layer)
     float ins1; const float* mrow;
     __device__ __forceinline__ void prefetch(int, int, int) const {}
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = st[1] = st[2] = MLP_LOG_ZERO; }
@@ -395,6 +396,7 @@ struct LocFwd {
         }
         nw[0] = m; nw[1] = x; nw[2] = y;
         F[slot] = m;
+        if (j <= L2) RM[i * (L2 + 1) + j] = m;
     }
 };
 
@@ -444,7 +446,7 @@ struct LocBwd {
             const int rj = s2[j - 1];
             vb = __fsub_rn(__fsub_rn(__fsub_rn(__fadd_rn(bm, mrowc[rj]), ins1c), ins[rj]), c_sc.r2);
         }
-        VB[slot] = vb;
+        VB[i * (L2 + 1) + j] = vb;   // row-major: read only by the sequential Z replay
         F[slot] = __fadd_rn(stage[(buf * Cmax + c) * 32 + lane], bm);
     }
 };
@@ -453,24 +455,20 @@ struct LocBwd {
 // (ProbabilisticModel.h:434-451).  The running sum is monotone (LOOKUP(d) > d's loss), so a
 // cell more than 7.5 below the sum can never change it: a warp tests 32 cells at once and applies only the
 // cells that fire, in order -- bit-identical to the serial chain.
-__device__ float replay_rowmajor(const float* layer, const SweepCtx& cx) {
+__device__ float replay_rowmajor(const float* __restrict__ rm /* row-major (L1+1)x(L2+1) */, const SweepCtx& cx) {
     float sum = MLP_LOG_ZERO;
     const int lane = cx.lane;
-    const int W = 32 * cx.C;
+    const int W = cx.L2 + 1;
     for (int i = 1; i <= cx.L1; ++i) {
-        for (int j0 = 0; j0 <= cx.L2; j0 += 32) {
+        const float* row = rm + (long long)i * W;
+        for (int j0 = 1; j0 <= cx.L2; j0 += 32) {
             const int j = j0 + lane;
-            float v = MLP_LOG_ZERO;
-            if (j >= 1 && j <= cx.L2) {
-                const int cb = j / W, rem = j - cb * W;
-                const int l = rem / cx.C, c = rem - l * cx.C;
-                v = layer[cx.off + ((long long)(cb * cx.T + i + l) * cx.C + c) * 32 + l];   // layer = batch base here
-            }
+            const bool in = (j <= cx.L2);
+            const float v = in ? row[j] : MLP_LOG_ZERO;
             int pos = 0;
             for (;;) {
                 // the cell changes the sum unless sum >= v and (v == LOG_ZERO or sum - v >= 7.5)
-                const bool fires = (lane >= pos) && (j >= 1 && j <= cx.L2) &&
-                                   !(sum >= v && (v == MLP_LOG_ZERO || __fsub_rn(sum, v) >= 7.5f));
+                const bool fires = (lane >= pos) && in && !(sum >= v && (v == MLP_LOG_ZERO || __fsub_rn(sum, v) >= 7.5f));
                 const unsigned mask = __ballot_sync(MLP_FULL, fires);
                 if (mask == 0) break;
                 const int l0 = __ffs(mask) - 1;
@@ -498,11 +496,11 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         LocFwd m;
-        m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerSL + t.off; m.L1 = t.L1; m.L2 = t.L2;
+        m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerSL + t.off; m.RM = a.layerVB + t.off; m.L1 = t.L1; m.L2 = t.L2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         __threadfence_block();
-        const float tF = replay_rowmajor(a.layerSL, cx);
+        const float tF = replay_rowmajor(a.layerVB + t.off, cx);
         if (lane == 0) a.pout[ti].tFL = tF;
     }
 }
@@ -527,7 +525,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         __threadfence_block();
-        const float tB = replay_rowmajor(a.layerVB, cx);
+        const float tB = replay_rowmajor(a.layerVB + t.off, cx);
         if (lane == 0) a.pout[ti].totalL = __fdiv_rn(__fadd_rn(a.pout[ti].tFL, tB), 2.0f);   // ProbabilisticModel.h:453
     }
 }

@@ -47,6 +47,41 @@ def test_guide_tree_weights_and_subtree_distances(name):
     assert (par >= -1).all() and (par == -1).sum() == 1
 
 
+def _upgma_bruteforce(dist):
+    """Literal restatement of the reference scan (ClusterTree.cpp:69-120): i ascending, j ascending, strict '<'."""
+    d = dist.astype(np.float32).copy(); n = d.shape[0]
+    alive = list(range(n)); node_of = list(range(n)); leaves = [1] * n + [0] * (n - 1)
+    parent = [-1] * (2 * n - 1)
+    for node in range(n, 2 * n - 1):
+        best = np.float32(2.0); bi = bj = -1
+        for i in alive:
+            for j in alive:
+                if j >= i:
+                    break
+                if d[i, j] < best:
+                    best = d[i, j]; bi, bj = i, j
+        ni, nj = node_of[bi], node_of[bj]
+        parent[ni] = parent[nj] = node; leaves[node] = leaves[ni] + leaves[nj]
+        alive.remove(bj)
+        isz, jsz = np.float32(leaves[ni]), np.float32(leaves[nj])
+        joins = {k: np.float32((d[bi, k] * isz + d[bj, k] * jsz) / (isz + jsz)) for k in alive}
+        node_of[bi] = node
+        for k in alive:
+            d[bi, k] = d[k, bi] = joins[k]
+    return np.array(parent, np.int32), d
+
+
+def test_guide_tree_tie_breaking_matches_the_reference_scan_order():
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        n = 37
+        d = (rng.integers(1, 12, size=(n, n)) / np.float32(16)).astype(np.float32)   # coarse values: many exact ties
+        d = np.maximum(d, d.T); np.fill_diagonal(d, 0)
+        w, sd, par, after = M.qp_guide_tree(d)
+        bpar, bafter = _upgma_bruteforce(d)
+        np.testing.assert_array_equal(par, bpar)
+
+
 def test_shard_pairs_partition_is_a_disjoint_cover():
     rng = np.random.default_rng(3)
     lens = rng.integers(20, 700, size=37)
