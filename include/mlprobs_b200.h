@@ -100,6 +100,17 @@ int mlp_total_cells(mlp_ctx* ctx, int64_t* cells);
  * col/val; row_ptr concatenated with len[a]+2 entries per pair. Any pointer may be NULL. */
 int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* row_ptr, int32_t* col, float* val);
 
+/* Zero-reshuffle bulk read-back for callers that keep the library's own pooled layout (fastest path: four plain
+ * device->host copies, use pinned buffers from mlp_alloc_pinned for full PCIe speed).
+ *   mlp_csr_layout : rp_off[n*n] (offset of the len[a]+2 row pointers of ordered pair (a,b) inside the row-pointer pool),
+ *                    *rp_total (ints in that pool), *cells_used (cells currently in the cell pool).
+ *   mlp_get_csr_raw: nz_off[n*n], nz_cnt[n*n], rp_pool[rp_total], cells[cells_used] as {int32 column, float value}.
+ * Matrix (a,b): rows i=1..len[a] -> cells[nz_off[a*n+b] + rp_pool[rp_off[a*n+b]+i] .. + rp_pool[rp_off[a*n+b]+i+1]). */
+int mlp_csr_layout(mlp_ctx* ctx, int64_t* rp_off, int64_t* rp_total, int64_t* cells_used);
+int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, int32_t* rp_pool, void* cells);
+int mlp_alloc_pinned(int64_t bytes, void** out);
+void mlp_free_pinned(void* p);
+
 /* Dense per-pair debug read-back (tests): runs one pair and returns the merged dense posterior
  * (len[a]+1 x len[b]+1) and, if non-NULL, each model's posterior. */
 int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_mask, int a, int b,

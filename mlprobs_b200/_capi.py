@@ -20,7 +20,8 @@ ERRORS = {0: "ok", -1: "no CUDA device", -2: "CUDA error", -3: "bad argument", -
 EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", "mlp_configure", "mlp_set_tables",
            "mlp_set_sequences", "mlp_set_shard", "mlp_posterior_all_pairs", "mlp_get_distances", "mlp_relax",
            "mlp_get_csr", "mlp_total_cells", "mlp_get_csr_bulk", "mlp_debug_pair_dense", "mlp_nccl_unique_id",
-           "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs"]
+           "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs", "mlp_csr_layout", "mlp_get_csr_raw",
+           "mlp_alloc_pinned", "mlp_free_pinned"]
 
 
 class HmmTables(C.Structure):
@@ -77,6 +78,11 @@ def load():
         lib.mlp_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.mlp_exchange.argtypes = [C.c_void_p]
         lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mlp_csr_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.mlp_get_csr_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_alloc_pinned.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+        lib.mlp_free_pinned.argtypes = [C.c_void_p]
+        lib.mlp_free_pinned.restype = None
         lib.mlp_qp_guide_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
@@ -130,6 +136,51 @@ def shard_pairs(lens, rank, world):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PinnedCsrBuffers:
+    """Page-locked host buffers (mlp_alloc_pinned) for Engine.csr_raw; grown on demand, freed on close()."""
+
+    def __init__(self, n, rp_total, cells):
+        self._ptrs = []
+        self.cap_rp = self.cap_cells = self.n = 0
+        self.ensure(n, rp_total, cells)
+
+    def _pinned(self, nbytes, dtype, count):
+        p = C.c_void_p()
+        rc = load().mlp_alloc_pinned(max(int(nbytes), 16), C.byref(p))
+        if rc:
+            raise MlpError(rc, "pinned host allocation failed")
+        self._ptrs.append(p)
+        buf = (C.c_char * max(int(nbytes), 16)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    def ensure(self, n, rp_total, cells):
+        if n != self.n:
+            self.nz_off = self._pinned(n * n * 8, np.int64, n * n)
+            self.nz_cnt = self._pinned(n * n * 4, np.int32, n * n)
+            self.n = n
+        if rp_total > self.cap_rp:
+            self.cap_rp = int(rp_total * 1.05) + 16
+            self.rp_pool = self._pinned(self.cap_rp * 4, np.int32, self.cap_rp)
+        if cells > self.cap_cells:
+            self.cap_cells = int(cells * 1.1) + 1024
+            self.cells = self._pinned(self.cap_cells * 8, np.dtype([("col", np.int32), ("val", np.float32)]), self.cap_cells)
+
+    def matrix(self, a, b, lens):
+        """(row_ptr, col, val) of ordered pair (a, b) as views into the pooled buffers."""
+        s = a * self.n + b
+        rp = self.rp_pool[self.rp_off[s]: self.rp_off[s] + int(lens[a]) + 2]
+        c = self.cells[self.nz_off[s]: self.nz_off[s] + self.nz_cnt[s]]
+        return rp, c["col"], c["val"]
+
+    def nbytes(self):
+        return self.n * self.n * 12 + self.rp_total * 4 + self.used * 8
+
+    def close(self):
+        for p in self._ptrs:
+            load().mlp_free_pinned(p)
+        self._ptrs = []
 
 
 class Engine:
@@ -218,6 +269,22 @@ class Engine:
         val = np.zeros(int(nnz.sum()), np.float32)
         self._ck(self._lib.mlp_get_csr_bulk(self._ctx, None, _ptr(rp), _ptr(col), _ptr(val)))
         return nnz, rp, col, val
+
+    def csr_layout(self):
+        rp_off = np.zeros(self.n * self.n, np.int64)
+        rp_total = C.c_int64(0); used = C.c_int64(0)
+        self._ck(self._lib.mlp_csr_layout(self._ctx, _ptr(rp_off), C.byref(rp_total), C.byref(used)))
+        return rp_off, rp_total.value, used.value
+
+    def csr_raw(self, out=None):
+        """Pooled read-back (no per-pair reshuffle). `out` = PinnedCsrBuffers to reuse page-locked host memory."""
+        rp_off, rp_total, used = self.csr_layout()
+        if out is None:
+            out = PinnedCsrBuffers(self.n, rp_total, used)
+        out.ensure(self.n, rp_total, used)
+        self._ck(self._lib.mlp_get_csr_raw(self._ctx, _ptr(out.nz_off), _ptr(out.nz_cnt), _ptr(out.rp_pool), _ptr(out.cells)))
+        out.rp_off, out.rp_total, out.used = rp_off, rp_total, used
+        return out
 
     def total_cells(self):
         c = C.c_int64(0)

@@ -652,6 +652,44 @@ extern "C" int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* ro
     return MLP_OK;
 }
 
+extern "C" int mlp_csr_layout(mlp_ctx* ctx, int64_t* rp_off, int64_t* rp_total, int64_t* cells_used) {
+    if (!ctx) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    if (rp_off) for (size_t k = 0; k < ctx->rp_off_h.size(); ++k) rp_off[k] = ctx->rp_off_h[k];
+    if (rp_total) *rp_total = ctx->rp_total;
+    if (cells_used) {
+        unsigned long long used = 0;
+        CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+        *cells_used = (int64_t)std::min<unsigned long long>(used, (unsigned long long)ctx->set[ctx->cur].cap);
+    }
+    return MLP_OK;
+}
+
+extern "C" int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, int32_t* rp_pool, void* cells) {
+    if (!ctx) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    const CsrSetDev& s = ctx->set[ctx->cur];
+    const size_t nn = (size_t)ctx->n * ctx->n;
+    unsigned long long used = 0;
+    CK(cudaMemcpy(&used, s.cursor, sizeof(used), cudaMemcpyDeviceToHost));
+    used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
+    if (nz_off) { CK(cudaMemcpyAsync(nz_off, s.nz_off, nn * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)nn * 8; }
+    if (nz_cnt) { CK(cudaMemcpyAsync(nz_cnt, s.nz_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)nn * 4; }
+    if (rp_pool) { CK(cudaMemcpyAsync(rp_pool, s.rp_pool, (size_t)ctx->rp_total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += ctx->rp_total * 4; }
+    if (cells && used) { CK(cudaMemcpyAsync(cells, s.cells, (size_t)used * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)used * 8; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MLP_OK;
+}
+
+extern "C" int mlp_alloc_pinned(int64_t bytes, void** out) {
+    if (!out || bytes <= 0) return MLP_E_ARG;
+    return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? MLP_OK : MLP_E_CUDA;
+}
+
+extern "C" void mlp_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
                          float selectivity, float selfweight, float cutoff) {
     if (!ctx) return MLP_E_ARG;

@@ -215,6 +215,13 @@ def test_properties_on_a_large_family():
             denseT[j, c_ba[rp_ba[j]:rp_ba[j + 1]]] = v_ba[rp_ba[j]:rp_ba[j + 1]]
         assert np.array_equal(dense.T, denseT)                                                  # stored transpose
         assert dense.sum(axis=1).max() < 1.5
+    # pooled pinned read-back == per-pair read-back
+    raw = eng.csr_raw()
+    for a, b in [(0, 1), (5, 3), (n - 1, 2)]:
+        rp1, c1, v1 = eng.csr(a, b)
+        rp2, c2, v2 = raw.matrix(a, b, eng.lens)
+        assert np.array_equal(rp1, rp2) and np.array_equal(c1, c2) and np.array_equal(v1, v2)
+    raw.close()
     # oracle spot-check of a few pairs at this size
     ht, pt = O.hmm_tables(), O.part_tables(O.QP)
     for a, b in [(0, 1), (17, 93), (118, 119)]:
