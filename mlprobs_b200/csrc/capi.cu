@@ -31,6 +31,7 @@ static void release_launch_scratch(mlp_ctx* ctx) {
     free_dev(ctx->d_tasks); ctx->d_tasks = nullptr; free_dev(ctx->d_pout); ctx->d_pout = nullptr; ctx->tasks_cap = 0;
     free_dev(ctx->d_stage); ctx->d_stage = nullptr; ctx->stage_warps = 0; ctx->stage_cap = 0;
     free_dev(ctx->d_tfill); ctx->d_tfill = nullptr; ctx->tfill_warps = 0;
+    free_dev(ctx->d_rowexp); ctx->d_rowexp = nullptr; ctx->rowexp_cap = 0;
     free_dev(ctx->d_edge); ctx->d_edge = nullptr; ctx->edge_warps = 0;
     free_dev(ctx->d_wk); ctx->d_wk = nullptr; ctx->wk_warps = 0;
 }
@@ -385,6 +386,12 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             ctx->scratch_bytes = need;
         }
         { int rc = ensure_tasks(ctx, batch.size()); if (rc != MLP_OK) return rc; }
+        const long long rowexp_stride = maxL1 + 4;
+        if (useP && flavour != MLP_QP && batch.size() * (size_t)rowexp_stride > ctx->rowexp_cap) {
+            free_dev(ctx->d_rowexp); ctx->d_rowexp = nullptr;
+            ctx->rowexp_cap = batch.size() * (size_t)rowexp_stride + 1024;
+            CK(cudaMalloc(&ctx->d_rowexp, ctx->rowexp_cap * sizeof(int)));
+        }
         CK(cudaMemcpyAsync(ctx->d_tasks, batch.data(), batch.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += (int64_t)(batch.size() * sizeof(PairTask));
         CK(cudaMemsetAsync(ctx->d_pout, 0, batch.size() * sizeof(PairOut), ctx->stream));
@@ -405,6 +412,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             if (useP) a.layerVB = (float*)a.layerZ; else { a.layerVB = (float*)p; p += (size_t)elems * 4; }
         }
         a.layerTB = (int*)(a.layerS5 ? a.layerS5 : (a.layerP ? a.layerP : a.layerSL));
+        a.rowexp = ctx->d_rowexp; a.rowexp_stride = rowexp_stride;
         a.edge_f = need_edge ? (float*)ctx->d_edge : nullptr;
         a.edge_d = need_edge ? (double*)ctx->d_edge : nullptr;
         a.edge_stride = ctx->edge_stride;   // in elements of the kernel's own type; the buffer is sized for doubles

@@ -55,6 +55,7 @@ struct mlp_ctx {
     PairTask* d_tasks = nullptr; PairOut* d_pout = nullptr; size_t tasks_cap = 0;
     int* d_counter = nullptr; int* d_err = nullptr;   // d_counter: 16 work-queue heads, one per kernel id
     int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
+    int* d_rowexp = nullptr; size_t rowexp_cap = 0;
     int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
     void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
     float* d_wk = nullptr; long long wk_warps = 0;

@@ -56,6 +56,8 @@ __device__ __forceinline__ void load_hmm_tables(unsigned char* smem, const KArgs
 // ------------------------------------------------------------------------------------------------ 5-state HMM
 // state order (reference numbering): 0 = M, 1 = X1, 2 = Y1, 3 = X2, 4 = Y2
 struct HmmFwd {
+    __device__ __forceinline__ void step_sync() const {}
+    __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 5, REV = 0, COLMASK = 0x1f, NIN = 0 };
     const float* match; const float* ins; const LogAddLut* lut;
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
 }
 
 struct HmmBwd {
+    __device__ __forceinline__ void step_sync() const {}
+    __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 5, REV = 1, COLMASK = 0x0b, NIN = 1 };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
     const float* match; const float* ins; const LogAddLut* lut;
@@ -245,39 +249,78 @@ __device__ __forceinline__ double sum3(double zm, double h, double v, bool h_fir
     return h_first ? __dadd_rn(__dadd_rn(zm, h), v) : __dadd_rn(__dadd_rn(zm, v), h);
 }
 
-struct PartFwd {
+// Rescaled variant (SC = true, cpnp flavour): the reference runs this recursion in 80-bit long double (range 1e+-4932),
+// FP64 would overflow for similar sequences longer than ~600.  Every row i carries a power-of-two scale 2^-e_i: stored
+// values are Z * 2^-e_i.  Scaling by powers of two commutes with IEEE rounding, so mantissas are exactly those of an
+// unbounded-range double.  e_i is chosen by the lane that starts the row (column 0 forward, column L2+1 reverse) from a
+// warp-wide maximum of the exponents seen in the last <= 32 rows and travels with the row (4th carried value, exact small
+// integer in a double); it changes only when the magnitude drifted by more than 2^48.  QP's own FP64 code is reproduced
+// unscaled (SC = false) because its silent overflow is part of its result.
+__device__ __forceinline__ double pow2d(int k) { return __hiloint2double((1023 + k) << 20, 0); }   // |k| <= 1022
+__device__ __forceinline__ int exp_of(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
+#define MLP_EXP_NONE (-1000000)
+
+template <bool SC>
+struct PartFwdT {
     typedef double T;
-    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
-    const double* sub; double* Z; int L1, L2; bool qp;
-    const double* srow; double zz; bool has_zz;
+    enum { NS = SC ? 4 : 3, REV = 0, COLMASK = 0x7, NIN = 0 };
+    const double* sub; double* Z; int* rowexp; int L1, L2; bool qp;
+    const double* srow; double zz; bool has_zz; int zexp;
+    int seen_exp, row_seen, gmax, e_prev, e_row; double f;   // seen_exp: largest true exponent in the row this lane finished last
+    __device__ __forceinline__ void reset() { has_zz = false; zz = 0; zexp = 0; seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; }
+    __device__ __forceinline__ void step_sync() { if (SC) gmax = __reduce_max_sync(MLP_FULL, seen_exp); }
     __device__ __forceinline__ void prefetch(int, int, int) const {}
-    __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0; st[1] = 0; st[2] = 0; }
-    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0; e[1] = 0; e[2] = 0; }
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) st[s] = 0;
+        e_prev = 0; seen_exp = MLP_EXP_NONE;
+    }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) e[s] = 0;
+    }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
-    __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
+    __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; }
     __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
+        if (SC) {
+            if (j == 0) {   // origin of the row: decide its scale
+                int e = (i == 0) ? 0 : e_prev;
+                if (i > 0 && gmax != MLP_EXP_NONE && (gmax - e > 48 || e - gmax > 48)) e = gmax;
+                nw[3] = (double)e;
+                rowexp[i] = e;
+            } else nw[3] = carry[3];
+            if (e_row == MLP_EXP_NONE) {   // first cell of this lane in this row
+                e_row = (int)nw[3];
+                const int d = e_prev - e_row;
+                f = (d == 0) ? 1.0 : pow2d(max(min(d, 1000), -1000));
+            }
+        }
         if (i == 0 || j == 0 || j > L2) {   // boundary: Zm(0,0)=1, H(0,j>=1)=1, V(i>=1,0)=1 (terminal gaps are exp(0))
             nw[0] = (i == 0 && j == 0) ? 1.0 : 0.0;
             nw[1] = (i == 0 && j >= 1 && j <= L2) ? 1.0 : 0.0;
-            nw[2] = (j == 0 && i >= 1) ? 1.0 : 0.0;
+            nw[2] = (j == 0 && i >= 1) ? (SC ? pow2d(max(min(-e_row, 1000), -1000)) : 1.0) : 0.0;
             Z[slot] = nw[0];
-            return;
+        } else {
+            const double score = srow[r2];
+            const double o0 = (i == L1) ? 1.0 : c_sc.go, e0 = (i == L1) ? 1.0 : c_sc.ge;
+            const double o1 = (j == L2) ? 1.0 : c_sc.go, e1 = (j == L2) ? 1.0 : c_sc.ge;
+            const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
+            double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
+            double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], qp), score);
+            if (SC && f != 1.0) { v = __dmul_rn(v, f); zm = __dmul_rn(zm, f); }   // previous-row operands -> this row's scale (exact)
+            nw[0] = zm; nw[1] = h; nw[2] = v;
+            Z[slot] = zm;
+            if (SC) row_seen = max(row_seen, exp_of(zm) + e_row);
+            if (i == L1 && j == L2) { has_zz = true; zz = sum3(zm, h, v, qp); zexp = SC ? e_row : 0; }
         }
-        const double score = srow[r2];
-        const double o0 = (i == L1) ? 1.0 : c_sc.go, e0 = (i == L1) ? 1.0 : c_sc.ge;
-        const double o1 = (j == L2) ? 1.0 : c_sc.go, e1 = (j == L2) ? 1.0 : c_sc.ge;
-        const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
-        const double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
-        const double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], qp), score);
-        nw[0] = zm; nw[1] = h; nw[2] = v;
-        Z[slot] = zm;
-        if (i == L1 && j == L2) { has_zz = true; zz = sum3(zm, h, v, qp); }
     }
+    __device__ __forceinline__ void end_row() { if (SC) { e_prev = e_row; if (row_seen != MLP_EXP_NONE) seen_exp = row_seen; } }
 };
 
-__global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd(KArgs a) {
+template <bool SC>
+__global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd_t(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* sub = reinterpret_cast<double*>(smem);
     for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
@@ -292,54 +335,84 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd(KArgs a) {
         if (ti >= a.ntasks) break;
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
-        PartFwd m;
-        m.sub = sub; m.Z = a.layerZ + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0); m.has_zz = false; m.zz = 0;
+        PartFwdT<SC> m;
+        m.reset();
+        m.sub = sub; m.Z = a.layerZ + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
+        m.rowexp = SC ? a.rowexp + (long long)ti * a.rowexp_stride : nullptr;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
-        if (m.has_zz) a.pout[ti].Zpart = m.zz;
+        if (m.has_zz) { a.pout[ti].Zpart = m.zz; a.pout[ti].zexp = m.zexp; }
     }
 }
 
-struct PartRev {
+template <bool SC>
+struct PartRevT {
     typedef double T;
-    enum { NS = 3, REV = 1, COLMASK = 0x7, NIN = 1 };
-    const double* sub; const double* Z; float* P; int L1, L2; bool qp; double Ztot;
+    enum { NS = SC ? 4 : 3, REV = 1, COLMASK = 0x7, NIN = 1 };
+    const double* sub; const double* Z; float* P; const int* rowexp; int L1, L2; bool qp; double Ztot; int zexp;
     const double* srow;
     double* stage; int Cmax, lane;
+    int seen_exp, row_seen, gmax, e_prev, e_row, fexp; double f;
+    __device__ __forceinline__ void reset() { seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; fexp = 0; }
+    __device__ __forceinline__ void step_sync() { if (SC) gmax = __reduce_max_sync(MLP_FULL, seen_exp); }
     __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
         for (int c = 0; c < C; ++c) cp_async8(stage + (buf * Cmax + c) * 32 + lane, Z + slotbase + c * 32);
     }
-    __device__ __forceinline__ void band_init(T (&st)[NS], int j) const {   // virtual row L1+1
+    __device__ __forceinline__ void band_init(T (&st)[NS], int j) {   // virtual row L1+1 (scale exponent 0)
         st[0] = (j == L2 + 1) ? 1.0 : 0.0;
         st[1] = (j >= 1 && j <= L2) ? 1.0 : 0.0;
         st[2] = 0.0;
+        if (SC) st[3] = 0.0;
+        e_prev = 0; seen_exp = MLP_EXP_NONE;
     }
-    __device__ __forceinline__ void edge_init(T (&e)[NS], int i) const {    // virtual column L2+1
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int i) const {    // virtual column L2+1 when it lies outside the strips
         e[0] = 0.0; e[1] = 0.0; e[2] = (i >= 1 && i <= L1) ? 1.0 : 0.0;
+        if (SC) e[3] = 0.0;
     }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
-    __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; }
+    __device__ __forceinline__ void begin_row(int i, int r1) { srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; if (SC) fexp = rowexp[i]; }
     __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
-        if (j > L2) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = (j == L2 + 1 && i >= 1) ? 1.0 : 0.0; return; }
+        if (SC) {
+            if (j == L2 + 1) {   // origin of the row in the reverse sweep
+                int e = e_prev;
+                if (gmax != MLP_EXP_NONE && (gmax - e > 48 || e - gmax > 48)) e = gmax;
+                nw[3] = (double)e;
+            } else nw[3] = (j > L2 + 1) ? 0.0 : carry[3];
+            if (e_row == MLP_EXP_NONE && j <= L2 + 1) {
+                e_row = (int)nw[3];
+                const int d = e_prev - e_row;
+                f = (d == 0) ? 1.0 : pow2d(max(min(d, 1000), -1000));
+            }
+        }
+        if (j > L2) {
+            nw[0] = 0.0; nw[1] = 0.0;
+            nw[2] = (j == L2 + 1 && i >= 1) ? (SC ? pow2d(max(min(-e_row, 1000), -1000)) : 1.0) : 0.0;
+            return;
+        }
         if (i == 0 || j == 0) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = 0.0; P[slot] = 0.0f; return; }
         const double score = srow[r2];
         const double o1 = (j == 1) ? 1.0 : c_sc.go, e1 = (j == 1) ? 1.0 : c_sc.ge;   // V-type terminal at the first column
         const double o0 = (i == 1) ? 1.0 : c_sc.go, e0 = (i == 1) ? 1.0 : c_sc.ge;   // H-type terminal at the first row
-        const double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
+        double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
         const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
-        const double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], !qp), score);
+        double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], !qp), score);
+        if (SC && f != 1.0) { v = __dmul_rn(v, f); zm = __dmul_rn(zm, f); }
         nw[0] = zm; nw[1] = h; nw[2] = v;
+        if (SC) row_seen = max(row_seen, exp_of(zm) + e_row);
         // PartitionFunction.cpp:259-270 / MSAPartProbs.cpp:286-297
         double tmp = __dmul_rn(stage[(buf * Cmax + c) * 32 + lane], zm);
         tmp = __ddiv_rn(tmp, __dmul_rn(score, Ztot));
+        if (SC) tmp = scalbn(tmp, fexp + e_row - zexp);
         float p = (float)tmp;
         if (qp && !(p <= 1.0f && (double)p >= 0.001)) p = 0.0f;
         P[slot] = p;
     }
+    __device__ __forceinline__ void end_row() { if (SC) { e_prev = e_row; if (row_seen != MLP_EXP_NONE) seen_exp = row_seen; } }
 };
 
-__global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
+template <bool SC>
+__global__ void __launch_bounds__(MLP_BLOCK) k_part_rev_t(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* sub = reinterpret_cast<double*>(smem);
     for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
@@ -354,10 +427,12 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
         if (ti >= a.ntasks) break;
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
-        PartRev m;
+        PartRevT<SC> m;
+        m.reset();
         m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
         m.sub = sub; m.Z = a.layerZ + t.off; m.P = a.layerP + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
-        m.Ztot = a.pout[ti].Zpart;
+        m.Ztot = a.pout[ti].Zpart; m.zexp = a.pout[ti].zexp;
+        m.rowexp = SC ? a.rowexp + (long long)ti * a.rowexp_stride : nullptr;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
     }
 }
@@ -365,6 +440,8 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev(KArgs a) {
 // ------------------------------------------------------------------------------------------------ local 3-state HMM
 // states: 0 = M, 1 = X, 2 = Y  (ProbabilisticModel.h flag=false branches)
 struct LocFwd {
+    __device__ __forceinline__ void step_sync() const {}
+    __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
     const float* match; const float* ins; const LogAddLut* lut; float* F; int L1, L2;
@@ -401,6 +478,8 @@ struct LocFwd {
 };
 
 struct LocBwd {
+    __device__ __forceinline__ void step_sync() const {}
+    __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 3, REV = 1, COLMASK = 0x3, NIN = 1 };   // keep B_M and X of row i+1; Y travels along the row
     const float* match; const float* ins; const LogAddLut* lut; float* F; float* VB; int L1, L2;
@@ -534,6 +613,8 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
 // states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
 template <bool DENSE>
 struct FinalSweep {
+    __device__ __forceinline__ void step_sync() const {}
+    __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 2, REV = 0, COLMASK = 0x1, NIN = 3 };
     const float* S5; const float* P; const float* SL;
@@ -807,9 +888,10 @@ cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
 cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, cudaStream_t st) {
     void (*fn)(KArgs) = nullptr;
     const bool a_dense = a.dense != nullptr;
+    const bool a_scaled = a.flavour != 0;
     switch (kernel) {
-        case MLP_K_PART_FWD: fn = k_part_fwd; break;
-        case MLP_K_PART_REV: fn = k_part_rev; break;
+        case MLP_K_PART_FWD: fn = a_scaled ? k_part_fwd_t<true> : k_part_fwd_t<false>; break;
+        case MLP_K_PART_REV: fn = a_scaled ? k_part_rev_t<true> : k_part_rev_t<false>; break;
         case MLP_K_HMM_FWD: fn = k_hmm_fwd; break;
         case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
         case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
@@ -828,10 +910,10 @@ cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, 
 
 int posterior_max_blocks_per_sm(int kernel, size_t smem) {
     void (*fn)(KArgs) = nullptr;
-    const bool a_dense = false;
+    const bool a_dense = false, a_scaled = false;
     switch (kernel) {
-        case MLP_K_PART_FWD: fn = k_part_fwd; break;
-        case MLP_K_PART_REV: fn = k_part_rev; break;
+        case MLP_K_PART_FWD: fn = a_scaled ? k_part_fwd_t<true> : k_part_fwd_t<false>; break;
+        case MLP_K_PART_REV: fn = a_scaled ? k_part_rev_t<true> : k_part_rev_t<false>; break;
         case MLP_K_HMM_FWD: fn = k_hmm_fwd; break;
         case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
         case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;

@@ -17,7 +17,7 @@ struct PairOut {
     float tF5, total5;     // 5-state: forward total, (forward+backward)/2
     float tFL, totalL;     // local model
     float mea;             // MEA score
-    float pad;
+    int zexp;              // binary exponent that scales Zpart (rescaled FP64 partition function, cpnp flavour)
 };
 
 // Device view of a sparse-posterior set: every ordered pair (a,b) owns len[a]+2 row pointers at rp_off[a*n+b]
@@ -36,6 +36,7 @@ struct KArgs {
     const float* match; const float* ins; const double* sub;
     // dense layers (slot layout)
     double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
+    int* rowexp; long long rowexp_stride;   // per task: scale exponent of every row of the forward partition layer (cpnp)
     int* layerTB;   // MEA traceback codes (MLP_CPNP_P1 only); aliases a dense layer whose slot has already been consumed
     // boundary-column hand-off between column blocks (only when some pair has nb > 1)
     float* edge_f; double* edge_d; long long edge_stride;

@@ -38,7 +38,8 @@ struct SweepCtx {
 //   void begin_row(int i, int r1)                       per-row setup (r1 = residue the model needs for this row)
 //   void cell(int i, int j, int c, int buf, int r2, int slot /* element index inside the pair's dense layer */, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS], T (&nw)[NS])
 //   int row_residue_index(int i) / col_residue_index(int j)   1-based residue used at row i / column j (0 = none)
-//   void prefetch(long long slotbase, int C, int buf)   issue cp.async of the dense inputs of one wavefront slot into
+//   void step_sync()                                    called by ALL lanes at the top of every step (warp-wide reductions)
+//   void prefetch(int slotbase, int C, int buf)   issue cp.async of the dense inputs of one wavefront slot into
 //                                                       staging buffer `buf` (models without dense inputs: no-op);
 //                                                       cell() receives `buf` and reads its inputs from there
 // rank of state s among the states kept in the row band (compile-time after unrolling)
@@ -87,6 +88,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
             const int i = M::REV ? (cx.L1 - t + 31 - lane) : (t - lane);
             const bool in_rows = (i >= 0 && i <= cx.L1);
             const bool active = in_rows && lane_has_cols;
+            m.step_sync();
             if (M::NIN > 0) {
                 cp_async_wait_all();
                 const int inext = M::REV ? (i - 1) : (i + 1);
@@ -133,6 +135,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                         carry[s] = nw[s];
                     }
                 }
+                m.end_row();
 #pragma unroll
                 for (int s = 0; s < NS; ++s) myout[s] = carry[s];
                 if (last_lane && cbi + 1 < cx.nb) {

@@ -162,6 +162,29 @@ def test_cpnp_p1_mix_against_reference_fixture():
     eng.close()
 
 
+def test_cpnp_partition_beyond_fp64_range_is_rescaled():
+    """Similar sequences of length 1500: Z ~ 1e600, beyond FP64 but inside the reference's 80-bit range.  The device runs
+    FP64 with per-row power-of-two rescaling and must agree with the long-double oracle to 1e-5 relative."""
+    seqs = synth.family(3, 1500, seed=77, p_sub=0.05, p_del=0.01, p_ins=0.01)
+    n = len(seqs)
+    eng = engine(M.CPNP_P0, seqs, 0.25)
+    ht, pt = O.hmm_tables(0.25), O.part_tables(O.CPNP_P0)
+    g = eng.debug_pair_dense(M.CPNP_P0, 2, 0, 1)
+    ref, _ = O.model_posterior("part_cpnp", ht, pt, seqs[0], seqs[1])
+    assert np.isfinite(g["part"]).all()
+    big = ref > 1e-12
+    np.testing.assert_allclose(g["part"][big], ref[big], rtol=REL_TOL_PARTITION)
+    assert np.abs(g["part"][~big]).max() < 2e-12
+    assert ref.max() > 0.9                                  # a real alignment, not a degenerate all-zero posterior
+    eng.posterior_all_pairs(M.CPNP_P0, 2, 0.01)
+    dist, S, rc = O.posterior_stage(O.CPNP_P0, 2, ht, pt, seqs, threads=4)
+    assert rc == 0
+    np.testing.assert_allclose(eng.distances(), dist, rtol=REL_TOL_PARTITION, atol=1e-6)
+    for a, b in pairs(n):
+        np.testing.assert_array_equal(eng.csr(a, b)[1], S.get(a, b)[1])
+    eng.close()
+
+
 def test_unknown_letters_and_identical_sequences():
     seqs = [b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"XXBZACDWWWWWYYHHKKLMNP", b"MKV"]
     n = len(seqs)
