@@ -386,7 +386,8 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             ctx->scratch_bytes = need;
         }
         { int rc = ensure_tasks(ctx, batch.size()); if (rc != MLP_OK) return rc; }
-        const long long rowexp_stride = maxL1 + 4;
+        int maxnb = 1; for (const PairTask& t : batch) maxnb = std::max(maxnb, t.nb);
+        const long long rowexp_stride = (long long)maxnb * (maxL1 + 4);   // [column block][row] scale exponents
         if (useP && flavour != MLP_QP && batch.size() * (size_t)rowexp_stride > ctx->rowexp_cap) {
             free_dev(ctx->d_rowexp); ctx->d_rowexp = nullptr;
             ctx->rowexp_cap = batch.size() * (size_t)rowexp_stride + 1024;

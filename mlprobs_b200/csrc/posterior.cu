@@ -56,6 +56,7 @@ __device__ __forceinline__ void load_hmm_tables(unsigned char* smem, const KArgs
 // ------------------------------------------------------------------------------------------------ 5-state HMM
 // state order (reference numbering): 0 = M, 1 = X1, 2 = Y1, 3 = X2, 4 = Y2
 struct HmmFwd {
+    __device__ __forceinline__ void begin_block(int, int) const {}
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
 }
 
 struct HmmBwd {
+    __device__ __forceinline__ void begin_block(int, int) const {}
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
@@ -264,16 +266,17 @@ template <bool SC>
 struct PartFwdT {
     typedef double T;
     enum { NS = SC ? 4 : 3, REV = 0, COLMASK = 0x7, NIN = 0 };
-    const double* sub; double* Z; int* rowexp; int L1, L2; bool qp;
+    const double* sub; double* Z; int* rowexp; int L1, L2, W; bool qp;
     const double* srow; double zz; bool has_zz; int zexp;
-    int seen_exp, row_seen, gmax, e_prev, e_row; double f;   // seen_exp: largest true exponent in the row this lane finished last
-    __device__ __forceinline__ void reset() { has_zz = false; zz = 0; zexp = 0; seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; }
+    // scale bookkeeping (SC): seen_exp = largest true exponent in the row this lane finished last (this column block)
+    int seen_exp, row_seen, gmax, e_prev, e_row, cb, cbi; double f;
+    __device__ __forceinline__ void reset() { has_zz = false; zz = 0; zexp = 0; seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; cb = 0; cbi = 0; }
+    __device__ __forceinline__ void begin_block(int cb_, int cbi_) { cb = cb_; cbi = cbi_; e_prev = 0; seen_exp = MLP_EXP_NONE; gmax = MLP_EXP_NONE; }
     __device__ __forceinline__ void step_sync() { if (SC) gmax = __reduce_max_sync(MLP_FULL, seen_exp); }
     __device__ __forceinline__ void prefetch(int, int, int) const {}
-    __device__ __forceinline__ void band_init(T (&st)[NS], int) {
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const {
 #pragma unroll
         for (int s = 0; s < NS; ++s) st[s] = 0;
-        e_prev = 0; seen_exp = MLP_EXP_NONE;
     }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const {
 #pragma unroll
@@ -284,17 +287,29 @@ struct PartFwdT {
     __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; }
     __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
+        double fz = 1.0, fc = 1.0;   // factors that bring the diagonal / left operands into this row's scale
         if (SC) {
-            if (j == 0) {   // origin of the row: decide its scale
+            const bool origin = (j == cb * W);        // first column of the column block: this cell fixes the row's scale
+            if (origin) {
                 int e = (i == 0) ? 0 : e_prev;
-                if (i > 0 && gmax != MLP_EXP_NONE && (gmax - e > 48 || e - gmax > 48)) e = gmax;
+                int t = gmax;
+                if (cbi > 0) {   // what flows in from the previous column block
+                    const double cm = fmax(fmax(carry[0], carry[1]), carry[2]);
+                    if (cm > 0.0) t = max(t, exp_of(cm) + (int)carry[3]);
+                }
+                if (i > 0 && t != MLP_EXP_NONE && (t - e > 48 || e - t > 48)) e = t;
                 nw[3] = (double)e;
-                rowexp[i] = e;
+                rowexp[cb * (L1 + 1) + i] = e;
             } else nw[3] = carry[3];
             if (e_row == MLP_EXP_NONE) {   // first cell of this lane in this row
                 e_row = (int)nw[3];
                 const int d = e_prev - e_row;
                 f = (d == 0) ? 1.0 : pow2d(max(min(d, 1000), -1000));
+            }
+            fz = f;
+            if (origin && cbi > 0) {       // operands handed over by the previous column block carry that block's exponents
+                fc = pow2d(max(min((int)carry[3] - e_row, 1000), -1000));
+                fz = pow2d(max(min((int)diag[3] - e_row, 1000), -1000));
             }
         }
         if (i == 0 || j == 0 || j > L2) {   // boundary: Zm(0,0)=1, H(0,j>=1)=1, V(i>=1,0)=1 (terminal gaps are exp(0))
@@ -306,10 +321,14 @@ struct PartFwdT {
             const double score = srow[r2];
             const double o0 = (i == L1) ? 1.0 : c_sc.go, e0 = (i == L1) ? 1.0 : c_sc.ge;
             const double o1 = (j == L2) ? 1.0 : c_sc.go, e1 = (j == L2) ? 1.0 : c_sc.ge;
-            const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
+            double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
             double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
             double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], qp), score);
-            if (SC && f != 1.0) { v = __dmul_rn(v, f); zm = __dmul_rn(zm, f); }   // previous-row operands -> this row's scale (exact)
+            if (SC) {   // power-of-two rescaling: exact
+                if (fc != 1.0) h = __dmul_rn(h, fc);
+                if (f != 1.0) v = __dmul_rn(v, f);
+                if (fz != 1.0) zm = __dmul_rn(zm, fz);
+            }
             nw[0] = zm; nw[1] = h; nw[2] = v;
             Z[slot] = zm;
             if (SC) row_seen = max(row_seen, exp_of(zm) + e_row);
@@ -337,7 +356,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd_t(KArgs a) {
         SweepCtx cx = make_ctx(t, a, lane);
         PartFwdT<SC> m;
         m.reset();
-        m.sub = sub; m.Z = a.layerZ + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
+        m.sub = sub; m.Z = a.layerZ + t.off; m.L1 = t.L1; m.L2 = t.L2; m.W = 32 * t.C; m.qp = (a.flavour == 0);
         m.rowexp = SC ? a.rowexp + (long long)ti * a.rowexp_stride : nullptr;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         if (m.has_zz) { a.pout[ti].Zpart = m.zz; a.pout[ti].zexp = m.zexp; }
@@ -348,21 +367,21 @@ template <bool SC>
 struct PartRevT {
     typedef double T;
     enum { NS = SC ? 4 : 3, REV = 1, COLMASK = 0x7, NIN = 1 };
-    const double* sub; const double* Z; float* P; const int* rowexp; int L1, L2; bool qp; double Ztot; int zexp;
+    const double* sub; const double* Z; float* P; const int* rowexp; int L1, L2, W, nb; bool qp; double Ztot; int zexp;
     const double* srow;
     double* stage; int Cmax, lane;
-    int seen_exp, row_seen, gmax, e_prev, e_row, fexp; double f;
-    __device__ __forceinline__ void reset() { seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; fexp = 0; }
+    int seen_exp, row_seen, gmax, e_prev, e_row, fexp, cb, cbi; double f;
+    __device__ __forceinline__ void reset() { seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; fexp = 0; cb = 0; cbi = 0; }
+    __device__ __forceinline__ void begin_block(int cb_, int cbi_) { cb = cb_; cbi = cbi_; e_prev = 0; seen_exp = MLP_EXP_NONE; gmax = MLP_EXP_NONE; }
     __device__ __forceinline__ void step_sync() { if (SC) gmax = __reduce_max_sync(MLP_FULL, seen_exp); }
     __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
         for (int c = 0; c < C; ++c) cp_async8(stage + (buf * Cmax + c) * 32 + lane, Z + slotbase + c * 32);
     }
-    __device__ __forceinline__ void band_init(T (&st)[NS], int j) {   // virtual row L1+1 (scale exponent 0)
+    __device__ __forceinline__ void band_init(T (&st)[NS], int j) const {   // virtual row L1+1 (scale exponent 0)
         st[0] = (j == L2 + 1) ? 1.0 : 0.0;
         st[1] = (j >= 1 && j <= L2) ? 1.0 : 0.0;
         st[2] = 0.0;
         if (SC) st[3] = 0.0;
-        e_prev = 0; seen_exp = MLP_EXP_NONE;
     }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int i) const {    // virtual column L2+1 when it lies outside the strips
         e[0] = 0.0; e[1] = 0.0; e[2] = (i >= 1 && i <= L1) ? 1.0 : 0.0;
@@ -370,19 +389,35 @@ struct PartRevT {
     }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
-    __device__ __forceinline__ void begin_row(int i, int r1) { srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; if (SC) fexp = rowexp[i]; }
+    __device__ __forceinline__ void begin_row(int i, int r1) {
+        srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE;
+        if (SC) fexp = rowexp[cb * (L1 + 1) + i];
+    }
     __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
+        double fz = 1.0, fc = 1.0;
         if (SC) {
-            if (j == L2 + 1) {   // origin of the row in the reverse sweep
+            // origin of the row inside this column block: the virtual column L2+1 in the last block, the block's last column otherwise
+            const bool origin = (cb == nb - 1) ? (j == L2 + 1) : (j == cb * W + W - 1);
+            if (origin) {
                 int e = e_prev;
-                if (gmax != MLP_EXP_NONE && (gmax - e > 48 || e - gmax > 48)) e = gmax;
+                int t = gmax;
+                if (cbi > 0) {
+                    const double cm = fmax(fmax(carry[0], carry[1]), carry[2]);
+                    if (cm > 0.0) t = max(t, exp_of(cm) + (int)carry[3]);
+                }
+                if (t != MLP_EXP_NONE && (t - e > 48 || e - t > 48)) e = t;
                 nw[3] = (double)e;
             } else nw[3] = (j > L2 + 1) ? 0.0 : carry[3];
             if (e_row == MLP_EXP_NONE && j <= L2 + 1) {
                 e_row = (int)nw[3];
                 const int d = e_prev - e_row;
                 f = (d == 0) ? 1.0 : pow2d(max(min(d, 1000), -1000));
+            }
+            fz = f;
+            if (origin && cbi > 0) {
+                fc = pow2d(max(min((int)carry[3] - e_row, 1000), -1000));
+                fz = pow2d(max(min((int)diag[3] - e_row, 1000), -1000));
             }
         }
         if (j > L2) {
@@ -395,9 +430,13 @@ struct PartRevT {
         const double o1 = (j == 1) ? 1.0 : c_sc.go, e1 = (j == 1) ? 1.0 : c_sc.ge;   // V-type terminal at the first column
         const double o0 = (i == 1) ? 1.0 : c_sc.go, e0 = (i == 1) ? 1.0 : c_sc.ge;   // H-type terminal at the first row
         double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
-        const double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
+        double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
         double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], !qp), score);
-        if (SC && f != 1.0) { v = __dmul_rn(v, f); zm = __dmul_rn(zm, f); }
+        if (SC) {
+            if (fc != 1.0) h = __dmul_rn(h, fc);
+            if (f != 1.0) v = __dmul_rn(v, f);
+            if (fz != 1.0) zm = __dmul_rn(zm, fz);
+        }
         nw[0] = zm; nw[1] = h; nw[2] = v;
         if (SC) row_seen = max(row_seen, exp_of(zm) + e_row);
         // PartitionFunction.cpp:259-270 / MSAPartProbs.cpp:286-297
@@ -430,7 +469,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev_t(KArgs a) {
         PartRevT<SC> m;
         m.reset();
         m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
-        m.sub = sub; m.Z = a.layerZ + t.off; m.P = a.layerP + t.off; m.L1 = t.L1; m.L2 = t.L2; m.qp = (a.flavour == 0);
+        m.sub = sub; m.Z = a.layerZ + t.off; m.P = a.layerP + t.off; m.L1 = t.L1; m.L2 = t.L2; m.W = 32 * t.C; m.nb = t.nb; m.qp = (a.flavour == 0);
         m.Ztot = a.pout[ti].Zpart; m.zexp = a.pout[ti].zexp;
         m.rowexp = SC ? a.rowexp + (long long)ti * a.rowexp_stride : nullptr;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
@@ -440,6 +479,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev_t(KArgs a) {
 // ------------------------------------------------------------------------------------------------ local 3-state HMM
 // states: 0 = M, 1 = X, 2 = Y  (ProbabilisticModel.h flag=false branches)
 struct LocFwd {
+    __device__ __forceinline__ void begin_block(int, int) const {}
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
@@ -478,6 +518,7 @@ struct LocFwd {
 };
 
 struct LocBwd {
+    __device__ __forceinline__ void begin_block(int, int) const {}
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
@@ -613,6 +654,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
 // states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
 template <bool DENSE>
 struct FinalSweep {
+    __device__ __forceinline__ void begin_block(int, int) const {}
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;

@@ -38,6 +38,7 @@ struct SweepCtx {
 //   void begin_row(int i, int r1)                       per-row setup (r1 = residue the model needs for this row)
 //   void cell(int i, int j, int c, int buf, int r2, int slot /* element index inside the pair's dense layer */, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS], T (&nw)[NS])
 //   int row_residue_index(int i) / col_residue_index(int j)   1-based residue used at row i / column j (0 = none)
+//   void begin_block(int cb, int cbi)                    called at the start of every column block
 //   void step_sync()                                    called by ALL lanes at the top of every step (warp-wide reductions)
 //   void prefetch(int slotbase, int C, int buf)   issue cp.async of the dense inputs of one wavefront slot into
 //                                                       staging buffer `buf` (models without dense inputs: no-op);
@@ -61,6 +62,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
     for (int cbi = 0; cbi < cx.nb; ++cbi) {
         const int cb = M::REV ? (cx.nb - 1 - cbi) : cbi;
         const int jbase = cb * 32 * C + lane * C;
+        m.begin_block(cb, cbi);
         const bool lane_has_cols = (jbase <= cx.L2 + 1);   // column L2+1 is the virtual column of reverse sweeps
         // stage the strip: boundary row values + residues of my columns
         for (int c = 0; c < C; ++c) {
