@@ -69,6 +69,16 @@ int mlp_set_shard(mlp_ctx* ctx, int rank, int world);
  * 2*count ints (a0,b0,a1,b1,...); pass NULL to query *count. Same rule as mlp_set_shard. */
 int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, int32_t* pairs_out, int64_t* count);
 
+/* All-pairs 3-state Viterbi alignment (model selection): for every pair in row-major a<b order
+ * the alignment length and the number of match columns with identical residues.
+ * Replaces the pair loop of MSA::ModelAdjustmentTest MSA.cpp:801-837 (ProbabilisticModel::ComputeViterbiAlignment
+ * ProbabilisticModel.h:1043-1170).  Uses the HMM tables of mlp_set_tables (local transitions + emissions). */
+int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len);
+/* Host part of ModelAdjustmentTest (MSA.cpp:838-881): sequential one-core float sums in pair order.
+ * Returns variance_mean = pid + (sigma > 0.115 ? 10 : 0), pid in 0..4; init_distrib2 = the overridden initDistrib[2]. */
+int mlp_cpnp_model_adjustment(int64_t npairs, const int32_t* n_identical, const int32_t* align_len,
+                              float* identity, float* sigma, float* init_distrib2);
+
 /* All-pairs posterior stage: for every owned pair a<b -> dense posteriors of the selected models, merge,
  * MEA score -> distance, threshold to CSR (both orientations).
  * Replaces cpnp MSA.cpp:927-1031 (and :1652-1765 for -p 1) / QP PosteriorStage::run PosteriorStage.cpp:58-121. */

@@ -21,7 +21,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_set_sequences", "mlp_set_shard", "mlp_posterior_all_pairs", "mlp_get_distances", "mlp_relax",
            "mlp_get_csr", "mlp_total_cells", "mlp_get_csr_bulk", "mlp_debug_pair_dense", "mlp_nccl_unique_id",
            "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs", "mlp_csr_layout", "mlp_get_csr_raw",
-           "mlp_alloc_pinned", "mlp_free_pinned"]
+           "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment"]
 
 
 class HmmTables(C.Structure):
@@ -83,6 +83,8 @@ def load():
         lib.mlp_alloc_pinned.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
         lib.mlp_free_pinned.argtypes = [C.c_void_p]
         lib.mlp_free_pinned.restype = None
+        lib.mlp_viterbi_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_cpnp_model_adjustment.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.mlp_qp_guide_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
@@ -94,6 +96,17 @@ def default_tables(flavour, init_distrib2=0.700645):
     if rc:
         raise MlpError(rc)
     return h, p
+
+
+def cpnp_model_adjustment(n_identical, align_len):
+    """-> (variance_mean, identity, sigma, init_distrib2) exactly as MSA::ModelAdjustmentTest derives them."""
+    ni = np.ascontiguousarray(n_identical, np.int32); al = np.ascontiguousarray(align_len, np.int32)
+    ident = C.c_float(0); sig = C.c_float(0); i2 = C.c_float(0)
+    vm = load().mlp_cpnp_model_adjustment(len(ni), ni.ctypes.data_as(C.c_void_p), al.ctypes.data_as(C.c_void_p),
+                                          C.byref(ident), C.byref(sig), C.byref(i2))
+    if vm < 0:
+        raise MlpError(vm)
+    return vm, ident.value, sig.value, i2.value
 
 
 def nccl_unique_id():
@@ -229,6 +242,13 @@ class Engine:
 
     def posterior_all_pairs(self, flavour, mask, cutoff=0.01):
         self._ck(self._lib.mlp_posterior_all_pairs(self._ctx, flavour, mask, C.c_float(cutoff)))
+
+    def viterbi_all_pairs(self):
+        """(n_identical, align_len) per pair in row-major a<b order (ModelAdjustmentTest's pair loop)."""
+        npairs = self.n * (self.n - 1) // 2
+        ident = np.zeros(npairs, np.int32); ln = np.zeros(npairs, np.int32)
+        self._ck(self._lib.mlp_viterbi_all_pairs(self._ctx, _ptr(ident), _ptr(ln)))
+        return ident, ln
 
     def distances(self):
         d = np.zeros((self.n, self.n), np.float32)

@@ -505,6 +505,73 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
     return MLP_OK;
 }
 
+extern "C" int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len) {
+    if (!ctx || !n_identical || !align_len) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
+    const std::vector<PairTask>& tasks_in = ctx->owned;
+    const size_t npairs_all = ctx->all_pairs.size();
+    int* d_ident = nullptr; int* d_len = nullptr;
+    CK(cudaMalloc(&d_ident, npairs_all * sizeof(int)));
+    CK(cudaMalloc(&d_len, npairs_all * sizeof(int)));
+    CK(cudaMemset(d_ident, 0, npairs_all * sizeof(int)));
+    CK(cudaMemset(d_len, 0, npairs_all * sizeof(int)));
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = ctx->scratch_budget > 0 ? (size_t)ctx->scratch_budget : (size_t)((free_b + ctx->scratch_bytes) * 0.5);
+    int maxL1 = 0, maxL2 = 0; bool need_edge = false;
+    for (const PairTask& t : tasks_in) { maxL1 = std::max(maxL1, t.L1); maxL2 = std::max(maxL2, t.L2); need_edge |= (t.nb > 1); }
+    const long long max_warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
+    int rc = ensure_warp_buffers(ctx, max_warps, maxL1, maxL2, need_edge, 1);
+    if (rc != MLP_OK) return rc;
+    ctx->stats = mlp_stage_stats{};
+    KernelTimer kt;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    size_t pos = 0;
+    std::vector<PairTask> batch;
+    while (pos < tasks_in.size()) {
+        batch.clear();
+        long long elems = 0; int Cmax = 1;
+        while (pos < tasks_in.size()) {
+            PairTask t = tasks_in[pos];
+            const long long e = (long long)t.nb * (t.L1 + 32) * t.C * 32;
+            if (!batch.empty() && (size_t)(elems + e) > budget) break;
+            t.off = elems; elems += e; Cmax = std::max(Cmax, t.C);
+            batch.push_back(t); ++pos;
+        }
+        const size_t need = (size_t)elems + 256;   // one traceback byte per cell
+        if (need > ctx->scratch_bytes) {
+            free_dev(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+            CK(cudaMalloc(&ctx->d_scratch, need));
+            ctx->scratch_bytes = need;
+        }
+        rc = ensure_tasks(ctx, batch.size());
+        if (rc != MLP_OK) return rc;
+        CK(cudaMemcpyAsync(ctx->d_tasks, batch.data(), batch.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
+        KArgs a = {};
+        a.tasks = ctx->d_tasks; a.ntasks = (int)batch.size(); a.pout = ctx->d_pout;
+        a.residues = ctx->d_res; a.seq_off = ctx->d_seq_off; a.n = ctx->n; a.Cmax = Cmax;
+        a.match = ctx->d_match; a.ins = ctx->d_ins; a.sub = ctx->d_sub;
+        a.layerTB8 = (unsigned char*)ctx->d_scratch; a.vit_ident = d_ident; a.vit_len = d_len;
+        a.vit_init0 = logf((float)0.6080327034); a.vit_init1 = logf((float)0.1959836632);   // ProbabilisticModel.h:1070-1072
+        a.edge_f = need_edge ? (float*)ctx->d_edge : nullptr; a.edge_stride = ctx->edge_stride; a.err = ctx->d_err;
+        if ((rc = launch_one(ctx, MLP_K_VITERBI, a, (int)batch.size(), kt, MLP_K_LOCAL_FWD)) != MLP_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (const PairTask& t : batch) ctx->stats.cells += (int64_t)(t.L1 + 1) * (t.L2 + 1);
+        ctx->stats.pairs += (int64_t)batch.size();
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_total = ms;
+    kt.collect(ctx->stats);
+    CK(cudaMemcpy(n_identical, d_ident, npairs_all * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(align_len, d_len, npairs_all * sizeof(int), cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += (int64_t)npairs_all * 8;
+    cudaFree(d_ident); cudaFree(d_len);
+    return MLP_OK;
+}
+
 extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model_mask, float cutoff) {
     if (!ctx) return MLP_E_ARG;
     cudaSetDevice(ctx->device);

@@ -114,3 +114,39 @@ extern "C" int mlp_default_tables(int flavour, float init_distrib2, mlp_hmm_tabl
     }
     return MLP_OK;
 }
+
+// MSA.cpp:838-881: average identity, its standard deviation, the initDistrib[2] override and the model class.
+extern "C" int mlp_cpnp_model_adjustment(int64_t npairs, const int32_t* n_identical, const int32_t* align_len,
+                                         float* identity_out, float* sigma_out, float* init_distrib2) {
+    if (npairs < 1 || !n_identical || !align_len) return MLP_E_ARG;
+    float identity = 0;
+    for (int64_t k = 0; k < npairs; ++k) identity += (float)n_identical[k] / align_len[k];
+    identity /= (int)npairs;
+    float variance = 0;
+    for (int64_t k = 0; k < npairs; ++k) {
+        const float pid = (float)n_identical[k] / align_len[k];
+        variance += (pid - identity) * (pid - identity);
+    }
+    variance /= (int)npairs;
+    variance = sqrtf(variance);
+    float i2 = 0.700645f;   // Defaults.h:22-23
+    if (identity <= 0.125) i2 = 0.108854f;
+    else if (identity <= 0.15) i2 = 0.132548f;
+    else if (identity <= 0.175) i2 = 0.165248f;
+    else if (identity <= 0.2) i2 = 0.168284f;
+    else if (identity <= 0.25) i2 = 0.170705f;
+    else if (identity <= 0.3) i2 = 0.100675f;
+    else if (identity <= 0.35) i2 = 0.090755f;
+    else if (identity <= 0.4) i2 = 0.146188f;
+    else if (identity <= 0.45) i2 = 0.167858f;
+    else if (identity <= 0.5) i2 = 0.250769f;
+    if (identity_out) *identity_out = identity;
+    if (sigma_out) *sigma_out = variance;
+    if (init_distrib2) *init_distrib2 = i2;
+    const int vm = (variance > 0.115) ? 10 : 0;
+    if (identity <= 0.18) return vm + 0;
+    if (identity <= 0.25) return vm + 1;
+    if (identity <= 0.4) return vm + 2;
+    if (identity <= 0.7) return vm + 3;
+    return vm + 4;
+}

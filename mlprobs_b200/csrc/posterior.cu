@@ -650,6 +650,105 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ Viterbi (model selection)
+// ProbabilisticModel.h:1043-1170: 3-state Viterbi with traceback; states 0 = M, 1 = X, 2 = Y.  The three traceback
+// entries of a cell are packed into one byte (M: 2 bits holding tb+1, X: bit 2, Y: bit 3) stored in slot layout.
+struct VitFwd {
+    typedef float T;
+    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
+    const float* match; const float* ins; unsigned char* TB; int L1, L2;
+    float ins1; const float* mrow; float init0, init1;
+    float fin[3]; bool has_fin;
+    __device__ __forceinline__ void begin_block(int, int) const {}
+    __device__ __forceinline__ void step_sync() const {}
+    __device__ __forceinline__ void end_row() const {}
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
+    __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = st[1] = st[2] = MLP_LOG_ZERO; }
+    __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = e[1] = e[2] = MLP_LOG_ZERO; }
+    __device__ __forceinline__ int row_residue_index(int i) const { return i; }
+    __device__ __forceinline__ int col_residue_index(int j) const { return j; }
+    __device__ __forceinline__ void begin_row(int, int r1) { ins1 = ins[r1]; mrow = match + r1 * 26; }
+    __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
+                                         const T (&diag)[NS], T (&nw)[NS]) {
+        float m = MLP_LOG_ZERO, x = MLP_LOG_ZERO, y = MLP_LOG_ZERO;
+        int tbm = -1, tbx = 0, tby = 0;
+        if (i > 0 && j > 0) {   // :1091-1099, strict '<' keeps the first maximum
+            const float mt = mrow[r2];
+            const float c0 = __fadd_rn(__fadd_rn(diag[0], c_sc.lt00), mt);
+            const float c1 = __fadd_rn(__fadd_rn(diag[1], c_sc.lt10), mt);
+            const float c2 = __fadd_rn(__fadd_rn(diag[2], c_sc.lt20), mt);
+            if (m < c0) { m = c0; tbm = 0; }
+            if (m < c1) { m = c1; tbm = 1; }
+            if (m < c2) { m = c2; tbm = 2; }
+        }
+        if (i > 0) {            // :1100-1113
+            const float fm = __fadd_rn(__fadd_rn(ins1, old[0]), c_sc.lt01);
+            const float fi = __fadd_rn(__fadd_rn(ins1, old[1]), c_sc.lt11);
+            if (fm >= fi) { x = fm; tbx = 0; } else { x = fi; tbx = 1; }
+        }
+        if (j > 0) {            // :1114-1127
+            const float ins2 = ins[r2];
+            const float fm = __fadd_rn(__fadd_rn(ins2, carry[0]), c_sc.lt02);
+            const float fi = __fadd_rn(__fadd_rn(ins2, carry[2]), c_sc.lt22);
+            if (fm >= fi) { y = fm; tby = 0; } else { y = fi; tby = 1; }
+        }
+        if (i == 0 && j == 0) { m = init0; x = init1; y = init1; }   // :1070-1072
+        nw[0] = m; nw[1] = x; nw[2] = y;
+        if (j <= L2) TB[slot] = (unsigned char)((tbm + 1) | (tbx << 2) | (tby << 3));
+        if (i == L1 && j == L2) { has_fin = true; fin[0] = m; fin[1] = x; fin[2] = y; }
+    }
+};
+
+__global__ void __launch_bounds__(MLP_BLOCK) k_viterbi(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* match; float* ins; LogAddLut* lut;
+    load_hmm_tables(smem, a, match, ins, lut);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* band; float* stage; uint8_t* colres; float* cap;
+    warp_smem<float, 3, 0>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
+    int* capi = reinterpret_cast<int*>(cap);
+    // ProbabilisticModel.h:1070-1072: LOG() of double literals narrowed to float, evaluated on the host with glibc logf
+    const float init0 = a.vit_init0, init1 = a.vit_init1;
+    for (;;) {
+        const int ti = next_task(a.counter, lane);
+        if (ti >= a.ntasks) break;
+        const PairTask t = a.tasks[ti];
+        SweepCtx cx = make_ctx(t, a, lane);
+        VitFwd m;
+        m.match = match; m.ins = ins; m.TB = a.layerTB8 + t.off; m.L1 = t.L1; m.L2 = t.L2; m.init0 = init0; m.init1 = init1; m.has_fin = false;
+        run_sweep(m, cx, band, colres, a.Cmax, edge);
+        if (m.has_fin) {   // best terminating state, :1137-1149 (strict '<', first maximum)
+            float best = MLP_LOG_ZERO; int state = -1;
+            const float iv[3] = {init0, init1, init1};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const float p = __fadd_rn(m.fin[k], iv[k]); if (best < p) { best = p; state = k; } }
+            capi[0] = state;
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) {   // traceback :1155-1163 and the identity count of MSA.cpp:819-836
+            int state = capi[0], r = t.L1, c = t.L2, len = 0, same = 0;
+            const int W = 32 * t.C;
+            const unsigned char* tb = a.layerTB8 + t.off;
+            while ((r != 0 || c != 0) && state >= 0) {
+                const int cb = c / W, rem = c - cb * W, l = rem / t.C, cc = rem - l * t.C;
+                const int byte = tb[((cb * cx.T + r + l) * t.C + cc) * 32 + l];
+                int ns;
+                if (state == 0) { ns = (byte & 3) - 1; same += (cx.s1[r - 1] == cx.s2[c - 1]); --r; --c; }
+                else if (state == 1) { ns = (byte >> 2) & 1; --r; }
+                else { ns = ((byte >> 3) & 1) ? 2 : 0; --c; }
+                ++len;
+                state = ns;
+            }
+            a.vit_ident[t.pidx] = same;
+            a.vit_len[t.pidx] = len;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ merge + MEA + sparsify
 // states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
 template <bool DENSE>
@@ -913,7 +1012,7 @@ size_t posterior_smem_bytes(int kernel, int Cmax, int warps) {
         case MLP_K_PART_REV: tables = MLP_PART_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 8; break;
         case MLP_K_HMM_FWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)5 * Cmax * 32 * 4; break;
         case MLP_K_HMM_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(3 + 2) * Cmax * 32 * 4; break;
-        case MLP_K_LOCAL_FWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)3 * Cmax * 32 * 4; break;
+        case MLP_K_LOCAL_FWD: case MLP_K_VITERBI: tables = MLP_HMM_TABLE_BYTES; per = (size_t)3 * Cmax * 32 * 4; break;
         case MLP_K_LOCAL_BWD: tables = MLP_HMM_TABLE_BYTES; per = (size_t)(2 + 2) * Cmax * 32 * 4; break;
         case MLP_K_FINAL: tables = MLP_FINAL_TABLE_BYTES; per = (size_t)(1 + 6) * Cmax * 32 * 4; break;
         default: return 0;
@@ -940,6 +1039,7 @@ cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, 
         case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
         case MLP_K_FINAL: fn = a_dense ? k_final_t<true> : k_final_t<false>; break;
         case MLP_K_TRANSPOSE: fn = k_transpose; break;
+        case MLP_K_VITERBI: fn = k_viterbi; break;
         default: return cudaErrorInvalidValue;
     }
     if (smem > 48 * 1024) {
@@ -962,6 +1062,7 @@ int posterior_max_blocks_per_sm(int kernel, size_t smem) {
         case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
         case MLP_K_FINAL: fn = a_dense ? k_final_t<true> : k_final_t<false>; break;
         case MLP_K_TRANSPOSE: fn = k_transpose; break;
+        case MLP_K_VITERBI: fn = k_viterbi; break;
         default: return 1;
     }
     if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -7,6 +7,7 @@
 #define MLP_HMM_TABLE_BYTES 3072       // 676 match + 26 ins floats padded to 2816 B, then the 256-byte LogAddLut
 #define MLP_PART_TABLE_BYTES 5408      // 676 doubles
 #define MLP_FINAL_TABLE_BYTES 288      // ExpLut: 6 pieces x 6 doubles
+#define MLP_K_VITERBI 9                // all-pairs 3-state Viterbi (model selection)
 #define MLP_K_TRANSPOSE 8              // extends the MLP_K_* kernel ids of mlprobs_b200.h
 #define MLP_K_RELAX_ID 7
 
@@ -37,6 +38,7 @@ struct KArgs {
     // dense layers (slot layout)
     double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
     int* rowexp; long long rowexp_stride;   // per task: scale exponent of every row of the forward partition layer (cpnp)
+    unsigned char* layerTB8; int* vit_ident; int* vit_len; float vit_init0, vit_init1;   // Viterbi: packed traceback bytes (slot layout), per-pair results by pidx
     int* layerTB;   // MEA traceback codes (MLP_CPNP_P1 only); aliases a dense layer whose slot has already been consumed
     // boundary-column hand-off between column blocks (only when some pair has nb > 1)
     float* edge_f; double* edge_d; long long edge_stride;

@@ -293,6 +293,84 @@ void orc_local_posterior(const orc_hmm_tables* t, const char* s1, int L1, const 
     for (int k = 0; k < 3; k++) { free(F[k]); free(B[k]); }
 }
 
+/* ---------------------------------------------------------------- Viterbi + model selection */
+/* ProbabilisticModel.h:1043-1170 */
+float orc_viterbi(const orc_hmm_tables* t, const char* s1, int L1, const char* s2, int L2, int* n_identical, int* aln_len, char* aln) {
+    const int W = L2 + 1;
+    const size_t cells = (size_t)(L1 + 1) * W;
+    float* V[3]; int* TB[3];
+    for (int k = 0; k < 3; k++) {
+        V[k] = (float*)malloc(cells * sizeof(float)); TB[k] = (int*)malloc(cells * sizeof(int));
+        for (size_t c = 0; c < cells; c++) { V[k][c] = LOG_ZERO; TB[k][c] = -1; }
+    }
+    const float init0 = logf((float)0.6080327034), init1 = logf((float)0.1959836632);
+    V[0][0] = init0; V[1][0] = init1; V[2][0] = init1;
+    for (int i = 0; i <= L1; i++)
+        for (int j = 0; j <= L2; j++) {
+            if (i > 0 && j > 0)
+                for (int k = 0; k < 3; k++) {
+                    float nv = V[k][IX(i - 1, j - 1)] + t->ltrans[k][0] + t->match[R1(i)][R2(j)];
+                    if (V[0][IX(i, j)] < nv) { V[0][IX(i, j)] = nv; TB[0][IX(i, j)] = k; }
+                }
+            if (i > 0) {
+                float fm = t->ins[R1(i)] + V[0][IX(i - 1, j)] + t->ltrans[0][1];
+                float fi = t->ins[R1(i)] + V[1][IX(i - 1, j)] + t->ltrans[1][1];
+                if (fm >= fi) { V[1][IX(i, j)] = fm; TB[1][IX(i, j)] = 0; } else { V[1][IX(i, j)] = fi; TB[1][IX(i, j)] = 1; }
+            }
+            if (j > 0) {
+                float fm = t->ins[R2(j)] + V[0][IX(i, j - 1)] + t->ltrans[0][2];
+                float fi = t->ins[R2(j)] + V[2][IX(i, j - 1)] + t->ltrans[2][2];
+                if (fm >= fi) { V[2][IX(i, j)] = fm; TB[2][IX(i, j)] = 0; } else { V[2][IX(i, j)] = fi; TB[2][IX(i, j)] = 2; }
+            }
+        }
+    float best = LOG_ZERO; int state = -1;
+    const float iv[3] = {init0, init1, init1};
+    for (int k = 0; k < 3; k++) {
+        float p = V[k][IX(L1, L2)] + iv[k];
+        if (best < p) { best = p; state = k; }
+    }
+    int r = L1, c = L2, len = 0, ident = 0;
+    while ((r != 0 || c != 0) && state >= 0) {
+        int ns = TB[state][IX(r, c)];
+        if (state == 0) { if (s1[r - 1] == s2[c - 1]) ident++; if (aln) aln[len] = 'B'; r--; c--; }
+        else if (state == 1) { if (aln) aln[len] = 'X'; r--; }
+        else { if (aln) aln[len] = 'Y'; c--; }
+        len++;
+        state = ns;
+    }
+    if (aln) { for (int a = 0, b = len - 1; a < b; a++, b--) { char x = aln[a]; aln[a] = aln[b]; aln[b] = x; } }
+    if (n_identical) *n_identical = ident;
+    if (aln_len) *aln_len = len;
+    for (int k = 0; k < 3; k++) { free(V[k]); free(TB[k]); }
+    return best;
+}
+
+/* MSA.cpp:838-881 */
+int orc_model_adjustment(int npairs, const int32_t* n_identical, const int32_t* aln_len, float* identity_out, float* sigma_out, float* init_distrib2) {
+    float identity = 0;
+    float* pid = (float*)malloc(sizeof(float) * (npairs + 1));
+    for (int k = 0; k < npairs; k++) {
+        float nc = (float)n_identical[k];
+        pid[k] = nc / aln_len[k];
+        identity += nc / aln_len[k];
+    }
+    identity /= npairs;
+    float variance = 0;
+    for (int k = 0; k < npairs; k++) variance += (pid[k] - identity) * (pid[k] - identity);
+    variance /= npairs;
+    variance = sqrtf(variance);
+    free(pid);
+    if (identity_out) *identity_out = identity;
+    if (sigma_out) *sigma_out = variance;
+    if (init_distrib2) *init_distrib2 = (identity <= 0.5) ? orc_init_distrib2_for_identity(identity) : 0.700645f;
+    int vm = (variance > 0.115) ? 10 : 0;
+    if (identity <= 0.18) return vm + 0;
+    else if (identity <= 0.25) return vm + 1;
+    else if (identity <= 0.4) return vm + 2;
+    else if (identity <= 0.7) return vm + 3;
+    return vm + 4;
+}
+
 /* ---------------------------------------------------------------- partition function */
 /* QP: PartitionFunction.cpp:71-157 (forward), :180-291 (reverse). FP64, no overflow check. */
 int orc_part_posterior_qp(const orc_part_tables* t, const char* s1, int L1, const char* s2, int L2, float* post) {

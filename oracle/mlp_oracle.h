@@ -53,6 +53,13 @@ float orc_combine_qp(int L1, int L2, const float* hmm, const float* part, float*
 void  orc_merge3_cpnp(int n, const float* p5, const float* pp, const float* pl, int p1_order, float* out); /* MSA.cpp:992-1007 / 1699-1714 */
 float orc_mea_score(int L1, int L2, const float* post, int* n_match);                      /* ProbabilisticModel.h:804-864 */
 
+/* 3-state Viterbi alignment used for model selection (ProbabilisticModel.h:1043-1170): returns the log probability, the
+ * alignment length and the number of 'B' columns with identical residues; aln (may be NULL) receives the B/X/Y string. */
+float orc_viterbi(const orc_hmm_tables* t, const char* s1, int L1, const char* s2, int L2, int* n_identical, int* aln_len, char* aln);
+/* ModelAdjustmentTest (MSA.cpp:775-882) from the per-pair counts in pair order (one-core summation order):
+ * returns variance_mean (pid + 10 if sigma > 0.115) and writes identity, sigma, the overridden initDistrib[2]. */
+int orc_model_adjustment(int npairs, const int32_t* n_identical, const int32_t* aln_len, float* identity, float* sigma, float* init_distrib2);
+
 /* one pair end to end: returns dense posterior and distance */
 int orc_pair_posterior(int flavour, int model_mask, const orc_hmm_tables* ht, const orc_part_tables* pt,
                        const char* s1, int L1, const char* s2, int L2, float* post, float* dist);

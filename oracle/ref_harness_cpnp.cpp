@@ -116,6 +116,24 @@ int main(int argc, char** argv) {
         w->f32("hmm.trans", &model.transProb[0][0], {5, 5});
         w->f32("hmm.ltrans", &model.local_transProb[0][0], {3, 3});
         w->f32("hmm.rtrans", model.random_transProb, {2});
+        // per-pair Viterbi statistics behind ModelAdjustmentTest (reference ComputeViterbiAlignment, counting glue as MSA.cpp:819-836)
+        std::vector<int32_t> vid(numPairs), vlen(numPairs);
+        for (int p = 0; p < numPairs; p++) {
+            Sequence* s1 = sequences->GetSequence(msa->seqsPairs[p].seq1);
+            Sequence* s2 = sequences->GetSequence(msa->seqsPairs[p].seq2);
+            pair<SafeVector<char>*, float> al = model.ComputeViterbiAlignment(s1, s2);
+            SafeVector<char>::iterator i1 = s1->GetDataPtr(), i2 = s2->GetDataPtr();
+            int i = 1, j = 1, same = 0;
+            for (SafeVector<char>::iterator it = al.first->begin(); it != al.first->end(); ++it) {
+                if (*it == 'B') { if (i1[i] == i2[j]) same++; i++; j++; }
+                else if (*it == 'X') i++; else if (*it == 'Y') j++;
+            }
+            vid[p] = same; vlen[p] = (int32_t)al.first->size();
+            delete al.first;
+        }
+        w->i32("vit.ident", vid.data(), {(uint64_t)numPairs});
+        w->i32("vit.len", vlen.data(), {(uint64_t)numPairs});
+        w->scalar_i("variance_mean", variance_mean);
         w->f64("part.sub_raw", &sub_matrix[0][0], {26, 26});
         w->i32("part.subst_index", subst_index, {26});
     }

@@ -92,6 +92,21 @@ def model_posterior(which, ht, pt, s1: bytes, s2: bytes, qp_quirk=0):
     return post, tot.value
 
 
+def viterbi(ht, s1: bytes, s2: bytes):
+    ident = C.c_int(0); ln = C.c_int(0)
+    aln = C.create_string_buffer(len(s1) + len(s2) + 2)
+    lib().orc_viterbi.restype = C.c_float
+    p = lib().orc_viterbi(C.byref(ht), s1, len(s1), s2, len(s2), C.byref(ident), C.byref(ln), aln)
+    return p, ident.value, ln.value, aln.raw[:ln.value]
+
+
+def model_adjustment(n_identical, aln_len):
+    ni = np.ascontiguousarray(n_identical, np.int32); al = np.ascontiguousarray(aln_len, np.int32)
+    ident = C.c_float(0); sig = C.c_float(0); i2 = C.c_float(0)
+    vm = lib().orc_model_adjustment(len(ni), _p(ni), _p(al), C.byref(ident), C.byref(sig), C.byref(i2))
+    return vm, ident.value, sig.value, i2.value
+
+
 class CsrSet:
     """Both orientations of every pair, pooled (mirrors orc_csr_set)."""
 

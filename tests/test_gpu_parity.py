@@ -185,6 +185,31 @@ def test_cpnp_partition_beyond_fp64_range_is_rescaled():
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_676s4_ref", "cpnp_sup139_mix"])
+def test_viterbi_all_pairs_against_reference_fixture(name):
+    d = load_golden(name)
+    seqs = split_seqs(d)
+    eng = engine(M.CPNP_P0, seqs, 0.700645)
+    ident, ln = eng.viterbi_all_pairs()
+    np.testing.assert_array_equal(ident, d["vit.ident"])
+    np.testing.assert_array_equal(ln, d["vit.len"])
+    vm, _, _, i2 = M.cpnp_model_adjustment(ident, ln)
+    assert vm == int(d["variance_mean"][0]) and np.float32(i2) == d["initDistrib2"][0]
+    eng.close()
+
+
+def test_viterbi_ragged_and_multiblock_vs_oracle():
+    seqs = [synth.family(1, L, seed=300 + L)[0] for L in (1, 2, 33, 64, 200)] + synth.family(2, 620, seed=4, p_sub=0.3)
+    n = len(seqs)
+    eng = engine(M.CPNP_P0, seqs, 0.700645)
+    ident, ln = eng.viterbi_all_pairs()
+    ht = O.hmm_tables()
+    want = [O.viterbi(ht, seqs[a], seqs[b])[1:3] for a, b in pairs(n)]
+    np.testing.assert_array_equal(ident, [w[0] for w in want])
+    np.testing.assert_array_equal(ln, [w[1] for w in want])
+    eng.close()
+
+
 def test_unknown_letters_and_identical_sequences():
     seqs = [b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"ACDEFGHIKLMNPQRSTVWYBZX" * 3, b"XXBZACDWWWWWYYHHKKLMNP", b"MKV"]
     n = len(seqs)

@@ -97,6 +97,15 @@ def test_shard_pairs_partition_is_a_disjoint_cover():
     assert max(sizes) / min(sizes) < 1.15          # cost-balanced
 
 
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_676s4_ref", "cpnp_sup139_mix"])
+def test_model_adjustment_host_helper(name):
+    d = load_golden(name)
+    vm, ident, sig, i2 = M.cpnp_model_adjustment(d["vit.ident"], d["vit.len"])
+    assert vm == int(d["variance_mean"][0])
+    assert np.float32(i2) == d["initDistrib2"][0]
+    assert (vm, ident, sig, i2) == O.model_adjustment(d["vit.ident"], d["vit.len"])
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

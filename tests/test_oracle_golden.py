@@ -127,3 +127,21 @@ def test_full_fixture_matches_digest():
     d = load_golden("qp_sup139")
     n = int(d["n"][0])
     assert_digest(d, "s0", lambda a, b: (d["pair.%d.%d.s0.rowptr" % (a, b)], d["pair.%d.%d.s0.col" % (a, b)], d["pair.%d.%d.s0.val" % (a, b)]), n)
+
+
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_676s4_ref", "cpnp_sup139_mix"])
+def test_viterbi_statistics_and_model_selection(name):
+    """ModelAdjustmentTest (MSA.cpp:775-882): per-pair Viterbi counts, model class and the initDistrib[2] override."""
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    ht = O.hmm_tables()
+    ids, lens = [], []
+    for a, b in pairs(n):
+        _, i, l, aln = O.viterbi(ht, seqs[a], seqs[b])
+        ids.append(i); lens.append(l)
+        assert aln.count(b"B") + aln.count(b"X") == len(seqs[a]) and aln.count(b"B") + aln.count(b"Y") == len(seqs[b])
+    np.testing.assert_array_equal(ids, d["vit.ident"])
+    np.testing.assert_array_equal(lens, d["vit.len"])
+    vm, ident, sig, i2 = O.model_adjustment(ids, lens)
+    assert vm == int(d["variance_mean"][0])
+    assert np.float32(i2) == d["initDistrib2"][0]
