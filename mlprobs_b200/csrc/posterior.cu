@@ -247,8 +247,9 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd(KArgs a) {
 // The 3-term sums are (Zm+H)+V or (Zm+V)+H depending on which reference statement is reproduced:
 //   forward Zm and zz: QP (Zm+H)+V  PartitionFunction.cpp:137,139 ; cpnp (Zm+V)+H  MSAPartProbs.cpp:583,589
 //   reverse Zm:        QP (Zm+V)+H  PartitionFunction.cpp:257     ; cpnp (Zm+H)+V  MSAPartProbs.cpp:283
-__device__ __forceinline__ double sum3(double zm, double h, double v, bool h_first) {
-    return h_first ? __dadd_rn(__dadd_rn(zm, h), v) : __dadd_rn(__dadd_rn(zm, v), h);
+template <bool H_FIRST>
+__device__ __forceinline__ double sum3(double zm, double h, double v) {
+    return H_FIRST ? __dadd_rn(__dadd_rn(zm, h), v) : __dadd_rn(__dadd_rn(zm, v), h);
 }
 
 // Rescaled variant (SC = true, cpnp flavour): the reference runs this recursion in 80-bit long double (range 1e+-4932),
@@ -266,8 +267,8 @@ template <bool SC>
 struct PartFwdT {
     typedef double T;
     enum { NS = SC ? 4 : 3, REV = 0, COLMASK = 0x7, NIN = 0 };
-    const double* sub; double* Z; int* rowexp; int L1, L2, W; bool qp;
-    const double* srow; double zz; bool has_zz; int zexp;
+    const double* sub; double* Z; int* rowexp; int L1, L2, W; bool qp;   // qp == !SC: QuickProbs order (Zm+H)+V, cpnp (Zm+V)+H
+    const double* srow; double zz; bool has_zz; int zexp; double o0, e0;
     // scale bookkeeping (SC): seen_exp = largest true exponent in the row this lane finished last (this column block)
     int seen_exp, row_seen, gmax, e_prev, e_row, cb, cbi; double f;
     __device__ __forceinline__ void reset() { has_zz = false; zz = 0; zexp = 0; seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; cb = 0; cbi = 0; }
@@ -284,7 +285,10 @@ struct PartFwdT {
     }
     __device__ __forceinline__ int row_residue_index(int i) const { return i; }
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
-    __device__ __forceinline__ void begin_row(int, int r1) { srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; }
+    __device__ __forceinline__ void begin_row(int i, int r1) {
+        srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE;
+        o0 = (i == L1) ? 1.0 : c_sc.go; e0 = (i == L1) ? 1.0 : c_sc.ge;   // H-type gap is terminal (exp(0)) in the last row
+    }
     __device__ __forceinline__ void cell(int i, int j, int, int, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         double fz = 1.0, fc = 1.0;   // factors that bring the diagonal / left operands into this row's scale
@@ -319,11 +323,10 @@ struct PartFwdT {
             Z[slot] = nw[0];
         } else {
             const double score = srow[r2];
-            const double o0 = (i == L1) ? 1.0 : c_sc.go, e0 = (i == L1) ? 1.0 : c_sc.ge;
-            const double o1 = (j == L2) ? 1.0 : c_sc.go, e1 = (j == L2) ? 1.0 : c_sc.ge;
             double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
-            double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
-            double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], qp), score);
+            double v = __dadd_rn(__dmul_rn(old[0], c_sc.go), __dmul_rn(old[2], c_sc.ge));
+            if (j == L2) v = __dadd_rn(old[0], old[2]);   // V-type gap is terminal in the last column: x * exp(0) == x
+            double zm = __dmul_rn(sum3<!SC>(diag[0], diag[1], diag[2]), score);
             if (SC) {   // power-of-two rescaling: exact
                 if (fc != 1.0) h = __dmul_rn(h, fc);
                 if (f != 1.0) v = __dmul_rn(v, f);
@@ -332,7 +335,7 @@ struct PartFwdT {
             nw[0] = zm; nw[1] = h; nw[2] = v;
             Z[slot] = zm;
             if (SC) row_seen = max(row_seen, exp_of(zm) + e_row);
-            if (i == L1 && j == L2) { has_zz = true; zz = sum3(zm, h, v, qp); zexp = SC ? e_row : 0; }
+            if (i == L1 && j == L2) { has_zz = true; zz = sum3<!SC>(zm, h, v); zexp = SC ? e_row : 0; }
         }
     }
     __device__ __forceinline__ void end_row() { if (SC) { e_prev = e_row; if (row_seen != MLP_EXP_NONE) seen_exp = row_seen; } }
@@ -368,7 +371,7 @@ struct PartRevT {
     typedef double T;
     enum { NS = SC ? 4 : 3, REV = 1, COLMASK = 0x7, NIN = 1 };
     const double* sub; const double* Z; float* P; const int* rowexp; int L1, L2, W, nb; bool qp; double Ztot; int zexp;
-    const double* srow;
+    const double* srow; double o0, e0;
     double* stage; int Cmax, lane;
     int seen_exp, row_seen, gmax, e_prev, e_row, fexp, cb, cbi; double f;
     __device__ __forceinline__ void reset() { seen_exp = MLP_EXP_NONE; row_seen = MLP_EXP_NONE; gmax = MLP_EXP_NONE; e_prev = 0; e_row = 0; f = 1.0; fexp = 0; cb = 0; cbi = 0; }
@@ -391,6 +394,7 @@ struct PartRevT {
     __device__ __forceinline__ int col_residue_index(int j) const { return j; }
     __device__ __forceinline__ void begin_row(int i, int r1) {
         srow = sub + r1 * 26; e_row = MLP_EXP_NONE; row_seen = MLP_EXP_NONE;
+        o0 = (i == 1) ? 1.0 : c_sc.go; e0 = (i == 1) ? 1.0 : c_sc.ge;   // H-type terminal at the first row
         if (SC) fexp = rowexp[cb * (L1 + 1) + i];
     }
     __device__ __forceinline__ void cell(int i, int j, int c, int buf, int r2, int slot, const T (&old)[NS], const T (&carry)[NS],
@@ -427,11 +431,10 @@ struct PartRevT {
         }
         if (i == 0 || j == 0) { nw[0] = 0.0; nw[1] = 0.0; nw[2] = 0.0; P[slot] = 0.0f; return; }
         const double score = srow[r2];
-        const double o1 = (j == 1) ? 1.0 : c_sc.go, e1 = (j == 1) ? 1.0 : c_sc.ge;   // V-type terminal at the first column
-        const double o0 = (i == 1) ? 1.0 : c_sc.go, e0 = (i == 1) ? 1.0 : c_sc.ge;   // H-type terminal at the first row
-        double v = __dadd_rn(__dmul_rn(old[0], o1), __dmul_rn(old[2], e1));
+        double v = __dadd_rn(__dmul_rn(old[0], c_sc.go), __dmul_rn(old[2], c_sc.ge));
+        if (j == 1) v = __dadd_rn(old[0], old[2]);   // V-type terminal at the first column
         double h = __dadd_rn(__dmul_rn(carry[0], o0), __dmul_rn(carry[1], e0));
-        double zm = __dmul_rn(sum3(diag[0], diag[1], diag[2], !qp), score);
+        double zm = __dmul_rn(sum3<SC>(diag[0], diag[1], diag[2]), score);
         if (SC) {
             if (fc != 1.0) h = __dmul_rn(h, fc);
             if (f != 1.0) v = __dmul_rn(v, f);

@@ -6,7 +6,7 @@
 // skewed by its lane index: at step t lane l is on row  t - l  (forward)  or  L1 - t + 31 - l  (reverse).
 // Lane l therefore needs, for its first column, the values lane l-1 (forward) / l+1 (reverse) produced one
 // step earlier: ONE warp shuffle per carried state per step, no block barrier, no global hand-off.
-// The previous row of the strip lives in a per-warp shared-memory band laid out [state][c][lane]
+// The previous row of the strip lives in a per-warp shared-memory band laid out [c][state][lane]
 // (lane-contiguous -> conflict free).  Between column blocks the boundary column travels through a small
 // per-warp global "edge" array.
 //
@@ -53,6 +53,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                                           typename M::T* edgebuf /* [(L1+1)][NS] per warp, only if nb>1 */) {
     typedef typename M::T T;
     constexpr int NS = M::NS;
+    constexpr int NSB = __builtin_popcount((int)M::COLMASK);   // states kept in the row band
     const int lane = cx.lane;
     const int C = cx.C;
     const int src = M::REV ? (lane + 1) : (lane - 1);
@@ -71,7 +72,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
             m.band_init(st, j);
 #pragma unroll
             for (int s = 0; s < NS; ++s)
-                if ((M::COLMASK >> s) & 1) band[(band_rank<M::COLMASK>(s) * Cmax + c) * 32 + lane] = st[s];
+                if ((M::COLMASK >> s) & 1) band[(c * NSB + band_rank<M::COLMASK>(s)) * 32 + lane] = st[s];
             const int rj = m.col_residue_index(j);
             colres[c * 32 + lane] = (rj >= 1 && rj <= cx.L2) ? cx.s2[rj - 1] : (uint8_t)0;
         }
@@ -126,13 +127,14 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                     const int c = M::REV ? (C - 1 - cc) : cc;
                     const int j = jbase + c;
                     T old[NS], nw[NS];
+                    T* bcell = band + (c * NSB) * 32 + lane;   // [c][state][lane]: one address per cell, states at immediate offsets
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
-                        if ((M::COLMASK >> s) & 1) old[s] = band[(band_rank<M::COLMASK>(s) * Cmax + c) * 32 + lane]; else old[s] = (T)0;
+                        if ((M::COLMASK >> s) & 1) old[s] = bcell[band_rank<M::COLMASK>(s) * 32]; else old[s] = (T)0;
                     m.cell(i, j, c, t & 1, colres[c * 32 + lane], slotbase + c * 32, old, carry, diag, nw);
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        if ((M::COLMASK >> s) & 1) band[(band_rank<M::COLMASK>(s) * Cmax + c) * 32 + lane] = nw[s];
+                        if ((M::COLMASK >> s) & 1) bcell[band_rank<M::COLMASK>(s) * 32] = nw[s];
                         diag[s] = old[s];
                         carry[s] = nw[s];
                     }
