@@ -74,6 +74,15 @@ int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, int32_t* pai
  * Replaces the pair loop of MSA::ModelAdjustmentTest MSA.cpp:801-837 (ProbabilisticModel::ComputeViterbiAlignment
  * ProbabilisticModel.h:1043-1170).  Uses the HMM tables of mlp_set_tables (local transitions + emissions). */
 int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len);
+/* Same, additionally returning every pair's Viterbi alignment as a B/X/Y string (what ComputeViterbiAlignment returns):
+ * aln receives the strings back to back, aln_off[p]..aln_off[p+1] is pair p (aln_off has npairs+1 entries); aln must hold
+ * sum over pairs of len[a]+len[b] bytes. */
+int mlp_viterbi_all_pairs_ex(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len, char* aln, int64_t* aln_off);
+/* The `c_p_np_aln -G` feature line (MSA::Alter_ModelAdjustmentTest MSA.cpp:646-762) from the Viterbi alignments, host only,
+ * one-core summation order: "identity\tsigma\tN\tavgLen\tavgSP\tpeakRatio\tfactor" with std::to_string formatting.
+ * Returns MLP_E_UNSUPPORTED if a residue is outside the 20 standard letters (the reference indexes out of bounds there). */
+int mlp_cpnp_g_features(int n, const int32_t* len, const uint8_t* residues, const char* aln, const int64_t* aln_off,
+                        float theta, char* line, int line_cap);
 /* Host part of ModelAdjustmentTest (MSA.cpp:838-881): sequential one-core float sums in pair order.
  * Returns variance_mean = pid + (sigma > 0.115 ? 10 : 0), pid in 0..4; init_distrib2 = the overridden initDistrib[2]. */
 int mlp_cpnp_model_adjustment(int64_t npairs, const int32_t* n_identical, const int32_t* align_len,

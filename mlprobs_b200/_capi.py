@@ -21,7 +21,8 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_set_sequences", "mlp_set_shard", "mlp_posterior_all_pairs", "mlp_get_distances", "mlp_relax",
            "mlp_get_csr", "mlp_total_cells", "mlp_get_csr_bulk", "mlp_debug_pair_dense", "mlp_nccl_unique_id",
            "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs", "mlp_csr_layout", "mlp_get_csr_raw",
-           "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment"]
+           "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
+           "mlp_cpnp_g_features"]
 
 
 class HmmTables(C.Structure):
@@ -84,6 +85,8 @@ def load():
         lib.mlp_free_pinned.argtypes = [C.c_void_p]
         lib.mlp_free_pinned.restype = None
         lib.mlp_viterbi_all_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_viterbi_all_pairs_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_cpnp_g_features.argtypes = [C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_float, C.c_char_p, C.c_int]
         lib.mlp_cpnp_model_adjustment.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         lib.mlp_qp_guide_tree.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
@@ -107,6 +110,17 @@ def cpnp_model_adjustment(n_identical, align_len):
     if vm < 0:
         raise MlpError(vm)
     return vm, ident.value, sig.value, i2.value
+
+
+def cpnp_g_features(seqs, aln, aln_off, theta=1.0):
+    """The `c_p_np_aln -G` line from the Viterbi alignments (host only)."""
+    lens = np.array([len(s) for s in seqs], np.int32)
+    line = C.create_string_buffer(256)
+    rc = load().mlp_cpnp_g_features(len(seqs), lens.ctypes.data_as(C.c_void_p), b"".join(seqs), aln.ctypes.data_as(C.c_void_p),
+                                    aln_off.ctypes.data_as(C.c_void_p), C.c_float(theta), line, 256)
+    if rc:
+        raise MlpError(rc)
+    return line.value
 
 
 def nccl_unique_id():
@@ -249,6 +263,15 @@ class Engine:
         ident = np.zeros(npairs, np.int32); ln = np.zeros(npairs, np.int32)
         self._ck(self._lib.mlp_viterbi_all_pairs(self._ctx, _ptr(ident), _ptr(ln)))
         return ident, ln
+
+    def viterbi_alignments(self):
+        """(n_identical, align_len, aln bytes, aln_off) -- the B/X/Y strings ComputeViterbiAlignment returns, for every pair."""
+        npairs = self.n * (self.n - 1) // 2
+        ident = np.zeros(npairs, np.int32); ln = np.zeros(npairs, np.int32)
+        total = int(sum(int(self.lens[a]) + int(self.lens[b]) for a in range(self.n) for b in range(a + 1, self.n)))
+        aln = np.zeros(total + 16, np.uint8); off = np.zeros(npairs + 1, np.int64)
+        self._ck(self._lib.mlp_viterbi_all_pairs_ex(self._ctx, _ptr(ident), _ptr(ln), _ptr(aln), _ptr(off)))
+        return ident, ln, aln, off
 
     def distances(self):
         d = np.zeros((self.n, self.n), np.float32)

@@ -506,7 +506,11 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
 }
 
 extern "C" int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len) {
-    if (!ctx || !n_identical || !align_len) return MLP_E_ARG;
+    return mlp_viterbi_all_pairs_ex(ctx, n_identical, align_len, nullptr, nullptr);
+}
+
+extern "C" int mlp_viterbi_all_pairs_ex(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len, char* aln, int64_t* aln_off) {
+    if (!ctx || !n_identical || !align_len || ((aln == nullptr) != (aln_off == nullptr))) return MLP_E_ARG;
     cudaSetDevice(ctx->device);
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     const std::vector<PairTask>& tasks_in = ctx->owned;
@@ -516,6 +520,16 @@ extern "C" int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t
     CK(cudaMalloc(&d_len, npairs_all * sizeof(int)));
     CK(cudaMemset(d_ident, 0, npairs_all * sizeof(int)));
     CK(cudaMemset(d_len, 0, npairs_all * sizeof(int)));
+    char* d_aln = nullptr; long long* d_aln_off = nullptr;
+    std::vector<long long> off_h;
+    if (aln) {   // strings by pair index (row-major a<b), each with room for len[a]+len[b] columns
+        off_h.assign(npairs_all + 1, 0);
+        size_t p = 0;
+        for (int a = 0; a < ctx->n; ++a) for (int b = a + 1; b < ctx->n; ++b, ++p) off_h[p + 1] = off_h[p] + ctx->len[a] + ctx->len[b];
+        CK(cudaMalloc(&d_aln, (size_t)off_h[npairs_all] + 16));
+        CK(cudaMalloc(&d_aln_off, (npairs_all + 1) * sizeof(long long)));
+        CK(cudaMemcpy(d_aln_off, off_h.data(), (npairs_all + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    }
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = ctx->scratch_budget > 0 ? (size_t)ctx->scratch_budget : (size_t)((free_b + ctx->scratch_bytes) * 0.5);
@@ -554,6 +568,7 @@ extern "C" int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t
         a.match = ctx->d_match; a.ins = ctx->d_ins; a.sub = ctx->d_sub;
         a.layerTB8 = (unsigned char*)ctx->d_scratch; a.vit_ident = d_ident; a.vit_len = d_len;
         a.vit_init0 = logf((float)0.6080327034); a.vit_init1 = logf((float)0.1959836632);   // ProbabilisticModel.h:1070-1072
+        a.vit_aln = d_aln; a.vit_aln_off = d_aln_off;
         a.edge_f = need_edge ? (float*)ctx->d_edge : nullptr; a.edge_stride = ctx->edge_stride; a.err = ctx->d_err;
         if ((rc = launch_one(ctx, MLP_K_VITERBI, a, (int)batch.size(), kt, MLP_K_LOCAL_FWD)) != MLP_OK) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
@@ -568,6 +583,19 @@ extern "C" int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t
     CK(cudaMemcpy(n_identical, d_ident, npairs_all * sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(align_len, d_len, npairs_all * sizeof(int), cudaMemcpyDeviceToHost));
     ctx->stats.d2h_bytes += (int64_t)npairs_all * 8;
+    if (aln) {   // compact the per-pair strings and turn them front to back (the traceback wrote them reversed)
+        std::vector<char> raw((size_t)off_h[npairs_all] + 16);
+        CK(cudaMemcpy(raw.data(), d_aln, (size_t)off_h[npairs_all], cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += off_h[npairs_all];
+        int64_t w = 0;
+        for (size_t p = 0; p < npairs_all; ++p) {
+            aln_off[p] = w;
+            const char* src = raw.data() + off_h[p];
+            for (int k = align_len[p] - 1; k >= 0; --k) aln[w++] = src[k];
+        }
+        aln_off[npairs_all] = w;
+        cudaFree(d_aln); cudaFree(d_aln_off);
+    }
     cudaFree(d_ident); cudaFree(d_len);
     return MLP_OK;
 }

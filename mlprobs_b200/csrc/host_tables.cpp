@@ -4,7 +4,9 @@
 #include "../../include/mlprobs_b200.h"
 #include "param_data.h"
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -149,4 +151,59 @@ extern "C" int mlp_cpnp_model_adjustment(int64_t npairs, const int32_t* n_identi
     if (identity <= 0.4) return vm + 2;
     if (identity <= 0.7) return vm + 3;
     return vm + 4;
+}
+
+// MSA::Alter_ModelAdjustmentTest, MSA.cpp:646-762 (the -G line MLProbs' first classifier reads).
+extern "C" int mlp_cpnp_g_features(int n, const int32_t* len, const uint8_t* residues, const char* aln, const int64_t* aln_off,
+                                   float theta, char* line, int line_cap) {
+    if (n < 2 || !len || !residues || !aln || !aln_off || !line || line_cap < 64) return MLP_E_ARG;
+    const char* al = MLP_HMM_ALPHABET;
+    int idx[26];
+    for (int k = 0; k < 26; k++) idx[k] = -1;
+    for (int k = 0; k < 20; k++) idx[al[k] - 'A'] = k;
+    std::vector<long long> off(n);
+    long long tot = 0;
+    for (int i = 0; i < n; i++) { off[i] = tot; tot += len[i]; }
+    for (long long k = 0; k < tot; k++) if (residues[k] < 'A' || residues[k] > 'Z' || idx[residues[k] - 'A'] < 0) return MLP_E_UNSUPPORTED;
+    const int npairs = n * (n - 1) / 2;
+    float identity = 0, tmp_sp = 0;
+    int avg_length = 0, max_len = 0, tmp_sp_idx = 0;
+    std::vector<float> arr(10000, 0.0f), pids(npairs);          // MAX_ARR, MSA.cpp:17
+    int p = 0;
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++, p++) {
+            const uint8_t* s1 = residues + off[a]; const uint8_t* s2 = residues + off[b];
+            const char* s = aln + aln_off[p];
+            const int alen = (int)(aln_off[p + 1] - aln_off[p]);
+            if (alen > 10000) return MLP_E_UNSUPPORTED;         // the reference overruns its fixed array here
+            avg_length += alen;
+            if (alen > max_len) max_len = alen;
+            int i = 1, j = 1, num_idx = 0;
+            float nc = 0;
+            for (int k = 0; k < alen; k++) {
+                if (s[k] == 'B') {
+                    const uint8_t c1 = s1[i - 1], c2 = s2[j - 1]; i++; j++;
+                    if (c1 == c2) nc += 1;
+                    const float bl = MLP_BLOSUM62[idx[c1 - 'A'] * 20 + idx[c2 - 'A']];
+                    if (bl < 10) { arr[num_idx] += bl; tmp_sp += bl; }
+                } else if (s[k] == 'X') i++;
+                else j++;
+                tmp_sp_idx += 1; num_idx++;
+            }
+            pids[p] = nc / alen;
+            identity += nc / alen;
+        }
+    tmp_sp /= tmp_sp_idx;
+    identity /= npairs;
+    avg_length /= npairs;
+    float peak = 0;
+    for (int k = 0; k < max_len; k++) { arr[k] /= npairs; if (theta <= arr[k]) peak += 1; }
+    peak /= max_len;
+    float variance = 0;
+    for (int k = 0; k < npairs; k++) variance += (pids[k] - identity) * (pids[k] - identity);
+    variance /= npairs;
+    variance = sqrtf(variance);
+    const float factor = 2 * (float)n - (float)avg_length;
+    std::snprintf(line, line_cap, "%f\t%f\t%d\t%d\t%f\t%f\t%f", identity, variance, n, avg_length, tmp_sp, peak, factor);
+    return MLP_OK;
 }

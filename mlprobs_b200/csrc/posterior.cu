@@ -735,10 +735,12 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_viterbi(KArgs a) {
             int state = capi[0], r = t.L1, c = t.L2, len = 0, same = 0;
             const int W = 32 * t.C;
             const unsigned char* tb = a.layerTB8 + t.off;
+            char* aln = a.vit_aln ? a.vit_aln + a.vit_aln_off[t.pidx] : nullptr;
             while ((r != 0 || c != 0) && state >= 0) {
                 const int cb = c / W, rem = c - cb * W, l = rem / t.C, cc = rem - l * t.C;
                 const int byte = tb[((cb * cx.T + r + l) * t.C + cc) * 32 + l];
                 int ns;
+                if (aln) aln[len] = (state == 0) ? 'B' : ((state == 1) ? 'X' : 'Y');   // written back to front
                 if (state == 0) { ns = (byte & 3) - 1; same += (cx.s1[r - 1] == cx.s2[c - 1]); --r; --c; }
                 else if (state == 1) { ns = (byte >> 2) & 1; --r; }
                 else { ns = ((byte >> 3) & 1) ? 2 : 0; --c; }

@@ -38,7 +38,8 @@ struct KArgs {
     // dense layers (slot layout)
     double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
     int* rowexp; long long rowexp_stride;   // per task: scale exponent of every row of the forward partition layer (cpnp)
-    unsigned char* layerTB8; int* vit_ident; int* vit_len; float vit_init0, vit_init1;   // Viterbi: packed traceback bytes (slot layout), per-pair results by pidx
+    unsigned char* layerTB8; int* vit_ident; int* vit_len; float vit_init0, vit_init1;
+    char* vit_aln; const long long* vit_aln_off;   // optional: reversed B/X/Y alignment string of every pair (by pidx)   // Viterbi: packed traceback bytes (slot layout), per-pair results by pidx
     int* layerTB;   // MEA traceback codes (MLP_CPNP_P1 only); aliases a dense layer whose slot has already been consumed
     // boundary-column hand-off between column blocks (only when some pair has nb > 1)
     float* edge_f; double* edge_d; long long edge_stride;

@@ -31,7 +31,7 @@ def pack(d, tags, full, dense):
     n = int(d["n"][0])
     out = {"n": d["n"], "lens": d["lens"], "residues": d["residues"], "distances": d["distances"]}
     for k in ("pid", "pid_ref", "initDistrib2", "weights", "seldist", "distances_after_tree", "cons.iterations",
-              "cons.selfweight", "reps", "p1", "vit.ident", "vit.len", "variance_mean"):
+              "cons.selfweight", "reps", "p1", "vit.ident", "vit.len", "variance_mean", "gline"):
         if k in d:
             out[k] = d[k]
     for k in d:

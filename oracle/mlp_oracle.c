@@ -371,6 +371,60 @@ int orc_model_adjustment(int npairs, const int32_t* n_identical, const int32_t* 
     return vm + 4;
 }
 
+/* MSA.cpp:646-762 */
+int orc_g_features(const orc_hmm_tables* t, int n, const int32_t* len, const char* residues, const int64_t* res_off,
+                   float theta, char* line, int cap) {
+    const char* al = MLP_HMM_ALPHABET;
+    int idx[26];
+    for (int k = 0; k < 26; k++) idx[k] = -1;
+    for (int k = 0; k < 20; k++) idx[al[k] - 'A'] = k;
+    for (int i = 0; i < n; i++) for (int k = 0; k < len[i]; k++) if (idx[residues[res_off[i] + k] - 'A'] < 0) return 1;
+    const int npairs = n * (n - 1) / 2;
+    float identity = 0, tmp_sp = 0;
+    int avg_length = 0, max_len = 0, tmp_sp_idx = 0;
+    float* arr = (float*)calloc(20000 + 16, sizeof(float));
+    float* pids = (float*)malloc(sizeof(float) * (npairs + 1));
+    int p = 0;
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++, p++) {
+            const char* s1 = residues + res_off[a]; const char* s2 = residues + res_off[b];
+            char* aln = (char*)malloc(len[a] + len[b] + 2);
+            int same = 0, alen = 0;
+            orc_viterbi(t, s1, len[a], s2, len[b], &same, &alen, aln);
+            avg_length += alen;
+            if (alen > max_len) max_len = alen;
+            int i = 1, j = 1, num_idx = 0;
+            float nc = 0;
+            for (int k = 0; k < alen; k++) {
+                if (aln[k] == 'B') {
+                    char c1 = s1[i - 1], c2 = s2[j - 1]; i++; j++;
+                    if (c1 == c2) nc += 1;
+                    float bl = MLP_BLOSUM62[idx[c1 - 'A'] * 20 + idx[c2 - 'A']];
+                    if (bl < 10) { arr[num_idx] += bl; tmp_sp += bl; } else { arr[num_idx] += 0; }
+                } else if (aln[k] == 'X') i++;
+                else j++;
+                tmp_sp_idx += 1; num_idx++;
+            }
+            pids[p] = nc / alen;
+            identity += nc / alen;
+            free(aln);
+        }
+    tmp_sp /= tmp_sp_idx;
+    identity /= npairs;
+    avg_length /= npairs;
+    float peak = 0;
+    for (int k = 0; k < max_len; k++) { arr[k] /= npairs; if (theta <= arr[k]) peak += 1; }
+    peak /= max_len;
+    float variance = 0;
+    for (int k = 0; k < npairs; k++) variance += (pids[k] - identity) * (pids[k] - identity);
+    variance /= npairs;
+    variance = sqrtf(variance);
+    float factor = 2 * (float)n - (float)avg_length;
+    snprintf(line, cap, "%f\t%f\t%d\t%d\t%f\t%f\t%f", identity, variance, n, avg_length, tmp_sp, peak, factor);
+    free(arr); free(pids);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- partition function */
 /* QP: PartitionFunction.cpp:71-157 (forward), :180-291 (reverse). FP64, no overflow check. */
 int orc_part_posterior_qp(const orc_part_tables* t, const char* s1, int L1, const char* s2, int L2, float* post) {

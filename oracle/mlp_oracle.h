@@ -60,6 +60,11 @@ float orc_viterbi(const orc_hmm_tables* t, const char* s1, int L1, const char* s
  * returns variance_mean (pid + 10 if sigma > 0.115) and writes identity, sigma, the overridden initDistrib[2]. */
 int orc_model_adjustment(int npairs, const int32_t* n_identical, const int32_t* aln_len, float* identity, float* sigma, float* init_distrib2);
 
+/* the `c_p_np_aln -G` feature line (MSA::Alter_ModelAdjustmentTest, MSA.cpp:646-762), one-core summation order.
+ * Returns 0, or 1 if a sequence holds a letter outside the 20 standard ones (the reference indexes out of bounds there). */
+int orc_g_features(const orc_hmm_tables* t, int n, const int32_t* len, const char* residues, const int64_t* res_off,
+                   float theta, char* line, int cap);
+
 /* one pair end to end: returns dense posterior and distance */
 int orc_pair_posterior(int flavour, int model_mask, const orc_hmm_tables* ht, const orc_part_tables* pt,
                        const char* s1, int L1, const char* s2, int L2, float* post, float* dist);

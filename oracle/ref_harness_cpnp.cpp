@@ -134,6 +134,10 @@ int main(int argc, char** argv) {
         w->i32("vit.ident", vid.data(), {(uint64_t)numPairs});
         w->i32("vit.len", vlen.data(), {(uint64_t)numPairs});
         w->scalar_i("variance_mean", variance_mean);
+        {   // the -G feature line, straight from MSA::Alter_ModelAdjustmentTest (MSA.cpp:646-762)
+            std::string g = msa->Alter_ModelAdjustmentTest(sequences, 1.0);
+            w->u8("gline", (const uint8_t*)g.data(), {(uint64_t)g.size()});
+        }
         w->f64("part.sub_raw", &sub_matrix[0][0], {26, 26});
         w->i32("part.subst_index", subst_index, {26});
     }

@@ -107,6 +107,13 @@ def model_adjustment(n_identical, aln_len):
     return vm, ident.value, sig.value, i2.value
 
 
+def g_features(ht, seqs, theta=1.0):
+    lens, off, cat = _seqs(seqs)
+    line = C.create_string_buffer(256)
+    rc = lib().orc_g_features(C.byref(ht), len(seqs), _p(lens), cat, _p(off), C.c_float(theta), line, 256)
+    return rc, line.value
+
+
 class CsrSet:
     """Both orientations of every pair, pooled (mirrors orc_csr_set)."""
 

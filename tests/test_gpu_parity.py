@@ -198,6 +198,19 @@ def test_viterbi_all_pairs_against_reference_fixture(name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_sup139_mix"])
+def test_g_feature_line_from_gpu_alignments(name):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.CPNP_P0, seqs, 0.700645)
+    ident, ln, aln, off = eng.viterbi_alignments()
+    ht = O.hmm_tables()
+    for p, (a, b) in enumerate(pairs(n)):
+        assert aln[off[p]:off[p + 1]].tobytes() == O.viterbi(ht, seqs[a], seqs[b])[3]
+    assert M.cpnp_g_features(seqs, aln, off) == d["gline"].tobytes()
+    eng.close()
+
+
 def test_viterbi_ragged_and_multiblock_vs_oracle():
     seqs = [synth.family(1, L, seed=300 + L)[0] for L in (1, 2, 33, 64, 200)] + synth.family(2, 620, seed=4, p_sub=0.3)
     n = len(seqs)

@@ -145,3 +145,17 @@ def test_viterbi_statistics_and_model_selection(name):
     vm, ident, sig, i2 = O.model_adjustment(ids, lens)
     assert vm == int(d["variance_mean"][0])
     assert np.float32(i2) == d["initDistrib2"][0]
+
+
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_sup139_mix"])
+def test_g_feature_line(name):
+    """`c_p_np_aln -G` (Alter_ModelAdjustmentTest, MSA.cpp:646-762): the oracle reproduces the reference's line byte for byte."""
+    d = load_golden(name)
+    rc, line = O.g_features(O.hmm_tables(), split_seqs(d))
+    assert rc == 0 and line == d["gline"].tobytes()
+
+
+def test_g_feature_line_refuses_non_standard_letters():
+    d = load_golden("cpnp_676s4_ref")       # holds X/B/Z: the reference indexes its tables out of bounds there
+    rc, _ = O.g_features(O.hmm_tables(), split_seqs(d))
+    assert rc == 1
