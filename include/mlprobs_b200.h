@@ -19,7 +19,7 @@ extern "C" {
 typedef struct mlp_ctx mlp_ctx;
 
 enum { MLP_OK = 0, MLP_E_NO_DEVICE = -1, MLP_E_CUDA = -2, MLP_E_ARG = -3, MLP_E_STATE = -4,
-       MLP_E_CAPACITY = -5, MLP_E_OVERFLOW = -6, MLP_E_UNSUPPORTED = -7, MLP_E_NCCL = -8 };
+       MLP_E_CAPACITY = -5, MLP_E_OVERFLOW = -6, MLP_E_UNSUPPORTED = -7, MLP_E_NCCL = -8, MLP_E_NOMEM = -9 };
 
 /* flavour = whose arithmetic is reproduced */
 enum { MLP_QP = 0,        /* quickprobs: PosteriorStage.cpp:58-196, ConsistencyStage.cpp:133-300            */
@@ -108,6 +108,29 @@ int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seld
  * Replaces ClusterTree::build ClusterTree.cpp:17-124, GuideTree::calculateSeqsWeights GuideTree.cpp:114-154 and
  * GuideTree::calculateSubtreeDistances GuideTree.cpp:189-221.  parent_out (2n-1 ints, -1 = root) may be NULL. */
 int mlp_qp_guide_tree(int n, float* dist_nxn_inout, float* weights_out, float* subtree_dist_nxn_out, int32_t* parent_out);
+/* Same, additionally returning the children of every internal node v (n <= v < 2n-1; entries below n are -1): left = the
+ * cluster found first by the reference's scan (connectNodes' leftChild, ClusterTree.cpp:88-89), right = the other one.
+ * The root is node 2n-2.  This is the tree mlp_qp_finish_alignment* walks. */
+int mlp_qp_guide_tree_ex(int n, float* dist_nxn_inout, float* weights_out, float* subtree_dist_nxn_out, int32_t* parent_out,
+                         int32_t* left_out, int32_t* right_out);
+
+/* QuickProbs flavour, the stages after consistency: progressive construction along the guide tree and column-based
+ * iterative refinement, giving the final multiple alignment.
+ * Replaces ConstructionStage::operator() ConstructionStage.cpp:11-127 and RefinementBase::operator() RefinementBase.cpp:13-63
+ * with ColumnRefinement.cpp (called from ExtendedMSA::doAlign ExtendedMSA.cpp:235-252), default configuration
+ * (finalSelectivity = FLT_MAX, acceptance by length, no recursion).  weights = tree weights saturated at 1e-6;
+ * ref_iters 0 or -1 selects the reference's default pass count (as `-r 0` does there), -2 skips refinement (construction
+ * only; an extension used by tests), ref_seed 0 keeps its default-seeded std::mt19937.
+ * rows_out receives a malloc'ed n x aln_len byte matrix (input order, '-' for gaps) to release with mlp_free_host.
+ *   _host: the sparse set is a host copy in the pooled layout of mlp_csr_layout/mlp_get_csr_raw (no GPU work);
+ *   the ctx variant sums the pair matrices with a CUDA kernel over the set resident in HBM (no read-back of the set). */
+int mlp_qp_finish_alignment_host(int n, const int32_t* len, const uint8_t* residues, const float* weights,
+                                 const int32_t* left, const int32_t* right, const int64_t* rp_off, const int64_t* nz_off,
+                                 const int32_t* rp_pool, const void* cells, int ref_iters, uint32_t ref_seed,
+                                 char** rows_out, int32_t* aln_len);
+int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const int32_t* left, const int32_t* right,
+                            int ref_iters, uint32_t ref_seed, char** rows_out, int32_t* aln_len);
+void mlp_free_host(void* p);
 
 /* Sparse posterior read-back. Ordered pair (a,b), a != b; rows 1..len[a]; row_ptr has len[a]+2 entries
  * (row_ptr[i]..row_ptr[i+1] = row i, row 0 empty).  val is the dequantised value for MLP_QP

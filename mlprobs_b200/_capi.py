@@ -22,7 +22,8 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_get_csr", "mlp_total_cells", "mlp_get_csr_bulk", "mlp_debug_pair_dense", "mlp_nccl_unique_id",
            "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs", "mlp_csr_layout", "mlp_get_csr_raw",
            "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
-           "mlp_cpnp_g_features"]
+           "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
+           "mlp_free_host"]
 
 
 class HmmTables(C.Structure):
@@ -143,6 +144,50 @@ def qp_guide_tree(distances):
     if rc:
         raise MlpError(rc)
     return w, sd, par, d
+
+
+def qp_guide_tree_ex(distances):
+    """UPGMA tree -> dict(weights, seldist, parent, left, right, dist_after); children as mlp_qp_finish_alignment* wants them."""
+    d = np.array(distances, np.float32, copy=True, order="C")
+    n = d.shape[0]
+    w = np.zeros(n, np.float32)
+    sd = np.zeros((n, n), np.float32)
+    par, left, right = (np.zeros(2 * n - 1, np.int32) for _ in range(3))
+    rc = load().mlp_qp_guide_tree_ex(n, _ptr(d), _ptr(w), _ptr(sd), _ptr(par), _ptr(left), _ptr(right))
+    if rc:
+        raise MlpError(rc)
+    return {"weights": w, "seldist": sd, "parent": par, "left": left, "right": right, "dist_after": d}
+
+
+def _take_rows(n, rows_p, alen):
+    lib = load()
+    lib.mlp_free_host.argtypes = [C.c_void_p]
+    lib.mlp_free_host.restype = None
+    raw = C.string_at(rows_p, n * alen.value)
+    lib.mlp_free_host(rows_p)
+    L = alen.value
+    return [raw[i * L:(i + 1) * L] for i in range(n)]
+
+
+def qp_finish_alignment_host(seqs, weights, left, right, rp_off, nz_off, rp_pool, cells, ref_iters=-1, ref_seed=0):
+    """Progressive construction + column refinement from a HOST copy of the pooled sparse set (no GPU work).
+    cells: structured/2-column array of {int32 column, float32 value}. Returns the aligned rows (bytes) in input order."""
+    n = len(seqs)
+    lens = np.array([len(x) for x in seqs], np.int32)
+    cat = np.frombuffer(b"".join(seqs), np.uint8)
+    cv = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+    keep = [cv(weights, np.float32), cv(left, np.int32), cv(right, np.int32), cv(rp_off, np.int64), cv(nz_off, np.int64),
+            cv(rp_pool, np.int32), None if cells is None else np.ascontiguousarray(cells)]
+    rows_p = C.c_void_p(0)
+    alen = C.c_int32(0)
+    lib = load()
+    lib.mlp_qp_finish_alignment_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.c_uint32,
+                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    rc = lib.mlp_qp_finish_alignment_host(n, _ptr(lens), _ptr(cat), *[_ptr(k) for k in keep], int(ref_iters), int(ref_seed),
+                                          C.byref(rows_p), C.byref(alen))
+    if rc:
+        raise MlpError(rc)
+    return _take_rows(n, rows_p, alen)
 
 
 def shard_pairs(lens, rank, world):
@@ -328,6 +373,17 @@ class Engine:
         self._ck(self._lib.mlp_get_csr_raw(self._ctx, _ptr(out.nz_off), _ptr(out.nz_cnt), _ptr(out.rp_pool), _ptr(out.cells)))
         out.rp_off, out.rp_total, out.used = rp_off, rp_total, used
         return out
+
+    def qp_finish_alignment(self, weights, left, right, ref_iters=-1, ref_seed=0):
+        """Progressive construction + column refinement over the sparse set resident on the device -> aligned rows (bytes)."""
+        keep = [np.ascontiguousarray(weights, np.float32), np.ascontiguousarray(left, np.int32), np.ascontiguousarray(right, np.int32)]
+        rows_p = C.c_void_p(0)
+        alen = C.c_int32(0)
+        self._lib.mlp_qp_finish_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32,
+                                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+        self._ck(self._lib.mlp_qp_finish_alignment(self._ctx, *[_ptr(k) for k in keep], int(ref_iters), int(ref_seed),
+                                                   C.byref(rows_p), C.byref(alen)))
+        return _take_rows(self.n, rows_p, alen)
 
     def total_cells(self):
         c = C.c_int64(0)

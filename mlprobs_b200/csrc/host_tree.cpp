@@ -7,10 +7,11 @@
 #include <algorithm>
 #include <vector>
 
-extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out) {
+extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out,
+                                    int32_t* left_out, int32_t* right_out) {
     if (n < 2 || !dist || !weights) return MLP_E_ARG;
     const int total = 2 * n - 1;
-    std::vector<int> parent(total, -1), leaves(total, 0), slot_node(n), alive;
+    std::vector<int> parent(total, -1), leaves(total, 0), slot_node(n), alive, lch(total, -1), rch(total, -1);
     std::vector<float> branch(total, 0.0f), joins(n);
     alive.reserve(n);
     for (int i = 0; i < n; ++i) { alive.push_back(i); slot_node[i] = i; leaves[i] = 1; }
@@ -38,6 +39,7 @@ extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subt
         const int ni = slot_node[si], nj = slot_node[sj];
         const float half = best * 0.5f;
         parent[ni] = node; parent[nj] = node; branch[ni] = half; branch[nj] = half;
+        lch[node] = ni; rch[node] = nj;
         leaves[node] = leaves[ni] + leaves[nj];
         alive.erase(std::lower_bound(alive.begin(), alive.end(), sj));
         is_alive[sj] = 0;
@@ -86,5 +88,11 @@ extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subt
         }
     }
     if (parent_out) for (int v = 0; v < total; ++v) parent_out[v] = parent[v];
+    if (left_out) for (int v = 0; v < total; ++v) left_out[v] = lch[v];
+    if (right_out) for (int v = 0; v < total; ++v) right_out[v] = rch[v];
     return MLP_OK;
+}
+
+extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out) {
+    return mlp_qp_guide_tree_ex(n, dist, weights, subtree_dist, parent_out, nullptr, nullptr);
 }

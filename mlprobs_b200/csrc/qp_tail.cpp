@@ -1,0 +1,292 @@
+// QuickProbs flavour, host tail: guide-tree driven progressive construction and column-based refinement.
+// Restates (flat arrays, no Sequence/MultiSequence objects):
+//   ConstructionStage::processTree / alignAlignments      ConstructionStage.cpp:51-127
+//   ParallelProbabilisticModel::buildPosterior            ParallelProbabilisticModel.cpp:301-444 (host provider)
+//   ProbabilisticModel::computeAlignment                  ProbabilisticModel.cpp:345-421
+//   Sequence::AddGaps / getMapping                        Sequence.cpp:67-119
+//   MultiSequence::extractSubset / SortByLabel            MultiSequence.cpp:390-460
+//   RefinementBase::operator() / checkAcceptance          RefinementBase.cpp:13-116
+//   ColumnRefinement::initialise/split/updateColumnScores ColumnRefinement.cpp:56-174
+//   det_uniform_int_distribution                          Common/deterministic_random.h:60-85
+#include "qp_tail.h"
+#include "../../include/mlprobs_b200.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <random>
+
+namespace qptail {
+
+namespace {
+
+struct Cell { int32_t col; float val; };
+
+// column mapping of a gapped row: map[k] = 1-based alignment column of the k-th residue (map[0] = 0)
+void row_mapping(const std::string& row, std::vector<int>& map) {
+    map.clear();
+    map.push_back(0);
+    for (int c = 0; c < (int)row.size(); ++c)
+        if (row[c] != '-') map.push_back(c + 1);
+}
+
+class HostProfilePosterior : public ProfilePosterior {
+public:
+    explicit HostProfilePosterior(const HostCsrView& v) : v_(v) {}
+    int build(const Profile& A, const Profile& B, const float* weights, const float** out) override {
+        const int l1 = A.length(), l2 = B.length();
+        std::vector<float>& dense = dense_;
+        dense.assign((size_t)(l1 + 1) * (l2 + 1), 0.0f);
+        double total = 0;                                     // finalSelectivity is FLT_MAX: every pair counts
+        for (int a : A.ids) { const double w1 = weights[a]; for (int b : B.ids) total += w1 * (double)weights[b]; }
+        std::vector<std::vector<int>> mapB(B.count());
+        for (int j = 0; j < B.count(); ++j) row_mapping(B.rows[j], mapB[j]);
+        std::vector<int> mapA;
+        const Cell* cells = (const Cell*)v_.cells;
+        for (int i = 0; i < A.count(); ++i) {
+            const int first = A.ids[i];
+            row_mapping(A.rows[i], mapA);
+            const double w1 = weights[first];
+            for (int j = 0; j < B.count(); ++j) {
+                const int second = B.ids[j];
+                const float w = (float)((w1 * (double)weights[second]) / total);
+                const int64_t slot = (int64_t)first * v_.n + second;
+                const int32_t* rp = v_.rp_pool + v_.rp_off[slot];
+                const Cell* base = cells + v_.nz_off[slot];
+                const int* mb = mapB[j].data();
+                const int L = v_.len[first];
+                for (int ii = 1; ii <= L; ++ii) {
+                    float* drow = dense.data() + (size_t)mapA[ii] * (l2 + 1);
+                    for (int k = rp[ii]; k < rp[ii + 1]; ++k) drow[mb[base[k].col]] += w * base[k].val;
+                }
+            }
+        }
+        *out = dense.data();
+        return 0;
+    }
+private:
+    HostCsrView v_;
+    std::vector<float> dense_;
+};
+
+// Sequence::AddGaps: consume the row where the path has 'B' or `id`, gap elsewhere
+std::string add_gaps(const std::string& row, const std::string& path, char id) {
+    std::string out(path.size(), '-');
+    const char* src = row.data();
+    const char* p = path.data();
+    char* dst = &out[0];
+    size_t k = 0;
+    const size_t n = path.size();
+    for (size_t q = 0; q < n; ++q)
+        if (p[q] == 'B' || p[q] == id) dst[q] = src[k++];
+    return out;
+}
+
+int align_profiles(const Profile& A, const Profile& B, const float* weights, ProfilePosterior& prov, Profile& out) {
+    std::string path;
+    int rc = prov.build_and_align(A, B, weights, path);
+    if (rc < 0) return rc;
+    if (rc > 0) {
+        const float* dense = nullptr;
+        rc = prov.build(A, B, weights, &dense);
+        if (rc < 0) return rc;
+        path = mea_path(A.length(), B.length(), dense);
+    }
+    // both groups arrive sorted by label (leaves, SortByLabel'ed results, index-ordered subsets): merge keeps that order
+    out.ids.clear(); out.rows.clear();
+    out.ids.reserve(A.count() + B.count()); out.rows.reserve(A.count() + B.count());
+    int i = 0, j = 0;
+    while (i < A.count() || j < B.count()) {
+        if (j >= B.count() || (i < A.count() && A.ids[i] < B.ids[j])) { out.ids.push_back(A.ids[i]); out.rows.push_back(add_gaps(A.rows[i], path, 'X')); ++i; }
+        else { out.ids.push_back(B.ids[j]); out.rows.push_back(add_gaps(B.rows[j], path, 'Y')); ++j; }
+    }
+    return 0;
+}
+
+// rows `idx` of P with the columns that are gaps in all of them removed
+void extract_subset(const Profile& P, const std::vector<int>& idx, Profile& out) {
+    const int len = P.length();
+    std::vector<char> keep(len, 0);
+    for (int r : idx) {
+        const char* s = P.rows[r].data();
+        for (int c = 0; c < len; ++c) keep[c] |= (char)(s[c] != '-');
+    }
+    std::vector<int> cols;
+    cols.reserve(len);
+    for (int c = 0; c < len; ++c) if (keep[c]) cols.push_back(c);
+    out.ids.clear(); out.rows.clear();
+    out.ids.reserve(idx.size()); out.rows.reserve(idx.size());
+    for (int r : idx) {
+        const char* src = P.rows[r].data();
+        std::string s(cols.size(), '-');
+        for (size_t k = 0; k < cols.size(); ++k) s[k] = src[cols[k]];
+        out.ids.push_back(P.ids[r]);
+        out.rows.push_back(std::move(s));
+    }
+}
+
+struct ColumnRefiner {
+    std::vector<std::pair<int, float>> scores;   // persists across passes exactly like the reference's member vector
+    std::vector<int> gaps;
+    std::mt19937 engine;
+
+    void update_scores(const Profile& P) {
+        const int n = P.count(), len = P.length();
+        scores.resize(len, std::pair<int, float>(0, 0.0f));
+        // the reference adds 1.0f per gap, column by column; counting first gives the same float as long as the running
+        // value stays an exactly representable integer (below 2^24), otherwise fall back to the literal loop
+        gaps.assign(len, 0);
+        for (int i = 0; i < n; ++i) {
+            const char* s = P.rows[i].data();
+            for (int c = 0; c < len; ++c) gaps[c] += (s[c] == '-');
+        }
+        for (int c = 0; c < len; ++c) {
+            scores[c].first = c;
+            const float before = scores[c].second;
+            if (before >= 0 && before + (float)gaps[c] < 16777216.0f && before == (float)(int)before) scores[c].second = before + (float)gaps[c];
+            else for (int k = 0; k < gaps[c]; ++k) scores[c].second += 1.0f;
+        }
+        std::stable_sort(scores.begin(), scores.end(), [n](const std::pair<int, float>& a, const std::pair<int, float>& b) {
+            return std::fabs((float)n / 2 - a.second) > std::fabs((float)n / 2 - b.second);
+        });
+        scores.erase(std::remove_if(scores.begin(), scores.end(), [](const std::pair<int, float>& e) { return e.second == 0; }), scores.end());
+    }
+
+    int draw(int lo, int hi_inclusive) {
+        typedef unsigned int U;
+        const U diff = (U)hi_inclusive - (U)lo + 1;
+        if (diff == 0) return (int)engine();
+        const U bad = std::numeric_limits<U>::max() / diff;
+        for (;;) {
+            const U r = (U)engine();
+            if (r / diff < bad) return (int)((r % diff) + (U)lo);
+        }
+    }
+};
+
+}  // namespace
+
+ProfilePosterior* make_host_provider(const HostCsrView& v) { return new HostProfilePosterior(v); }
+
+std::string mea_path(int l1, int l2, const float* dense) {
+    const size_t W = (size_t)l2 + 1;
+    std::vector<float> two(2 * W, 0.0f);
+    float* oldr = two.data();
+    float* newr = two.data() + W;
+    std::vector<char> tb((size_t)(l1 + 1) * W);
+    for (int j = 0; j <= l2; ++j) tb[j] = 'L';
+    for (int i = 1; i <= l1; ++i) {
+        const float* p = dense + (size_t)i * W;
+        char* t = tb.data() + (size_t)i * W;
+        newr[0] = 0;
+        t[0] = 'U';
+        for (int j = 1; j <= l2; ++j) {
+            const float x1 = p[j] + oldr[j - 1], x2 = newr[j - 1], x3 = oldr[j];
+            if (x1 >= x2) {
+                if (x1 >= x3) { newr[j] = x1; t[j] = 'D'; } else { newr[j] = x3; t[j] = 'U'; }
+            } else if (x2 >= x3) { newr[j] = x2; t[j] = 'L'; }
+            else { newr[j] = x3; t[j] = 'U'; }
+        }
+        std::swap(oldr, newr);
+    }
+    std::string path;
+    int r = l1, c = l2;
+    while (r != 0 || c != 0) {
+        const char ch = tb[(size_t)r * W + c];
+        if (ch == 'L') { --c; path.push_back('Y'); }
+        else if (ch == 'U') { --r; path.push_back('X'); }
+        else { --c; --r; path.push_back('B'); }
+    }
+    std::reverse(path.begin(), path.end());
+    return path;
+}
+
+int run_tail(int n, const int32_t* len, const uint8_t* residues, const float* weights, const int32_t* left, const int32_t* right,
+             ProfilePosterior& prov, const TailOptions& opt, Profile& out, std::string& err) {
+    if (n < 1) { err = "no sequences"; return MLP_E_ARG; }
+    std::vector<long long> off(n);
+    long long tot = 0;
+    for (int i = 0; i < n; ++i) { off[i] = tot; tot += len[i]; }
+    if (n == 1) {
+        out.ids = {0};
+        out.rows = {std::string((const char*)residues, (size_t)len[0])};
+        return 0;
+    }
+    // progressive construction: children always have smaller node ids than their parent, so an ascending sweep is a post-order walk
+    const int total = 2 * n - 1;
+    std::vector<std::unique_ptr<Profile>> prof(total);
+    auto leaf = [&](int v) {
+        std::unique_ptr<Profile> p(new Profile());
+        p->ids = {v};
+        p->rows = {std::string((const char*)residues + off[v], (size_t)len[v])};
+        return p;
+    };
+    for (int v = n; v < total; ++v) {
+        const int l = left[v], r = right[v];
+        if (l < 0 || r < 0 || l >= v || r >= v) { err = "malformed guide tree"; return MLP_E_ARG; }
+        if (l < n) prof[l] = leaf(l);
+        if (r < n) prof[r] = leaf(r);
+        if (!prof[l] || !prof[r]) { err = "guide tree node used twice"; return MLP_E_ARG; }
+        prof[v].reset(new Profile());
+        const int rc = align_profiles(*prof[l], *prof[r], weights, prov, *prof[v]);
+        if (rc < 0) { err = "profile posterior failed"; return rc; }
+        prof[l].reset();
+        prof[r].reset();
+    }
+    std::unique_ptr<Profile> aln = std::move(prof[total - 1]);
+
+    // column refinement
+    const int iters = opt.ref_iters > 0 ? opt.ref_iters : (opt.ref_iters == -2 ? 0 : (aln->count() > 200 ? 200 : 30));
+    ColumnRefiner cr;
+    if (opt.ref_seed != 0) cr.engine.seed(opt.ref_seed);
+    cr.update_scores(*aln);
+    const bool prepared = !cr.scores.empty();
+    Profile one, two;
+    std::vector<int> g1, g2;
+    for (int it = 0; it < iters && prepared; ++it) {
+        cr.update_scores(*aln);
+        const int hi = (int)cr.scores.size();
+        if (hi <= 0) continue;
+        const int rnd = cr.draw(0, hi - 1);
+        const int col = std::min((size_t)cr.scores[rnd].first, (size_t)aln->length() - 1);
+        g1.clear(); g2.clear();
+        for (int i = 0; i < aln->count(); ++i) (aln->rows[i][col] == '-' ? g1 : g2).push_back(i);
+        if (g1.empty() || g2.empty()) continue;
+        extract_subset(*aln, g1, one);
+        extract_subset(*aln, g2, two);
+        std::unique_ptr<Profile> cand(new Profile());
+        const int rc = align_profiles(one, two, weights, prov, *cand);
+        if (rc < 0) { err = "profile posterior failed"; return rc; }
+        if (aln->length() >= cand->length()) aln = std::move(cand);
+    }
+    out = std::move(*aln);
+    return 0;
+}
+
+}  // namespace qptail
+
+extern "C" int mlp_qp_finish_alignment_host(int n, const int32_t* len, const uint8_t* residues, const float* weights,
+                                            const int32_t* left, const int32_t* right, const int64_t* rp_off, const int64_t* nz_off,
+                                            const int32_t* rp_pool, const void* cells, int ref_iters, uint32_t ref_seed,
+                                            char** rows_out, int32_t* aln_len) {
+    if (!len || !residues || !rows_out || !aln_len) return MLP_E_ARG;
+    if (n > 1 && (!weights || !left || !right || !rp_off || !nz_off || !rp_pool || !cells)) return MLP_E_ARG;
+    qptail::HostCsrView v{n, len, rp_off, nz_off, rp_pool, cells};
+    std::unique_ptr<qptail::ProfilePosterior> prov(qptail::make_host_provider(v));
+    qptail::TailOptions opt;
+    opt.ref_iters = ref_iters;
+    opt.ref_seed = ref_seed;
+    qptail::Profile out;
+    std::string err;
+    const int rc = qptail::run_tail(n, len, residues, weights, left, right, *prov, opt, out, err);
+    if (rc < 0) return rc;
+    const int L = out.length();
+    char* buf = (char*)std::malloc((size_t)n * (size_t)std::max(L, 1));
+    if (!buf) return MLP_E_NOMEM;
+    for (int i = 0; i < n; ++i) std::memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+    *rows_out = buf;
+    *aln_len = L;
+    return MLP_OK;
+}
+
+extern "C" void mlp_free_host(void* p) { std::free(p); }

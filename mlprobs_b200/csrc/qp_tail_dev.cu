@@ -1,0 +1,379 @@
+// QuickProbs flavour, device side of the tail: the profile-profile posterior (weighted sum of the pairwise sparse
+// posteriors of two aligned groups, ParallelProbabilisticModel::buildPosterior ParallelProbabilisticModel.cpp:301-444)
+// computed from the sparse set that is already resident in HBM, so the set never travels to the host.
+//
+// Exactness: every dense cell receives its contributions in the reference's order (group-1 sequence major, group-2
+// sequence minor) with separate FP32 multiply and add.  A pair contributes at most once to a cell, so all cells of one
+// pair are applied concurrently and successive pairs are applied one after the other.
+//
+// Kernel layout: one CTA per row of the dense matrix (= one column of group 1's alignment).  All 256 threads gather:
+// thread t takes pair (i, j0+t), follows rp_off/nz_off -> row pointers -> cells -> column mapping and stages
+// (dense column, w*v) records in shared memory; warp 0 then applies the staged pairs in order to the row accumulator
+// kept in shared memory.  HBM traffic is one read of the sparse rows involved (8 B/cell) plus the dense row written once.
+#include "ctx.h"
+#include "qp_tail.h"
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+namespace {
+
+constexpr int PP_THREADS = 256;
+constexpr int PP_CAP = 8;            // staged cells per pair; longer sparse rows take the in-place path
+
+struct PPArgs {
+    const int* invA;                 // [nA][l1+1]    residue index of group-1 sequence i at alignment column r (0 = gap)
+    const int* mapB;                 // [nB][ldB]     alignment column of residue k of group-2 sequence j
+    const int* idsA; const int* idsB;
+    const double* wA; const double* wB;
+    double total;
+    int nA, nB, l1, l2, ldB, n;
+    const long long* rp_off; const long long* nz_off; const int* rp_pool; const int2* cells;
+    float* dense;                    // (l1+1) x (l2+1)
+};
+
+__global__ void __launch_bounds__(PP_THREADS) k_profile_posterior(PPArgs a) {
+    extern __shared__ float sm[];
+    float* acc = sm;                                              // l2+1 floats (rounded up to a multiple of 4)
+    const int accn = (a.l2 + 1 + 3) & ~3;
+    int* st_c = (int*)(sm + accn);                                // [PP_THREADS][PP_CAP]
+    float* st_x = (float*)(st_c + PP_THREADS * PP_CAP);
+    int* s_cnt = (int*)(st_x + PP_THREADS * PP_CAP);
+    float* s_w = (float*)(s_cnt + PP_THREADS);
+    long long* s_base = (long long*)(s_w + PP_THREADS);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x;                                     // dense row, row 0 stays zero
+    int* s_ii = (int*)(s_base + PP_THREADS);                      // nA ints: this row's residue index in every group-1 sequence
+    for (int c = tid; c <= a.l2; c += PP_THREADS) acc[c] = 0.0f;
+    for (int i = tid; i < a.nA; i += PP_THREADS) s_ii[i] = a.invA[(size_t)i * (a.l1 + 1) + r];
+    __syncthreads();
+    if (r > 0) {
+        for (int i = 0; i < a.nA; ++i) {
+            const int ii = s_ii[i];
+            if (ii == 0) continue;                                // CTA-uniform
+            const int sa = a.idsA[i];
+            const double wa = a.wA[i];
+            for (int j0 = 0; j0 < a.nB; j0 += PP_THREADS) {
+                const int j = j0 + tid;
+                int cnt = 0;
+                if (j < a.nB) {
+                    const long long slot = (long long)sa * a.n + a.idsB[j];
+                    const long long rpo = a.rp_off[slot];
+                    const int s = a.rp_pool[rpo + ii], e = a.rp_pool[rpo + ii + 1];
+                    const long long base = a.nz_off[slot] + s;
+                    const float w = (float)((wa * a.wB[j]) / a.total);
+                    cnt = e - s;
+                    const int* mb = a.mapB + (size_t)j * a.ldB;
+                    const int m = cnt < PP_CAP ? cnt : PP_CAP;
+                    for (int k = 0; k < m; ++k) {
+                        const int2 cell = a.cells[base + k];
+                        st_c[tid * PP_CAP + k] = mb[cell.x];
+                        st_x[tid * PP_CAP + k] = __fmul_rn(w, __int_as_float(cell.y));
+                    }
+                    s_w[tid] = w;
+                    s_base[tid] = base;
+                }
+                s_cnt[tid] = cnt;
+                __syncthreads();
+                if (warp == 0) {
+                    const int np = min(PP_THREADS, a.nB - j0);
+                    for (int t = 0; t < np; ++t) {
+                        const int ct = s_cnt[t];
+                        if (lane < ct && lane < PP_CAP) {
+                            const int c = st_c[t * PP_CAP + lane];
+                            acc[c] = __fadd_rn(acc[c], st_x[t * PP_CAP + lane]);
+                        }
+                        if (ct > PP_CAP) {                        // long sparse row: remaining cells straight from HBM
+                            const int* mb = a.mapB + (size_t)(j0 + t) * a.ldB;
+                            for (int k = PP_CAP + lane; k < ct; k += 32) {
+                                const int2 cell = a.cells[s_base[t] + k];
+                                const int c = mb[cell.x];
+                                acc[c] = __fadd_rn(acc[c], __fmul_rn(s_w[t], __int_as_float(cell.y)));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    float* out = a.dense + (size_t)r * (a.l2 + 1);
+    for (int c = tid; c <= a.l2; c += PP_THREADS) out[c] = acc[c];
+}
+
+
+// MEA dynamic programme over the dense profile posterior (ProbabilisticModel::computeAlignment ProbabilisticModel.cpp:345-421)
+// as a skewed wavefront inside ONE CTA: thread t owns C consecutive columns and is one row behind thread t-1, so the value
+// it needs from its left neighbour was produced one step earlier.  Scores are exact (each cell is the reference's own
+// max-of-three with its tie order), the 2-bit choices go to HBM and the host walks them back.
+constexpr int MEA_MAXC = 8;
+struct MeaArgs {
+    const float* dense; int l1, l2, C, T, B;
+    unsigned char* tb;                 // [(l1)][T][B] 2-bit choices (0 = diagonal, 1 = left, 2 = up), rows 1..l1
+};
+
+__global__ void __launch_bounds__(1024) k_mea_wavefront(MeaArgs a) {
+    extern __shared__ float sm[];
+    float* row = sm;                                              // T*C floats
+    float2* edge = (float2*)(sm + (size_t)a.T * a.C);             // [2][T]
+    const int t = threadIdx.x, C = a.C, j0 = t * C;
+    const int W = a.l2 + 1;
+    for (int c = 0; c < C; ++c) row[j0 + c] = 0.0f;
+    edge[t] = make_float2(0.0f, 0.0f);
+    edge[a.T + t] = make_float2(0.0f, 0.0f);
+    float pf[MEA_MAXC];
+#pragma unroll
+    for (int c = 0; c < MEA_MAXC; ++c) pf[c] = 0.0f;
+    if (t == 0 && a.l1 >= 1) {
+#pragma unroll
+        for (int c = 0; c < MEA_MAXC; ++c) if (c < C && j0 + c < W) pf[c] = a.dense[(size_t)W + j0 + c];
+    }
+    __syncthreads();
+    const int steps = a.l1 + a.T - 1;
+    for (int s = 0; s < steps; ++s) {
+        const int i = s - t + 1;
+        float nx[MEA_MAXC];
+#pragma unroll
+        for (int c = 0; c < MEA_MAXC; ++c) nx[c] = 0.0f;
+        if (i + 1 >= 1 && i + 1 <= a.l1) {
+            const float* p = a.dense + (size_t)(i + 1) * W + j0;
+#pragma unroll
+            for (int c = 0; c < MEA_MAXC; ++c) if (c < C && j0 + c < W) nx[c] = p[c];
+        }
+        if (i >= 1 && i <= a.l1 && j0 < W) {
+            float d = 0.0f, l = 0.0f;
+            if (t > 0) { const float2 e = edge[((s + 1) & 1) * a.T + t - 1]; d = e.x; l = e.y; }
+            unsigned bits = 0;
+            float o = 0.0f, v = 0.0f;
+#pragma unroll
+            for (int c = 0; c < MEA_MAXC; ++c) {
+                if (c < C && j0 + c < W) {
+                    const int j = j0 + c;
+                    o = row[j];
+                    if (j == 0) v = 0.0f;
+                    else {
+                        const float x1 = __fadd_rn(pf[c], d);
+                        unsigned dir;
+                        if (x1 >= l) { if (x1 >= o) { v = x1; dir = 0; } else { v = o; dir = 2; } }
+                        else if (l >= o) { v = l; dir = 1; }
+                        else { v = o; dir = 2; }
+                        bits |= dir << (2 * c);
+                    }
+                    d = o; l = v; row[j] = v;
+                }
+            }
+            edge[(s & 1) * a.T + t] = make_float2(o, v);
+            unsigned char* q = a.tb + ((size_t)(i - 1) * a.T + t) * a.B;
+            q[0] = (unsigned char)(bits & 0xff);
+            if (a.B > 1) q[1] = (unsigned char)(bits >> 8);
+        }
+#pragma unroll
+        for (int c = 0; c < MEA_MAXC; ++c) pf[c] = nx[c];
+        __syncthreads();
+    }
+}
+
+size_t pp_smem_bytes(int l2, int nA) {
+    const size_t accn = ((size_t)l2 + 1 + 3) & ~(size_t)3;
+    return accn * 4 + (size_t)PP_THREADS * PP_CAP * 8 + (size_t)PP_THREADS * (4 + 4 + 8) + (size_t)nA * 4;
+}
+
+class DeviceProfilePosterior : public qptail::ProfilePosterior {
+public:
+    explicit DeviceProfilePosterior(mlp_ctx* c) : ctx(c) {}
+    ~DeviceProfilePosterior() override {
+        if (d_blob) cudaFree(d_blob);
+        if (h_blob) cudaFreeHost(h_blob);
+        if (d_dense) cudaFree(d_dense);
+        if (h_dense) cudaFreeHost(h_dense);
+        if (d_tb) cudaFree(d_tb);
+        if (h_tb) cudaFreeHost(h_tb);
+    }
+    int launch_profile(const qptail::Profile& A, const qptail::Profile& B, const float* weights) {
+        const int nA = A.count(), nB = B.count(), l1 = A.length(), l2 = B.length();
+        int ldB = 1;
+        for (int j = 0; j < nB; ++j) ldB = std::max(ldB, ctx->len[B.ids[j]] + 1);
+        // blob layout: doubles first, then ints
+        const size_t n_dbl = (size_t)nA + nB;
+        const size_t n_inv = (size_t)(l1 + 1) * nA, n_map = (size_t)nB * ldB;
+        const size_t bytes = n_dbl * 8 + (n_inv + n_map + nA + nB) * 4;
+        if (bytes > blob_cap) {
+            if (d_blob) cudaFree(d_blob);
+            if (h_blob) cudaFreeHost(h_blob);
+            d_blob = nullptr; h_blob = nullptr;
+            blob_cap = bytes + bytes / 2;
+            CK(cudaMalloc(&d_blob, blob_cap));
+            CK(cudaHostAlloc(&h_blob, blob_cap, cudaHostAllocDefault));
+        }
+        const size_t dn = (size_t)(l1 + 1) * (l2 + 1);
+        if (dn > dense_cap) {
+            if (d_dense) cudaFree(d_dense);
+            if (h_dense) cudaFreeHost(h_dense);
+            d_dense = nullptr; h_dense = nullptr;
+            dense_cap = dn + dn / 2;
+            CK(cudaMalloc(&d_dense, dense_cap * 4));
+            CK(cudaHostAlloc(&h_dense, dense_cap * 4, cudaHostAllocDefault));
+        }
+        double* wA = (double*)h_blob;
+        double* wB = wA + nA;
+        int* invA = (int*)(wB + nB);
+        int* mapB = invA + n_inv;
+        int* idsA = mapB + n_map;
+        int* idsB = idsA + nA;
+        double total = 0;                                         // finalSelectivity = FLT_MAX: every pair counts
+        for (int i = 0; i < nA; ++i) { const double w1 = weights[A.ids[i]]; for (int j = 0; j < nB; ++j) total += w1 * (double)weights[B.ids[j]]; }
+        for (int i = 0; i < nA; ++i) { wA[i] = weights[A.ids[i]]; idsA[i] = A.ids[i]; }
+        for (int j = 0; j < nB; ++j) { wB[j] = weights[B.ids[j]]; idsB[j] = B.ids[j]; }
+        for (int i = 0; i < nA; ++i) {                            // [i][column], row-major: sequential writes
+            const char* row = A.rows[i].data();
+            int* dst = invA + (size_t)i * (l1 + 1);
+            int k = 0;
+            dst[0] = 0;
+            for (int c = 0; c < l1; ++c) dst[c + 1] = (row[c] != '-') ? ++k : 0;
+        }
+        for (int j = 0; j < nB; ++j) {
+            const std::string& row = B.rows[j];
+            int* m = mapB + (size_t)j * ldB;
+            int k = 0;
+            m[0] = 0;
+            for (int c = 0; c < l2; ++c) if (row[c] != '-') m[++k] = c + 1;
+        }
+        const size_t smem = pp_smem_bytes(l2, nA);
+        if (smem > 200 * 1024) { ctx->err = "profile too long for the row accumulator"; return MLP_E_UNSUPPORTED; }
+        if (smem > smem_set) {
+            CK(cudaFuncSetAttribute(k_profile_posterior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        CK(cudaMemcpyAsync(d_blob, h_blob, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        PPArgs a;
+        a.wA = (const double*)d_blob; a.wB = a.wA + nA;
+        a.invA = (const int*)(a.wB + nB); a.mapB = a.invA + n_inv; a.idsA = a.mapB + n_map; a.idsB = a.idsA + nA;
+        a.total = total; a.nA = nA; a.nB = nB; a.l1 = l1; a.l2 = l2; a.ldB = ldB; a.n = ctx->n;
+        const CsrSetDev& S = ctx->set[ctx->cur];
+        a.rp_off = ctx->d_rp_off; a.nz_off = S.nz_off; a.rp_pool = S.rp_pool; a.cells = S.cells;
+        a.dense = d_dense;
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        k_profile_posterior<<<l1 + 1, PP_THREADS, smem, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ctx->stats.launches += 1;
+        ctx->stats.h2d_bytes += (int64_t)bytes;
+        ctx->stats.pairs += (int64_t)nA * nB;
+        return 0;
+    }
+
+    int finish_timing() {
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        ctx->stats.ms_total += ms;
+        return 0;
+    }
+
+    int build(const qptail::Profile& A, const qptail::Profile& B, const float* weights, const float** out) override {
+        int rc = launch_profile(A, B, weights);
+        if (rc < 0) return rc;
+        const size_t dn = (size_t)(A.length() + 1) * (B.length() + 1);
+        CK(cudaMemcpyAsync(h_dense, d_dense, dn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        rc = finish_timing();
+        if (rc < 0) return rc;
+        ctx->stats.d2h_bytes += (int64_t)dn * 4;
+        *out = h_dense;
+        return 0;
+    }
+
+    // profile posterior + MEA wavefront on the device, 2-bit choices back to the host, traceback there
+    int build_and_align(const qptail::Profile& A, const qptail::Profile& B, const float* weights, std::string& path) override {
+        const int l1 = A.length(), l2 = B.length();
+        const int W = l2 + 1;
+        if (W > 1024 * MEA_MAXC || l1 < 1 || l2 < 1) return 1;    // very wide profile: host dynamic programme on the dense matrix
+        int T = std::min(1024, ((W + 3) / 4 + 31) / 32 * 32);
+        const int C = (W + T - 1) / T;
+        const int Bb = (C + 3) / 4;
+        const size_t smem = ((size_t)T * C + 4 * (size_t)T) * 4;
+        if (smem > 200 * 1024) return 1;
+        int rc = launch_profile(A, B, weights);
+        if (rc < 0) return rc;
+        const size_t tbn = (size_t)l1 * T * Bb;
+        if (tbn > tb_cap) {
+            if (d_tb) cudaFree(d_tb);
+            if (h_tb) cudaFreeHost(h_tb);
+            d_tb = nullptr; h_tb = nullptr;
+            tb_cap = tbn + tbn / 2;
+            CK(cudaMalloc(&d_tb, tb_cap));
+            CK(cudaHostAlloc(&h_tb, tb_cap, cudaHostAllocDefault));
+        }
+        if (smem > mea_smem_set) {
+            CK(cudaFuncSetAttribute(k_mea_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mea_smem_set = smem;
+        }
+        MeaArgs m;
+        m.dense = d_dense; m.l1 = l1; m.l2 = l2; m.C = C; m.T = T; m.B = Bb; m.tb = d_tb;
+        k_mea_wavefront<<<1, T, smem, ctx->stream>>>(m);
+        CK(cudaGetLastError());
+        ctx->stats.launches += 1;
+        CK(cudaMemcpyAsync(h_tb, d_tb, tbn, cudaMemcpyDeviceToHost, ctx->stream));
+        rc = finish_timing();
+        if (rc < 0) return rc;
+        ctx->stats.d2h_bytes += (int64_t)tbn;
+        path.clear();
+        path.reserve((size_t)l1 + l2);
+        int r = l1, c = l2;
+        while (r != 0 || c != 0) {
+            int dir;
+            if (r == 0) dir = 1;
+            else if (c == 0) dir = 2;
+            else {
+                const int t = c / C, k = c - t * C;
+                dir = (h_tb[((size_t)(r - 1) * T + t) * Bb + (k >> 2)] >> ((k & 3) * 2)) & 3;
+            }
+            if (dir == 1) { --c; path.push_back('Y'); }
+            else if (dir == 2) { --r; path.push_back('X'); }
+            else { --c; --r; path.push_back('B'); }
+        }
+        std::reverse(path.begin(), path.end());
+        return 0;
+    }
+
+private:
+    mlp_ctx* ctx;
+    void* d_blob = nullptr; void* h_blob = nullptr; size_t blob_cap = 0;
+    float* d_dense = nullptr; float* h_dense = nullptr; size_t dense_cap = 0;
+    size_t smem_set = 48 * 1024, mea_smem_set = 48 * 1024;
+    unsigned char* d_tb = nullptr; unsigned char* h_tb = nullptr; size_t tb_cap = 0;
+};
+
+}  // namespace
+
+extern "C" int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const int32_t* left, const int32_t* right,
+                                       int ref_iters, uint32_t ref_seed, char** rows_out, int32_t* aln_len) {
+    if (!ctx) return MLP_E_ARG;
+    if (!rows_out || !aln_len) { ctx->err = "null output"; return MLP_E_ARG; }
+    if (ctx->n < 1) { ctx->err = "no sequences"; return MLP_E_STATE; }
+    if (ctx->n > 1) {
+        if (!weights || !left || !right) { ctx->err = "weights and tree required"; return MLP_E_ARG; }
+        if (!ctx->have_sets || ctx->flavour_of_set != MLP_QP) { ctx->err = "no QuickProbs sparse set on the device"; return MLP_E_STATE; }
+        if (ctx->world > 1 && !ctx->nccl_comm) { ctx->err = "sharded set: call mlp_exchange first"; return MLP_E_STATE; }
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->stats = mlp_stage_stats{};
+    std::vector<uint8_t> letters(ctx->codes_h.size());
+    for (size_t k = 0; k < letters.size(); ++k) letters[k] = (uint8_t)('A' + ctx->codes_h[k]);
+    std::vector<int32_t> len(ctx->len.begin(), ctx->len.end());
+    DeviceProfilePosterior prov(ctx);
+    qptail::TailOptions opt;
+    opt.ref_iters = ref_iters;
+    opt.ref_seed = ref_seed;
+    qptail::Profile out;
+    std::string err;
+    const int rc = qptail::run_tail(ctx->n, len.data(), letters.data(), weights, left, right, prov, opt, out, err);
+    if (rc < 0) { if (ctx->err.empty() || rc != MLP_E_CUDA) ctx->err = err; return rc; }
+    const int L = out.length();
+    char* buf = (char*)malloc((size_t)ctx->n * (size_t)std::max(L, 1));
+    if (!buf) { ctx->err = "out of host memory"; return MLP_E_NOMEM; }
+    for (int i = 0; i < ctx->n; ++i) memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+    *rows_out = buf;
+    *aln_len = L;
+    return MLP_OK;
+}

@@ -69,6 +69,16 @@ def run_cpnp(name, fasta, full, dense, pid=None, p1=False, reps=2):
     print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def read_rows(path):
+    """FASTA alignment -> (n, columns) uint8 matrix"""
+    rows = []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"): rows.append("")
+        elif line: rows[-1] += line
+    return np.frombuffer("".join(rows).encode(), np.uint8).reshape(len(rows), -1).copy()
+
+
 def run_qp(name, fasta, full, dense):
     with tempfile.TemporaryDirectory() as td:
         dump = os.path.join(td, "d.bin")
@@ -76,7 +86,13 @@ def run_qp(name, fasta, full, dense):
         if not dense: cmd += ["--nodense"]
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
         d = read_dump(dump)
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(d, ["s0", "t0", "sF", "tF"], full, dense))
+        # the reference's final alignment (ConstructionStage + ColumnRefinement) and the one before refinement
+        msa = os.path.join(td, "msa.fa")
+        subprocess.check_call([QP, "msa", fasta, msa, "--threads", "8"], stdout=subprocess.DEVNULL)
+        extra = {"msa": read_rows(msa), "msa_construct": read_rows(msa + ".construct")}
+    out = pack(d, ["s0", "t0", "sF", "tF"], full, dense)
+    out.update(extra)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <iostream>
+#include <fstream>
 #include <memory>
 #include <chrono>
 #include <cstdio>
@@ -16,6 +17,8 @@
 #include "Alignment/Alignment.h"
 #include "Alignment/Multiple/PosteriorStage.h"
 #include "Alignment/Multiple/ConsistencyStage.h"
+#include "Alignment/Multiple/ConstructionStage.h"
+#include "Alignment/Multiple/ColumnRefinement.h"
 #include "Alignment/Multiple/ClusterTree.h"
 #include "Alignment/Multiple/PartitionFunction.h"
 #include "Alignment/Multiple/ExpPartitionFunctionParams.h"
@@ -49,15 +52,16 @@ static void dump_sparse(DumpWriter& w, const std::string& tag, const SparseMatri
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: ref_qp dump|bench <fasta> [out.bin] [--threads T] [--nodense] [--iters K]\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: ref_qp dump|bench|msa <fasta> [out.bin|out.fasta] [--threads T] [--nodense] [--iters K] [--ref-count R]\n"); return 2; }
     std::string mode = argv[1], fasta = argv[2], out;
-    int ai = 3, threads = 1, dense = 1, iters = -1;
-    if (mode == "dump") { out = argv[3]; ai = 4; }
+    int ai = 3, threads = 1, dense = 1, iters = -1, refcount = -1;
+    if (mode == "dump" || mode == "msa") { out = argv[3]; ai = 4; }
     for (; ai < argc; ai++) {
         std::string a = argv[ai];
         if (a == "--threads") threads = atoi(argv[++ai]);
         else if (a == "--nodense") dense = 0;
         else if (a == "--iters") iters = atoi(argv[++ai]);
+        else if (a == "--ref-count") refcount = atoi(argv[++ai]);
     }
     // same configuration path as Console/main.cpp:30-46
     auto config = std::shared_ptr<Configuration>(new Configuration());
@@ -67,6 +71,7 @@ int main(int argc, char** argv) {
     config->optimisation.useDoublePartition = true;
     if (config->hardware.numThreads <= 0) config->hardware.numThreads = omp_get_num_procs();
     if (iters >= 0) config->algorithm.consistency.itertions = iters;
+    if (refcount >= 0) config->algorithm.refinement.iterations = refcount;
 
     MultiSequence* sequences = new MultiSequence();
     sequences->LoadMFA(fasta, true);
@@ -150,6 +155,29 @@ int main(int argc, char** argv) {
             dump_sparse(*w, t + ".tF", sparse[b][a]);
         }
         delete w;
+    }
+    if (mode == "msa") {
+        // ExtendedMSA.cpp:235-252: final weights, thread count of the model, construction then refinement
+        auto fw = tree.getWeights();
+        for (float& x : fw) x = std::max(x, config->algorithm.finalSaturation);
+        auto model = ps.getModel();
+        model->setNumThreads(std::max(std::min(config->hardware.numThreads / 2, 8), 1));
+        omp_set_num_threads(model->getNumThreads());
+        auto constructor = std::shared_ptr<ConstructionStage>(new ConstructionStage(config));
+        ColumnRefinement refiner(config, constructor);
+        t1 = now_s();
+        auto alignment = (*constructor)(fw.data(), cd, &tree, *sequences, sparse, *model);
+        double t_build = now_s() - t1;
+        {
+            std::ofstream f0((out + ".construct").c_str(), std::ios::binary);
+            alignment->WriteMFA(f0);
+        }
+        t1 = now_s();
+        alignment = refiner(tree, fw.data(), cd, sparse, *model, std::move(alignment));
+        double t_ref = now_s() - t1;
+        std::ofstream f(out.c_str(), std::ios::binary);
+        alignment->WriteMFA(f);
+        printf("{\"tool\": \"ref_qp\", \"mode\": \"msa\", \"t_construct_s\": %.6f, \"t_refine_s\": %.6f}\n", t_build, t_ref);
     }
     printf("{\"tool\": \"ref_qp\", \"n\": %d, \"pairs\": %d, \"threads\": %d, \"cells\": %.0f, \"models\": 2, "
            "\"t_posterior_s\": %.6f, \"t_tree_s\": %.6f, \"t_relax_s\": %.6f, \"reps\": %d}\n",

@@ -50,3 +50,15 @@ def assert_digest(d, tag, getter, n, transposed=False):
 def cpnp_mask(pid):
     pid = int(pid) % 10
     return 7 if pid <= 1 else (4 if pid == 2 else 2)
+
+
+def tail_from_csrset(S, seqs, distances, ref_iters=-1):
+    """QuickProbs tail on the host (mlp_qp_finish_alignment_host) from an oracle_lib.CsrSet: tree from `distances`
+    (before the in-place update), final weights saturated at 1e-6 (ExtendedMSA.cpp:237-238)."""
+    import mlprobs_b200 as M
+    t = M.qp_guide_tree_ex(distances)
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    cells = np.zeros(len(S.col), dtype=[("c", np.int32), ("v", np.float32)])
+    cells["c"] = S.col
+    cells["v"] = S.val
+    return M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], S.rp_off, S.nz_off, S.rowptr, cells, ref_iters)

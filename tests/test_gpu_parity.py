@@ -39,6 +39,40 @@ def test_qp_against_reference_fixture(name):
         eng.relax(M.QP, w, sd, 200.0, 3.0, cutoff)
     assert_digest(d, "sF", eng.csr, n)
     assert_digest(d, "tF", eng.csr, n, transposed=True)
+    # the tail on the device-resident set: progressive construction, then column refinement (reference alignments)
+    t = M.qp_guide_tree_ex(d["distances"])
+    np.testing.assert_array_equal(t["weights"], M.qp_guide_tree(d["distances"])[0])
+    for key, ref_iters in (("msa_construct", -2), ("msa", -1)):
+        rows = eng.qp_finish_alignment(w, t["left"], t["right"], ref_iters)
+        assert rows == [r.tobytes() for r in d[key]], key
+    st = eng.stats()
+    assert st["launches"] >= n - 1 and st["ms_total"] > 0
+    # the host tail over the read-back pooled set gives the same alignment
+    raw = eng.csr_raw()
+    rows_h = M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], raw.rp_off, raw.nz_off, raw.rp_pool, raw.cells)
+    assert rows_h == rows
+    raw.close()
+    eng.close()
+
+
+def test_qp_tail_long_rows_and_wide_profiles_vs_host():
+    """Device profile posterior vs the host provider on a diffuse family (sparse rows longer than the staging cap)."""
+    seqs = synth.family(24, 180, seed=77, p_sub=0.7)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    t = M.qp_guide_tree_ex(eng.distances())
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, 0.01)
+    eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, float(np.float32(1e-5)))
+    raw = eng.csr_raw()
+    rp = raw.rp_pool[:raw.rp_total]
+    assert int(np.max(np.diff(rp.astype(np.int64)))) > 8            # at least one sparse row beyond the staged 8 cells
+    dev = eng.qp_finish_alignment(w, t["left"], t["right"], 12, 7)
+    host = M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], raw.rp_off, raw.nz_off, raw.rp_pool, raw.cells, 12, 7)
+    assert dev == host
+    for r, s in zip(dev, seqs):
+        assert r.replace(b"-", b"") == s
+    raw.close()
     eng.close()
 
 

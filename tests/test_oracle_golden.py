@@ -120,6 +120,11 @@ def test_qp_stage_and_consistency(name):
         S = O.relax_qp(S, d["weights"], d["seldist"], cutoff, 200.0, sw, threads=8)
     assert_digest(d, "sF", S.get, n)
     assert_digest(d, "tF", S.get, n, transposed=True)
+    # the host tail (product code, no GPU) fed with this sparse set reproduces the reference's alignments byte for byte
+    from common import tail_from_csrset
+    for key, iters_ref in (("msa_construct", -2), ("msa", -1)):
+        rows = tail_from_csrset(S, seqs, d["distances"], iters_ref)
+        assert rows == [r.tobytes() for r in d[key]], key
 
 
 def test_full_fixture_matches_digest():

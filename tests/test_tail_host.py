@@ -1,0 +1,73 @@
+"""QuickProbs tail (progressive construction + column refinement) on the host, fed with the REFERENCE's own final sparse
+matrices from the full fixtures: checks mlp_qp_guide_tree_ex + mlp_qp_finish_alignment_host against the reference's
+alignments with nothing of the oracle in between (ConstructionStage.cpp:51-127, ColumnRefinement.cpp, RefinementBase.cpp)."""
+import numpy as np
+import pytest
+import mlprobs_b200 as M
+from common import load_golden, split_seqs, pairs
+
+
+def pooled_from_fixture(d, n, lens):
+    rp_off = np.zeros(n * n, np.int64); nz_off = np.zeros(n * n, np.int64)
+    rps, cols, vals = [], [], []
+    rp_at = 0; nz_at = 0
+    for a in range(n):
+        for b in range(n):
+            if a == b:
+                continue
+            tag = "pair.%d.%d.sF" % (a, b) if a < b else "pair.%d.%d.tF" % (b, a)
+            rp = d[tag + ".rowptr"].astype(np.int32); c = d[tag + ".col"].astype(np.int32); v = d[tag + ".val"].astype(np.float32)
+            assert len(rp) == lens[a] + 2
+            rp_off[a * n + b] = rp_at; nz_off[a * n + b] = nz_at
+            rps.append(rp); cols.append(c); vals.append(v)
+            rp_at += len(rp); nz_at += len(c)
+    cells = np.zeros(nz_at, dtype=[("c", np.int32), ("v", np.float32)])
+    cells["c"] = np.concatenate(cols); cells["v"] = np.concatenate(vals)
+    return rp_off, nz_off, np.concatenate(rps), cells
+
+
+@pytest.mark.parametrize("name", ["qp_sup139", "qp_sup002"])
+def test_tail_from_reference_matrices(name):
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    lens = [len(s) for s in seqs]
+    t = M.qp_guide_tree_ex(d["distances"])
+    np.testing.assert_array_equal(t["weights"], np.asarray(d["weights"]) if np.all(d["weights"] > 1e-6) else t["weights"])
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    rp_off, nz_off, rp_pool, cells = pooled_from_fixture(d, n, lens)
+    for key, it in (("msa_construct", -2), ("msa", -1)):
+        rows = M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], rp_off, nz_off, rp_pool, cells, it)
+        assert rows == [r.tobytes() for r in d[key]], key
+        for r, s in zip(rows, seqs):
+            assert r.replace(b"-", b"") == s
+
+
+def test_tree_children_are_consistent_with_parents():
+    d = load_golden("qp_sup002")
+    t = M.qp_guide_tree_ex(d["distances"])
+    n = len(d["lens"])
+    par, left, right = t["parent"], t["left"], t["right"]
+    assert par[2 * n - 2] == -1 and np.all(left[:n] == -1) and np.all(right[:n] == -1)
+    for v in range(n, 2 * n - 1):
+        assert par[left[v]] == v and par[right[v]] == v and left[v] < v and right[v] < v and left[v] != right[v]
+    w2, sd2, par2, _ = M.qp_guide_tree(d["distances"])
+    np.testing.assert_array_equal(par2, par); np.testing.assert_array_equal(w2, t["weights"])
+
+
+def test_single_sequence_and_refinement_options():
+    rows = M.qp_finish_alignment_host([b"ACDEFG"], None, None, None, None, None, None, None)
+    assert rows == [b"ACDEFG"]
+    d = load_golden("qp_sup139")
+    seqs = split_seqs(d); n = len(seqs)
+    t = M.qp_guide_tree_ex(d["distances"])
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    rp_off, nz_off, rp_pool, cells = pooled_from_fixture(d, n, [len(s) for s in seqs])
+    a = M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], rp_off, nz_off, rp_pool, cells, 5, 0)
+    b = M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], rp_off, nz_off, rp_pool, cells, 5, 12345)
+    for rows in (a, b):
+        assert len({len(r) for r in rows}) == 1
+        for r, s in zip(rows, seqs):
+            assert r.replace(b"-", b"") == s
+    # `-r 0` means "reference default" there (RefinementBase.cpp:33): same result as -1
+    assert M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], rp_off, nz_off, rp_pool, cells, 0) == \
+        [r.tobytes() for r in d["msa"]]
