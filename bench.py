@@ -132,7 +132,8 @@ def one_step(eng, M, n, e2e, seqs=None, world=1, read_back=True, host_out=None):
             eng.exchange(); stats.append(("exchange", eng.stats()))
     out = None
     if e2e and read_back:
-        out = eng.csr_raw(host_out)                   # device -> host read of the step's result into (pinned) host buffers
+        out = eng.csr_packed(host_out)                # device -> host read of the step's result (QuickProbs' own packed cell
+                                                      # format, PackedSparseMatrix) into caller-owned page-locked buffers
     return stats, out
 
 
@@ -205,7 +206,9 @@ def main():
     host_out = None
     if rank == 0:   # caller-owned page-locked result buffers, allocated once outside the timed region
         lay = eng.csr_layout()
-        host_out = M.PinnedCsrBuffers(n, lay[1], int(lay[2] * 1.05))
+        host_out = M.PinnedPackedBuffers(n, lay[1], int(lay[2] * 1.05))
+    for _ in range(min(args.warmup, 2)):   # untimed: first use of the host->device / read-back path (allocations, page-locking)
+        one_step(eng, M, n, True, seqs, world=world, read_back=(rank == 0), host_out=host_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

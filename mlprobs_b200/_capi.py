@@ -23,7 +23,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs", "mlp_csr_layout", "mlp_get_csr_raw",
            "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
-           "mlp_free_host"]
+           "mlp_free_host", "mlp_get_csr_packed"]
 
 
 class HmmTables(C.Structure):
@@ -82,6 +82,8 @@ def load():
         lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_csr_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.mlp_get_csr_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_get_csr_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_qp_guide_tree_ex.argtypes = [C.c_int] + [C.c_void_p] * 6
         lib.mlp_alloc_pinned.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
         lib.mlp_free_pinned.argtypes = [C.c_void_p]
         lib.mlp_free_pinned.restype = None
@@ -255,6 +257,35 @@ class PinnedCsrBuffers:
         self._ptrs = []
 
 
+class PinnedPackedBuffers(PinnedCsrBuffers):
+    """Page-locked host buffers for Engine.csr_packed: QuickProbs' own format (uint16 column | uint16 value code per cell,
+    uint16 row sizes) -- half the PCIe bytes of the {int32, float32} pool."""
+
+    def ensure(self, n, rp_total, cells):
+        if n != self.n:
+            self.nz_off = self._pinned(n * n * 8, np.int64, n * n)
+            self.nz_cnt = self._pinned(n * n * 4, np.int32, n * n)
+            self.n = n
+        if rp_total > self.cap_rp:
+            self.cap_rp = int(rp_total * 1.05) + 16
+            self.row_sizes = self._pinned(self.cap_rp * 2, np.uint16, self.cap_rp)
+        if cells > self.cap_cells:
+            self.cap_cells = int(cells * 1.1) + 1024
+            self.cells = self._pinned(self.cap_cells * 4, np.uint32, self.cap_cells)
+
+    def matrix(self, a, b, lens):
+        """(row_ptr, col, val) of ordered pair (a, b), decoded (value = code / 65535 in float32, SparseEntry.h:31-32)."""
+        s = a * self.n + b
+        sizes = self.row_sizes[self.rp_off[s]: self.rp_off[s] + int(lens[a]) + 2].astype(np.int32)
+        rp = np.zeros(int(lens[a]) + 2, np.int32)
+        rp[1:] = np.cumsum(sizes)[:-1]
+        c = self.cells[self.nz_off[s]: self.nz_off[s] + self.nz_cnt[s]]
+        return rp, (c >> 16).astype(np.int32), (c & 0xffff).astype(np.float32) / np.float32(65535.0)
+
+    def nbytes(self):
+        return self.n * self.n * 12 + self.rp_total * 2 + self.used * 4
+
+
 class Engine:
     """One GPU context (mlp_ctx)."""
 
@@ -384,6 +415,16 @@ class Engine:
         self._ck(self._lib.mlp_qp_finish_alignment(self._ctx, *[_ptr(k) for k in keep], int(ref_iters), int(ref_seed),
                                                    C.byref(rows_p), C.byref(alen)))
         return _take_rows(self.n, rows_p, alen)
+
+    def csr_packed(self, out=None):
+        """Pooled read-back in QuickProbs' packed cell format (QP flavour only). `out` = PinnedPackedBuffers to reuse."""
+        rp_off, rp_total, used = self.csr_layout()
+        if out is None:
+            out = PinnedPackedBuffers(self.n, rp_total, used)
+        out.ensure(self.n, rp_total, used)
+        self._ck(self._lib.mlp_get_csr_packed(self._ctx, _ptr(out.nz_off), _ptr(out.nz_cnt), _ptr(out.row_sizes), _ptr(out.cells)))
+        out.rp_off, out.rp_total, out.used = rp_off, rp_total, used
+        return out
 
     def total_cells(self):
         c = C.c_int64(0)

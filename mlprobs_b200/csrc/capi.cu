@@ -169,7 +169,10 @@ extern "C" int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, i
 extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* residues) {
     if (!ctx || n < 2 || !len || !residues) return MLP_E_ARG;
     cudaSetDevice(ctx->device);
-    release_sets(ctx);
+    // same family shape as before (same n and lengths): the pooled layout is unchanged, keep the device pools
+    const bool same_layout = ctx->have_sets && ctx->n == n && std::equal(len, len + n, ctx->len.begin());
+    if (!same_layout) release_sets(ctx);
+    ctx->flavour_of_set = -1;
     ctx->n = n;
     ctx->len.assign(len, len + n);
     ctx->seq_off.resize(n);
@@ -204,6 +207,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     ctx->rp_total = rp;
     ctx->rank = 0; ctx->world = 1;
     ctx->owned = ctx->all_pairs;
+    ctx->relax_tasks.clear();
     return MLP_OK;
 }
 
@@ -213,6 +217,7 @@ extern "C" int mlp_set_shard(mlp_ctx* ctx, int rank, int world) {
     ctx->owned.clear();
     for (size_t k = 0; k < ctx->all_pairs.size(); ++k)
         if ((int)(k % world) == rank) ctx->owned.push_back(ctx->all_pairs[k]);
+    ctx->relax_tasks.clear();
     return MLP_OK;
 }
 
@@ -229,11 +234,11 @@ static int ensure_sets(mlp_ctx* ctx) {
     CK(cudaMemcpy(ctx->d_rp_off, ctx->rp_off_h.data(), (size_t)n * n * sizeof(long long), cudaMemcpyHostToDevice));
     ctx->stats.h2d_bytes += (int64_t)n * n * 8;
     for (int s = 0; s < 2; ++s) {
-        CK(cudaMalloc(&ctx->set[s].rp_pool, (size_t)ctx->rp_total * sizeof(int)));
+        CK(cudaMalloc(&ctx->set[s].rp_pool, ((size_t)ctx->rp_total + 8) * sizeof(int)));     // +8: 16-byte aligned bulk copies may read past the end
         CK(cudaMalloc(&ctx->set[s].nz_off, (size_t)n * n * sizeof(long long)));
         CK(cudaMalloc(&ctx->set[s].nz_cnt, (size_t)n * n * sizeof(int)));
         const long long this_cap = (s == 0) ? cap : 1024;   // the relax output pool is sized when mlp_relax runs
-        CK(cudaMalloc(&ctx->set[s].cells, (size_t)this_cap * sizeof(int2)));
+        CK(cudaMalloc(&ctx->set[s].cells, ((size_t)this_cap + 4) * sizeof(int2)));
         CK(cudaMalloc(&ctx->set[s].cursor, sizeof(unsigned long long)));
         CK(cudaMemset(ctx->set[s].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int)));
         CK(cudaMemset(ctx->set[s].nz_off, 0, (size_t)n * n * sizeof(long long)));
@@ -251,7 +256,7 @@ static int ensure_sets(mlp_ctx* ctx) {
 // Re-allocate the cell pool of one set to new_cap cells, keeping the first `keep` cells.
 int grow_cells(mlp_ctx* ctx, int which, long long new_cap, unsigned long long keep) {
     int2* fresh = nullptr;
-    CK(cudaMalloc(&fresh, (size_t)new_cap * sizeof(int2)));
+    CK(cudaMalloc(&fresh, ((size_t)new_cap + 4) * sizeof(int2)));
     if (keep) CK(cudaMemcpy(fresh, ctx->set[which].cells, (size_t)keep * sizeof(int2), cudaMemcpyDeviceToDevice));
     cudaFree(ctx->set[which].cells);
     ctx->set[which].cells = fresh;
@@ -787,6 +792,63 @@ extern "C" int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, i
     return MLP_OK;
 }
 
+// QuickProbs' own cell format (PackedSparseMatrix: uint16 column, uint16 fixed-point value): half the bytes of {int32, float}.
+__global__ void k_pack_cells(const int2* __restrict__ cells, unsigned* __restrict__ out, long long ncell) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 2;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < ncell; i += stride) {
+        const int4 two = *reinterpret_cast<const int4*>(cells + i);           // cells + i is 16-byte aligned (i even); the pool has slack
+        const unsigned c0 = __float2uint_rn(__fmul_rn(__int_as_float(two.y), 65535.0f)), c1 = __float2uint_rn(__fmul_rn(__int_as_float(two.w), 65535.0f));
+        *reinterpret_cast<uint2*>(out + i) = make_uint2(((unsigned)two.x << 16) | (c0 & 0xffffu), ((unsigned)two.z << 16) | (c1 & 0xffffu));
+    }
+}
+// cumulative row pointers -> uint16 row sizes, same pooled positions (entry r = cells in row r; the last entry of a pair is 0)
+__global__ void k_row_sizes(const int* __restrict__ rp, unsigned short* __restrict__ out, long long total) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int d = (i + 1 < total) ? rp[i + 1] - rp[i] : 0;
+        out[i] = (unsigned short)(d > 0 ? d : 0);                            // negative = boundary to the next pair's block
+    }
+}
+
+extern "C" int mlp_get_csr_packed(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells) {
+    if (!ctx) return MLP_E_ARG;
+    if (!ctx->have_sets) return MLP_E_STATE;
+    if (ctx->flavour_of_set != MLP_QP) { ctx->err = "packed cells are the QuickProbs format (uint16 fixed-point values)"; return MLP_E_UNSUPPORTED; }
+    cudaSetDevice(ctx->device);
+    const CsrSetDev& s = ctx->set[ctx->cur];
+    const int other = 1 - ctx->cur;
+    const size_t nn = (size_t)ctx->n * ctx->n;
+    unsigned long long used = 0;
+    CK(cudaMemcpy(&used, s.cursor, sizeof(used), cudaMemcpyDeviceToHost));
+    used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
+    // scratch: the cell pool of the set that is not current (dead after a relaxation, unused before one)
+    const unsigned long long used_even = (used + 1) & ~1ull;
+    const size_t need_bytes = (size_t)used_even * 4 + (size_t)ctx->rp_total * 2 + 64;
+    if ((size_t)ctx->set[other].cap * sizeof(int2) < need_bytes) {
+        const int rc = grow_cells(ctx, other, (long long)(need_bytes / sizeof(int2) + 16), 0);
+        if (rc != MLP_OK) return rc;
+    }
+    unsigned* d_cells = reinterpret_cast<unsigned*>(ctx->set[other].cells);
+    unsigned short* d_sizes = reinterpret_cast<unsigned short*>(d_cells + used_even);
+    const int grid = ctx->num_sms * 8;
+    if (nz_off) { CK(cudaMemcpyAsync(nz_off, s.nz_off, nn * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)nn * 8; }
+    if (nz_cnt) { CK(cudaMemcpyAsync(nz_cnt, s.nz_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)nn * 4; }
+    if (row_sizes) {
+        k_row_sizes<<<grid, 256, 0, ctx->stream>>>(s.rp_pool, d_sizes, ctx->rp_total);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(row_sizes, d_sizes, (size_t)ctx->rp_total * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += ctx->rp_total * 2; ctx->stats.launches += 1;
+    }
+    if (cells && used) {
+        k_pack_cells<<<grid, 256, 0, ctx->stream>>>(s.cells, d_cells, (long long)used);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cells, d_cells, (size_t)used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (int64_t)used * 4; ctx->stats.launches += 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MLP_OK;
+}
+
 extern "C" int mlp_alloc_pinned(int64_t bytes, void** out) {
     if (!out || bytes <= 0) return MLP_E_ARG;
     return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? MLP_OK : MLP_E_CUDA;
@@ -809,29 +871,39 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
         CK(cudaMemcpyAsync(ctx->d_seldist, seldist_nxn, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += (int64_t)n * 4 + (int64_t)n * n * 4;
     }
-    // Task order = 2-D tiles of the pair grid: the ~2-5 k warps resident together then work on a TxT block of pairs and,
+    // Task order = 2-D tiles of the pair grid: the CTAs resident together then work on a TxT block of pairs and,
     // for each third sequence z, touch only 2T matrices (S_x z for T values of x, S_y z for T values of y) -> L2 reuse.
-    std::vector<PairTask> tasks = ctx->owned;
-    const int T = 48;
-    std::sort(tasks.begin(), tasks.end(), [T](const PairTask& x, const PairTask& y) {
-        const int xa = x.a / T, xb = x.b / T, ya = y.a / T, yb = y.b / T;
-        if (xa != ya) return xa < ya;
-        if (xb != yb) return xb < yb;
-        return x.pidx < y.pidx;
-    });
+    // The order depends only on the owned pair list, so it is computed once per shard (cached in the context).
+    if (ctx->relax_tasks.size() != ctx->owned.size() || ctx->relax_tasks_n != n) {
+        ctx->relax_tasks = ctx->owned;
+        const int T = 48;
+        std::sort(ctx->relax_tasks.begin(), ctx->relax_tasks.end(), [T](const PairTask& x, const PairTask& y) {
+            const int xa = x.a / T, xb = x.b / T, ya = y.a / T, yb = y.b / T;
+            if (xa != ya) return xa < ya;
+            if (xb != yb) return xb < yb;
+            return x.pidx < y.pidx;
+        });
+        ctx->relax_tasks_n = n;
+    }
+    const std::vector<PairTask>& tasks = ctx->relax_tasks;
     int rc = ensure_tasks(ctx, tasks.size());
     if (rc != MLP_OK) return rc;
     int maxL1 = 0, maxL2 = 0;
     for (const PairTask& t : tasks) { maxL1 = std::max(maxL1, t.L1); maxL2 = std::max(maxL2, t.L2); }
-    int bps = std::min(relax_max_blocks_per_sm(), 16);
-    int grid = std::max(1, std::min(ctx->num_sms * bps, (int)((tasks.size() + 3) / 4)));
+    static const bool use_warp_kernel = getenv("MLP_RELAX_WARP") != nullptr;   // developer knob: the older warp-per-pair kernel
+    int bps = use_warp_kernel ? std::min(relax_max_blocks_per_sm(), 16) : relax_blk_max_blocks_per_sm();
+    int grid = use_warp_kernel ? std::max(1, std::min(ctx->num_sms * bps, (int)((tasks.size() + 3) / 4)))
+                               : std::max(1, std::min(ctx->num_sms * bps, (int)tasks.size()));
     const long long warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
     rc = ensure_warp_buffers(ctx, warps, maxL1, maxL2, false, 1);
     if (rc != MLP_OK) return rc;
-    if (warps > ctx->wk_warps) {
+    // per-warp (old kernel: n weights + n indices) or per-CTA (weights, indices, slice descriptors) scratch
+    const long long wk_stride = use_warp_kernel ? 2LL * n : relax_blk_scratch_words(n);
+    const long long wk_units = use_warp_kernel ? warps : (long long)ctx->num_sms * bps;
+    if (wk_units * wk_stride > ctx->wk_warps) {
         free_dev(ctx->d_wk); ctx->d_wk = nullptr;
-        CK(cudaMalloc(&ctx->d_wk, (size_t)warps * 2 * n * sizeof(float)));   // per warp: n weights + n indices
-        ctx->wk_warps = warps;
+        CK(cudaMalloc(&ctx->d_wk, (size_t)(wk_units * wk_stride) * sizeof(float)));
+        ctx->wk_warps = wk_units * wk_stride;
     }
     {   // the relaxed set can only shrink: size the output pool to what the input set holds
         unsigned long long used = 0;
@@ -852,11 +924,12 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     ra.n = n; ra.flavour = flavour; ra.cutoff = cutoff; ra.rp_off = ctx->d_rp_off;
     ra.in = ctx->set[in]; ra.out = ctx->set[out];
     ra.weights = ctx->d_weights; ra.seldist = ctx->d_seldist; ra.selectivity = selectivity; ra.selfweight = selfweight;
-    ra.wk_scratch = ctx->d_wk; ra.wk_stride = 2LL * n; ra.err = ctx->d_err;
+    ra.wk_scratch = ctx->d_wk; ra.wk_stride = wk_stride; ra.err = ctx->d_err;
+    ra.wide_span = getenv("MLP_RELAX_WIDE") ? atoi(getenv("MLP_RELAX_WIDE")) : (1 << 30);   // measured: merging wide rows is slower than giving them strips
     KernelTimer kt;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     kt.begin(MLP_K_RELAX_ID, ctx->stream);
-    CK(relax_launch(ra, grid, ctx->stream));
+    CK(use_warp_kernel ? relax_launch(ra, grid, ctx->stream) : relax_blk_launch(ra, grid, ctx->stream));
     kt.end(ctx->stream);
     ctx->stats.launches += 1;
     // second orientation of every new matrix
@@ -873,7 +946,12 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     kt.collect(ctx->stats);
     int err = 0;
     CK(cudaMemcpy(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) { cudaMemset(ctx->d_err, 0, sizeof(int)); ctx->err = "sparse cell pool exhausted during relaxation"; return MLP_E_CAPACITY; }
+    if (err) {
+        cudaMemset(ctx->d_err, 0, sizeof(int));
+        if (err & 4) { ctx->err = "relaxation: a staged copy never arrived"; return MLP_E_CUDA; }
+        ctx->err = "sparse cell pool exhausted during relaxation";
+        return MLP_E_CAPACITY;
+    }
     ctx->cur = out;
     ctx->stats.pairs = (int64_t)tasks.size();
     unsigned long long cur = 0;

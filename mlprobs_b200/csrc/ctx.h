@@ -40,6 +40,8 @@ struct mlp_ctx {
     // pairs
     std::vector<PairTask> all_pairs;     // cost-sorted (descending)
     std::vector<PairTask> owned;         // this shard
+    std::vector<PairTask> relax_tasks;   // owned pairs in the tile order mlp_relax processes them (cached)
+    int relax_tasks_n = 0;
     int rank = 0, world = 1;
     // sparse sets (double buffered for relax)
     std::vector<long long> rp_off_h;

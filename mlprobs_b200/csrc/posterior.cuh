@@ -62,9 +62,14 @@ struct RelaxArgs {
     const float* weights; const float* seldist; float selectivity, selfweight;
     float* wk_scratch; long long wk_stride;   // per warp: n floats (weight of z for this pair, < 0 = z not accepted)
     int* err;
+    int wide_span;                            // S_yz rows spanning more q than this are merged instead of getting a dense strip
 };
 cudaError_t relax_launch(const RelaxArgs& a, int grid, cudaStream_t st);
 int relax_max_blocks_per_sm();
+// CTA-per-pair relaxation with TMA-staged slices (relax_blk.cu)
+cudaError_t relax_blk_launch(const RelaxArgs& a, int grid, cudaStream_t st);
+int relax_blk_max_blocks_per_sm();
+long long relax_blk_scratch_words(int n);
 
 size_t posterior_smem_bytes(int kernel, int Cmax, int warps);
 cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st);

@@ -1,0 +1,144 @@
+// quickprobs_b200: command-line drop-in for `quickprobs` (realign/QuickProbs, Console/main.cpp:18-66) in its default
+// protein configuration, every stage on the GPU through the C ABI of include/mlprobs_b200.h:
+//   FASTA in (SequenceIO::loadFasta SequenceIO.cpp:98-155, checkAndCorrect :70-93) -> posterior stage -> UPGMA tree ->
+//   consistency (1 repetition above 50 sequences, else 2; last one unfiltered, ConsistencyStage.cpp:73-123) ->
+//   progressive construction + column refinement -> FASTA out, 60 columns per line (SequenceIO::saveFasta :175-193).
+// Options kept: positional infile, -o/--outfile, -c/--con-iters, -r/--ref-count, --ref-seed, -t/--num-threads (accepted,
+// ignored: there is no thread team), -v.  Anything else the reference offers (nucleotide mode, other trees, OpenCL
+// device selection, ClustalW output) is refused loudly rather than approximated.  There is no CPU fallback.
+#include "../../include/mlprobs_b200.h"
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Input { std::vector<std::string> headers, seqs; };
+
+bool load_fasta(const std::string& path, Input& in, std::string& err) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f.is_open()) { err = "unable to open input file"; return false; }
+    std::string line;
+    bool have = false;
+    while (std::getline(f, line)) {
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            std::string h = line.substr(1);
+            while (!h.empty() && isspace((unsigned char)h[0])) h.erase(0, 1);
+            while (!h.empty() && isspace((unsigned char)h[h.size() - 1])) h.erase(h.size() - 1);
+            in.headers.push_back(h);
+            in.seqs.push_back(std::string());
+            have = true;
+        } else if (have) {
+            if (line[line.size() - 1] == '\r') line.erase(line.size() - 1);
+            in.seqs.back() += line;
+        }
+    }
+    if (in.seqs.empty()) { err = "no sequences read"; return false; }
+    bool ok = true;
+    for (auto& s : in.seqs)
+        for (auto& c : s) {
+            if (isalpha((unsigned char)c)) c = (char)toupper((unsigned char)c);
+            else { std::cout << "illegal sequence character:" << c << std::endl; ok = false; }
+        }
+    if (!ok) { err = "Illegal characters in sequence set!"; return false; }
+    for (auto& s : in.seqs) if (s.empty()) { err = "empty sequence in input"; return false; }
+    return true;
+}
+
+void write_fasta(std::ostream& out, const std::vector<std::string>& headers, const char* rows, int n, int len) {
+    for (int i = 0; i < n; ++i) {
+        out << ">" << headers[i] << "\n";
+        const char* r = rows + (size_t)i * len;
+        for (int p = 0; p < len; p += 60) { out.write(r + p, std::min(60, len - p)); out << "\n"; }
+    }
+}
+
+int fail(mlp_ctx* ctx, const char* what, int rc) {
+    std::fprintf(stderr, "quickprobs_b200: %s failed (%d)%s%s\n", what, rc, ctx ? ": " : "", ctx ? mlp_last_error(ctx) : "");
+    if (ctx) mlp_destroy(ctx);
+    return 1;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string infile, outfile;
+    int con_iters = -1, ref_count = -1, device = 0, verbose = 0;
+    unsigned ref_seed = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::fprintf(stderr, "quickprobs_b200: option %s needs a value\n", name); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "-o" || a == "--outfile") outfile = need("-o");
+        else if (a == "-c" || a == "--con-iters") con_iters = std::atoi(need("-c"));
+        else if (a == "-r" || a == "--ref-count") ref_count = std::atoi(need("-r"));
+        else if (a == "--ref-seed") ref_seed = (unsigned)std::strtoul(need("--ref-seed"), nullptr, 10);
+        else if (a == "-t" || a == "--num-threads") (void)need("-t");
+        else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
+        else if (a == "-v" || a == "--verbose") verbose = 1;
+        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "quickprobs_b200: unsupported option %s\n", a.c_str()); return 2; }
+        else if (infile.empty()) infile = a;
+        else { std::fprintf(stderr, "quickprobs_b200: more than one input file\n"); return 2; }
+    }
+    if (infile.empty()) {
+        std::fprintf(stderr, "usage: quickprobs_b200 <infile> [-o outfile] [-c con-iters] [-r ref-count] [--ref-seed S] [-d cuda-device]\n");
+        return 2;
+    }
+    Input in;
+    std::string err;
+    if (!load_fasta(infile, in, err)) { std::fprintf(stderr, "quickprobs_b200: %s\n", err.c_str()); return 255; }
+    const int n = (int)in.seqs.size();
+    std::ofstream fout;
+    if (!outfile.empty()) {
+        fout.open(outfile.c_str(), std::ios::binary | std::ios::out | std::ios::trunc);
+        if (!fout.is_open()) { std::fprintf(stderr, "quickprobs_b200: unable to open output file\n"); return 255; }
+    }
+    std::ostream& out = outfile.empty() ? std::cout : fout;
+
+    mlp_ctx* ctx = nullptr;
+    int rc = mlp_create(device, &ctx);                 // no CUDA device -> MLP_E_NO_DEVICE: stop here, nothing falls back to the CPU
+    if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
+    if (n == 1) {
+        write_fasta(out, in.headers, in.seqs[0].data(), 1, (int)in.seqs[0].size());
+        mlp_destroy(ctx);
+        return 0;
+    }
+    std::vector<int32_t> len(n);
+    std::string cat;
+    for (int i = 0; i < n; ++i) { len[i] = (int32_t)in.seqs[i].size(); cat += in.seqs[i]; }
+    mlp_hmm_tables hmm;
+    mlp_part_tables part;
+    if ((rc = mlp_default_tables(MLP_QP, 0.0f, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
+    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
+    if ((rc = mlp_set_sequences(ctx, n, len.data(), (const uint8_t*)cat.data()))) return fail(ctx, "mlp_set_sequences", rc);
+    if ((rc = mlp_posterior_all_pairs(ctx, MLP_QP, MLP_M_HMM5 | MLP_M_PART, 0.01f))) return fail(ctx, "mlp_posterior_all_pairs", rc);
+    std::vector<float> dist((size_t)n * n), weights(n), seldist((size_t)n * n);
+    std::vector<int32_t> left(2 * n - 1), right(2 * n - 1);
+    if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
+    if ((rc = mlp_qp_guide_tree_ex(n, dist.data(), weights.data(), seldist.data(), nullptr, left.data(), right.data())))
+        return fail(ctx, "mlp_qp_guide_tree_ex", rc);
+    for (auto& w : weights) w = std::max(w, 1e-6f);    // consistency.saturation == finalSaturation == 1e-6
+    const int iters = con_iters >= 0 ? con_iters : (n > 50 ? 1 : 2);
+    for (int it = 0; it < iters; ++it) {
+        const float cutoff = (it == iters - 1) ? 1e-5f : 0.01f;
+        if ((rc = mlp_relax(ctx, MLP_QP, weights.data(), seldist.data(), 200.0f, 3.0f, cutoff))) return fail(ctx, "mlp_relax", rc);
+    }
+    char* rows = nullptr;
+    int32_t alen = 0;
+    if ((rc = mlp_qp_finish_alignment(ctx, weights.data(), left.data(), right.data(), ref_count, ref_seed, &rows, &alen)))
+        return fail(ctx, "mlp_qp_finish_alignment", rc);
+    write_fasta(out, in.headers, rows, n, alen);
+    if (verbose) std::fprintf(stderr, "quickprobs_b200: %d sequences, %d columns\n", n, alen);
+    mlp_free_host(rows);
+    mlp_destroy(ctx);
+    return 0;
+}

@@ -1,0 +1,68 @@
+"""quickprobs_b200 (mlprobs_b200/bin): the command-line drop-in for `quickprobs` over the C ABI."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from common import load_golden, split_seqs, HERE
+
+CLI = os.path.join(os.path.dirname(HERE), "mlprobs_b200", "bin", "quickprobs_b200")
+
+
+def fasta_text(headers, rows):
+    out = []
+    for h, r in zip(headers, rows):
+        out.append(">" + h)
+        out += [r[p:p + 60] for p in range(0, len(r), 60)]
+    return "\n".join(out) + "\n"
+
+
+def write_input(tmp_path, seqs):
+    fa = tmp_path / "in.fa"
+    heads = ["seq%d  some description " % i for i in range(len(seqs))]
+    # lower case + Windows line ends + blank lines: all normalised by the loader (SequenceIO.cpp:70-155)
+    fa.write_bytes(b"".join(b">" + h.encode() + b"\r\n\n" + s.lower() + b"\r\n" for h, s in zip(heads, seqs)))
+    return str(fa), [h.strip() for h in heads]
+
+
+def test_cli_is_built():
+    assert os.path.exists(CLI), "run __graft_entry__.build()"
+
+
+def test_cli_refuses_to_run_without_a_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fa, _ = write_input(tmp_path, [b"ACDEFGHIK", b"ACDEFGHIK"])
+    r = subprocess.run([CLI, fa], capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA device is required" in r.stderr and r.stdout == ""
+
+
+def test_cli_rejects_illegal_characters_and_unknown_options(tmp_path):
+    fa = tmp_path / "bad.fa"
+    fa.write_text(">a\nACD*EF\n>b\nACDEF\n")
+    r = subprocess.run([CLI, str(fa)], capture_output=True, text=True)
+    assert r.returncode == 255 and "illegal sequence character:*" in r.stdout and "Illegal characters" in r.stderr
+    r = subprocess.run([CLI, str(fa), "--nucleotide"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unsupported option" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["qp_sup139", "qp_676s4"])
+def test_cli_reproduces_the_reference_alignment(tmp_path, name):
+    d = load_golden(name)
+    seqs = split_seqs(d)
+    fa, heads = write_input(tmp_path, seqs)
+    want = fasta_text(heads, [r.tobytes().decode() for r in d["msa"]])
+    out = tmp_path / "out.fa"
+    r = subprocess.run([CLI, fa, "-o", str(out), "-t", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == want
+    r = subprocess.run([CLI, fa], capture_output=True, text=True)      # stdout when no -o is given
+    assert r.returncode == 0 and r.stdout == want
+
+
+@pytest.mark.gpu
+def test_cli_single_sequence_is_echoed(tmp_path):
+    fa, heads = write_input(tmp_path, [b"ACDEFGHIKLMNPQRSTVWY" * 4])
+    r = subprocess.run([CLI, fa], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == fasta_text(heads, [("ACDEFGHIKLMNPQRSTVWY" * 4)])

@@ -317,6 +317,14 @@ def test_properties_on_a_large_family():
         rp2, c2, v2 = raw.matrix(a, b, eng.lens)
         assert np.array_equal(rp1, rp2) and np.array_equal(c1, c2) and np.array_equal(v1, v2)
     raw.close()
+    # the packed read-back (QuickProbs' uint16|uint16 cells + uint16 row sizes) decodes to the same matrices
+    pk = eng.csr_packed()
+    assert pk.nbytes() < 0.55 * (n * n * 12 + pk.rp_total * 4 + pk.used * 8)
+    for a, b in [(0, 1), (5, 3), (n - 1, 2), (n - 2, n - 1)]:
+        rp1, c1, v1 = eng.csr(a, b)
+        rp2, c2, v2 = pk.matrix(a, b, eng.lens)
+        assert np.array_equal(rp1, rp2) and np.array_equal(c1, c2) and np.array_equal(v1, v2)
+    pk.close()
     # oracle spot-check of a few pairs at this size
     ht, pt = O.hmm_tables(), O.part_tables(O.QP)
     for a, b in [(0, 1), (17, 93), (118, 119)]:
