@@ -152,7 +152,8 @@ int mlp_csr_layout(mlp_ctx* ctx, int64_t* rp_off, int64_t* rp_total, int64_t* ce
 int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, int32_t* rp_pool, void* cells);
 /* QuickProbs flavour only: the same pooled layout in the reference's own storage format (PackedSparseMatrix.h:9-80,
  * SparseEntry.h: uint16 column + uint16 fixed-point value per cell, row sizes next to row indices) -- half the bytes
- * of mlp_get_csr_raw over PCIe.  cells[k] = (column << 16) | code with value = code / 65535.0f; row_sizes has the
+ * of mlp_get_csr_raw over PCIe.  cells[k] = column | (code << 16), i.e. the bytes of SparseEntry<uint16_t, uint16_t>{first = column, second = code} on a
+ * little-endian host, value = code / 65535.0f; row_sizes has the
  * rp_total entries of the row-pointer pool, entry rp_off[a*n+b] + i = number of cells in row i (row 0 and the entry
  * after the last row are 0), so rowIndices are their running sum.  Any pointer may be NULL.  Packing runs on the device
  * into the idle half of the double-buffered cell pool. */

@@ -258,7 +258,7 @@ class PinnedCsrBuffers:
 
 
 class PinnedPackedBuffers(PinnedCsrBuffers):
-    """Page-locked host buffers for Engine.csr_packed: QuickProbs' own format (uint16 column | uint16 value code per cell,
+    """Page-locked host buffers for Engine.csr_packed: QuickProbs' own format (SparseEntry<uint16,uint16>: column in the low half, value code in the high half,
     uint16 row sizes) -- half the PCIe bytes of the {int32, float32} pool."""
 
     def ensure(self, n, rp_total, cells):
@@ -280,7 +280,7 @@ class PinnedPackedBuffers(PinnedCsrBuffers):
         rp = np.zeros(int(lens[a]) + 2, np.int32)
         rp[1:] = np.cumsum(sizes)[:-1]
         c = self.cells[self.nz_off[s]: self.nz_off[s] + self.nz_cnt[s]]
-        return rp, (c >> 16).astype(np.int32), (c & 0xffff).astype(np.float32) / np.float32(65535.0)
+        return rp, (c & 0xffff).astype(np.int32), (c >> 16).astype(np.float32) / np.float32(65535.0)
 
     def nbytes(self):
         return self.n * self.n * 12 + self.rp_total * 2 + self.used * 4

@@ -798,7 +798,7 @@ __global__ void k_pack_cells(const int2* __restrict__ cells, unsigned* __restric
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < ncell; i += stride) {
         const int4 two = *reinterpret_cast<const int4*>(cells + i);           // cells + i is 16-byte aligned (i even); the pool has slack
         const unsigned c0 = __float2uint_rn(__fmul_rn(__int_as_float(two.y), 65535.0f)), c1 = __float2uint_rn(__fmul_rn(__int_as_float(two.w), 65535.0f));
-        *reinterpret_cast<uint2*>(out + i) = make_uint2(((unsigned)two.x << 16) | (c0 & 0xffffu), ((unsigned)two.z << 16) | (c1 & 0xffffu));
+        *reinterpret_cast<uint2*>(out + i) = make_uint2(((unsigned)two.x & 0xffffu) | (c0 << 16), ((unsigned)two.z & 0xffffu) | (c1 << 16));   // {uint16 first = column, uint16 second = value}
     }
 }
 // cumulative row pointers -> uint16 row sizes, same pooled positions (entry r = cells in row r; the last entry of a pair is 0)
