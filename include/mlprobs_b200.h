@@ -132,6 +132,28 @@ int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const int32_t* l
                             int ref_iters, uint32_t ref_seed, char** rows_out, int32_t* aln_len);
 void mlp_free_host(void* p);
 
+/* c_p_np_aln flavour, the stages after consistency for `-p 0` (progressive): guide tree, progressive alignment with
+ * weighted profile posteriors, iterative refinement by random bipartition.
+ * mlp_cpnp_guide_tree replaces MSAClusterTree::create(vpid) (MSAClusterTree.cpp:30-39,170-296: UPGMA, plain average of the
+ * two joined rows when variance_id == 0, size-weighted otherwise; distances updated IN PLACE) and
+ * MSAGuideTree::getSeqsWeights (MSAGuideTree.cpp:274-322: integer weights normalised to 1000, at least 1).
+ * mlp_cpnp_finish_alignment* replace MSA::ComputeFinalAlignment (MSA.cpp:1481-1534) with ProcessTree / AlignAlignments
+ * (:1369-1471) and DoIterativeRefinement (:1537-1623).  refine_reps = -ir (reference default 100), pid = model class
+ * (variance_mean % 10).  The reference draws its bipartitions from an unseeded glibc rand(); the library carries a private
+ * replica of that generator (seed 1).  With more than one OpenMP thread the reference's refinement races on the shared
+ * posterior and its output changes from run to run; this is its one-thread result.
+ * rows_out: malloc'ed n x aln_len matrix in the reference's OUTPUT order (refinement never re-sorts the rows);
+ * order_out[k] = input index of row k (may be NULL).  Release rows_out with mlp_free_host. */
+int mlp_cpnp_guide_tree(int n, float* dist_nxn_inout, int variance_id, int32_t* weights_out, int32_t* left_out, int32_t* right_out);
+int mlp_cpnp_finish_alignment_host(int n, const int32_t* len, const uint8_t* residues, const int32_t* iweights,
+                                   const int32_t* left, const int32_t* right, const int64_t* rp_off, const int64_t* nz_off,
+                                   const int32_t* rp_pool, const void* cells, int refine_reps, int pid,
+                                   char** rows_out, int32_t* aln_len, int32_t* order_out);
+int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, const int32_t* left, const int32_t* right,
+                              int refine_reps, int pid, char** rows_out, int32_t* aln_len, int32_t* order_out);
+/* test hook: first `count` outputs of the private glibc rand() replica */
+int mlp_debug_glibc_rand(int count, int32_t* out);
+
 /* Sparse posterior read-back. Ordered pair (a,b), a != b; rows 1..len[a]; row_ptr has len[a]+2 entries
  * (row_ptr[i]..row_ptr[i+1] = row i, row 0 empty).  val is the dequantised value for MLP_QP
  * (SparseEntry.h:31-32).  Pass NULL col/val to query *nnz only. */

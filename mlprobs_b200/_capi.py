@@ -23,7 +23,8 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_comm_init", "mlp_exchange", "mlp_last_stats", "mlp_qp_guide_tree", "mlp_shard_pairs", "mlp_csr_layout", "mlp_get_csr_raw",
            "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
-           "mlp_free_host", "mlp_get_csr_packed"]
+           "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
+           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand"]
 
 
 class HmmTables(C.Structure):
@@ -190,6 +191,51 @@ def qp_finish_alignment_host(seqs, weights, left, right, rp_off, nz_off, rp_pool
     if rc:
         raise MlpError(rc)
     return _take_rows(n, rows_p, alen)
+
+
+def cpnp_guide_tree(distances, variance_id):
+    """c_p_np_aln's UPGMA (MSAClusterTree::create(vpid)) -> dict(weights int32, left, right, dist_after)."""
+    d = np.array(distances, np.float32, copy=True, order="C")
+    n = d.shape[0]
+    w = np.zeros(n, np.int32)
+    left, right = (np.zeros(2 * n - 1, np.int32) for _ in range(2))
+    lib = load()
+    lib.mlp_cpnp_guide_tree.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.mlp_cpnp_guide_tree(n, _ptr(d), int(variance_id), _ptr(w), _ptr(left), _ptr(right))
+    if rc:
+        raise MlpError(rc)
+    return {"weights": w, "left": left, "right": right, "dist_after": d}
+
+
+def cpnp_finish_alignment_host(seqs, iweights, left, right, rp_off, nz_off, rp_pool, cells, refine_reps=100, pid=0):
+    """c_p_np_aln -p 0 tail from a HOST copy of the pooled set -> (rows in the reference's output order, order of input indices)."""
+    n = len(seqs)
+    lens = np.array([len(x) for x in seqs], np.int32)
+    cat = np.frombuffer(b"".join(seqs), np.uint8)
+    keep = [np.ascontiguousarray(iweights, np.int32), np.ascontiguousarray(left, np.int32), np.ascontiguousarray(right, np.int32),
+            np.ascontiguousarray(rp_off, np.int64), np.ascontiguousarray(nz_off, np.int64), np.ascontiguousarray(rp_pool, np.int32),
+            np.ascontiguousarray(cells)]
+    rows_p = C.c_void_p(0)
+    alen = C.c_int32(0)
+    order = np.zeros(n, np.int32)
+    lib = load()
+    lib.mlp_cpnp_finish_alignment_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p] + [C.c_void_p] * 7 + [C.c_int, C.c_int,
+                                                   C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p]
+    rc = lib.mlp_cpnp_finish_alignment_host(n, _ptr(lens), _ptr(cat), *[_ptr(k) for k in keep], int(refine_reps), int(pid),
+                                            C.byref(rows_p), C.byref(alen), _ptr(order))
+    if rc:
+        raise MlpError(rc)
+    return _take_rows(n, rows_p, alen), order
+
+
+def debug_glibc_rand(count):
+    out = np.zeros(count, np.int32)
+    lib = load()
+    lib.mlp_debug_glibc_rand.argtypes = [C.c_int, C.c_void_p]
+    rc = lib.mlp_debug_glibc_rand(count, _ptr(out))
+    if rc:
+        raise MlpError(rc)
+    return out
 
 
 def shard_pairs(lens, rank, world):
@@ -415,6 +461,18 @@ class Engine:
         self._ck(self._lib.mlp_qp_finish_alignment(self._ctx, *[_ptr(k) for k in keep], int(ref_iters), int(ref_seed),
                                                    C.byref(rows_p), C.byref(alen)))
         return _take_rows(self.n, rows_p, alen)
+
+    def cpnp_finish_alignment(self, iweights, left, right, refine_reps=100, pid=0):
+        """c_p_np_aln -p 0 tail over the device-resident set -> (rows in the reference's output order, input index of each row)."""
+        keep = [np.ascontiguousarray(iweights, np.int32), np.ascontiguousarray(left, np.int32), np.ascontiguousarray(right, np.int32)]
+        rows_p = C.c_void_p(0)
+        alen = C.c_int32(0)
+        order = np.zeros(self.n, np.int32)
+        self._lib.mlp_cpnp_finish_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_void_p]
+        self._ck(self._lib.mlp_cpnp_finish_alignment(self._ctx, *[_ptr(k) for k in keep], int(refine_reps), int(pid),
+                                                     C.byref(rows_p), C.byref(alen), _ptr(order)))
+        return _take_rows(self.n, rows_p, alen), order
 
     def csr_packed(self, out=None):
         """Pooled read-back in QuickProbs' packed cell format (QP flavour only). `out` = PinnedPackedBuffers to reuse."""

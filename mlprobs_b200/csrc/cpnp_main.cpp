@@ -1,0 +1,170 @@
+// c_p_np_aln_b200: command-line drop-in for `c_p_np_aln` (baseMSA/C_P_NP_Aln, MSA::MSA MSA.cpp:123-187) for the two ways
+// MLProbs calls it (utils/prepare_features_4_classifier_1.py:12, utils/classifier_c_p_np_aln.py:14,37):
+//   c_p_np_aln -G file      -> the feature line of MSA::Alter_ModelAdjustmentTest on stdout
+//   c_p_np_aln -p 0 file    -> model selection, all-pairs posteriors, tree, consistency, progressive alignment, refinement
+// every O(N^2 L^2) stage on the GPU through the C ABI of include/mlprobs_b200.h.  `-p 1` (non-progressive strategy) is not
+// built: the reference seeds rand() with the wall clock there (MSA.cpp:1896), so it has no reproducible output to match.
+// Options kept: -p, -G, -o/--outfile, -c/--consistency, -ir/--iterative-refinement, -v.  No CPU fallback.
+#include "../../include/mlprobs_b200.h"
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Input { std::vector<std::string> headers, seqs; };
+
+// Sequence::Sequence(FileBuffer&, stripGaps = true), Sequence.h:52-122
+bool load_mfa(const std::string& path, Input& in) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f.is_open()) { std::cerr << "ERROR: Could not open file '" << path << "' for reading." << std::endl; std::exit(1); }
+    std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    size_t p = 0;
+    while (p < all.size()) {
+        std::string header;
+        while (p < all.size()) {                               // first non-blank line
+            size_t e = all.find('\n', p);
+            if (e == std::string::npos) e = all.size();
+            header = all.substr(p, e - p);
+            p = std::min(all.size(), e + 1);
+            if (!header.empty()) break;
+        }
+        if (header.empty() || header[0] != '>') break;
+        header = header.substr(1);
+        while (!header.empty() && isspace((unsigned char)header[0])) header.erase(0, 1);
+        while (!header.empty() && isspace((unsigned char)header[header.size() - 1])) header.erase(header.size() - 1);
+        std::string data;
+        while (p < all.size() && all[p] != '>') {
+            char ch = all[p++];
+            if (isspace((unsigned char)ch)) continue;
+            if (ch == '.' || ch == '-') continue;               // stripGaps
+            if (!((ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z'))) {
+                std::cerr << "ERROR: Unknown character encountered: " << ch << std::endl;
+                std::exit(1);
+            }
+            if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 'a' + 'A');
+            data.push_back(ch);
+        }
+        if (data.empty()) break;                               // an empty record ends the file for the reference too
+        in.headers.push_back(header);
+        in.seqs.push_back(data);
+    }
+    return !in.seqs.empty();
+}
+
+void write_mfa(std::ostream& out, const std::string& header, const char* row, int len) {
+    out << ">" << header << "\n";
+    for (int p = 0; p < len; p += 60) { out.write(row + p, std::min(60, len - p)); out << "\n"; }
+}
+
+int fail(mlp_ctx* ctx, const char* what, int rc) {
+    std::fprintf(stderr, "c_p_np_aln_b200: %s failed (%d)%s%s\n", what, rc, ctx ? ": " : "", ctx ? mlp_last_error(ctx) : "");
+    if (ctx) mlp_destroy(ctx);
+    return 1;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    std::string infile, outfile;
+    int program = 0, getpid = 0, reps = 2, refine = 100, device = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::cerr << "ERROR: Must specify a value after option " << name << "." << std::endl; std::exit(1); }
+            return argv[++i];
+        };
+        if (a == "-o" || a == "--outfile") outfile = need("-o");
+        else if (a == "-p" || a == "--program") {
+            program = std::atoi(need("-p"));
+            if (program < 0 || program > 1) { std::cerr << "ERROR: For option -p, integer must be 0 or 1." << std::endl; return 1; }
+        }
+        else if (a == "-G" || a == "--getPID") getpid = 1;
+        else if (a == "-c" || a == "--consistency") reps = std::atoi(need("-c"));
+        else if (a == "-ir" || a == "--iterative-refinement") refine = std::atoi(need("-ir"));
+        else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
+        else if (a == "-v" || a == "--verbose") {}
+        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "c_p_np_aln_b200: unsupported option %s\n", a.c_str()); return 2; }
+        else if (infile.empty()) infile = a;
+        else { std::fprintf(stderr, "c_p_np_aln_b200: more than one input file\n"); return 2; }
+    }
+    if (infile.empty()) { std::fprintf(stderr, "usage: c_p_np_aln_b200 (-G | -p 0) [-o outfile] [-c reps] [-ir passes] <fasta>\n"); return 2; }
+    if (program == 1 && !getpid) {
+        std::fprintf(stderr, "c_p_np_aln_b200: -p 1 (non-progressive strategy) is not built; the reference seeds rand() with the clock there\n");
+        return 2;
+    }
+    Input in;
+    if (!load_mfa(infile, in)) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
+    const int n = (int)in.seqs.size();
+    std::ofstream fout;
+    if (!outfile.empty()) {
+        fout.open(outfile.c_str(), std::ios::binary | std::ios::out | std::ios::trunc);
+        if (!fout.is_open()) { std::cerr << "ERROR: Failed to open the file " << outfile << std::endl; return 1; }
+    }
+    std::ostream& out = outfile.empty() ? std::cout : fout;
+
+    mlp_ctx* ctx = nullptr;
+    int rc = mlp_create(device, &ctx);                 // no CUDA device -> stop: nothing falls back to the CPU
+    if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
+    if (n < 2) {
+        if (!getpid) write_mfa(out, in.headers[0], in.seqs[0].data(), (int)in.seqs[0].size());
+        mlp_destroy(ctx);
+        return getpid ? 1 : 0;
+    }
+    std::vector<int32_t> len(n);
+    std::string cat;
+    for (int i = 0; i < n; ++i) { len[i] = (int32_t)in.seqs[i].size(); cat += in.seqs[i]; }
+    const long long npairs = (long long)n * (n - 1) / 2;
+    mlp_hmm_tables hmm;
+    mlp_part_tables part;
+    if ((rc = mlp_default_tables(MLP_CPNP_P0, 0.700645f, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
+    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
+    if ((rc = mlp_set_sequences(ctx, n, len.data(), (const uint8_t*)cat.data()))) return fail(ctx, "mlp_set_sequences", rc);
+    std::vector<int32_t> ident(npairs), alen(npairs);
+    if (getpid) {
+        // MSA::Alter_ModelAdjustmentTest(sequences, 1.0), MSA.cpp:154-165,646-762
+        long long cap = 0;
+        for (int a = 0; a < n; ++a) for (int b = a + 1; b < n; ++b) cap += len[a] + len[b];
+        std::vector<char> aln((size_t)cap + 16);
+        std::vector<int64_t> off(npairs + 1);
+        if ((rc = mlp_viterbi_all_pairs_ex(ctx, ident.data(), alen.data(), aln.data(), off.data()))) return fail(ctx, "mlp_viterbi_all_pairs_ex", rc);
+        char line[512];
+        if ((rc = mlp_cpnp_g_features(n, len.data(), (const uint8_t*)cat.data(), aln.data(), off.data(), 1.0f, line, (int)sizeof line)))
+            return fail(ctx, "mlp_cpnp_g_features", rc);
+        out << line << "\n";
+        mlp_destroy(ctx);
+        return 0;
+    }
+    // MSA::ModelAdjustmentTest, MSA.cpp:775-882
+    if ((rc = mlp_viterbi_all_pairs(ctx, ident.data(), alen.data()))) return fail(ctx, "mlp_viterbi_all_pairs", rc);
+    float identity = 0, sigma = 0, init2 = 0;
+    const int variance_mean = mlp_cpnp_model_adjustment(npairs, ident.data(), alen.data(), &identity, &sigma, &init2);
+    if (variance_mean < 0) return fail(ctx, "mlp_cpnp_model_adjustment", variance_mean);
+    const int pid = variance_mean % 10, vpid = variance_mean / 10;
+    if ((rc = mlp_default_tables(MLP_CPNP_P0, init2, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
+    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
+    const uint32_t mask = pid <= 1 ? (MLP_M_HMM5 | MLP_M_PART | MLP_M_LOCAL) : (pid == 2 ? MLP_M_LOCAL : MLP_M_PART);   // MSA.cpp:946-1010
+    rc = mlp_posterior_all_pairs(ctx, MLP_CPNP_P0, mask, 0.01f);
+    if (rc == MLP_E_OVERFLOW) { std::printf("ERROR: huge val error for zM\n"); mlp_destroy(ctx); return 1; }            // MSAPartProbs.cpp:547-589
+    if (rc) return fail(ctx, "mlp_posterior_all_pairs", rc);
+    std::vector<float> dist((size_t)n * n);
+    std::vector<int32_t> weights(n), left(2 * n - 1), right(2 * n - 1), order(n);
+    if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
+    if ((rc = mlp_cpnp_guide_tree(n, dist.data(), vpid, weights.data(), left.data(), right.data()))) return fail(ctx, "mlp_cpnp_guide_tree", rc);
+    for (int r = 0; r < reps; ++r)
+        if ((rc = mlp_relax(ctx, MLP_CPNP_P0, nullptr, nullptr, 0.0f, 0.0f, 0.01f))) return fail(ctx, "mlp_relax", rc);
+    char* rows = nullptr;
+    int32_t cols = 0;
+    if ((rc = mlp_cpnp_finish_alignment(ctx, weights.data(), left.data(), right.data(), refine, pid, &rows, &cols, order.data())))
+        return fail(ctx, "mlp_cpnp_finish_alignment", rc);
+    for (int k = 0; k < n; ++k) write_mfa(out, in.headers[order[k]], rows + (size_t)k * cols, cols);
+    mlp_free_host(rows);
+    mlp_destroy(ctx);
+    return 0;
+}

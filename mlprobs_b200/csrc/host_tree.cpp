@@ -7,9 +7,11 @@
 #include <algorithm>
 #include <vector>
 
-extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out,
-                                    int32_t* left_out, int32_t* right_out) {
-    if (n < 2 || !dist || !weights) return MLP_E_ARG;
+// first_best: the reference's initial minDist (2.0 QuickProbs, 1.1 cpnp); plain_average: cpnp's varianceid == 0 join
+// (idist + jdist) / 2 instead of the size-weighted mean (MSAClusterTree.cpp:274-275); iweights: cpnp's integer weights.
+static int upgma_core(int n, float* dist, float first_best, bool plain_average, float* weights, int32_t* iweights, float* subtree_dist,
+                      int32_t* parent_out, int32_t* left_out, int32_t* right_out) {
+    if (n < 2 || !dist || (!weights && !iweights)) return MLP_E_ARG;
     const int total = 2 * n - 1;
     std::vector<int> parent(total, -1), leaves(total, 0), slot_node(n), alive, lch(total, -1), rch(total, -1);
     std::vector<float> branch(total, 0.0f), joins(n);
@@ -31,7 +33,7 @@ extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* s
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < i; ++j) if (dist[(size_t)i * n + j] < 0) return MLP_E_ARG;
     for (int node = n; node < total; ++node) {
-        float best = 2.0f;
+        float best = first_best;
         int si = -1;
         for (int i : alive) if (rowarg[i] >= 0 && rowmin[i] < best) { best = rowmin[i]; si = i; }
         if (si < 0) return MLP_E_ARG;
@@ -46,7 +48,7 @@ extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* s
         const unsigned isize = (unsigned)leaves[ni], jsize = (unsigned)leaves[nj];
         for (int idx : alive) {
             const float idist = dist[(size_t)si * n + idx], jdist = dist[(size_t)sj * n + idx];
-            joins[idx] = (idist * isize + jdist * jsize) / (isize + jsize);
+            joins[idx] = plain_average ? (idist + jdist) / 2 : (idist * isize + jdist * jsize) / (isize + jsize);
         }
         slot_node[si] = node;
         for (int idx : alive) { dist[(size_t)si * n + idx] = joins[idx]; dist[(size_t)idx * n + si] = joins[idx]; }
@@ -62,15 +64,29 @@ extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* s
         }
     }
     // weights: sum over the path to the root of branch / leaves-below, float accumulation from the leaf upwards
-    float wsum = 0.0f;
-    for (int i = 0; i < n; ++i) {
-        float w = 0;
-        for (int c = i; parent[c] >= 0; c = parent[c]) w += branch[c] / leaves[c];
-        weights[i] = w;
+    if (iweights) {
+        // MSAGuideTree::getSeqsWeights MSAGuideTree.cpp:274-322: integer weights, (int)(100 w) normalised to INT_MULTIPLY = 1000, at least 1
+        int wsum = 0;
+        for (int i = 0; i < n; ++i) {
+            float w = 0;
+            for (int c = i; parent[c] >= 0; c = parent[c]) w += branch[c] / leaves[c];
+            iweights[i] = (int)(100 * w);
+            wsum += iweights[i];
+        }
+        if (wsum == 0) { for (int i = 0; i < n; ++i) iweights[i] = 1; wsum = n; }
+        for (int i = 0; i < n; ++i) { iweights[i] = (iweights[i] * 1000) / wsum; if (iweights[i] < 1) iweights[i] = 1; }
     }
-    for (int i = 0; i < n; ++i) wsum += weights[i];
-    if (wsum == 0) { for (int i = 0; i < n; ++i) weights[i] = 1.0f; wsum = (float)n; }
-    for (int i = 0; i < n; ++i) weights[i] = weights[i] / wsum;
+    if (weights) {
+        float wsum = 0.0f;
+        for (int i = 0; i < n; ++i) {
+            float w = 0;
+            for (int c = i; parent[c] >= 0; c = parent[c]) w += branch[c] / leaves[c];
+            weights[i] = w;
+        }
+        for (int i = 0; i < n; ++i) wsum += weights[i];
+        if (wsum == 0) { for (int i = 0; i < n; ++i) weights[i] = 1.0f; wsum = (float)n; }
+        for (int i = 0; i < n; ++i) weights[i] = weights[i] / wsum;
+    }
     if (subtree_dist) {
         // distance(i,j) = number of leaves under the lowest common ancestor = leaves[child_i] + leaves[child_j]
         std::vector<int> depth(total, 0);
@@ -91,6 +107,18 @@ extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* s
     if (left_out) for (int v = 0; v < total; ++v) left_out[v] = lch[v];
     if (right_out) for (int v = 0; v < total; ++v) right_out[v] = rch[v];
     return MLP_OK;
+}
+
+extern "C" int mlp_qp_guide_tree_ex(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out,
+                                    int32_t* left_out, int32_t* right_out) {
+    if (!weights) return MLP_E_ARG;
+    return upgma_core(n, dist, 2.0f, false, weights, nullptr, subtree_dist, parent_out, left_out, right_out);
+}
+
+// cpnp: MSAClusterTree::generateClusterTree(varianceid) MSAClusterTree.cpp:170-296 + MSAGuideTree::getSeqsWeights
+extern "C" int mlp_cpnp_guide_tree(int n, float* dist, int variance_id, int32_t* weights_out, int32_t* left_out, int32_t* right_out) {
+    if (!weights_out) return MLP_E_ARG;
+    return upgma_core(n, dist, 1.1f, variance_id == 0, nullptr, weights_out, nullptr, nullptr, left_out, right_out);
 }
 
 extern "C" int mlp_qp_guide_tree(int n, float* dist, float* weights, float* subtree_dist, int32_t* parent_out) {

@@ -33,12 +33,11 @@ void row_mapping(const std::string& row, std::vector<int>& map) {
 class HostProfilePosterior : public ProfilePosterior {
 public:
     explicit HostProfilePosterior(const HostCsrView& v) : v_(v) {}
-    int build(const Profile& A, const Profile& B, const float* weights, const float** out) override {
+    int build(const Profile& A, const Profile& B, const WeightSpec& ws, const float** out) override {
         const int l1 = A.length(), l2 = B.length();
         std::vector<float>& dense = dense_;
         dense.assign((size_t)(l1 + 1) * (l2 + 1), 0.0f);
-        double total = 0;                                     // finalSelectivity is FLT_MAX: every pair counts
-        for (int a : A.ids) { const double w1 = weights[a]; for (int b : B.ids) total += w1 * (double)weights[b]; }
+        const double total = ws.total(A, B);
         std::vector<std::vector<int>> mapB(B.count());
         for (int j = 0; j < B.count(); ++j) row_mapping(B.rows[j], mapB[j]);
         std::vector<int> mapA;
@@ -46,10 +45,10 @@ public:
         for (int i = 0; i < A.count(); ++i) {
             const int first = A.ids[i];
             row_mapping(A.rows[i], mapA);
-            const double w1 = weights[first];
+            const double w1 = ws.weight_of(first);
             for (int j = 0; j < B.count(); ++j) {
                 const int second = B.ids[j];
-                const float w = (float)((w1 * (double)weights[second]) / total);
+                const float w = ws.pair_weight(w1, ws.weight_of(second), total);
                 const int64_t slot = (int64_t)first * v_.n + second;
                 const int32_t* rp = v_.rp_pool + v_.rp_off[slot];
                 const Cell* base = cells + v_.nz_off[slot];
@@ -82,7 +81,7 @@ std::string add_gaps(const std::string& row, const std::string& path, char id) {
     return out;
 }
 
-int align_profiles(const Profile& A, const Profile& B, const float* weights, ProfilePosterior& prov, Profile& out) {
+int align_profiles(const Profile& A, const Profile& B, const WeightSpec& weights, ProfilePosterior& prov, Profile& out) {
     std::string path;
     int rc = prov.build_and_align(A, B, weights, path);
     if (rc < 0) return rc;
@@ -168,7 +167,147 @@ struct ColumnRefiner {
 
 ProfilePosterior* make_host_provider(const HostCsrView& v) { return new HostProfilePosterior(v); }
 
-std::string mea_path(int l1, int l2, const float* dense) {
+double WeightSpec::total(const Profile& A, const Profile& B) const {
+    if (mode == QP_DOUBLE) {
+        double t = 0;                                         // finalSelectivity is FLT_MAX: every pair counts
+        for (int a : A.ids) { const double w1 = wf[a]; for (int b : B.ids) t += w1 * (double)wf[b]; }
+        return t;
+    }
+    if (mode == CPNP_INT) {
+        float t = 0;                                          // `float totalWeights += w1 * w2` with int operands
+        for (int a : A.ids) { const int w1 = wi[a]; for (int b : B.ids) t += w1 * wi[b]; }
+        return (double)t;
+    }
+    return 1.0;
+}
+
+// glibc's rand() (TYPE_3 additive feedback, r[i] = r[i-3] + r[i-31]) seeded with 1, which is what an unseeded program
+// gets; kept private so that the library neither depends on nor disturbs the host application's generator.
+struct GlibcRand {
+    std::vector<uint32_t> state;
+    size_t pos;
+    GlibcRand() {
+        std::vector<int64_t> s(34);
+        s[0] = 1;
+        for (int i = 1; i < 31; ++i) {
+            s[i] = (16807 * s[i - 1]) % 2147483647;
+            if (s[i] < 0) s[i] += 2147483647;
+        }
+        for (int i = 31; i < 34; ++i) s[i] = s[i - 31];
+        state.resize(34);
+        for (int i = 0; i < 34; ++i) state[i] = (uint32_t)s[i];
+        for (int i = 34; i < 344; ++i) state.push_back(state[i - 31] + state[i - 3]);
+        pos = state.size();
+    }
+    int next() {
+        state.push_back(state[pos - 31] + state[pos - 3]);
+        const uint32_t v = state[pos++];
+        if (state.size() > (1u << 16)) {                      // keep the history window small
+            state.erase(state.begin(), state.end() - 64);
+            pos = state.size();
+        }
+        return (int)(v >> 1);
+    }
+};
+
+int run_cpnp_tail(int n, const int32_t* len, const uint8_t* residues, const int32_t* iweights, const int32_t* left, const int32_t* right,
+                  ProfilePosterior& prov, int refine_reps, int pid, Profile& out, std::string& err) {
+    if (n < 1) { err = "no sequences"; return MLP_E_ARG; }
+    std::vector<long long> off(n);
+    long long tot = 0;
+    for (int i = 0; i < n; ++i) { off[i] = tot; tot += len[i]; }
+    if (n == 1) {
+        out.ids = {0};
+        out.rows = {std::string((const char*)residues, (size_t)len[0])};
+        return 0;
+    }
+    WeightSpec wtd;
+    wtd.mode = WeightSpec::CPNP_INT;
+    wtd.wi = iweights;
+    WeightSpec flat;
+    flat.mode = WeightSpec::UNWEIGHTED;
+    // MSA::ProcessTree (MSA.cpp:1369-1402): post-order, weighted profile posterior, rows sorted by label after every merge
+    const int total = 2 * n - 1;
+    std::vector<std::unique_ptr<Profile>> prof(total);
+    auto leaf = [&](int v) {
+        std::unique_ptr<Profile> p(new Profile());
+        p->ids = {v};
+        p->rows = {std::string((const char*)residues + off[v], (size_t)len[v])};
+        return p;
+    };
+    for (int v = n; v < total; ++v) {
+        const int l = left[v], r = right[v];
+        if (l < 0 || r < 0 || l >= v || r >= v) { err = "malformed guide tree"; return MLP_E_ARG; }
+        if (l < n) prof[l] = leaf(l);
+        if (r < n) prof[r] = leaf(r);
+        if (!prof[l] || !prof[r]) { err = "guide tree node used twice"; return MLP_E_ARG; }
+        prof[v].reset(new Profile());
+        const int rc = align_profiles(*prof[l], *prof[r], wtd, prov, *prof[v]);
+        if (rc < 0) { err = "profile posterior failed"; return rc; }
+        prof[l].reset();
+        prof[r].reset();
+    }
+    std::unique_ptr<Profile> aln = std::move(prof[total - 1]);
+
+    // MSA::ComputeFinalAlignment (MSA.cpp:1481-1534): the pass count adapts to what the passes report
+    int reps = refine_reps;
+    if (pid > 3 || n > 150) reps = 0;
+    if (n <= 50) reps = 2 * reps;
+    GlibcRand rng;
+    int ineffectiveness = 0;
+    const int cutoff_iter = 100;
+    Profile one, two;
+    std::vector<int> g1, g2;
+    for (int it = 0; it < reps; ++it) {
+        // MSA::DoIterativeRefinement (MSA.cpp:1537-1623): random bipartition by position in the CURRENT row order
+        int flag;
+        g1.clear(); g2.clear();
+        for (int i = 0; i < n; ++i) ((rng.next() % 2) ? g1 : g2).push_back(i);
+        if (g1.empty() || g2.empty()) flag = 2;
+        else {
+            extract_subset(*aln, g1, one);
+            extract_subset(*aln, g2, two);
+            const float* dense = nullptr;
+            const int rc = prov.build(one, two, flat, &dense);
+            if (rc < 0) { err = "profile posterior failed"; return rc; }
+            const int l1 = one.length(), l2 = two.length();
+            // "accuracy" of the current alignment: posterior mass on its own columns, float sum in column order
+            float before = 0;
+            {
+                const int L = aln->length();
+                int i1 = 0, i2 = 0;
+                for (int c = 0; c < L; ++c) {
+                    bool f1 = false, f2 = false;
+                    for (int k : g1) if (aln->rows[k][c] != '-') { f1 = true; break; }
+                    for (int k : g2) if (aln->rows[k][c] != '-') { f2 = true; break; }
+                    if (f1) ++i1;
+                    if (f2) ++i2;
+                    if (f1 && f2) before += dense[(size_t)i1 * (l2 + 1) + i2];
+                }
+            }
+            float score = 0;
+            const std::string path = mea_path(l1, l2, dense, &score);
+            std::unique_ptr<Profile> next(new Profile());
+            for (int k = 0; k < one.count(); ++k) { next->ids.push_back(one.ids[k]); next->rows.push_back(add_gaps(one.rows[k], path, 'X')); }
+            for (int k = 0; k < two.count(); ++k) { next->ids.push_back(two.ids[k]); next->rows.push_back(add_gaps(two.rows[k], path, 'Y')); }
+            aln = std::move(next);                            // no label sort here: the row order drifts, as in the reference
+            flag = (before == score) ? 1 : 0;
+        }
+        if (n > 20) {
+            if (n < 200) {
+                if (flag > 0) {
+                    if (reps < 4 * n) ++reps;
+                    if (flag == 1) ++ineffectiveness;
+                }
+                if (ineffectiveness > 2 * n && it > cutoff_iter) break;
+            } else if (n > 200) reps = 10;
+        }
+    }
+    out = std::move(*aln);
+    return 0;
+}
+
+std::string mea_path(int l1, int l2, const float* dense, float* score) {
     const size_t W = (size_t)l2 + 1;
     std::vector<float> two(2 * W, 0.0f);
     float* oldr = two.data();
@@ -189,6 +328,7 @@ std::string mea_path(int l1, int l2, const float* dense) {
         }
         std::swap(oldr, newr);
     }
+    if (score) *score = oldr[l2];
     std::string path;
     int r = l1, c = l2;
     while (r != 0 || c != 0) {
@@ -204,6 +344,9 @@ std::string mea_path(int l1, int l2, const float* dense) {
 int run_tail(int n, const int32_t* len, const uint8_t* residues, const float* weights, const int32_t* left, const int32_t* right,
              ProfilePosterior& prov, const TailOptions& opt, Profile& out, std::string& err) {
     if (n < 1) { err = "no sequences"; return MLP_E_ARG; }
+    WeightSpec ws;
+    ws.mode = WeightSpec::QP_DOUBLE;
+    ws.wf = weights;
     std::vector<long long> off(n);
     long long tot = 0;
     for (int i = 0; i < n; ++i) { off[i] = tot; tot += len[i]; }
@@ -228,7 +371,7 @@ int run_tail(int n, const int32_t* len, const uint8_t* residues, const float* we
         if (r < n) prof[r] = leaf(r);
         if (!prof[l] || !prof[r]) { err = "guide tree node used twice"; return MLP_E_ARG; }
         prof[v].reset(new Profile());
-        const int rc = align_profiles(*prof[l], *prof[r], weights, prov, *prof[v]);
+        const int rc = align_profiles(*prof[l], *prof[r], ws, prov, *prof[v]);
         if (rc < 0) { err = "profile posterior failed"; return rc; }
         prof[l].reset();
         prof[r].reset();
@@ -255,7 +398,7 @@ int run_tail(int n, const int32_t* len, const uint8_t* residues, const float* we
         extract_subset(*aln, g1, one);
         extract_subset(*aln, g2, two);
         std::unique_ptr<Profile> cand(new Profile());
-        const int rc = align_profiles(one, two, weights, prov, *cand);
+        const int rc = align_profiles(one, two, ws, prov, *cand);
         if (rc < 0) { err = "profile posterior failed"; return rc; }
         if (aln->length() >= cand->length()) aln = std::move(cand);
     }
@@ -290,3 +433,35 @@ extern "C" int mlp_qp_finish_alignment_host(int n, const int32_t* len, const uin
 }
 
 extern "C" void mlp_free_host(void* p) { std::free(p); }
+
+extern "C" int mlp_cpnp_finish_alignment_host(int n, const int32_t* len, const uint8_t* residues, const int32_t* iweights,
+                                              const int32_t* left, const int32_t* right, const int64_t* rp_off, const int64_t* nz_off,
+                                              const int32_t* rp_pool, const void* cells, int refine_reps, int pid,
+                                              char** rows_out, int32_t* aln_len, int32_t* order_out) {
+    if (!len || !residues || !rows_out || !aln_len) return MLP_E_ARG;
+    if (n > 1 && (!iweights || !left || !right || !rp_off || !nz_off || !rp_pool || !cells)) return MLP_E_ARG;
+    qptail::HostCsrView v{n, len, rp_off, nz_off, rp_pool, cells};
+    std::unique_ptr<qptail::ProfilePosterior> prov(qptail::make_host_provider(v));
+    qptail::Profile out;
+    std::string err;
+    const int rc = qptail::run_cpnp_tail(n, len, residues, iweights, left, right, *prov, refine_reps, pid, out, err);
+    if (rc < 0) return rc;
+    const int L = out.length();
+    char* buf = (char*)std::malloc((size_t)n * (size_t)std::max(L, 1));
+    if (!buf) return MLP_E_NOMEM;
+    for (int i = 0; i < n; ++i) {
+        std::memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+        if (order_out) order_out[i] = out.ids[i];
+    }
+    *rows_out = buf;
+    *aln_len = L;
+    return MLP_OK;
+}
+
+// test hook: the first `count` values of the private glibc rand() replica (seed 1)
+extern "C" int mlp_debug_glibc_rand(int count, int32_t* out) {
+    if (count < 0 || !out) return MLP_E_ARG;
+    qptail::GlibcRand g;
+    for (int i = 0; i < count; ++i) out[i] = g.next();
+    return MLP_OK;
+}

@@ -17,14 +17,33 @@ struct Profile {
     int count() const { return (int)ids.size(); }
 };
 
+// How a pair (a in A, b in B) is weighted inside a profile-profile posterior.
+//   QP_DOUBLE     : w = (float)((double)wf[a] * wf[b] / total), total = double sum over all pairs   (ParallelProbabilisticModel.cpp:318-360)
+//   CPNP_INT      : w = (float)(wi[a] * wi[b]) / total, total = FLOAT running sum of the int products (cpnp ProbabilisticModel.h:1304-1331)
+//   UNWEIGHTED    : w = 1                                                                             (cpnp ProbabilisticModel.h:1197-1285)
+struct WeightSpec {
+    enum Mode { QP_DOUBLE = 0, CPNP_INT = 1, UNWEIGHTED = 2 };
+    int mode = QP_DOUBLE;
+    const float* wf = nullptr;
+    const int32_t* wi = nullptr;
+    double weight_of(int id) const { return mode == QP_DOUBLE ? (double)wf[id] : (mode == CPNP_INT ? (double)wi[id] : 1.0); }
+    // the reference's normaliser, accumulated in its order and precision (returned as double; exact for the float case)
+    double total(const Profile& A, const Profile& B) const;
+    float pair_weight(double wa, double wb, double tot) const {
+        if (mode == QP_DOUBLE) return (float)((wa * wb) / tot);
+        if (mode == CPNP_INT) return (float)(wa * wb) / (float)tot;      // int product (exact in float) / float total
+        return 1.0f;
+    }
+};
+
 // Produces the weighted sum of the pairwise sparse posteriors of every (a in A, b in B), scattered through the
 // profiles' column mappings, as a dense (lenA+1) x (lenB+1) row-major float matrix (row/column 0 unused, zero).
 struct ProfilePosterior {
     virtual ~ProfilePosterior() {}
     // returns 0 or a negative MLP_E_* code; *dense points at a provider-owned buffer valid until the next call
-    virtual int build(const Profile& A, const Profile& B, const float* weights, const float** dense) = 0;
+    virtual int build(const Profile& A, const Profile& B, const WeightSpec& ws, const float** dense) = 0;
     // optional fused path: MEA traceback string directly (returns 1 = not supported, caller runs the host DP on `dense`)
-    virtual int build_and_align(const Profile& A, const Profile& B, const float* weights, std::string& path) { (void)A; (void)B; (void)weights; path.clear(); return 1; }
+    virtual int build_and_align(const Profile& A, const Profile& B, const WeightSpec& ws, std::string& path) { (void)A; (void)B; (void)ws; path.clear(); return 1; }
 };
 
 struct HostCsrView {
@@ -47,7 +66,14 @@ struct TailOptions {
 int run_tail(int n, const int32_t* len, const uint8_t* residues, const float* weights, const int32_t* left, const int32_t* right,
              ProfilePosterior& prov, const TailOptions& opt, Profile& out, std::string& err);
 
-// MEA traceback over a dense profile posterior (ProbabilisticModel::computeAlignment, ProbabilisticModel.cpp:345-421)
-std::string mea_path(int l1, int l2, const float* dense);
+// c_p_np_aln -p 0 (cpnp flavour): ProcessTree with weighted profile posteriors, then DoIterativeRefinement's random
+// bipartitions (MSA.cpp:1369-1623).  iweights: MSAGuideTree's integer weights; refine_reps: -ir (default 100); pid: model
+// class (variance_mean % 10).  `out` keeps the reference's row order (refinement never re-sorts), ids = input indices.
+int run_cpnp_tail(int n, const int32_t* len, const uint8_t* residues, const int32_t* iweights, const int32_t* left, const int32_t* right,
+                  ProfilePosterior& prov, int refine_reps, int pid, Profile& out, std::string& err);
+
+// MEA traceback over a dense profile posterior (ProbabilisticModel::computeAlignment, ProbabilisticModel.cpp:345-421);
+// *score (may be NULL) receives the maximum sum, i.e. the last cell of the last row
+std::string mea_path(int l1, int l2, const float* dense, float* score = nullptr);
 
 }  // namespace qptail

@@ -27,6 +27,7 @@ struct PPArgs {
     const int* idsA; const int* idsB;
     const double* wA; const double* wB;
     double total;
+    int wmode;                       // qptail::WeightSpec::Mode
     int nA, nB, l1, l2, ldB, n;
     const long long* rp_off; const long long* nz_off; const int* rp_pool; const int2* cells;
     float* dense;                    // (l1+1) x (l2+1)
@@ -61,7 +62,9 @@ __global__ void __launch_bounds__(PP_THREADS) k_profile_posterior(PPArgs a) {
                     const long long rpo = a.rp_off[slot];
                     const int s = a.rp_pool[rpo + ii], e = a.rp_pool[rpo + ii + 1];
                     const long long base = a.nz_off[slot] + s;
-                    const float w = (float)((wa * a.wB[j]) / a.total);
+                    const double wb = a.wB[j];
+                    const float w = a.wmode == 0 ? (float)((wa * wb) / a.total)
+                                  : (a.wmode == 1 ? __fdiv_rn((float)(wa * wb), (float)a.total) : 1.0f);
                     cnt = e - s;
                     const int* mb = a.mapB + (size_t)j * a.ldB;
                     const int m = cnt < PP_CAP ? cnt : PP_CAP;
@@ -190,7 +193,7 @@ public:
         if (d_tb) cudaFree(d_tb);
         if (h_tb) cudaFreeHost(h_tb);
     }
-    int launch_profile(const qptail::Profile& A, const qptail::Profile& B, const float* weights) {
+    int launch_profile(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws) {
         const int nA = A.count(), nB = B.count(), l1 = A.length(), l2 = B.length();
         int ldB = 1;
         for (int j = 0; j < nB; ++j) ldB = std::max(ldB, ctx->len[B.ids[j]] + 1);
@@ -221,10 +224,9 @@ public:
         int* mapB = invA + n_inv;
         int* idsA = mapB + n_map;
         int* idsB = idsA + nA;
-        double total = 0;                                         // finalSelectivity = FLT_MAX: every pair counts
-        for (int i = 0; i < nA; ++i) { const double w1 = weights[A.ids[i]]; for (int j = 0; j < nB; ++j) total += w1 * (double)weights[B.ids[j]]; }
-        for (int i = 0; i < nA; ++i) { wA[i] = weights[A.ids[i]]; idsA[i] = A.ids[i]; }
-        for (int j = 0; j < nB; ++j) { wB[j] = weights[B.ids[j]]; idsB[j] = B.ids[j]; }
+        const double total = ws.total(A, B);                      // the reference's normaliser, in its order and precision
+        for (int i = 0; i < nA; ++i) { wA[i] = ws.weight_of(A.ids[i]); idsA[i] = A.ids[i]; }
+        for (int j = 0; j < nB; ++j) { wB[j] = ws.weight_of(B.ids[j]); idsB[j] = B.ids[j]; }
         for (int i = 0; i < nA; ++i) {                            // [i][column], row-major: sequential writes
             const char* row = A.rows[i].data();
             int* dst = invA + (size_t)i * (l1 + 1);
@@ -249,7 +251,7 @@ public:
         PPArgs a;
         a.wA = (const double*)d_blob; a.wB = a.wA + nA;
         a.invA = (const int*)(a.wB + nB); a.mapB = a.invA + n_inv; a.idsA = a.mapB + n_map; a.idsB = a.idsA + nA;
-        a.total = total; a.nA = nA; a.nB = nB; a.l1 = l1; a.l2 = l2; a.ldB = ldB; a.n = ctx->n;
+        a.total = total; a.wmode = ws.mode; a.nA = nA; a.nB = nB; a.l1 = l1; a.l2 = l2; a.ldB = ldB; a.n = ctx->n;
         const CsrSetDev& S = ctx->set[ctx->cur];
         a.rp_off = ctx->d_rp_off; a.nz_off = S.nz_off; a.rp_pool = S.rp_pool; a.cells = S.cells;
         a.dense = d_dense;
@@ -271,8 +273,8 @@ public:
         return 0;
     }
 
-    int build(const qptail::Profile& A, const qptail::Profile& B, const float* weights, const float** out) override {
-        int rc = launch_profile(A, B, weights);
+    int build(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws, const float** out) override {
+        int rc = launch_profile(A, B, ws);
         if (rc < 0) return rc;
         const size_t dn = (size_t)(A.length() + 1) * (B.length() + 1);
         CK(cudaMemcpyAsync(h_dense, d_dense, dn * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -284,7 +286,7 @@ public:
     }
 
     // profile posterior + MEA wavefront on the device, 2-bit choices back to the host, traceback there
-    int build_and_align(const qptail::Profile& A, const qptail::Profile& B, const float* weights, std::string& path) override {
+    int build_and_align(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws, std::string& path) override {
         const int l1 = A.length(), l2 = B.length();
         const int W = l2 + 1;
         if (W > 1024 * MEA_MAXC || l1 < 1 || l2 < 1) return 1;    // very wide profile: host dynamic programme on the dense matrix
@@ -293,7 +295,7 @@ public:
         const int Bb = (C + 3) / 4;
         const size_t smem = ((size_t)T * C + 4 * (size_t)T) * 4;
         if (smem > 200 * 1024) return 1;
-        int rc = launch_profile(A, B, weights);
+        int rc = launch_profile(A, B, ws);
         if (rc < 0) return rc;
         const size_t tbn = (size_t)l1 * T * Bb;
         if (tbn > tb_cap) {
@@ -373,6 +375,36 @@ extern "C" int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const
     char* buf = (char*)malloc((size_t)ctx->n * (size_t)std::max(L, 1));
     if (!buf) { ctx->err = "out of host memory"; return MLP_E_NOMEM; }
     for (int i = 0; i < ctx->n; ++i) memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+    *rows_out = buf;
+    *aln_len = L;
+    return MLP_OK;
+}
+
+extern "C" int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, const int32_t* left, const int32_t* right,
+                                         int refine_reps, int pid, char** rows_out, int32_t* aln_len, int32_t* order_out) {
+    if (!ctx) return MLP_E_ARG;
+    if (!rows_out || !aln_len) { ctx->err = "null output"; return MLP_E_ARG; }
+    if (ctx->n < 2) { ctx->err = "no sequences"; return MLP_E_STATE; }
+    if (!iweights || !left || !right) { ctx->err = "weights and tree required"; return MLP_E_ARG; }
+    if (!ctx->have_sets || (ctx->flavour_of_set != MLP_CPNP_P0 && ctx->flavour_of_set != MLP_CPNP_P1)) { ctx->err = "no c_p_np_aln sparse set on the device"; return MLP_E_STATE; }
+    if (ctx->world > 1 && !ctx->nccl_comm) { ctx->err = "sharded set: call mlp_exchange first"; return MLP_E_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->stats = mlp_stage_stats{};
+    std::vector<uint8_t> letters(ctx->codes_h.size());
+    for (size_t k = 0; k < letters.size(); ++k) letters[k] = (uint8_t)('A' + ctx->codes_h[k]);
+    std::vector<int32_t> len(ctx->len.begin(), ctx->len.end());
+    DeviceProfilePosterior prov(ctx);
+    qptail::Profile out;
+    std::string err;
+    const int rc = qptail::run_cpnp_tail(ctx->n, len.data(), letters.data(), iweights, left, right, prov, refine_reps, pid, out, err);
+    if (rc < 0) { if (ctx->err.empty() || rc != MLP_E_CUDA) ctx->err = err; return rc; }
+    const int L = out.length();
+    char* buf = (char*)malloc((size_t)ctx->n * (size_t)std::max(L, 1));
+    if (!buf) { ctx->err = "out of host memory"; return MLP_E_NOMEM; }
+    for (int i = 0; i < ctx->n; ++i) {
+        memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+        if (order_out) order_out[i] = out.ids[i];
+    }
     *rows_out = buf;
     *aln_len = L;
     return MLP_OK;

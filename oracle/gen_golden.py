@@ -55,6 +55,16 @@ def pack(d, tags, full, dense):
     return out
 
 
+def read_rows(path):
+    """FASTA alignment -> (n, columns) uint8 matrix"""
+    rows = []
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"): rows.append("")
+        elif line: rows[-1] += line
+    return np.frombuffer("".join(rows).encode(), np.uint8).reshape(len(rows), -1).copy()
+
+
 def run_cpnp(name, fasta, full, dense, pid=None, p1=False, reps=2):
     with tempfile.TemporaryDirectory() as td:
         dump = os.path.join(td, "d.bin")
@@ -64,19 +74,25 @@ def run_cpnp(name, fasta, full, dense, pid=None, p1=False, reps=2):
         if not dense: cmd += ["--nodense"]
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
         d = read_dump(dump)
+        extra = {}
+        if pid is None and not p1:
+            # the reference's whole `-p 0` program (tree, progressive alignment, iterative refinement) on one OpenMP thread:
+            # with more threads its refinement races on the shared posterior and the output changes from run to run
+            tmpfa = os.path.join(td, "in.fa")
+            res = d["residues"].tobytes().decode(); at = 0
+            with open(tmpfa, "w") as f:
+                for i, L in enumerate(d["lens"]):
+                    f.write(">s%d\n%s\n" % (i, res[at:at + int(L)])); at += int(L)
+            for key, ir in (("msa", None), ("msa_ir0", 0)):
+                out = os.path.join(td, key + ".fa")
+                subprocess.check_call([CPNP, "msa", tmpfa, out, "--threads", "1"] + ([] if ir is None else ["--ir", str(ir)]), stdout=subprocess.DEVNULL)
+                extra[key] = read_rows(out)
+                extra[key + "_order"] = np.array([int(l[2:]) for l in open(out) if l.startswith(">")], np.int32)
     tags = ["s%d" % r for r in range(reps + 1)]
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), **pack(d, tags, full, dense))
+    out = pack(d, tags, full, dense)
+    out.update(extra)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
-
-
-def read_rows(path):
-    """FASTA alignment -> (n, columns) uint8 matrix"""
-    rows = []
-    for line in open(path):
-        line = line.strip()
-        if line.startswith(">"): rows.append("")
-        elif line: rows[-1] += line
-    return np.frombuffer("".join(rows).encode(), np.uint8).reshape(len(rows), -1).copy()
 
 
 def run_qp(name, fasta, full, dense):

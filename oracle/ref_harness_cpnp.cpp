@@ -63,14 +63,27 @@ int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: ref_cpnp dump|bench <fasta> [out.bin] [--pid P] [--reps R] [--threads T] [--p1] [--nodense]\n"); return 2; }
     o.mode = argv[1]; o.fasta = argv[2];
     int ai = 3;
-    if (o.mode == "dump") { o.out = argv[3]; ai = 4; }
+    if (o.mode == "dump" || o.mode == "msa") { o.out = argv[3]; ai = 4; }
+    int ir = -1;
     for (; ai < argc; ai++) {
         std::string a = argv[ai];
+        if (a == "--ir") { ir = atoi(argv[++ai]); continue; }
         if (a == "--pid") o.pid = atoi(argv[++ai]);
         else if (a == "--reps") o.reps = atoi(argv[++ai]);
         else if (a == "--threads") o.threads = atoi(argv[++ai]);
         else if (a == "--p1") o.p1 = 1;
         else if (a == "--nodense") o.dense = 0;
+    }
+    if (o.mode == "msa") {
+        // the reference's complete program flow (MSA::MSA, MSA.cpp:123-187): `c_p_np_aln -p 0 [-ir R] -o out fasta`, with the
+        // OpenMP team pinned to o.threads (1 = the deterministic summation order of BuildPosterior)
+        numThreads = o.threads;
+        std::string irs = std::to_string(ir);
+        std::vector<const char*> av = {"c_p_np_aln", "-p", "0", "-o", o.out.c_str()};
+        if (ir >= 0) { av.push_back("-ir"); av.push_back(irs.c_str()); }
+        av.push_back(o.fasta.c_str());
+        MSA whole((int)av.size(), (char**)av.data());
+        return 0;
     }
     // An MSA object without running its all-in-one constructor (MSA.cpp:123-187); only the
     // members the called methods touch (numPairs, seqsPairs) are initialised.

@@ -62,3 +62,14 @@ def tail_from_csrset(S, seqs, distances, ref_iters=-1):
     cells["c"] = S.col
     cells["v"] = S.val
     return M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], S.rp_off, S.nz_off, S.rowptr, cells, ref_iters)
+
+
+def cpnp_tail_from_csrset(S, seqs, distances, variance_mean, refine_reps=100):
+    """c_p_np_aln -p 0 tail on the host (mlp_cpnp_guide_tree + mlp_cpnp_finish_alignment_host) from an oracle_lib.CsrSet."""
+    import mlprobs_b200 as M
+    t = M.cpnp_guide_tree(distances, int(variance_mean) // 10)
+    cells = np.zeros(len(S.col), dtype=[("c", np.int32), ("v", np.float32)])
+    cells["c"] = S.col
+    cells["v"] = S.val
+    return M.cpnp_finish_alignment_host(seqs, t["weights"], t["left"], t["right"], S.rp_off, S.nz_off, S.rowptr, cells,
+                                        refine_reps, int(variance_mean) % 10)

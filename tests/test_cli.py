@@ -66,3 +66,32 @@ def test_cli_single_sequence_is_echoed(tmp_path):
     fa, heads = write_input(tmp_path, [b"ACDEFGHIKLMNPQRSTVWY" * 4])
     r = subprocess.run([CLI, fa], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout == fasta_text(heads, [("ACDEFGHIKLMNPQRSTVWY" * 4)])
+
+
+CPNP = os.path.join(os.path.dirname(HERE), "mlprobs_b200", "bin", "c_p_np_aln_b200")
+
+
+def test_cpnp_cli_is_built_and_refuses_without_gpu_or_for_p1(tmp_path):
+    assert os.path.exists(CPNP), "run __graft_entry__.build()"
+    fa, _ = write_input(tmp_path, [b"ACDEFGHIK", b"ACDEFGHIK"])
+    r = subprocess.run([CPNP, "-p", "1", fa], capture_output=True, text=True)
+    assert r.returncode == 2 and "not built" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([CPNP, "-p", "0", fa], capture_output=True, text=True)
+        assert r.returncode != 0 and "CUDA device is required" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_676s4_ref"])
+def test_cpnp_cli_reproduces_the_reference(tmp_path, name):
+    d = load_golden(name)
+    seqs = split_seqs(d)
+    fa, heads = write_input(tmp_path, seqs)
+    want = fasta_text([heads[i] for i in d["msa_order"]], [r.tobytes().decode() for r in d["msa"]])
+    r = subprocess.run([CPNP, "-p", "0", fa], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want
+    if name == "cpnp_sup002_ref":           # the -G feature line (20 standard letters only)
+        r = subprocess.run([CPNP, "-G", fa], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout == d["gline"].tobytes().decode() + "\n"

@@ -112,6 +112,29 @@ def test_cpnp_against_reference_fixture(name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["cpnp_sup002_ref", "cpnp_676s4_ref"])
+def test_cpnp_tail_against_reference_alignment(name):
+    """`c_p_np_aln -p 0` to the end on the device-resident set: tree, weighted progressive alignment, random-bipartition
+    refinement -> the reference's one-thread output, rows in its order (MSA.cpp:1369-1623)."""
+    d = load_golden(name)
+    seqs = split_seqs(d); n = len(seqs)
+    vm = int(d["variance_mean"][0])
+    eng = engine(M.CPNP_P0, seqs, float(d["initDistrib2"][0]))
+    eng.posterior_all_pairs(M.CPNP_P0, cpnp_mask(vm % 10), 0.01)
+    t = M.cpnp_guide_tree(eng.distances(), vm // 10)
+    for r in range(2):
+        eng.relax(M.CPNP_P0, cutoff=0.01)
+    for key, ir in (("msa_ir0", 0), ("msa", 100)):
+        rows, order = eng.cpnp_finish_alignment(t["weights"], t["left"], t["right"], ir, vm % 10)
+        np.testing.assert_array_equal(order, d[key + "_order"], err_msg=key)
+        assert rows == [r.tobytes() for r in d[key]], key
+    raw = eng.csr_raw()
+    rows_h, order_h = M.cpnp_finish_alignment_host(seqs, t["weights"], t["left"], t["right"], raw.rp_off, raw.nz_off, raw.rp_pool, raw.cells, 100, vm % 10)
+    assert rows_h == rows and np.array_equal(order_h, order)
+    raw.close()
+    eng.close()
+
+
 def test_cpnp_dense_models_fixture():
     d = load_golden("cpnp_sup139_mix")
     seqs = split_seqs(d); n = len(seqs)

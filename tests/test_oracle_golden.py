@@ -102,6 +102,14 @@ def test_cpnp_stage_and_relaxation(name, flav):
     for r in range(int(d["reps"][0])):
         S = O.relax_cpnp(S, 0.01, threads=4)
         assert_digest(d, "s%d" % (r + 1), S.get, n)
+    if "msa" in d:
+        # `c_p_np_aln -p 0` to the end (tree, weighted progressive alignment, random-bipartition refinement): the host tail fed
+        # with this sparse set reproduces the reference's one-thread output, rows in its order
+        from common import cpnp_tail_from_csrset
+        for key, ir in (("msa_ir0", 0), ("msa", 100)):
+            rows, order = cpnp_tail_from_csrset(S, seqs, d["distances"], int(d["variance_mean"][0]), ir)
+            np.testing.assert_array_equal(order, d[key + "_order"], err_msg=key)
+            assert rows == [r.tobytes() for r in d[key]], key
 
 
 @pytest.mark.parametrize("name", ["qp_sup139", "qp_sup002", "qp_676s4", "qp_75t2"])

@@ -71,3 +71,12 @@ def test_single_sequence_and_refinement_options():
     # `-r 0` means "reference default" there (RefinementBase.cpp:33): same result as -1
     assert M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], rp_off, nz_off, rp_pool, cells, 0) == \
         [r.tobytes() for r in d["msa"]]
+
+
+def test_private_glibc_rand_replica_matches_libc():
+    """DoIterativeRefinement (MSA.cpp:1545) draws from an unseeded rand(); the library carries its own copy of that stream."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    want = [libc.rand() for _ in range(5000)]
+    assert M.debug_glibc_rand(5000).tolist() == want

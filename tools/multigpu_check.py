@@ -28,10 +28,12 @@ def run(sharded):
     w, sd, _, _ = M.qp_guide_tree(d)
     eng.relax(M.QP, np.maximum(w, np.float32(1e-6)), sd, 200.0, 3.0, float(np.float32(1e-5)))
     if sharded: eng.exchange()
+    t = M.qp_guide_tree_ex(d)      # the tail runs on every rank over the exchanged (complete) set
+    rows = eng.qp_finish_alignment(np.maximum(t["weights"], np.float32(1e-6)), t["left"], t["right"], 6)
     nnz, rp, col, val = eng.csr_bulk()
     tr = [eng.csr(b, a) for a, b in [(0, 1), (n - 2, n - 1), (3, n // 2)]]
     sig = (zlib.crc32(d.tobytes()), zlib.crc32(nnz.tobytes()), zlib.crc32(rp.tobytes()), zlib.crc32(col.tobytes()), zlib.crc32(val.tobytes()),
-           tuple(zlib.crc32(x[1].tobytes()) ^ zlib.crc32(x[2].tobytes()) for x in tr))
+           tuple(zlib.crc32(x[1].tobytes()) ^ zlib.crc32(x[2].tobytes()) for x in tr), zlib.crc32(b"".join(rows)))
     eng.close()
     return sig
 
