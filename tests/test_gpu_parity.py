@@ -76,6 +76,27 @@ def test_qp_tail_long_rows_and_wide_profiles_vs_host():
     eng.close()
 
 
+def test_qp_tail_profiles_wider_than_the_device_wavefront_fall_back_to_the_host_dp():
+    """Three unrelated sequences of 8300 residues: every profile is wider than the 8192 columns the MEA wavefront kernel
+    handles, so the dense matrix comes back and the host walks it; device tail == host tail."""
+    rng = np.random.default_rng(11)
+    al = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    seqs = [al[rng.integers(0, 20, 8300)].tobytes() for _ in range(3)]
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    t = M.qp_guide_tree_ex(eng.distances())
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    for it in range(2):
+        eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, 0.01 if it == 0 else float(np.float32(1e-5)))
+    dev = eng.qp_finish_alignment(w, t["left"], t["right"], 3)
+    raw = eng.csr_raw()
+    host = M.qp_finish_alignment_host(seqs, w, t["left"], t["right"], raw.rp_off, raw.nz_off, raw.rp_pool, raw.cells, 3)
+    assert len(dev[0]) > 8192
+    assert dev == host
+    raw.close()
+    eng.close()
+
+
 def test_qp_dense_posteriors_fixture():
     d = load_golden("qp_sup139")
     seqs = split_seqs(d); n = len(seqs)
