@@ -88,18 +88,32 @@ static int upgma_core(int n, float* dist, float first_best, bool plain_average, 
         for (int i = 0; i < n; ++i) weights[i] = weights[i] / wsum;
     }
     if (subtree_dist) {
-        // distance(i,j) = number of leaves under the lowest common ancestor = leaves[child_i] + leaves[child_j]
-        std::vector<int> depth(total, 0);
-        for (int v = total - 2; v >= 0; --v) depth[v] = depth[parent[v]] + 1;   // parents have larger indices
-        for (int i = 0; i < n; ++i) {
-            subtree_dist[(size_t)i * n + i] = 0.0f;
-            for (int j = i + 1; j < n; ++j) {
-                int a = i, b = j;
-                while (depth[a] > depth[b]) a = parent[a];
-                while (depth[b] > depth[a]) b = parent[b];
-                while (parent[a] != parent[b]) { a = parent[a]; b = parent[b]; }
-                const float d = (float)(size_t)(leaves[a] + leaves[b]);
-                subtree_dist[(size_t)i * n + j] = d; subtree_dist[(size_t)j * n + i] = d;
+        // distance(i,j) = number of leaves under the lowest common ancestor = leaves[left child] + leaves[right child].
+        // Every internal node is the LCA of exactly (leaves under left) x (leaves under right) pairs, so one pass over the nodes
+        // with the leaves laid out in depth-first order writes each of the N(N-1)/2 entries once: O(N^2) instead of an
+        // ancestor walk per pair.
+        std::vector<int> lo(total, 0), order;
+        order.reserve(n);
+        {
+            std::vector<int> stack;
+            stack.push_back(total - 1);
+            std::vector<int> pre;                     // preorder, left before right
+            while (!stack.empty()) {
+                const int v = stack.back(); stack.pop_back();
+                if (v < n) { lo[v] = (int)order.size(); order.push_back(v); }
+                else { stack.push_back(rch[v]); stack.push_back(lch[v]); pre.push_back(v); }
+            }
+            for (size_t k = pre.size(); k-- > 0;) { const int v = pre[k]; lo[v] = lo[lch[v]]; }   // children appear after their parent in preorder
+        }
+        for (int i = 0; i < n; ++i) subtree_dist[(size_t)i * n + i] = 0.0f;
+        for (int v = n; v < total; ++v) {
+            const int l = lch[v], r = rch[v];
+            const float d = (float)(size_t)(leaves[l] + leaves[r]);
+            const int* L = order.data() + lo[l]; const int nl = leaves[l];
+            const int* R = order.data() + lo[r]; const int nr = leaves[r];
+            for (int x = 0; x < nl; ++x) {
+                const int a = L[x];
+                for (int y = 0; y < nr; ++y) { const int b = R[y]; subtree_dist[(size_t)a * n + b] = d; subtree_dist[(size_t)b * n + a] = d; }
             }
         }
     }
