@@ -109,6 +109,12 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+# ncu --set full, main batch of tools/prof_run.py 192 300 (17,073 of the 18,336 pairs; the first 1,263 go to the small
+# density-measuring batch): k_hmm_fwd 1.394 + 6.868 GB, k_hmm_bwd 7.421 + 6.852 GB of DRAM traffic -> 14.57 B per DP cell against
+# 12 algorithmic (the slot layout pads 301 x 301 cells to 332 x 320 elements, x1.17)
+NCU_DRAM_BYTES_PER_CELL_HMM5 = (1.393716 + 6.868421 + 7.421081 + 6.852403) * 1e9 / (17073 * 301 * 301)
+
+
 def one_step(eng, M, n, e2e, seqs=None, world=1, read_back=True, host_out=None):
     """posterior stage [+ exchange] + host tree + consistency [+ exchange]. Returns the per-stage stats."""
     if e2e:
@@ -253,7 +259,12 @@ def main():
                 "roofline": {"bound": "fp32_issue", "kernel": "k_hmm_fwd+k_hmm_bwd", "achieved": slot_rate / 1e12, "peak": FP32_ISSUE_PEAK / 1e12,
                              "unit": "Tlane-op/s", "frac": slot_rate / FP32_ISSUE_PEAK,
                              "peak_source": "148 SMs x 128 FP32 lanes x 1.965 GHz (MEASURED_PEAKS.json sm_max_mhz); no measured FP32-issue peak exists in MEASURED_PEAKS.json",
-                             "algorithmic_ops_per_cell": SLOTS_PER_CELL["hmm5"], "traffic": None,
+                             "algorithmic_ops_per_cell": SLOTS_PER_CELL["hmm5"],
+                             # DRAM bytes (dram__bytes_read + write) of the two launches per step, from the ncu --set full capture
+                             # profiles/r1c_all_kernels_ncu_full.txt: 14.57 B per cell (k_hmm_fwd + k_hmm_bwd) against
+                             # 12 algorithmic, scaled to this workload's cells per launch
+                             "traffic": cells_rank * NCU_DRAM_BYTES_PER_CELL_HMM5,
+                             "traffic_source": "ncu dram bytes per cell measured at 192 x 300 (profiles/r1c_all_kernels_ncu_full.txt) x cells per step",
                              "hbm": {"bound": "hbm", "achieved": cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
                                      "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
                                      "frac": (cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9) / (peaks["hbm_gbs"] if peaks else 6650.0) if hmm_ms else None,
