@@ -92,35 +92,49 @@ int align_profiles(const Profile& A, const Profile& B, const WeightSpec& weights
         path = mea_path(A.length(), B.length(), dense);
     }
     // both groups arrive sorted by label (leaves, SortByLabel'ed results, index-ordered subsets): merge keeps that order
-    out.ids.clear(); out.rows.clear();
-    out.ids.reserve(A.count() + B.count()); out.rows.reserve(A.count() + B.count());
-    int i = 0, j = 0;
-    while (i < A.count() || j < B.count()) {
-        if (j >= B.count() || (i < A.count() && A.ids[i] < B.ids[j])) { out.ids.push_back(A.ids[i]); out.rows.push_back(add_gaps(A.rows[i], path, 'X')); ++i; }
-        else { out.ids.push_back(B.ids[j]); out.rows.push_back(add_gaps(B.rows[j], path, 'Y')); ++j; }
+    const int total = A.count() + B.count();
+    out.ids.assign(total, 0);
+    out.rows.assign(total, std::string());
+    std::vector<int> src(total);                      // >= 0: row of A, < 0: ~row of B
+    {
+        int i = 0, j = 0, k = 0;
+        while (i < A.count() || j < B.count()) {
+            if (j >= B.count() || (i < A.count() && A.ids[i] < B.ids[j])) { out.ids[k] = A.ids[i]; src[k++] = i++; }
+            else { out.ids[k] = B.ids[j]; src[k++] = ~(j++); }
+        }
     }
+#pragma omp parallel for schedule(static) if (total >= 64)
+    for (int k = 0; k < total; ++k)
+        out.rows[k] = src[k] >= 0 ? add_gaps(A.rows[src[k]], path, 'X') : add_gaps(B.rows[~src[k]], path, 'Y');
     return 0;
 }
 
 // rows `idx` of P with the columns that are gaps in all of them removed
 void extract_subset(const Profile& P, const std::vector<int>& idx, Profile& out) {
     const int len = P.length();
+    const int m = (int)idx.size();
     std::vector<char> keep(len, 0);
-    for (int r : idx) {
-        const char* s = P.rows[r].data();
-        for (int c = 0; c < len; ++c) keep[c] |= (char)(s[c] != '-');
+#pragma omp parallel for schedule(static) if ((long long)m * len >= (1 << 16))
+    for (int c0 = 0; c0 < len; c0 += 256) {           // column blocks: each thread ORs its own slice of `keep`
+        const int c1 = std::min(len, c0 + 256);
+        for (int r : idx) {
+            const char* s = P.rows[r].data();
+            for (int c = c0; c < c1; ++c) keep[c] |= (char)(s[c] != '-');
+        }
     }
     std::vector<int> cols;
     cols.reserve(len);
     for (int c = 0; c < len; ++c) if (keep[c]) cols.push_back(c);
-    out.ids.clear(); out.rows.clear();
-    out.ids.reserve(idx.size()); out.rows.reserve(idx.size());
-    for (int r : idx) {
-        const char* src = P.rows[r].data();
-        std::string s(cols.size(), '-');
-        for (size_t k = 0; k < cols.size(); ++k) s[k] = src[cols[k]];
-        out.ids.push_back(P.ids[r]);
-        out.rows.push_back(std::move(s));
+    out.ids.assign(m, 0);
+    out.rows.assign(m, std::string());
+    const int nc = (int)cols.size();
+#pragma omp parallel for schedule(static) if ((long long)m * len >= (1 << 16))
+    for (int k = 0; k < m; ++k) {
+        const char* src = P.rows[idx[k]].data();
+        std::string s((size_t)nc, '-');
+        for (int q = 0; q < nc; ++q) s[q] = src[cols[q]];
+        out.ids[k] = P.ids[idx[k]];
+        out.rows[k] = std::move(s);
     }
 }
 
@@ -135,9 +149,13 @@ struct ColumnRefiner {
         // the reference adds 1.0f per gap, column by column; counting first gives the same float as long as the running
         // value stays an exactly representable integer (below 2^24), otherwise fall back to the literal loop
         gaps.assign(len, 0);
-        for (int i = 0; i < n; ++i) {
-            const char* s = P.rows[i].data();
-            for (int c = 0; c < len; ++c) gaps[c] += (s[c] == '-');
+#pragma omp parallel for schedule(static) if ((long long)n * len >= (1 << 16))
+        for (int c0 = 0; c0 < len; c0 += 256) {
+            const int c1 = std::min(len, c0 + 256);
+            for (int i = 0; i < n; ++i) {
+                const char* s = P.rows[i].data();
+                for (int c = c0; c < c1; ++c) gaps[c] += (s[c] == '-');
+            }
         }
         for (int c = 0; c < len; ++c) {
             scores[c].first = c;

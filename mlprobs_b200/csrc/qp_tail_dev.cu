@@ -33,7 +33,7 @@ struct PPArgs {
     float* dense;                    // (l1+1) x (l2+1)
 };
 
-__global__ void __launch_bounds__(PP_THREADS) k_profile_posterior(PPArgs a) {
+__global__ void __launch_bounds__(PP_THREADS, 4) k_profile_posterior(PPArgs a) {
     extern __shared__ float sm[];
     float* acc = sm;                                              // l2+1 floats (rounded up to a multiple of 4)
     const int accn = (a.l2 + 1 + 3) & ~3;
@@ -44,61 +44,79 @@ __global__ void __launch_bounds__(PP_THREADS) k_profile_posterior(PPArgs a) {
     long long* s_base = (long long*)(s_w + PP_THREADS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = blockIdx.x;                                     // dense row, row 0 stays zero
-    int* s_ii = (int*)(s_base + PP_THREADS);                      // nA ints: this row's residue index in every group-1 sequence
+    int* s_ii = (int*)(s_base + PP_THREADS);                      // residue index of this row in the k-th group-1 sequence that has one
+    int* s_ik = s_ii + a.nA;                                      // ... and which sequence that is
+    __shared__ int s_nk;
     for (int c = tid; c <= a.l2; c += PP_THREADS) acc[c] = 0.0f;
-    for (int i = tid; i < a.nA; i += PP_THREADS) s_ii[i] = a.invA[(size_t)i * (a.l1 + 1) + r];
+    // ordered compaction of the group-1 sequences with a residue in this column (warp 0, ballot scan)
+    if (warp == 0) {
+        int nk = 0;
+        for (int i0 = 0; i0 < a.nA; i0 += 32) {
+            const int i = i0 + lane;
+            const int ii = (i < a.nA && r > 0) ? a.invA[(size_t)i * (a.l1 + 1) + r] : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, ii != 0);
+            if (ii != 0) { const int k = nk + __popc(m & ((1u << lane) - 1u)); s_ii[k] = ii; s_ik[k] = i; }
+            nk += __popc(m);
+        }
+        if (lane == 0) s_nk = nk;
+    }
     __syncthreads();
-    if (r > 0) {
-        for (int i = 0; i < a.nA; ++i) {
-            const int ii = s_ii[i];
-            if (ii == 0) continue;                                // CTA-uniform
-            const int sa = a.idsA[i];
-            const double wa = a.wA[i];
-            for (int j0 = 0; j0 < a.nB; j0 += PP_THREADS) {
-                const int j = j0 + tid;
-                int cnt = 0;
-                if (j < a.nB) {
-                    const long long slot = (long long)sa * a.n + a.idsB[j];
-                    const long long rpo = a.rp_off[slot];
-                    const int s = a.rp_pool[rpo + ii], e = a.rp_pool[rpo + ii + 1];
-                    const long long base = a.nz_off[slot] + s;
-                    const double wb = a.wB[j];
-                    const float w = a.wmode == 0 ? (float)((wa * wb) / a.total)
-                                  : (a.wmode == 1 ? __fdiv_rn((float)(wa * wb), (float)a.total) : 1.0f);
-                    cnt = e - s;
-                    const int* mb = a.mapB + (size_t)j * a.ldB;
-                    const int m = cnt < PP_CAP ? cnt : PP_CAP;
-                    for (int k = 0; k < m; ++k) {
-                        const int2 cell = a.cells[base + k];
-                        st_c[tid * PP_CAP + k] = mb[cell.x];
-                        st_x[tid * PP_CAP + k] = __fmul_rn(w, __int_as_float(cell.y));
-                    }
-                    s_w[tid] = w;
-                    s_base[tid] = base;
+    {
+        // pairs in the reference's order: p = k * nB + j (k over the compacted group-1 list, j over group 2), 256 per chunk
+        const long long npairs = (long long)s_nk * a.nB;
+        for (long long p0 = 0; p0 < npairs; p0 += PP_THREADS) {
+            const long long p = p0 + tid;
+            int cnt = 0;
+            if (p < npairs) {
+                const int k = (int)(p / a.nB), j = (int)(p - (long long)k * a.nB);
+                const int ii = s_ii[k], i = s_ik[k];
+                const long long slot = (long long)a.idsA[i] * a.n + a.idsB[j];
+                const long long rpo = a.rp_off[slot];
+                const int s = a.rp_pool[rpo + ii], e = a.rp_pool[rpo + ii + 1];
+                const long long base = a.nz_off[slot] + s;
+                const double wa = a.wA[i], wb = a.wB[j];
+                const float w = a.wmode == 0 ? (float)((wa * wb) / a.total)
+                              : (a.wmode == 1 ? __fdiv_rn((float)(wa * wb), (float)a.total) : 1.0f);
+                cnt = e - s;
+                const int* mb = a.mapB + (size_t)j * a.ldB;
+                const int m = cnt < PP_CAP ? cnt : PP_CAP;
+                for (int q = 0; q < m; ++q) {
+                    const int2 cell = a.cells[base + q];
+                    st_c[tid * PP_CAP + q] = mb[cell.x];
+                    st_x[tid * PP_CAP + q] = __fmul_rn(w, __int_as_float(cell.y));
                 }
-                s_cnt[tid] = cnt;
-                __syncthreads();
-                if (warp == 0) {
-                    const int np = min(PP_THREADS, a.nB - j0);
-                    for (int t = 0; t < np; ++t) {
-                        const int ct = s_cnt[t];
-                        if (lane < ct && lane < PP_CAP) {
-                            const int c = st_c[t * PP_CAP + lane];
-                            acc[c] = __fadd_rn(acc[c], st_x[t * PP_CAP + lane]);
-                        }
-                        if (ct > PP_CAP) {                        // long sparse row: remaining cells straight from HBM
-                            const int* mb = a.mapB + (size_t)(j0 + t) * a.ldB;
-                            for (int k = PP_CAP + lane; k < ct; k += 32) {
-                                const int2 cell = a.cells[s_base[t] + k];
-                                const int c = mb[cell.x];
-                                acc[c] = __fadd_rn(acc[c], __fmul_rn(s_w[t], __int_as_float(cell.y)));
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                __syncthreads();
+                s_w[tid] = w;
+                s_base[tid] = base;
             }
+            s_cnt[tid] = cnt;
+            __syncthreads();
+            if (warp == 0) {
+                const int np = (int)min((long long)PP_THREADS, npairs - p0);
+                // software pipeline: the record of pair t+1 is fetched before the read-modify-write of pair t, so the only
+                // serial chain left per pair is LDS(acc) -> FADD -> STS
+                const int sl = lane < PP_CAP ? lane : 0;
+                int ct = s_cnt[0], c = st_c[sl];
+                float x = st_x[sl];
+                for (int t = 0; t < np; ++t) {
+                    const int tn = (t + 1 < np) ? t + 1 : t;
+                    const int ct_n = s_cnt[tn], c_n = st_c[tn * PP_CAP + sl];
+                    const float x_n = st_x[tn * PP_CAP + sl];
+                    if (lane < ct && lane < PP_CAP) acc[c] = __fadd_rn(acc[c], x);
+                    if (ct > PP_CAP) {                            // long sparse row: remaining cells straight from HBM
+                        const long long pt = p0 + t;
+                        const int jt = (int)(pt - (pt / a.nB) * a.nB);
+                        const int* mb = a.mapB + (size_t)jt * a.ldB;
+                        for (int q = PP_CAP + lane; q < ct; q += 32) {
+                            const int2 cell = a.cells[s_base[t] + q];
+                            const int cq = mb[cell.x];
+                            acc[cq] = __fadd_rn(acc[cq], __fmul_rn(s_w[t], __int_as_float(cell.y)));
+                        }
+                    }
+                    __syncwarp();
+                    ct = ct_n; c = c_n; x = x_n;
+                }
+            }
+            __syncthreads();
         }
     }
     float* out = a.dense + (size_t)r * (a.l2 + 1);
@@ -111,6 +129,7 @@ __global__ void __launch_bounds__(PP_THREADS) k_profile_posterior(PPArgs a) {
 // it needs from its left neighbour was produced one step earlier.  Scores are exact (each cell is the reference's own
 // max-of-three with its tie order), the 2-bit choices go to HBM and the host walks them back.
 constexpr int MEA_MAXC = 8;
+constexpr int MEA_DEPTH = 4;
 struct MeaArgs {
     const float* dense; int l1, l2, C, T, B;
     unsigned char* tb;                 // [(l1)][T][B] 2-bit choices (0 = diagonal, 1 = left, 2 = up), rows 1..l1
@@ -125,61 +144,63 @@ __global__ void __launch_bounds__(1024) k_mea_wavefront(MeaArgs a) {
     for (int c = 0; c < C; ++c) row[j0 + c] = 0.0f;
     edge[t] = make_float2(0.0f, 0.0f);
     edge[a.T + t] = make_float2(0.0f, 0.0f);
-    float pf[MEA_MAXC];
+    // posteriors of the rows this thread reaches in the next MEA_DEPTH steps, in registers (one row per step; the loads of
+    // row i + MEA_DEPTH are issued when row i is consumed, far enough ahead to cover the L2 latency)
+    float pf[MEA_DEPTH][MEA_MAXC];
+    auto load_row = [&](int i, float (&dst)[MEA_MAXC]) {
 #pragma unroll
-    for (int c = 0; c < MEA_MAXC; ++c) pf[c] = 0.0f;
-    if (t == 0 && a.l1 >= 1) {
+        for (int c = 0; c < MEA_MAXC; ++c) dst[c] = 0.0f;
+        if (i >= 1 && i <= a.l1) {
+            const float* p = a.dense + (size_t)i * W + j0;
 #pragma unroll
-        for (int c = 0; c < MEA_MAXC; ++c) if (c < C && j0 + c < W) pf[c] = a.dense[(size_t)W + j0 + c];
-    }
+            for (int c = 0; c < MEA_MAXC; ++c) if (c < C && j0 + c < W) dst[c] = p[c];
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < MEA_DEPTH; ++u) load_row(u - t + 1, pf[u]);
     __syncthreads();
     const int steps = a.l1 + a.T - 1;
-    for (int s = 0; s < steps; ++s) {
-        const int i = s - t + 1;
-        float nx[MEA_MAXC];
+    for (int s0 = 0; s0 < steps; s0 += MEA_DEPTH) {
 #pragma unroll
-        for (int c = 0; c < MEA_MAXC; ++c) nx[c] = 0.0f;
-        if (i + 1 >= 1 && i + 1 <= a.l1) {
-            const float* p = a.dense + (size_t)(i + 1) * W + j0;
+        for (int u = 0; u < MEA_DEPTH; ++u) {
+            const int s = s0 + u;
+            const int i = s - t + 1;
+            if (s < steps && i >= 1 && i <= a.l1 && j0 < W) {
+                float d = 0.0f, l = 0.0f;
+                if (t > 0) { const float2 e = edge[((s + 1) & 1) * a.T + t - 1]; d = e.x; l = e.y; }
+                unsigned bits = 0;
+                float o = 0.0f, v = 0.0f;
 #pragma unroll
-            for (int c = 0; c < MEA_MAXC; ++c) if (c < C && j0 + c < W) nx[c] = p[c];
-        }
-        if (i >= 1 && i <= a.l1 && j0 < W) {
-            float d = 0.0f, l = 0.0f;
-            if (t > 0) { const float2 e = edge[((s + 1) & 1) * a.T + t - 1]; d = e.x; l = e.y; }
-            unsigned bits = 0;
-            float o = 0.0f, v = 0.0f;
-#pragma unroll
-            for (int c = 0; c < MEA_MAXC; ++c) {
-                if (c < C && j0 + c < W) {
-                    const int j = j0 + c;
-                    o = row[j];
-                    if (j == 0) v = 0.0f;
-                    else {
-                        const float x1 = __fadd_rn(pf[c], d);
-                        unsigned dir;
-                        if (x1 >= l) { if (x1 >= o) { v = x1; dir = 0; } else { v = o; dir = 2; } }
-                        else if (l >= o) { v = l; dir = 1; }
-                        else { v = o; dir = 2; }
-                        bits |= dir << (2 * c);
+                for (int c = 0; c < MEA_MAXC; ++c) {
+                    if (c < C && j0 + c < W) {
+                        const int j = j0 + c;
+                        o = row[j];
+                        if (j == 0) v = 0.0f;
+                        else {
+                            const float x1 = __fadd_rn(pf[u][c], d);
+                            unsigned dir;
+                            if (x1 >= l) { if (x1 >= o) { v = x1; dir = 0; } else { v = o; dir = 2; } }
+                            else if (l >= o) { v = l; dir = 1; }
+                            else { v = o; dir = 2; }
+                            bits |= dir << (2 * c);
+                        }
+                        d = o; l = v; row[j] = v;
                     }
-                    d = o; l = v; row[j] = v;
                 }
+                edge[(s & 1) * a.T + t] = make_float2(o, v);
+                unsigned char* q = a.tb + ((size_t)(i - 1) * a.T + t) * a.B;
+                q[0] = (unsigned char)(bits & 0xff);
+                if (a.B > 1) q[1] = (unsigned char)(bits >> 8);
             }
-            edge[(s & 1) * a.T + t] = make_float2(o, v);
-            unsigned char* q = a.tb + ((size_t)(i - 1) * a.T + t) * a.B;
-            q[0] = (unsigned char)(bits & 0xff);
-            if (a.B > 1) q[1] = (unsigned char)(bits >> 8);
+            load_row(i + MEA_DEPTH, pf[u]);
+            __syncthreads();
         }
-#pragma unroll
-        for (int c = 0; c < MEA_MAXC; ++c) pf[c] = nx[c];
-        __syncthreads();
     }
 }
 
 size_t pp_smem_bytes(int l2, int nA) {
     const size_t accn = ((size_t)l2 + 1 + 3) & ~(size_t)3;
-    return accn * 4 + (size_t)PP_THREADS * PP_CAP * 8 + (size_t)PP_THREADS * (4 + 4 + 8) + (size_t)nA * 4;
+    return accn * 4 + (size_t)PP_THREADS * PP_CAP * 8 + (size_t)PP_THREADS * (4 + 4 + 8) + (size_t)nA * 8;
 }
 
 class DeviceProfilePosterior : public qptail::ProfilePosterior {
@@ -227,6 +248,7 @@ public:
         const double total = ws.total(A, B);                      // the reference's normaliser, in its order and precision
         for (int i = 0; i < nA; ++i) { wA[i] = ws.weight_of(A.ids[i]); idsA[i] = A.ids[i]; }
         for (int j = 0; j < nB; ++j) { wB[j] = ws.weight_of(B.ids[j]); idsB[j] = B.ids[j]; }
+#pragma omp parallel for schedule(static) if ((long long)nA * l1 >= (1 << 16))
         for (int i = 0; i < nA; ++i) {                            // [i][column], row-major: sequential writes
             const char* row = A.rows[i].data();
             int* dst = invA + (size_t)i * (l1 + 1);
@@ -234,6 +256,7 @@ public:
             dst[0] = 0;
             for (int c = 0; c < l1; ++c) dst[c + 1] = (row[c] != '-') ? ++k : 0;
         }
+#pragma omp parallel for schedule(static) if ((long long)nB * l2 >= (1 << 16))
         for (int j = 0; j < nB; ++j) {
             const std::string& row = B.rows[j];
             int* m = mapB + (size_t)j * ldB;

@@ -20,7 +20,7 @@ for it in range(iters):
     eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, 0.01 if it < iters - 1 else float(np.float32(1e-5)))
 t2 = time.perf_counter()
 print("n=%d L=%d posterior %.1f ms, tree+relax %.1f ms, cells %d" % (n, L, (t1 - t0) * 1e3, (t2 - t1) * 1e3, eng.total_cells()))
-for ref_iters, tag in ((-2, "construction only"), (-1, "construction + refinement")):
+for ref_iters, tag in ((-2, "warm-up (construction only)"), (-2, "construction only"), (-1, "construction + refinement"), (-1, "construction + refinement (again)")):
     t3 = time.perf_counter(); rows = eng.qp_finish_alignment(w, t["left"], t["right"], ref_iters); t4 = time.perf_counter()
     st = eng.stats()
     print("%s: wall %.1f ms, kernels %.1f ms over %d launches, pair-matrices summed %d, h2d %.1f MB d2h %.1f MB, columns %d"
