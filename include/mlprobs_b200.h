@@ -151,6 +151,11 @@ int mlp_cpnp_finish_alignment_host(int n, const int32_t* len, const uint8_t* res
                                    char** rows_out, int32_t* aln_len, int32_t* order_out);
 int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, const int32_t* left, const int32_t* right,
                               int refine_reps, int pid, char** rows_out, int32_t* aln_len, int32_t* order_out);
+/* MLProbs' Python-side column scores of an alignment (utils/calculate_column_scores.py:37-82 calculateColScore, :123-137
+ * getSD / getPeakLengthRatio): rows = n x columns bytes.  col_score (may be NULL) receives the per-column values; the mean
+ * over columns, the standard deviation and the fraction of columns >= 1 go to the three outputs.  Host only; same doubles
+ * as the Python code, computed from letter counts instead of the O(N^2) pair loop. */
+int mlp_column_scores(int n, int columns, const char* rows, double* col_score, double* mean, double* sd, double* peak_ratio);
 /* test hook: first `count` outputs of the private glibc rand() replica */
 int mlp_debug_glibc_rand(int count, int32_t* out);
 

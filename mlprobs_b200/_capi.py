@@ -24,7 +24,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
-           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand"]
+           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores"]
 
 
 class HmmTables(C.Structure):
@@ -226,6 +226,22 @@ def cpnp_finish_alignment_host(seqs, iweights, left, right, rp_off, nz_off, rp_p
     if rc:
         raise MlpError(rc)
     return _take_rows(n, rows_p, alen), order
+
+
+def column_scores(rows):
+    """calculateColScore of MLProbs' Python driver for an alignment given as equal-length byte rows ->
+    (col_score float64 array, mean, sd, peak_length_ratio)."""
+    n = len(rows)
+    L = len(rows[0]) if n else 0
+    buf = np.frombuffer(b"".join(rows), np.uint8)
+    out = np.zeros(L, np.float64)
+    mean, sd, ratio = C.c_double(0), C.c_double(0), C.c_double(0)
+    lib = load()
+    lib.mlp_column_scores.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rc = lib.mlp_column_scores(n, L, _ptr(buf), _ptr(out), C.byref(mean), C.byref(sd), C.byref(ratio))
+    if rc:
+        raise MlpError(rc)
+    return out, mean.value, sd.value, ratio.value
 
 
 def debug_glibc_rand(count):

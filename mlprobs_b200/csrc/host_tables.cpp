@@ -207,3 +207,48 @@ extern "C" int mlp_cpnp_g_features(int n, const int32_t* len, const uint8_t* res
     std::snprintf(line, line_cap, "%f\t%f\t%d\t%d\t%f\t%f\t%f", identity, variance, n, avg_length, tmp_sp, peak, factor);
     return MLP_OK;
 }
+
+// MLProbs' Python-side column scoring (utils/calculate_column_scores.py:37-82,123-137): per column the
+// BLOSUM62 sum over all sequence pairs (letters outside the 20 standard ones and gaps score 0) divided by N(N-1)/2, then the
+// mean over columns, the standard deviation around it and the fraction of columns scoring >= 1.  The Python loop is
+// O(columns * N^2); the pair sum only depends on the letter counts of the column, so this is O(columns * (N + 400)) with
+// the same value: every partial sum there is an integer, exactly representable in a double, and the divisions, the running
+// double sums (column order) and pow(x, 2) are the ones CPython performs.
+extern "C" int mlp_column_scores(int n, int columns, const char* rows, double* col_score, double* mean_out, double* sd_out, double* peak_ratio_out) {
+    if (n < 2 || columns < 0 || !rows) return MLP_E_ARG;
+    const char* al = MLP_HMM_ALPHABET;                 // "ARNDCQEGHILKMFPSTWYV", the order of tmp_str
+    int idx[256];
+    for (int k = 0; k < 256; k++) idx[k] = -1;
+    for (int k = 0; k < 20; k++) idx[(unsigned char)al[k]] = k;
+    const double pairs = ((double)n * (double)(n - 1)) / 2;
+    std::vector<double> local;
+    if (!col_score) { local.resize((size_t)columns); col_score = local.data(); }
+    double sum = 0.0;
+    for (int c = 0; c < columns; c++) {
+        long long cnt[20] = {0};
+        for (int i = 0; i < n; i++) { const int k = idx[(unsigned char)rows[(size_t)i * columns + c]]; if (k >= 0) cnt[k]++; }
+        long long s = 0;
+        for (int a = 0; a < 20; a++) {
+            if (!cnt[a]) continue;
+            s += (long long)MLP_BLOSUM62[a * 20 + a] * (cnt[a] * (cnt[a] - 1) / 2);
+            for (int b = a + 1; b < 20; b++) s += (long long)MLP_BLOSUM62[a * 20 + b] * cnt[a] * cnt[b];
+        }
+        double v = (double)s;
+        v /= pairs;
+        sum += v;
+        col_score[c] = v;
+    }
+    double mean = 0.0, sd = 0.0, ratio = 0.0;
+    if (columns != 0) {
+        mean = sum / columns;
+        for (int c = 0; c < columns; c++) sd += std::pow(col_score[c] - mean, 2.0);
+        sd /= columns;
+        sd = std::sqrt(sd);
+        for (int c = 0; c < columns; c++) if (col_score[c] >= 1.0) ratio += 1;
+        ratio = ratio / columns;
+    }
+    if (mean_out) *mean_out = mean;
+    if (sd_out) *sd_out = sd;
+    if (peak_ratio_out) *peak_ratio_out = ratio;
+    return MLP_OK;
+}

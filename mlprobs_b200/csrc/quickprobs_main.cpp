@@ -16,6 +16,8 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <dirent.h>
+#include <sys/stat.h>
 
 namespace {
 
@@ -68,31 +70,13 @@ int fail(mlp_ctx* ctx, const char* what, int rc) {
 
 }  // namespace
 
-int main(int argc, char** argv) {
-    std::string infile, outfile;
-    int con_iters = -1, ref_count = -1, device = 0, verbose = 0;
-    unsigned ref_seed = 0;
-    for (int i = 1; i < argc; ++i) {
-        const std::string a = argv[i];
-        auto need = [&](const char* name) -> const char* {
-            if (i + 1 >= argc) { std::fprintf(stderr, "quickprobs_b200: option %s needs a value\n", name); std::exit(2); }
-            return argv[++i];
-        };
-        if (a == "-o" || a == "--outfile") outfile = need("-o");
-        else if (a == "-c" || a == "--con-iters") con_iters = std::atoi(need("-c"));
-        else if (a == "-r" || a == "--ref-count") ref_count = std::atoi(need("-r"));
-        else if (a == "--ref-seed") ref_seed = (unsigned)std::strtoul(need("--ref-seed"), nullptr, 10);
-        else if (a == "-t" || a == "--num-threads") (void)need("-t");
-        else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
-        else if (a == "-v" || a == "--verbose") verbose = 1;
-        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "quickprobs_b200: unsupported option %s\n", a.c_str()); return 2; }
-        else if (infile.empty()) infile = a;
-        else { std::fprintf(stderr, "quickprobs_b200: more than one input file\n"); return 2; }
-    }
-    if (infile.empty()) {
-        std::fprintf(stderr, "usage: quickprobs_b200 <infile> [-o outfile] [-c con-iters] [-r ref-count] [--ref-seed S] [-d cuda-device]\n");
-        return 2;
-    }
+// one input file -> one alignment; returns the process exit status for this file (0 = ok)
+int align_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int con_iters, int ref_count, unsigned ref_seed, int verbose) {
+    auto fail = [&](mlp_ctx* c, const char* what, int rc) {
+        std::fprintf(stderr, "quickprobs_b200: %s: %s failed (%d): %s\n", infile.c_str(), what, rc, c ? mlp_last_error(c) : "");
+        return 1;
+    };
+    int rc = 0;
     Input in;
     std::string err;
     if (!load_fasta(infile, in, err)) { std::fprintf(stderr, "quickprobs_b200: %s\n", err.c_str()); return 255; }
@@ -104,12 +88,8 @@ int main(int argc, char** argv) {
     }
     std::ostream& out = outfile.empty() ? std::cout : fout;
 
-    mlp_ctx* ctx = nullptr;
-    int rc = mlp_create(device, &ctx);                 // no CUDA device -> MLP_E_NO_DEVICE: stop here, nothing falls back to the CPU
-    if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
     if (n == 1) {
         write_fasta(out, in.headers, in.seqs[0].data(), 1, (int)in.seqs[0].size());
-        mlp_destroy(ctx);
         return 0;
     }
     std::vector<int32_t> len(n);
@@ -139,6 +119,64 @@ int main(int argc, char** argv) {
     write_fasta(out, in.headers, rows, n, alen);
     if (verbose) std::fprintf(stderr, "quickprobs_b200: %d sequences, %d columns\n", n, alen);
     mlp_free_host(rows);
-    mlp_destroy(ctx);
     return 0;
+}
+
+int main(int argc, char** argv) {
+    std::string infile, outfile;
+    int con_iters = -1, ref_count = -1, device = 0, verbose = 0;
+    unsigned ref_seed = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { std::fprintf(stderr, "quickprobs_b200: option %s needs a value\n", name); std::exit(2); }
+            return argv[++i];
+        };
+        if (a == "-o" || a == "--outfile") outfile = need("-o");
+        else if (a == "-c" || a == "--con-iters") con_iters = std::atoi(need("-c"));
+        else if (a == "-r" || a == "--ref-count") ref_count = std::atoi(need("-r"));
+        else if (a == "--ref-seed") ref_seed = (unsigned)std::strtoul(need("--ref-seed"), nullptr, 10);
+        else if (a == "-t" || a == "--num-threads") (void)need("-t");
+        else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
+        else if (a == "-v" || a == "--verbose") verbose = 1;
+        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "quickprobs_b200: unsupported option %s\n", a.c_str()); return 2; }
+        else if (infile.empty()) infile = a;
+        else { std::fprintf(stderr, "quickprobs_b200: more than one input file\n"); return 2; }
+    }
+    if (infile.empty()) {
+        std::fprintf(stderr, "usage: quickprobs_b200 <infile | indir> [-o outfile | outdir] [-c con-iters] [-r ref-count] [--ref-seed S] [-d cuda-device]\n");
+        return 2;
+    }
+    // directory mode (Configuration.cpp:248-267): every regular file of the input directory is aligned into a file of the same
+    // name in the output directory -- one process, one CUDA context for all of them
+    struct stat si, so;
+    const bool dir_mode = !outfile.empty() && stat(infile.c_str(), &si) == 0 && S_ISDIR(si.st_mode) &&
+                          stat(outfile.c_str(), &so) == 0 && S_ISDIR(so.st_mode);
+    if (!dir_mode) {                                   // input errors are reported before a device is required
+        Input probe;
+        std::string err;
+        if (!load_fasta(infile, probe, err)) { std::fprintf(stderr, "quickprobs_b200: %s\n", err.c_str()); return 255; }
+    }
+    mlp_ctx* ctx = nullptr;
+    int rc = mlp_create(device, &ctx);                 // no CUDA device -> MLP_E_NO_DEVICE: stop here, nothing falls back to the CPU
+    if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
+    int status = 0;
+    if (dir_mode) {
+        std::vector<std::string> names;
+        if (DIR* d = opendir(infile.c_str())) {
+            while (struct dirent* e = readdir(d)) {
+                struct stat st;
+                const std::string path = infile + "/" + e->d_name;
+                if (stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode)) names.push_back(e->d_name);
+            }
+            closedir(d);
+        }
+        std::sort(names.begin(), names.end());
+        for (const std::string& nm : names) {
+            const int r1 = align_file(ctx, infile + "/" + nm, outfile + "/" + nm, con_iters, ref_count, ref_seed, verbose);
+            if (r1) status = r1;
+        }
+    } else status = align_file(ctx, infile, outfile, con_iters, ref_count, ref_seed, verbose);
+    mlp_destroy(ctx);
+    return status;
 }

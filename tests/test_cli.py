@@ -62,6 +62,23 @@ def test_cli_reproduces_the_reference_alignment(tmp_path, name):
 
 
 @pytest.mark.gpu
+def test_cli_directory_mode_aligns_every_file_with_one_context(tmp_path):
+    """QuickProbs' bulk entry (Configuration.cpp:248-267): input directory -> output directory, same file names."""
+    indir = tmp_path / "in"; outdir = tmp_path / "out"
+    indir.mkdir(); outdir.mkdir()
+    want = {}
+    for name in ("qp_sup139", "qp_sup002"):
+        d = load_golden(name)
+        fa, heads = write_input(tmp_path, split_seqs(d))
+        os.rename(fa, indir / (name + ".fa"))
+        want[name + ".fa"] = fasta_text(heads, [r.tobytes().decode() for r in d["msa"]])
+    r = subprocess.run([CLI, str(indir), "-o", str(outdir)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for nm, text in want.items():
+        assert (outdir / nm).read_text() == text
+
+
+@pytest.mark.gpu
 def test_cli_single_sequence_is_echoed(tmp_path):
     fa, heads = write_input(tmp_path, [b"ACDEFGHIKLMNPQRSTVWY" * 4])
     r = subprocess.run([CLI, fa], capture_output=True, text=True)

@@ -122,3 +122,14 @@ def test_argument_errors_are_reported_not_thrown():
     lens = np.array([5], np.int32)
     lib.mlp_shard_pairs.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
     assert lib.mlp_shard_pairs(1, lens.ctypes.data_as(C.c_void_p), 0, 1, None, C.byref(cnt)) == -3
+
+
+def test_column_scores_equal_the_reference_python_function():
+    """mlp_column_scores vs utils/calculate_column_scores.py (fixture written by oracle/gen_golden_colscore.py): same doubles."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "colscore.npz"))
+    for name in ("qp_sup139", "qp_sup002", "qp_676s4", "cpnp_676s4_ref"):
+        d = load_golden(name)
+        rows = [r.tobytes() for r in d["msa"]]
+        col, mean, sd, ratio = M.column_scores(rows)
+        assert np.array_equal(col, g[name + ".col"])
+        assert [mean, sd, ratio] == g[name + ".stats"].tolist()
