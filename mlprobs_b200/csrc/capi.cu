@@ -870,7 +870,13 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     const int in = ctx->cur, out = 1 - ctx->cur;
     ctx->stats = mlp_stage_stats{};
     if (flavour == MLP_QP) {
-        if (!ctx->d_weights) { CK(cudaMalloc(&ctx->d_weights, n * sizeof(float))); CK(cudaMalloc(&ctx->d_seldist, (size_t)n * n * sizeof(float))); }
+        if (n > ctx->weights_cap) {                   // sized for the current family (a context may see many families)
+            free_dev(ctx->d_weights); free_dev(ctx->d_seldist);
+            ctx->d_weights = nullptr; ctx->d_seldist = nullptr; ctx->weights_cap = 0;
+            CK(cudaMalloc(&ctx->d_weights, n * sizeof(float)));
+            CK(cudaMalloc(&ctx->d_seldist, (size_t)n * n * sizeof(float)));
+            ctx->weights_cap = n;
+        }
         CK(cudaMemcpyAsync(ctx->d_weights, weights, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_seldist, seldist_nxn, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += (int64_t)n * 4 + (int64_t)n * n * 4;

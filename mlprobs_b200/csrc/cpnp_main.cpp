@@ -15,6 +15,8 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <dirent.h>
+#include <sys/stat.h>
 
 namespace {
 
@@ -71,6 +73,77 @@ int fail(mlp_ctx* ctx, const char* what, int rc) {
 
 }  // namespace
 
+// one input file; returns the exit status for it
+int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int getpid, int reps, int refine) {
+    auto fail = [&](mlp_ctx* c, const char* what, int rc) {
+        std::fprintf(stderr, "c_p_np_aln_b200: %s: %s failed (%d): %s\n", infile.c_str(), what, rc, c ? mlp_last_error(c) : "");
+        return 1;
+    };
+    Input in;
+    if (!load_mfa(infile, in)) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
+    const int n = (int)in.seqs.size();
+    std::ofstream fout;
+    if (!outfile.empty()) {
+        fout.open(outfile.c_str(), std::ios::binary | std::ios::out | std::ios::trunc);
+        if (!fout.is_open()) { std::cerr << "ERROR: Failed to open the file " << outfile << std::endl; return 1; }
+    }
+    std::ostream& out = outfile.empty() ? std::cout : fout;
+
+    int rc = 0;
+    if (n < 2) {
+        if (!getpid) write_mfa(out, in.headers[0], in.seqs[0].data(), (int)in.seqs[0].size());
+        return getpid ? 1 : 0;
+    }
+    std::vector<int32_t> len(n);
+    std::string cat;
+    for (int i = 0; i < n; ++i) { len[i] = (int32_t)in.seqs[i].size(); cat += in.seqs[i]; }
+    const long long npairs = (long long)n * (n - 1) / 2;
+    mlp_hmm_tables hmm;
+    mlp_part_tables part;
+    if ((rc = mlp_default_tables(MLP_CPNP_P0, 0.700645f, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
+    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
+    if ((rc = mlp_set_sequences(ctx, n, len.data(), (const uint8_t*)cat.data()))) return fail(ctx, "mlp_set_sequences", rc);
+    std::vector<int32_t> ident(npairs), alen(npairs);
+    if (getpid) {
+        // MSA::Alter_ModelAdjustmentTest(sequences, 1.0), MSA.cpp:154-165,646-762
+        long long cap = 0;
+        for (int a = 0; a < n; ++a) for (int b = a + 1; b < n; ++b) cap += len[a] + len[b];
+        std::vector<char> aln((size_t)cap + 16);
+        std::vector<int64_t> off(npairs + 1);
+        if ((rc = mlp_viterbi_all_pairs_ex(ctx, ident.data(), alen.data(), aln.data(), off.data()))) return fail(ctx, "mlp_viterbi_all_pairs_ex", rc);
+        char line[512];
+        if ((rc = mlp_cpnp_g_features(n, len.data(), (const uint8_t*)cat.data(), aln.data(), off.data(), 1.0f, line, (int)sizeof line)))
+            return fail(ctx, "mlp_cpnp_g_features", rc);
+        out << line << "\n";
+        return 0;
+    }
+    // MSA::ModelAdjustmentTest, MSA.cpp:775-882
+    if ((rc = mlp_viterbi_all_pairs(ctx, ident.data(), alen.data()))) return fail(ctx, "mlp_viterbi_all_pairs", rc);
+    float identity = 0, sigma = 0, init2 = 0;
+    const int variance_mean = mlp_cpnp_model_adjustment(npairs, ident.data(), alen.data(), &identity, &sigma, &init2);
+    if (variance_mean < 0) return fail(ctx, "mlp_cpnp_model_adjustment", variance_mean);
+    const int pid = variance_mean % 10, vpid = variance_mean / 10;
+    if ((rc = mlp_default_tables(MLP_CPNP_P0, init2, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
+    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
+    const uint32_t mask = pid <= 1 ? (MLP_M_HMM5 | MLP_M_PART | MLP_M_LOCAL) : (pid == 2 ? MLP_M_LOCAL : MLP_M_PART);   // MSA.cpp:946-1010
+    rc = mlp_posterior_all_pairs(ctx, MLP_CPNP_P0, mask, 0.01f);
+    if (rc == MLP_E_OVERFLOW) { std::printf("ERROR: huge val error for zM\n"); return 1; }            // MSAPartProbs.cpp:547-589
+    if (rc) return fail(ctx, "mlp_posterior_all_pairs", rc);
+    std::vector<float> dist((size_t)n * n);
+    std::vector<int32_t> weights(n), left(2 * n - 1), right(2 * n - 1), order(n);
+    if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
+    if ((rc = mlp_cpnp_guide_tree(n, dist.data(), vpid, weights.data(), left.data(), right.data()))) return fail(ctx, "mlp_cpnp_guide_tree", rc);
+    for (int r = 0; r < reps; ++r)
+        if ((rc = mlp_relax(ctx, MLP_CPNP_P0, nullptr, nullptr, 0.0f, 0.0f, 0.01f))) return fail(ctx, "mlp_relax", rc);
+    char* rows = nullptr;
+    int32_t cols = 0;
+    if ((rc = mlp_cpnp_finish_alignment(ctx, weights.data(), left.data(), right.data(), refine, pid, &rows, &cols, order.data())))
+        return fail(ctx, "mlp_cpnp_finish_alignment", rc);
+    for (int k = 0; k < n; ++k) write_mfa(out, in.headers[order[k]], rows + (size_t)k * cols, cols);
+    mlp_free_host(rows);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     std::string infile, outfile;
     int program = 0, getpid = 0, reps = 2, refine = 100, device = 0;
@@ -99,72 +172,30 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "c_p_np_aln_b200: -p 1 (non-progressive strategy) is not built; the reference seeds rand() with the clock there\n");
         return 2;
     }
-    Input in;
-    if (!load_mfa(infile, in)) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
-    const int n = (int)in.seqs.size();
-    std::ofstream fout;
-    if (!outfile.empty()) {
-        fout.open(outfile.c_str(), std::ios::binary | std::ios::out | std::ios::trunc);
-        if (!fout.is_open()) { std::cerr << "ERROR: Failed to open the file " << outfile << std::endl; return 1; }
-    }
-    std::ostream& out = outfile.empty() ? std::cout : fout;
-
+    struct stat si, so;
+    const bool dir_mode = !outfile.empty() && stat(infile.c_str(), &si) == 0 && S_ISDIR(si.st_mode) &&
+                          stat(outfile.c_str(), &so) == 0 && S_ISDIR(so.st_mode);   // extension: a directory of families, one CUDA context
+    if (!dir_mode) { Input probe; if (!load_mfa(infile, probe)) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; } }
     mlp_ctx* ctx = nullptr;
     int rc = mlp_create(device, &ctx);                 // no CUDA device -> stop: nothing falls back to the CPU
     if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
-    if (n < 2) {
-        if (!getpid) write_mfa(out, in.headers[0], in.seqs[0].data(), (int)in.seqs[0].size());
-        mlp_destroy(ctx);
-        return getpid ? 1 : 0;
-    }
-    std::vector<int32_t> len(n);
-    std::string cat;
-    for (int i = 0; i < n; ++i) { len[i] = (int32_t)in.seqs[i].size(); cat += in.seqs[i]; }
-    const long long npairs = (long long)n * (n - 1) / 2;
-    mlp_hmm_tables hmm;
-    mlp_part_tables part;
-    if ((rc = mlp_default_tables(MLP_CPNP_P0, 0.700645f, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
-    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
-    if ((rc = mlp_set_sequences(ctx, n, len.data(), (const uint8_t*)cat.data()))) return fail(ctx, "mlp_set_sequences", rc);
-    std::vector<int32_t> ident(npairs), alen(npairs);
-    if (getpid) {
-        // MSA::Alter_ModelAdjustmentTest(sequences, 1.0), MSA.cpp:154-165,646-762
-        long long cap = 0;
-        for (int a = 0; a < n; ++a) for (int b = a + 1; b < n; ++b) cap += len[a] + len[b];
-        std::vector<char> aln((size_t)cap + 16);
-        std::vector<int64_t> off(npairs + 1);
-        if ((rc = mlp_viterbi_all_pairs_ex(ctx, ident.data(), alen.data(), aln.data(), off.data()))) return fail(ctx, "mlp_viterbi_all_pairs_ex", rc);
-        char line[512];
-        if ((rc = mlp_cpnp_g_features(n, len.data(), (const uint8_t*)cat.data(), aln.data(), off.data(), 1.0f, line, (int)sizeof line)))
-            return fail(ctx, "mlp_cpnp_g_features", rc);
-        out << line << "\n";
-        mlp_destroy(ctx);
-        return 0;
-    }
-    // MSA::ModelAdjustmentTest, MSA.cpp:775-882
-    if ((rc = mlp_viterbi_all_pairs(ctx, ident.data(), alen.data()))) return fail(ctx, "mlp_viterbi_all_pairs", rc);
-    float identity = 0, sigma = 0, init2 = 0;
-    const int variance_mean = mlp_cpnp_model_adjustment(npairs, ident.data(), alen.data(), &identity, &sigma, &init2);
-    if (variance_mean < 0) return fail(ctx, "mlp_cpnp_model_adjustment", variance_mean);
-    const int pid = variance_mean % 10, vpid = variance_mean / 10;
-    if ((rc = mlp_default_tables(MLP_CPNP_P0, init2, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
-    if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
-    const uint32_t mask = pid <= 1 ? (MLP_M_HMM5 | MLP_M_PART | MLP_M_LOCAL) : (pid == 2 ? MLP_M_LOCAL : MLP_M_PART);   // MSA.cpp:946-1010
-    rc = mlp_posterior_all_pairs(ctx, MLP_CPNP_P0, mask, 0.01f);
-    if (rc == MLP_E_OVERFLOW) { std::printf("ERROR: huge val error for zM\n"); mlp_destroy(ctx); return 1; }            // MSAPartProbs.cpp:547-589
-    if (rc) return fail(ctx, "mlp_posterior_all_pairs", rc);
-    std::vector<float> dist((size_t)n * n);
-    std::vector<int32_t> weights(n), left(2 * n - 1), right(2 * n - 1), order(n);
-    if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
-    if ((rc = mlp_cpnp_guide_tree(n, dist.data(), vpid, weights.data(), left.data(), right.data()))) return fail(ctx, "mlp_cpnp_guide_tree", rc);
-    for (int r = 0; r < reps; ++r)
-        if ((rc = mlp_relax(ctx, MLP_CPNP_P0, nullptr, nullptr, 0.0f, 0.0f, 0.01f))) return fail(ctx, "mlp_relax", rc);
-    char* rows = nullptr;
-    int32_t cols = 0;
-    if ((rc = mlp_cpnp_finish_alignment(ctx, weights.data(), left.data(), right.data(), refine, pid, &rows, &cols, order.data())))
-        return fail(ctx, "mlp_cpnp_finish_alignment", rc);
-    for (int k = 0; k < n; ++k) write_mfa(out, in.headers[order[k]], rows + (size_t)k * cols, cols);
-    mlp_free_host(rows);
+    int status = 0;
+    if (dir_mode) {
+        std::vector<std::string> names;
+        if (DIR* d = opendir(infile.c_str())) {
+            while (struct dirent* e = readdir(d)) {
+                struct stat st;
+                const std::string path = infile + "/" + e->d_name;
+                if (stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode)) names.push_back(e->d_name);
+            }
+            closedir(d);
+        }
+        std::sort(names.begin(), names.end());
+        for (const std::string& nm : names) {
+            const int r1 = run_file(ctx, infile + "/" + nm, outfile + "/" + nm, getpid, reps, refine);
+            if (r1) status = r1;
+        }
+    } else status = run_file(ctx, infile, outfile, getpid, reps, refine);
     mlp_destroy(ctx);
-    return 0;
+    return status;
 }

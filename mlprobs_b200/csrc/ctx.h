@@ -9,6 +9,7 @@
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \
         if (e__ != cudaSuccess) {                                                                  \
+            (void)cudaGetLastError();   /* clear the per-thread error so that it cannot surface at a later launch */ \
             ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
             return MLP_E_CUDA;                                                                     \
         }                                                                                          \
@@ -61,7 +62,7 @@ struct mlp_ctx {
     int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
     void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
     float* d_wk = nullptr; long long wk_warps = 0;
-    float* d_weights = nullptr; float* d_seldist = nullptr;
+    float* d_weights = nullptr; float* d_seldist = nullptr; int weights_cap = 0;
     // nccl
     void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
     // stats

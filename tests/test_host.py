@@ -133,3 +133,14 @@ def test_column_scores_equal_the_reference_python_function():
         col, mean, sd, ratio = M.column_scores(rows)
         assert np.array_equal(col, g[name + ".col"])
         assert [mean, sd, ratio] == g[name + ".stats"].tolist()
+
+
+def test_suite_fixture_is_consistent():
+    """tests/golden/suites: every family of the manifest has its input in the archive and both reference digests."""
+    import json, tarfile
+    base = os.path.join(os.path.dirname(__file__), "golden", "suites")
+    man = json.load(open(os.path.join(base, "manifest.json")))["families"]
+    with tarfile.open(os.path.join(base, "inputs.tar.gz")) as t:
+        names = {m.name for m in t.getmembers() if m.isfile()}
+    assert {m["suite"] + "/" + m["name"] for m in man} == names and len(man) > 1000
+    assert all(m["qp_sha"] and m["cpnp_sha"] for m in man)

@@ -1,0 +1,18 @@
+"""Suite-level parity of the two drop-in executables: byte-identical FASTA output on bundled benchmark families
+(tests/golden/suites, written by oracle/gen_suite_golden.py from the reference programs).  The ox and oxx suites run here
+(530 families, both tools, about a minute); tools/suite_parity.py runs all four suites (1219 families)."""
+import os
+import sys
+import pytest
+from common import HERE
+
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+pytestmark = pytest.mark.gpu
+
+
+def test_ox_and_oxx_families_are_byte_identical_to_the_reference_programs():
+    import suite_parity
+    rep = suite_parity.run(None, suites=("ox", "oxx"))
+    assert rep["mismatches"] == [] and rep["failures"] == []
+    for key, v in rep["suites"].items():
+        assert v["identical"] == v["families"] - v["reference_failed"] > 0, (key, v)
