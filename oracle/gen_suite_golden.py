@@ -45,10 +45,15 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--budget", type=float, nargs=4, default=[3e9, 1e12, 1.5e9, 1e12], help="N^2/2*L^2 cell budget per suite: bali3 ox oxx sabre")
     ap.add_argument("--workers", type=int, default=8)
+    ap.add_argument("--append", action="store_true", help="keep the families already in the manifest, run only the new ones")
     a = ap.parse_args()
     import tempfile
     tmp = tempfile.mkdtemp()
     jobs = []
+    have = {}
+    if a.append and os.path.exists(os.path.join(OUT, "manifest.json")):
+        for m in json.load(open(os.path.join(OUT, "manifest.json")))["families"]:
+            have[(m["suite"], m["name"])] = m
     for suite, budget in zip(("bali3", "ox", "oxx", "sabre"), a.budget):
         fams = []
         for f in sorted(os.listdir(os.path.join(REF, suite, "in"))):
@@ -63,8 +68,12 @@ if __name__ == "__main__":
             jobs.append((suite, f, p, tmp))
         print(suite, "selected", sum(1 for j in jobs if j[0] == suite), "of", len(fams), "families, %.2e cells" % used, flush=True)
     t0 = time.time()
+    todo = [j for j in jobs if (j[0], j[1]) not in have]
+    todo.sort(key=lambda j: -os.path.getsize(j[2]))           # big families first: better packing of the worker pool
+    print("to run:", len(todo), "already have:", len(jobs) - len(todo), flush=True)
     with ThreadPoolExecutor(a.workers) as ex:
-        results = list(ex.map(run_one, jobs))
+        fresh = {(r["suite"], r["name"]): r for r in ex.map(run_one, todo)}
+    results = [have.get((j[0], j[1])) or fresh[(j[0], j[1])] for j in jobs]
     print("reference runs: %.0f s" % (time.time() - t0))
     os.makedirs(OUT, exist_ok=True)
     with tarfile.open(os.path.join(OUT, "inputs.tar.gz"), "w:gz") as tar:
