@@ -16,6 +16,7 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <chrono>
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -77,6 +78,8 @@ int align_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfi
         return 1;
     };
     int rc = 0;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     Input in;
     std::string err;
     if (!load_fasta(infile, in, err)) { std::fprintf(stderr, "quickprobs_b200: %s\n", err.c_str()); return 255; }
@@ -100,7 +103,9 @@ int align_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfi
     if ((rc = mlp_default_tables(MLP_QP, 0.0f, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
     if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
     if ((rc = mlp_set_sequences(ctx, n, len.data(), (const uint8_t*)cat.data()))) return fail(ctx, "mlp_set_sequences", rc);
+    const double t1 = now();
     if ((rc = mlp_posterior_all_pairs(ctx, MLP_QP, MLP_M_HMM5 | MLP_M_PART, 0.01f))) return fail(ctx, "mlp_posterior_all_pairs", rc);
+    const double t2 = now();
     std::vector<float> dist((size_t)n * n), weights(n), seldist((size_t)n * n);
     std::vector<int32_t> left(2 * n - 1), right(2 * n - 1);
     if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
@@ -112,12 +117,14 @@ int align_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfi
         const float cutoff = (it == iters - 1) ? 1e-5f : 0.01f;
         if ((rc = mlp_relax(ctx, MLP_QP, weights.data(), seldist.data(), 200.0f, 3.0f, cutoff))) return fail(ctx, "mlp_relax", rc);
     }
+    const double t3 = now();
     char* rows = nullptr;
     int32_t alen = 0;
     if ((rc = mlp_qp_finish_alignment(ctx, weights.data(), left.data(), right.data(), ref_count, ref_seed, &rows, &alen)))
         return fail(ctx, "mlp_qp_finish_alignment", rc);
     write_fasta(out, in.headers, rows, n, alen);
-    if (verbose) std::fprintf(stderr, "quickprobs_b200: %d sequences, %d columns\n", n, alen);
+    if (verbose) std::fprintf(stderr, "quickprobs_b200: %d sequences, %d columns; ms: load+upload %.1f, posterior %.1f, tree+consistency %.1f, construction+refinement %.1f\n",
+                              n, alen, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     mlp_free_host(rows);
     return 0;
 }
