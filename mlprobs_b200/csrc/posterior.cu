@@ -756,7 +756,9 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_viterbi(KArgs a) {
 
 // ------------------------------------------------------------------------------------------------ merge + MEA + sparsify
 // states: 0 = MEA row score, 1 = number of kept cells so far in this row (exact small integer in a float)
-template <bool DENSE>
+// QPSPEC: compile-time constants for the QuickProbs default (flavour 0, models HMM5|PART, no traceback layer): the per-cell
+// branches on mask / flavour / tb fold away
+template <bool DENSE, bool QPSPEC>
 struct FinalSweep {
     __device__ __forceinline__ void begin_block(int, int) const {}
     __device__ __forceinline__ void step_sync() const {}
@@ -766,6 +768,7 @@ struct FinalSweep {
     const float* S5; const float* P; const float* SL;
     float* dstage; int Cmax, lane;
     __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
+        const unsigned mask = QPSPEC ? 3u : this->mask;
         for (int c = 0; c < C; ++c) {
             const int g = slotbase + c * 32;
             float* d = dstage + ((buf * 3) * Cmax + c) * 32 + lane;
@@ -792,6 +795,9 @@ struct FinalSweep {
     __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
         if (j > L2) { nw[0] = carry[0]; nw[1] = carry[1]; return; }
+        const unsigned mask = QPSPEC ? 3u : this->mask;
+        const int flavour = QPSPEC ? 0 : this->flavour;
+        int* const tb = QPSPEC ? nullptr : this->tb;
         float v5 = 0.0f, vp = 0.0f, vl = 0.0f, p;
         const float* sg = dstage + ((buf * 3) * Cmax + c) * 32 + lane;
         if (mask & 1u) v5 = dev_exp_lut(fminf(0.0f, __fsub_rn(sg[0], total5)), elut);
@@ -844,7 +850,7 @@ struct FinalSweep {
     }
 };
 
-template <bool DENSE>
+template <bool DENSE, bool QPSPEC>
 __global__ void __launch_bounds__(MLP_BLOCK) k_final_t(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     ExpLut* elut = reinterpret_cast<ExpLut*>(smem);
@@ -866,7 +872,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_final_t(KArgs a) {
         int* rowptr = a.out.rp_pool + a.rp_off[slotAB];
         if (lane == 0) { *stage_n = 0; rowptr[0] = 0; rowptr[1] = 0; }
         __syncwarp();
-        FinalSweep<DENSE> m;
+        FinalSweep<DENSE, QPSPEC> m;
         m.elut = elut;
         m.S5 = a.layerS5 ? a.layerS5 + t.off : nullptr; m.P = a.layerP ? a.layerP + t.off : nullptr; m.SL = a.layerSL ? a.layerSL + t.off : nullptr; m.dstage = stg; m.Cmax = a.Cmax; m.lane = lane;
         m.total5 = a.pout[ti].total5; m.totalL = a.pout[ti].totalL;
@@ -1042,7 +1048,7 @@ cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, 
         case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
         case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
         case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
-        case MLP_K_FINAL: fn = a_dense ? k_final_t<true> : k_final_t<false>; break;
+        case MLP_K_FINAL: fn = a_dense ? k_final_t<true, false> : ((a.flavour == 0 && a.mask == 3u) ? k_final_t<false, true> : k_final_t<false, false>); break;
         case MLP_K_TRANSPOSE: fn = k_transpose; break;
         case MLP_K_VITERBI: fn = k_viterbi; break;
         default: return cudaErrorInvalidValue;
@@ -1065,7 +1071,7 @@ int posterior_max_blocks_per_sm(int kernel, size_t smem) {
         case MLP_K_HMM_BWD: fn = k_hmm_bwd; break;
         case MLP_K_LOCAL_FWD: fn = k_loc_fwd; break;
         case MLP_K_LOCAL_BWD: fn = k_loc_bwd; break;
-        case MLP_K_FINAL: fn = a_dense ? k_final_t<true> : k_final_t<false>; break;
+        case MLP_K_FINAL: fn = a_dense ? k_final_t<true, false> : k_final_t<false, true>; break;
         case MLP_K_TRANSPOSE: fn = k_transpose; break;
         case MLP_K_VITERBI: fn = k_viterbi; break;
         default: return 1;

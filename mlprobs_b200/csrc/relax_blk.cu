@@ -89,6 +89,7 @@ __device__ __forceinline__ float rb_merge(const int2* pa, const int2* ea, const 
     return acc;
 }
 
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
     extern __shared__ __align__(16) unsigned char rb_raw[];
     RbSmem& sm = *reinterpret_cast<RbSmem*>(rb_raw);
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
     float* wk = a.wk_scratch + (long long)blockIdx.x * a.wk_stride;   // [npad] weight of the m-th accepted z
     int* kl = reinterpret_cast<int*>(wk + npad);                      // [npad] index  of the m-th accepted z
     RbDesc* desc = reinterpret_cast<RbDesc*>(kl + npad);              // [n]    slice descriptors of the current band
-    const bool weighted = (a.flavour == 0);
+    constexpr bool weighted = WEIGHTED;              // QuickProbs (weights, selectivity) vs cpnp (all z, unweighted): compile-time
     if (tid == 0) {
         rb_mbar_init(&sm.bar[0], 1);
         rb_mbar_init(&sm.bar[1], 1);
@@ -393,15 +394,18 @@ int relax_blk_threads() { return RB_THREADS; }
 long long relax_blk_scratch_words(int n) { const long long npad = (n + 3) & ~3; return 2 * npad + (long long)n * (sizeof(RbDesc) / 4); }
 
 cudaError_t relax_blk_launch(const RelaxArgs& a, int grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_relax_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_blk_smem());
+    cudaError_t e = cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_blk_smem());
     if (e != cudaSuccess) return e;
-    k_relax_blk<<<grid, RB_THREADS, relax_blk_smem(), st>>>(a);
+    e = cudaFuncSetAttribute(k_relax_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_blk_smem());
+    if (e != cudaSuccess) return e;
+    if (a.flavour == 0) k_relax_blk<true><<<grid, RB_THREADS, relax_blk_smem(), st>>>(a);
+    else k_relax_blk<false><<<grid, RB_THREADS, relax_blk_smem(), st>>>(a);
     return cudaGetLastError();
 }
 
 int relax_blk_max_blocks_per_sm() {
     int nb = 0;
-    cudaFuncSetAttribute(k_relax_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_blk_smem());
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_relax_blk, RB_THREADS, relax_blk_smem()) != cudaSuccess || nb < 1) nb = 1;
+    cudaFuncSetAttribute(k_relax_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)relax_blk_smem());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_relax_blk<true>, RB_THREADS, relax_blk_smem()) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }

@@ -13,7 +13,7 @@ def run(report_path=None, suites=None):
     man = json.load(open(os.path.join(SUITES, "manifest.json")))["families"]
     tmp = tempfile.mkdtemp()
     with tarfile.open(os.path.join(SUITES, "inputs.tar.gz")) as tar:
-        tar.extractall(tmp)
+        tar.extractall(tmp, filter="data")
     report = {"suites": {}, "mismatches": [], "failures": []}
     for suite in sorted({m["suite"] for m in man}):
         if suites and suite not in suites:
