@@ -447,7 +447,7 @@ struct PartRevT {
         tmp = __ddiv_rn(tmp, __dmul_rn(score, Ztot));
         if (SC) tmp = scalbn(tmp, fexp + e_row - zexp);
         float p = (float)tmp;
-        if (qp && !(p <= 1.0f && (double)p >= 0.001)) p = 0.0f;
+        if (!SC && !(p <= 1.0f && (double)p >= 0.001)) p = 0.0f;   // QuickProbs only (SC == cpnp)
         P[slot] = p;
     }
     __device__ __forceinline__ void end_row() { if (SC) { e_prev = e_row; if (row_seen != MLP_EXP_NONE) seen_exp = row_seen; } }
