@@ -129,7 +129,7 @@ extern "C" int mlp_set_tables(mlp_ctx* ctx, const mlp_hmm_tables* hmm, const mlp
 
 static void pair_geometry(int L2, int& C, int& nb) {
     const int cols = L2 + 2;   // columns 0..L2 plus the virtual column L2+1 of the reverse sweeps
-    // Columns per lane are capped at 8 (kCmaxLimit = 16 is what the kernels support): two column blocks of 5 columns per lane
+    // Columns per lane are capped at 8 (kCmaxLimit, the unroll width of the sweep kernels): two column blocks of 5 columns per lane
     // instead of one of 10 halve the per-warp band in shared memory, which lifts the FP64 reverse sweep from 12 to 24 resident
     // warps per SM (measured at 1000 x 300: part_rev 284 -> 228 ms, final 348 -> 330, hmm sweeps +25 ms).  MLP_CMAX overrides.
     static const int lim = []() { const char* e = getenv("MLP_CMAX"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kCmaxLimit) ? v : 8; }();

@@ -15,7 +15,7 @@
         }                                                                                          \
     } while (0)
 
-static const int kCmaxLimit = 16;   // columns per lane; 32*16 = 512 columns per column block
+static const int kCmaxLimit = 8;    // columns per lane (= MLP_SWEEP_MAXC, the unroll width of sweep.cuh); 32*8 = 256 columns per column block
 
 struct mlp_ctx {
     int device = 0, num_sms = 0;

@@ -60,7 +60,7 @@ struct HmmFwd {
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
-    enum { NS = 5, REV = 0, COLMASK = 0x1f, NIN = 0 };
+    enum { NS = 5, REV = 0, COLMASK = 0x1f, NIN = 0, UNROLLC = 0 };
     const float* match; const float* ins; const LogAddLut* lut;
     float* F;
     int L1, L2;
@@ -143,7 +143,7 @@ struct HmmBwd {
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
-    enum { NS = 5, REV = 1, COLMASK = 0x0b, NIN = 1 };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
+    enum { NS = 5, REV = 1, COLMASK = 0x0b, NIN = 1, UNROLLC = 0 };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
     const float* match; const float* ins; const LogAddLut* lut;
     float* F;      // in: forward M, out: F + B (ProbabilisticModel.h:483 evaluates (F+B)-total)
     float* stage; int Cmax;
@@ -266,7 +266,7 @@ __device__ __forceinline__ int exp_of(double x) { return ((__double2hiint(x) >> 
 template <bool SC>
 struct PartFwdT {
     typedef double T;
-    enum { NS = SC ? 4 : 3, REV = 0, COLMASK = 0x7, NIN = 0 };
+    enum { NS = SC ? 4 : 3, REV = 0, COLMASK = 0x7, NIN = 0, UNROLLC = 1 };
     const double* sub; double* Z; int* rowexp; int L1, L2, W; bool qp;   // qp == !SC: QuickProbs order (Zm+H)+V, cpnp (Zm+V)+H
     const double* srow; double zz; bool has_zz; int zexp; double o0, e0;
     // scale bookkeeping (SC): seen_exp = largest true exponent in the row this lane finished last (this column block)
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd_t(KArgs a) {
 template <bool SC>
 struct PartRevT {
     typedef double T;
-    enum { NS = SC ? 4 : 3, REV = 1, COLMASK = 0x7, NIN = 1 };
+    enum { NS = SC ? 4 : 3, REV = 1, COLMASK = 0x7, NIN = 1, UNROLLC = 1 };
     const double* sub; const double* Z; float* P; const int* rowexp; int L1, L2, W, nb; bool qp; double Ztot; int zexp;
     const double* srow; double o0, e0;
     double* stage; int Cmax, lane;
@@ -486,7 +486,7 @@ struct LocFwd {
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
-    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
+    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0, UNROLLC = 0 };
     const float* match; const float* ins; const LogAddLut* lut; float* F; int L1, L2;
     float* RM;   // row-major copy of F_M for the sequential Z replay (lives in the not-yet-used Z-term layer)
     float ins1; const float* mrow;
@@ -525,7 +525,7 @@ struct LocBwd {
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
-    enum { NS = 3, REV = 1, COLMASK = 0x3, NIN = 1 };   // keep B_M and X of row i+1; Y travels along the row
+    enum { NS = 3, REV = 1, COLMASK = 0x3, NIN = 1, UNROLLC = 0 };   // keep B_M and X of row i+1; Y travels along the row
     const float* match; const float* ins; const LogAddLut* lut; float* F; float* VB; int L1, L2;
     float* stage; int Cmax, lane;
     __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
 // entries of a cell are packed into one byte (M: 2 bits holding tb+1, X: bit 2, Y: bit 3) stored in slot layout.
 struct VitFwd {
     typedef float T;
-    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0 };
+    enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0, UNROLLC = 0 };
     const float* match; const float* ins; unsigned char* TB; int L1, L2;
     float ins1; const float* mrow; float init0, init1;
     float fin[3]; bool has_fin;
@@ -764,7 +764,7 @@ struct FinalSweep {
     __device__ __forceinline__ void step_sync() const {}
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
-    enum { NS = 2, REV = 0, COLMASK = 0x1, NIN = 3 };
+    enum { NS = 2, REV = 0, COLMASK = 0x1, NIN = 3, UNROLLC = 1 };
     const float* S5; const float* P; const float* SL;
     float* dstage; int Cmax, lane;
     __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {

@@ -14,6 +14,7 @@
 // Forward step t and reverse step (L1 + 31 - t) touch the SAME slot on every lane, so each dense access is a
 // fully coalesced 128-byte line per c, in both directions.
 #pragma once
+#define MLP_SWEEP_MAXC 8   // columns per lane the sweep kernels are unrolled for (ctx.h: kCmaxLimit)
 #include "dev_common.cuh"
 
 template <int N, class T>
@@ -123,8 +124,7 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                 const int r1 = (ri >= 1 && ri <= cx.L1) ? cx.s1[ri - 1] : 0;
                 m.begin_row(i, r1);
                 const int slotbase = ((cb * cx.T + (M::REV ? (cx.L1 + 31 - t) : t)) * C) * 32 + lane;   // element index inside this pair's layer
-                for (int cc = 0; cc < C; ++cc) {
-                    const int c = M::REV ? (C - 1 - cc) : cc;
+                auto do_cell = [&](const int c) {
                     const int j = jbase + c;
                     T old[NS], nw[NS];
                     T* bcell = band + (c * NSB) * 32 + lane;   // [c][state][lane]: one address per cell, states at immediate offsets
@@ -138,6 +138,18 @@ __device__ __forceinline__ void run_sweep(M& m, const SweepCtx& cx, typename M::
                         diag[s] = old[s];
                         carry[s] = nw[s];
                     }
+                };
+                if (M::UNROLLC) {
+                    // fully unrolled over the 8 columns a lane can own (c is a compile-time constant in every copy, so the band,
+                    // residue and slot addresses are immediates); copies beyond C are skipped by a warp-uniform branch.  Measured
+                    // per kernel at 1000 x 300: helps the partition and final sweeps, not the 5-state ones.
+#pragma unroll
+                    for (int cc = 0; cc < MLP_SWEEP_MAXC; ++cc) {
+                        const int c = M::REV ? (MLP_SWEEP_MAXC - 1 - cc) : cc;
+                        if (c < C) do_cell(c);
+                    }
+                } else {
+                    for (int cc = 0; cc < C; ++cc) do_cell(M::REV ? (C - 1 - cc) : cc);
                 }
                 m.end_row();
 #pragma unroll
