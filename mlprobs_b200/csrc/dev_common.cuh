@@ -78,6 +78,34 @@ __device__ __forceinline__ float dev_log_add_lut(float x, float y, const LogAddL
     return (d >= 7.5f) ? mx : r;
 }
 
+// Same function with the table addressed through a pre-biased 32-bit shared address (log_add_lut_bias): d is clamped to 7.5
+// so ceil(2d) <= 15 needs no mask, and 8 * ceil(2d) is (u << 3) - (0x4B000000 << 3) in modular arithmetic -- the subtraction
+// is folded into the loop-invariant base, leaving FMNMX + FFMA + LEA + 2 LDS.64 (one instruction less than mask + shift + add).
+// For d >= 7.5 the polynomial value is discarded, as in dev_log_add.
+__device__ __forceinline__ unsigned log_add_lut_bias(const LogAddLut* lut) {
+    // The value travels through a shared-memory word: ptxas would otherwise fold "base - constant" back into every address
+    // computation (one extra integer add per LOG_ADD) instead of keeping the biased base in a register.
+    __shared__ unsigned s_bias;
+    if (threadIdx.x == 0) s_bias = (unsigned)__cvta_generic_to_shared(lut) - 0x58000000u;
+    __syncthreads();
+    return *reinterpret_cast<volatile unsigned*>(&s_bias);
+}
+__device__ __forceinline__ float dev_log_add_lutb(float x, float y, unsigned lutb) {
+    const float mx = fmaxf(x, y);
+    const float mn = fminf(x, y);
+    const float d = __fsub_rn(mx, mn);
+    const unsigned u = __float_as_uint(__fmaf_ru(fminf(d, 7.5f), 2.0f, 8388608.0f));
+    const unsigned sa = lutb + (u << 3);
+    float a, b, c, e;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(sa));
+    asm("ld.shared.v2.f32 {%0, %1}, [%2+128];" : "=f"(c), "=f"(e) : "r"(sa));
+    float r = __fadd_rn(__fmul_rn(a, d), b);
+    r = __fadd_rn(__fmul_rn(r, d), c);
+    r = __fadd_rn(__fmul_rn(r, d), e);
+    r = __fadd_rn(r, mn);
+    return (d >= 7.5f) ? mx : r;
+}
+
 // cp.async (LDGSTS) helpers: stage the next wavefront slot of a dense layer into shared memory while the
 // current row is being computed.
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {

@@ -61,7 +61,7 @@ struct HmmFwd {
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 5, REV = 0, COLMASK = 0x1f, NIN = 0, UNROLLC = 0 };
-    const float* match; const float* ins; const LogAddLut* lut;
+    const float* match; const float* ins; const LogAddLut* lut; unsigned lutb;
     float* F;
     int L1, L2;
     float ins1; const float* mrow;
@@ -87,16 +87,16 @@ struct HmmFwd {
                                          const T (&diag)[NS], T (&nw)[NS]) {
         // ProbabilisticModel.h:213-245 / ParallelProbabilisticModel.cpp:91-113
         float m = __fadd_rn(diag[0], tq0[0]);
-        m = dev_log_add_lut(m, __fadd_rn(diag[1], tq0[1]), lut);
-        m = dev_log_add_lut(m, __fadd_rn(diag[2], tq0[2]), lut);
-        m = dev_log_add_lut(m, __fadd_rn(diag[3], tq0[3]), lut);
-        m = dev_log_add_lut(m, __fadd_rn(diag[4], tq0[4]), lut);
+        m = dev_log_add_lutb(m, __fadd_rn(diag[1], tq0[1]), lutb);
+        m = dev_log_add_lutb(m, __fadd_rn(diag[2], tq0[2]), lutb);
+        m = dev_log_add_lutb(m, __fadd_rn(diag[3], tq0[3]), lutb);
+        m = dev_log_add_lutb(m, __fadd_rn(diag[4], tq0[4]), lutb);
         m = __fadd_rn(m, mrow[r2]);
         const float ins2 = ins[r2];
-        float x1 = __fadd_rn(ins1, dev_log_add_lut(__fadd_rn(old[0], t0q[1]), __fadd_rn(old[1], tqq[1]), lut));
-        float x2 = __fadd_rn(ins1, dev_log_add_lut(__fadd_rn(old[0], t0q[3]), __fadd_rn(old[3], tqq[3]), lut));
-        float y1 = __fadd_rn(ins2, dev_log_add_lut(__fadd_rn(carry[0], t0q[2]), __fadd_rn(carry[2], tqq[2]), lut));
-        float y2 = __fadd_rn(ins2, dev_log_add_lut(__fadd_rn(carry[0], t0q[4]), __fadd_rn(carry[4], tqq[4]), lut));
+        float x1 = __fadd_rn(ins1, dev_log_add_lutb(__fadd_rn(old[0], t0q[1]), __fadd_rn(old[1], tqq[1]), lutb));
+        float x2 = __fadd_rn(ins1, dev_log_add_lutb(__fadd_rn(old[0], t0q[3]), __fadd_rn(old[3], tqq[3]), lutb));
+        float y1 = __fadd_rn(ins2, dev_log_add_lutb(__fadd_rn(carry[0], t0q[2]), __fadd_rn(carry[2], tqq[2]), lutb));
+        float y2 = __fadd_rn(ins2, dev_log_add_lutb(__fadd_rn(carry[0], t0q[4]), __fadd_rn(carry[4], tqq[4]), lutb));
         if (i <= 1 && j <= 1) {   // initialisation cells, ProbabilisticModel.h:173-184 (the recurrence is skipped there)
             m = (i == 1 && j == 1) ? __fadd_rn(c_sc.init[0], mrow[r2]) : MLP_LOG_ZERO;
             x1 = (i == 1 && j == 0) ? __fadd_rn(c_sc.init[1], ins1) : MLP_LOG_ZERO;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd(KArgs a) {
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     HmmFwd m;
-    m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerS5;
+    m.match = match; m.ins = ins; m.lut = lut; m.lutb = log_add_lut_bias(lut); m.F = a.layerS5;
     m.load_consts();
     for (;;) {
         const int ti = next_task(a.counter, lane);
@@ -144,7 +144,7 @@ struct HmmBwd {
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 5, REV = 1, COLMASK = 0x0b, NIN = 1, UNROLLC = 0 };   // keep B_M, X1, X2 of row i+1; Y1, Y2 travel along the row
-    const float* match; const float* ins; const LogAddLut* lut;
+    const float* match; const float* ins; const LogAddLut* lut; unsigned lutb;
     float* F;      // in: forward M, out: F + B (ProbabilisticModel.h:483 evaluates (F+B)-total)
     float* stage; int Cmax;
     float* cap;    // [0]=B_M(1,1) [1]=B_X1(1,0) [2]=B_Y1(0,1) [3]=B_X2(1,0) [4]=B_Y2(0,1)
@@ -185,17 +185,17 @@ struct HmmBwd {
         float x2 = __fadd_rn(pxy, tq0[3]);
         float y2 = __fadd_rn(pxy, tq0[4]);
         const float a1 = __fadd_rn(old[1], ins1);
-        bm = dev_log_add_lut(bm, __fadd_rn(a1, t0q[1]), lut);
-        x1 = dev_log_add_lut(x1, __fadd_rn(a1, tqq[1]), lut);
+        bm = dev_log_add_lutb(bm, __fadd_rn(a1, t0q[1]), lutb);
+        x1 = dev_log_add_lutb(x1, __fadd_rn(a1, tqq[1]), lutb);
         const float a2 = __fadd_rn(old[3], ins1);
-        bm = dev_log_add_lut(bm, __fadd_rn(a2, t0q[3]), lut);
-        x2 = dev_log_add_lut(x2, __fadd_rn(a2, tqq[3]), lut);
+        bm = dev_log_add_lutb(bm, __fadd_rn(a2, t0q[3]), lutb);
+        x2 = dev_log_add_lutb(x2, __fadd_rn(a2, tqq[3]), lutb);
         const float b1 = __fadd_rn(carry[2], ins2);
-        bm = dev_log_add_lut(bm, __fadd_rn(b1, t0q[2]), lut);
-        y1 = dev_log_add_lut(y1, __fadd_rn(b1, tqq[2]), lut);
+        bm = dev_log_add_lutb(bm, __fadd_rn(b1, t0q[2]), lutb);
+        y1 = dev_log_add_lutb(y1, __fadd_rn(b1, tqq[2]), lutb);
         const float b2 = __fadd_rn(carry[4], ins2);
-        bm = dev_log_add_lut(bm, __fadd_rn(b2, t0q[4]), lut);
-        y2 = dev_log_add_lut(y2, __fadd_rn(b2, tqq[4]), lut);
+        bm = dev_log_add_lutb(bm, __fadd_rn(b2, t0q[4]), lutb);
+        y2 = dev_log_add_lutb(y2, __fadd_rn(b2, tqq[4]), lutb);
         if (i == L1 && j == L2) { bm = c_sc.init[0]; x1 = c_sc.init[1]; y1 = c_sc.init[2]; x2 = c_sc.init[3]; y2 = c_sc.init[4]; }
         nw[0] = bm; nw[1] = x1; nw[2] = y1; nw[3] = x2; nw[4] = y2;
         F[slot] = __fadd_rn(stage[(buf * Cmax + c) * 32 + lane], bm);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd(KArgs a) {
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     HmmBwd m;
-    m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerS5; m.cap = cap; m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
+    m.match = match; m.ins = ins; m.lut = lut; m.lutb = log_add_lut_bias(lut); m.F = a.layerS5; m.cap = cap; m.stage = stage; m.Cmax = a.Cmax; m.lane = lane;
     m.load_consts();
     for (;;) {
         const int ti = next_task(a.counter, lane);
