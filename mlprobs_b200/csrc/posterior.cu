@@ -794,7 +794,10 @@ struct FinalSweep {
     __device__ __forceinline__ void begin_row(int, int) {}
     __device__ __forceinline__ void cell(int i, int j, int c, int buf, int, int slot, const T (&old)[NS], const T (&carry)[NS],
                                          const T (&diag)[NS], T (&nw)[NS]) {
-        if (j > L2) { nw[0] = carry[0]; nw[1] = carry[1]; return; }
+        // Written branch-free except for the (rare) kept-cell staging: padding columns j > L2 compute on whatever the stage holds
+        // and are masked out at the end, which is cheaper than a divergent early return per cell.
+        const bool valid = (j <= L2);
+        const bool inner = valid && i >= 1 && j >= 1;
         const unsigned mask = QPSPEC ? 3u : this->mask;
         const int flavour = QPSPEC ? 0 : this->flavour;
         int* const tb = QPSPEC ? nullptr : this->tb;
@@ -803,10 +806,13 @@ struct FinalSweep {
         if (mask & 1u) v5 = dev_exp_lut(fminf(0.0f, __fsub_rn(sg[0], total5)), elut);
         if (mask & 2u) vp = sg[Cmax * 32];
         if (mask & 4u) vl = dev_exp_lut(fminf(0.0f, __fsub_rn(sg[2 * Cmax * 32], totalL)), elut);
-        if (i == 0 && j == 0) { v5 = 0.0f; vl = 0.0f; }   // posterior[0] = 0, ProbabilisticModel.h:490
+        const bool origin = (i == 0 && j == 0);
+        v5 = origin ? 0.0f : v5;                          // posterior[0] = 0, ProbabilisticModel.h:490
+        vl = origin ? 0.0f : vl;
         if (flavour == 0) {
             // PosteriorStage.cpp:169-177: borders forced to 0, sqrt((v1^2+v2^2)*0.5)
-            p = (i == 0 || j == 0) ? 0.0f : __fsqrt_rn(__fmul_rn(__fadd_rn(__fmul_rn(v5, v5), __fmul_rn(vp, vp)), 0.5f));
+            p = __fsqrt_rn(__fmul_rn(__fadd_rn(__fmul_rn(v5, v5), __fmul_rn(vp, vp)), 0.5f));
+            p = (i == 0 || j == 0) ? 0.0f : p;
         } else if (mask == 7u) {
             // MSA.cpp:1001 ((dbl^2+glob^2)+loc^2)/3 ; MSA.cpp:1708 ((glob^2+loc^2)+dbl^2)/3
             const float q5 = __fmul_rn(v5, v5), qp = __fmul_rn(vp, vp), ql = __fmul_rn(vl, vl);
@@ -816,32 +822,31 @@ struct FinalSweep {
             p = (mask & 1u) ? v5 : ((mask & 2u) ? vp : vl);
         }
         if (DENSE) {
-            const long long d = (long long)i * (L2 + 1) + j;
-            dense[d] = p;
-            if (dense5) dense5[d] = v5;
-            if (denseP) denseP[d] = vp;
-            if (denseL) denseL[d] = vl;
+            if (valid) {
+                const long long d = (long long)i * (L2 + 1) + j;
+                dense[d] = p;
+                if (dense5) dense5[d] = v5;
+                if (denseP) denseP[d] = vp;
+                if (denseL) denseL[d] = vl;
+            }
         }
         // MEA row DP: ProbabilisticModel.h:834-836 / PosteriorStage.cpp:177 (row 0 / column 0 stay 0)
-        float sc = 0.0f;
-        if (i >= 1 && j >= 1) sc = fmaxf(fmaxf(__fadd_rn(p, diag[0]), carry[0]), old[0]);
+        const float x1 = __fadd_rn(p, diag[0]), x2 = carry[0], x3 = old[0];
+        float sc = inner ? fmaxf(fmaxf(x1, x2), x3) : 0.0f;
         if (tb) {   // ChooseBestOfThree tie order D >= L >= U (ScoreType.h:347-366); row 0 = 'L', column 0 = 'U'
-            int code = 1;
-            if (i >= 1) {
-                code = 2;
-                if (j >= 1) {
-                    const float x1 = __fadd_rn(p, diag[0]), x2 = carry[0], x3 = old[0];
-                    code = (x1 >= x2) ? ((x1 >= x3) ? 0 : 2) : ((x2 >= x3) ? 1 : 2);
-                }
-            }
-            tb[slot] = code;
+            int code = (x1 >= x2) ? ((x1 >= x3) ? 0 : 2) : ((x2 >= x3) ? 1 : 2);
+            code = (j >= 1) ? code : 2;
+            code = (i >= 1) ? code : 1;
+            if (valid) tb[slot] = code;
         }
         float cnt = (j == 0) ? 0.0f : carry[1];
-        if (i >= 1 && j >= 1 && p >= cutoff) {   // SparseMatrix.h:89 / PackedSparseMatrix.cpp:68
+        if (inner && p >= cutoff) {   // SparseMatrix.h:89 / PackedSparseMatrix.cpp:68
             const int k = atomicAdd(stage_n, 1);
             if (k < stage_cap) stage[k] = make_int4(i, (int)cnt, j, __float_as_int(p));
             cnt += 1.0f;
         }
+        sc = valid ? sc : carry[0];
+        cnt = valid ? cnt : carry[1];
         nw[0] = sc; nw[1] = cnt;
         if (j == L2) {
             rowcnt[i + 1] = (int)cnt;
