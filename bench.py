@@ -125,10 +125,12 @@ def one_step(eng, M, n, e2e, seqs=None, world=1, read_back=True, host_out=None):
     eng.posterior_all_pairs(M.QP, 3, 0.01)
     stats.append(("posterior", eng.stats()))
     if world > 1:
-        eng.exchange(); stats.append(("exchange", eng.stats()))
+        eng.exchange_begin()                          # cell broadcasts run over NVLink while the host builds the tree
     d = eng.distances()                               # the guide tree is host work between the stages, as in the reference
     w, sd, _, _ = M.qp_guide_tree(d)
     w = np.maximum(w, np.float32(1e-6))
+    if world > 1:
+        eng.exchange_end(); stats.append(("exchange", eng.stats()))
     iters = 1 if n > 50 else 2
     for it in range(iters):
         cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))

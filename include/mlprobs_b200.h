@@ -199,6 +199,10 @@ int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_mask, int a, 
 int mlp_nccl_unique_id(uint8_t id128[128]);
 int mlp_comm_init(mlp_ctx* ctx, const uint8_t id128[128], int rank, int world);
 int mlp_exchange(mlp_ctx* ctx);
+/* The same exchange in two halves: _begin enqueues everything and returns; mlp_get_distances then only waits for the distance
+ * all-reduce, so the host guide tree overlaps the cell broadcasts; _end (or any later stage call) waits for the rest. */
+int mlp_exchange_begin(mlp_ctx* ctx);
+int mlp_exchange_end(mlp_ctx* ctx);
 
 /* timing / accounting of the last stage call, measured with CUDA events on the library's stream */
 typedef struct {

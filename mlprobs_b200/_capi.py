@@ -24,7 +24,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
-           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores"]
+           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end"]
 
 
 class HmmTables(C.Structure):
@@ -429,6 +429,15 @@ class Engine:
     def exchange(self):
         """All-gather the sparse posteriors + distances of every rank's shard (NCCL)."""
         self._ck(self._lib.mlp_exchange(self._ctx))
+
+    def exchange_begin(self):
+        """Start the exchange; distances() then only waits for the distance all-reduce (the tree overlaps the cell broadcasts)."""
+        self._lib.mlp_exchange_begin.argtypes = [C.c_void_p]
+        self._ck(self._lib.mlp_exchange_begin(self._ctx))
+
+    def exchange_end(self):
+        self._lib.mlp_exchange_end.argtypes = [C.c_void_p]
+        self._ck(self._lib.mlp_exchange_end(self._ctx))
 
     def csr(self, a, b):
         nnz = C.c_int64(0)

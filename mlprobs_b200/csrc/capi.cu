@@ -52,6 +52,7 @@ extern "C" int mlp_create(int device, mlp_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
     cudaEventCreate(&ctx->ev[0]); cudaEventCreate(&ctx->ev[1]);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_dist, cudaEventDisableTiming);
     if (const char* e = getenv("MLP_OVERLAP")) ctx->overlap = atoi(e);
     if (const char* e = getenv("MLP_BPS_PART")) ctx->bps_part = atoi(e);
     if (const char* e = getenv("MLP_BPS_HMM")) ctx->bps_hmm = atoi(e);
@@ -79,6 +80,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_dist) cudaEventDestroy(ctx->ev_dist);
     delete ctx;
 }
 
@@ -611,6 +613,7 @@ extern "C" int mlp_viterbi_all_pairs_ex(mlp_ctx* ctx, int32_t* n_identical, int3
 
 extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model_mask, float cutoff) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     cudaSetDevice(ctx->device);
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
@@ -683,6 +686,13 @@ extern "C" int mlp_get_distances(mlp_ctx* ctx, float* nxn) {
     if (!ctx || !nxn) return MLP_E_ARG;
     if (!ctx->have_sets) return MLP_E_STATE;
     cudaSetDevice(ctx->device);
+    if (ctx->exch_pending) {   // split exchange in flight: the distances are ready once their all-reduce has run
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_dist, 0));
+        CK(cudaMemcpyAsync(nxn, ctx->d_dist, (size_t)ctx->n * ctx->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream2));
+        CK(cudaStreamSynchronize(ctx->stream2));
+        ctx->stats.d2h_bytes += (int64_t)ctx->n * ctx->n * 4;
+        return MLP_OK;
+    }
     CK(cudaMemcpy(nxn, ctx->d_dist, (size_t)ctx->n * ctx->n * sizeof(float), cudaMemcpyDeviceToHost));
     ctx->stats.d2h_bytes += (int64_t)ctx->n * ctx->n * 4;
     return MLP_OK;
@@ -690,6 +700,7 @@ extern "C" int mlp_get_distances(mlp_ctx* ctx, float* nxn) {
 
 extern "C" int mlp_get_csr(mlp_ctx* ctx, int a, int b, int32_t* row_ptr, int32_t* col, float* val, int64_t* nnz) {
     if (!ctx || a < 0 || b < 0 || a >= ctx->n || b >= ctx->n || a == b) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     if (!ctx->have_sets) return MLP_E_STATE;
     cudaSetDevice(ctx->device);
     const CsrSetDev& s = ctx->set[ctx->cur];
@@ -781,6 +792,7 @@ extern "C" int mlp_csr_layout(mlp_ctx* ctx, int64_t* rp_off, int64_t* rp_total, 
 
 extern "C" int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, int32_t* rp_pool, void* cells) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     if (!ctx->have_sets) return MLP_E_STATE;
     cudaSetDevice(ctx->device);
     const CsrSetDev& s = ctx->set[ctx->cur];
@@ -816,6 +828,7 @@ __global__ void k_row_sizes(const int* __restrict__ rp, unsigned short* __restri
 
 extern "C" int mlp_get_csr_packed(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     if (!ctx->have_sets) return MLP_E_STATE;
     if (ctx->flavour_of_set != MLP_QP) { ctx->err = "packed cells are the QuickProbs format (uint16 fixed-point values)"; return MLP_E_UNSUPPORTED; }
     cudaSetDevice(ctx->device);
@@ -863,6 +876,7 @@ extern "C" void mlp_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
                          float selectivity, float selfweight, float cutoff) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     if (!ctx->have_sets || ctx->flavour_of_set < 0) { ctx->err = "run mlp_posterior_all_pairs first"; return MLP_E_STATE; }
     cudaSetDevice(ctx->device);
     const int n = ctx->n;

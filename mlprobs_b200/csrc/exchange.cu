@@ -83,9 +83,33 @@ extern "C" int mlp_comm_init(mlp_ctx* ctx, const uint8_t id128[128], int rank, i
     return mlp_set_shard(ctx, rank, world);
 }
 
+// Second half of an exchange started with mlp_exchange_begin: wait for the copies and fill the statistics.
+extern "C" int mlp_exchange_end(mlp_ctx* ctx) {
+    if (!ctx) return MLP_E_ARG;
+    if (!ctx->exch_pending) return MLP_OK;
+    cudaSetDevice(ctx->device);
+    ctx->exch_pending = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats = mlp_stage_stats{};
+    ctx->stats.ms_total = ms;
+    ctx->stats.nnz = (int64_t)(ctx->exch_total / 2);
+    ctx->stats.launches = 1;
+    return MLP_OK;
+}
+
 extern "C" int mlp_exchange(mlp_ctx* ctx) {
+    const int rc = mlp_exchange_begin(ctx);
+    return rc != MLP_OK ? rc : mlp_exchange_end(ctx);
+}
+
+// Enqueue the whole exchange and return without waiting for the cell broadcasts.  The distances are complete as soon as
+// their all-reduce has run (event ev_dist): mlp_get_distances waits for that event only, so the host guide tree can be built
+// while the sparse cells are still travelling over NVLink.
+extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     if (!ctx) return MLP_E_ARG;
     if (ctx->comm_world <= 1) return MLP_OK;
+    if (ctx->exch_pending) { const int rc0 = mlp_exchange_end(ctx); if (rc0 != MLP_OK) return rc0; }
     if (!ctx->nccl_comm || !ctx->have_sets) { ctx->err = "mlp_comm_init and a posterior/relax stage must come first"; return MLP_E_STATE; }
     cudaSetDevice(ctx->device);
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
@@ -123,6 +147,7 @@ extern "C" int mlp_exchange(mlp_ctx* ctx) {
     }
     // 3. fixed-layout tables: sum == union
     NK(g_nccl.AllReduce(ctx->d_dist, ctx->d_dist, (size_t)n * n, ncclFloat32, ncclSum, comm, st));
+    CK(cudaEventRecord(ctx->ev_dist, st));
     NK(g_nccl.AllReduce(ctx->set[cur].rp_pool, ctx->set[cur].rp_pool, (size_t)ctx->rp_total, ncclInt32, ncclSum, comm, st));
     NK(g_nccl.AllReduce(ctx->set[cur].nz_cnt, ctx->set[cur].nz_cnt, (size_t)n * n, ncclInt32, ncclSum, comm, st));
     NK(g_nccl.AllReduce(ctx->set[cur].nz_off, ctx->set[cur].nz_off, (size_t)n * n, ncclInt64, ncclSum, comm, st));
@@ -132,16 +157,11 @@ extern "C" int mlp_exchange(mlp_ctx* ctx) {
         if (used[r])
             NK(g_nccl.Broadcast(ctx->set[cur].cells, ctx->set[oth].cells + base[r], (size_t)used[r], ncclUint64, r, comm, st));
     NK(g_nccl.GroupEnd());
-    const unsigned long long tot = (unsigned long long)total;
-    CK(cudaMemcpyAsync(ctx->set[cur].cursor, &tot, sizeof(tot), cudaMemcpyHostToDevice, st));
+    ctx->exch_total = (unsigned long long)total;     // lives in the context: the copy below may read it after this call returns
+    CK(cudaMemcpyAsync(ctx->set[cur].cursor, &ctx->exch_total, sizeof(ctx->exch_total), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[1], st));
-    CK(cudaStreamSynchronize(st));
-    std::swap(ctx->set[cur].cells, ctx->set[oth].cells);
+    std::swap(ctx->set[cur].cells, ctx->set[oth].cells);   // everything enqueued later on this stream sees the common pool
     std::swap(ctx->set[cur].cap, ctx->set[oth].cap);
-    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    ctx->stats = mlp_stage_stats{};
-    ctx->stats.ms_total = ms;
-    ctx->stats.nnz = total / 2;
-    ctx->stats.launches = 1;
+    ctx->exch_pending = true;
     return MLP_OK;
 }

@@ -23,8 +23,9 @@ def run(sharded):
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(uid[0], rank, world)
     eng.posterior_all_pairs(M.QP, 3, 0.01)
-    if sharded: eng.exchange()
+    if sharded: eng.exchange_begin()       # split exchange: distances() overlaps the cell broadcasts, the next stage call ends it
     d = eng.distances()
+    if sharded: eng.exchange_end()
     w, sd, _, _ = M.qp_guide_tree(d)
     eng.relax(M.QP, np.maximum(w, np.float32(1e-6)), sd, 200.0, 3.0, float(np.float32(1e-5)))
     if sharded: eng.exchange()
