@@ -1,6 +1,6 @@
 """Suite-level parity of the two drop-in executables: byte-identical FASTA output on bundled benchmark families
 (tests/golden/suites, written by oracle/gen_suite_golden.py from the reference programs).  The ox and oxx suites run here
-(530 families, both tools, about a minute); tools/suite_parity.py runs all four suites (1219 families)."""
+(546 families, both tools, about a minute and a half); tools/suite_parity.py runs all four suites (1276 families)."""
 import os
 import sys
 import pytest
