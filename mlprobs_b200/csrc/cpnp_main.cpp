@@ -15,6 +15,7 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <chrono>
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -74,7 +75,9 @@ int fail(mlp_ctx* ctx, const char* what, int rc) {
 }  // namespace
 
 // one input file; returns the exit status for it
-int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int getpid, int reps, int refine) {
+int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int getpid, int reps, int refine, int verbose) {
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     auto fail = [&](mlp_ctx* c, const char* what, int rc) {
         std::fprintf(stderr, "c_p_np_aln_b200: %s: %s failed (%d): %s\n", infile.c_str(), what, rc, c ? mlp_last_error(c) : "");
         return 1;
@@ -118,6 +121,7 @@ int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile
         return 0;
     }
     // MSA::ModelAdjustmentTest, MSA.cpp:775-882
+    const double t1 = now();
     if ((rc = mlp_viterbi_all_pairs(ctx, ident.data(), alen.data()))) return fail(ctx, "mlp_viterbi_all_pairs", rc);
     float identity = 0, sigma = 0, init2 = 0;
     const int variance_mean = mlp_cpnp_model_adjustment(npairs, ident.data(), alen.data(), &identity, &sigma, &init2);
@@ -125,28 +129,33 @@ int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile
     const int pid = variance_mean % 10, vpid = variance_mean / 10;
     if ((rc = mlp_default_tables(MLP_CPNP_P0, init2, &hmm, &part))) return fail(ctx, "mlp_default_tables", rc);
     if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
+    const double t2 = now();
     const uint32_t mask = pid <= 1 ? (MLP_M_HMM5 | MLP_M_PART | MLP_M_LOCAL) : (pid == 2 ? MLP_M_LOCAL : MLP_M_PART);   // MSA.cpp:946-1010
     rc = mlp_posterior_all_pairs(ctx, MLP_CPNP_P0, mask, 0.01f);
     if (rc == MLP_E_OVERFLOW) { std::printf("ERROR: huge val error for zM\n"); return 1; }            // MSAPartProbs.cpp:547-589
     if (rc) return fail(ctx, "mlp_posterior_all_pairs", rc);
+    const double t3 = now();
     std::vector<float> dist((size_t)n * n);
     std::vector<int32_t> weights(n), left(2 * n - 1), right(2 * n - 1), order(n);
     if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
     if ((rc = mlp_cpnp_guide_tree(n, dist.data(), vpid, weights.data(), left.data(), right.data()))) return fail(ctx, "mlp_cpnp_guide_tree", rc);
     for (int r = 0; r < reps; ++r)
         if ((rc = mlp_relax(ctx, MLP_CPNP_P0, nullptr, nullptr, 0.0f, 0.0f, 0.01f))) return fail(ctx, "mlp_relax", rc);
+    const double t4 = now();
     char* rows = nullptr;
     int32_t cols = 0;
     if ((rc = mlp_cpnp_finish_alignment(ctx, weights.data(), left.data(), right.data(), refine, pid, &rows, &cols, order.data())))
         return fail(ctx, "mlp_cpnp_finish_alignment", rc);
     for (int k = 0; k < n; ++k) write_mfa(out, in.headers[order[k]], rows + (size_t)k * cols, cols);
+    if (verbose) std::fprintf(stderr, "c_p_np_aln_b200: %d sequences, model class %d, %d columns; ms: load+upload %.1f, viterbi %.1f, posterior %.1f, tree+consistency %.1f, alignment+refinement %.1f\n",
+                              n, variance_mean, cols, t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
     mlp_free_host(rows);
     return 0;
 }
 
 int main(int argc, char** argv) {
     std::string infile, outfile;
-    int program = 0, getpid = 0, reps = 2, refine = 100, device = 0;
+    int program = 0, getpid = 0, reps = 2, refine = 100, device = 0, verbose = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char* name) -> const char* {
@@ -162,7 +171,7 @@ int main(int argc, char** argv) {
         else if (a == "-c" || a == "--consistency") reps = std::atoi(need("-c"));
         else if (a == "-ir" || a == "--iterative-refinement") refine = std::atoi(need("-ir"));
         else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
-        else if (a == "-v" || a == "--verbose") {}
+        else if (a == "-v" || a == "--verbose") verbose = 1;
         else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "c_p_np_aln_b200: unsupported option %s\n", a.c_str()); return 2; }
         else if (infile.empty()) infile = a;
         else { std::fprintf(stderr, "c_p_np_aln_b200: more than one input file\n"); return 2; }
@@ -192,10 +201,10 @@ int main(int argc, char** argv) {
         }
         std::sort(names.begin(), names.end());
         for (const std::string& nm : names) {
-            const int r1 = run_file(ctx, infile + "/" + nm, outfile + "/" + nm, getpid, reps, refine);
+            const int r1 = run_file(ctx, infile + "/" + nm, outfile + "/" + nm, getpid, reps, refine, verbose);
             if (r1) status = r1;
         }
-    } else status = run_file(ctx, infile, outfile, getpid, reps, refine);
+    } else status = run_file(ctx, infile, outfile, getpid, reps, refine, verbose);
     mlp_destroy(ctx);
     return status;
 }

@@ -285,14 +285,12 @@ int run_cpnp_tail(int n, const int32_t* len, const uint8_t* residues, const int3
         else {
             extract_subset(*aln, g1, one);
             extract_subset(*aln, g2, two);
-            const float* dense = nullptr;
-            const int rc = prov.build(one, two, flat, &dense);
-            if (rc < 0) { err = "profile posterior failed"; return rc; }
             const int l1 = one.length(), l2 = two.length();
             // "accuracy" of the current alignment: posterior mass on its own columns, float sum in column order
-            float before = 0;
+            std::vector<long long> offs;
             {
                 const int L = aln->length();
+                offs.reserve(L);
                 int i1 = 0, i2 = 0;
                 for (int c = 0; c < L; ++c) {
                     bool f1 = false, f2 = false;
@@ -300,11 +298,23 @@ int run_cpnp_tail(int n, const int32_t* len, const uint8_t* residues, const int3
                     for (int k : g2) if (aln->rows[k][c] != '-') { f2 = true; break; }
                     if (f1) ++i1;
                     if (f2) ++i2;
-                    if (f1 && f2) before += dense[(size_t)i1 * (l2 + 1) + i2];
+                    if (f1 && f2) offs.push_back((long long)i1 * (l2 + 1) + i2);
                 }
             }
-            float score = 0;
-            const std::string path = mea_path(l1, l2, dense, &score);
+            float before = 0, score = 0;
+            std::string path;
+            std::vector<float> vals;
+            int rc = prov.build_align_score(one, two, flat, offs, path, &score, vals);
+            if (rc < 0) { err = "profile posterior failed"; return rc; }
+            if (rc > 0) {                                     // provider without the fused path: dense matrix + host DP
+                const float* dense = nullptr;
+                rc = prov.build(one, two, flat, &dense);
+                if (rc < 0) { err = "profile posterior failed"; return rc; }
+                for (long long o : offs) before += dense[o];
+                path = mea_path(l1, l2, dense, &score);
+            } else {
+                for (float v : vals) before += v;
+            }
             std::unique_ptr<Profile> next(new Profile());
             for (int k = 0; k < one.count(); ++k) { next->ids.push_back(one.ids[k]); next->rows.push_back(add_gaps(one.rows[k], path, 'X')); }
             for (int k = 0; k < two.count(); ++k) { next->ids.push_back(two.ids[k]); next->rows.push_back(add_gaps(two.rows[k], path, 'Y')); }

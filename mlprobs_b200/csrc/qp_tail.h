@@ -44,6 +44,12 @@ struct ProfilePosterior {
     virtual int build(const Profile& A, const Profile& B, const WeightSpec& ws, const float** dense) = 0;
     // optional fused path: MEA traceback string directly (returns 1 = not supported, caller runs the host DP on `dense`)
     virtual int build_and_align(const Profile& A, const Profile& B, const WeightSpec& ws, std::string& path) { (void)A; (void)B; (void)ws; path.clear(); return 1; }
+    // optional fused path for cpnp's refinement: MEA path, its score (last cell of the DP) and the dense values at the given
+    // element offsets (the posterior mass on the old alignment's columns); returns 1 = not supported
+    virtual int build_align_score(const Profile& A, const Profile& B, const WeightSpec& ws, const std::vector<long long>& offsets,
+                                  std::string& path, float* score, std::vector<float>& values) {
+        (void)A; (void)B; (void)ws; (void)offsets; (void)score; (void)values; path.clear(); return 1;
+    }
 };
 
 struct HostCsrView {

@@ -133,6 +133,7 @@ constexpr int MEA_DEPTH = 4;
 struct MeaArgs {
     const float* dense; int l1, l2, C, T, B;
     unsigned char* tb;                 // [(l1)][T][B] 2-bit choices (0 = diagonal, 1 = left, 2 = up), rows 1..l1
+    float* score;                      // the maximum sum = DP value of cell (l1, l2)
 };
 
 __global__ void __launch_bounds__(1024) k_mea_wavefront(MeaArgs a) {
@@ -196,6 +197,12 @@ __global__ void __launch_bounds__(1024) k_mea_wavefront(MeaArgs a) {
             __syncthreads();
         }
     }
+    if (a.score && j0 <= a.l2 && a.l2 < j0 + C) *a.score = row[a.l2];   // all rows done (the loop ends with a barrier)
+}
+
+__global__ void k_gather_dense(const float* __restrict__ dense, const long long* __restrict__ off, float* __restrict__ out, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = dense[off[k]];
 }
 
 size_t pp_smem_bytes(int l2, int nA) {
@@ -213,6 +220,8 @@ public:
         if (h_dense) cudaFreeHost(h_dense);
         if (d_tb) cudaFree(d_tb);
         if (h_tb) cudaFreeHost(h_tb);
+        if (d_gx) cudaFree(d_gx);
+        if (h_gx) cudaFreeHost(h_gx);
     }
     int launch_profile(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws) {
         const int nA = A.count(), nB = B.count(), l1 = A.length(), l2 = B.length();
@@ -310,6 +319,14 @@ public:
 
     // profile posterior + MEA wavefront on the device, 2-bit choices back to the host, traceback there
     int build_and_align(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws, std::string& path) override {
+        return align_common(A, B, ws, path, nullptr, nullptr, nullptr);
+    }
+    int build_align_score(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws, const std::vector<long long>& offsets,
+                          std::string& path, float* score, std::vector<float>& values) override {
+        return align_common(A, B, ws, path, &offsets, score, &values);
+    }
+    int align_common(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws, std::string& path,
+                     const std::vector<long long>* offsets, float* score, std::vector<float>* values) {
         const int l1 = A.length(), l2 = B.length();
         const int W = l2 + 1;
         if (W > 1024 * MEA_MAXC || l1 < 1 || l2 < 1) return 1;    // very wide profile: host dynamic programme on the dense matrix
@@ -334,14 +351,41 @@ public:
             mea_smem_set = smem;
         }
         MeaArgs m;
-        m.dense = d_dense; m.l1 = l1; m.l2 = l2; m.C = C; m.T = T; m.B = Bb; m.tb = d_tb;
+        const size_t ng = offsets ? offsets->size() : 0;
+        if (score || ng) {                                        // extras: score word + gathered posterior values
+            const size_t need = 16 + ng * 12;
+            if (need > gx_cap) {
+                if (d_gx) cudaFree(d_gx);
+                if (h_gx) cudaFreeHost(h_gx);
+                d_gx = nullptr; h_gx = nullptr;
+                gx_cap = need + need / 2 + 4096;
+                CK(cudaMalloc(&d_gx, gx_cap));
+                CK(cudaHostAlloc(&h_gx, gx_cap, cudaHostAllocDefault));
+            }
+        }
+        // extras buffer layout: [score float, pad to 16] [ng offsets (8 B)] [ng values (4 B)]
+        float* d_score = score ? reinterpret_cast<float*>(d_gx) : nullptr;
+        long long* d_off = ng ? reinterpret_cast<long long*>(d_gx + 16) : nullptr;
+        float* d_val = ng ? reinterpret_cast<float*>(d_gx + 16 + ng * 8) : nullptr;
+        m.dense = d_dense; m.l1 = l1; m.l2 = l2; m.C = C; m.T = T; m.B = Bb; m.tb = d_tb; m.score = d_score;
         k_mea_wavefront<<<1, T, smem, ctx->stream>>>(m);
         CK(cudaGetLastError());
         ctx->stats.launches += 1;
+        if (ng) {
+            memcpy(h_gx + 16, offsets->data(), ng * 8);
+            CK(cudaMemcpyAsync(d_off, h_gx + 16, ng * 8, cudaMemcpyHostToDevice, ctx->stream));
+            k_gather_dense<<<(unsigned)((ng + 255) / 256), 256, 0, ctx->stream>>>(d_dense, d_off, d_val, (int)ng);
+            CK(cudaGetLastError());
+            ctx->stats.launches += 1;
+            CK(cudaMemcpyAsync(h_gx + 16 + ng * 8, d_val, ng * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (score) CK(cudaMemcpyAsync(h_gx, d_score, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_tb, d_tb, tbn, cudaMemcpyDeviceToHost, ctx->stream));
         rc = finish_timing();
         if (rc < 0) return rc;
-        ctx->stats.d2h_bytes += (int64_t)tbn;
+        ctx->stats.d2h_bytes += (int64_t)tbn + (int64_t)ng * 4;
+        if (score) *score = *reinterpret_cast<float*>(h_gx);
+        if (values) { values->resize(ng); if (ng) memcpy(values->data(), h_gx + 16 + ng * 8, ng * 4); }
         path.clear();
         path.reserve((size_t)l1 + l2);
         int r = l1, c = l2;
@@ -367,6 +411,7 @@ private:
     float* d_dense = nullptr; float* h_dense = nullptr; size_t dense_cap = 0;
     size_t smem_set = 48 * 1024, mea_smem_set = 48 * 1024;
     unsigned char* d_tb = nullptr; unsigned char* h_tb = nullptr; size_t tb_cap = 0;
+    unsigned char* d_gx = nullptr; unsigned char* h_gx = nullptr; size_t gx_cap = 0;   // score + gathered values (cpnp refinement)
 };
 
 }  // namespace
