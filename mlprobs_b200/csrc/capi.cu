@@ -73,7 +73,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
-    free_dev(ctx->d_weights); free_dev(ctx->d_seldist);
+    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

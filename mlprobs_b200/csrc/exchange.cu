@@ -83,6 +83,22 @@ extern "C" int mlp_comm_init(mlp_ctx* ctx, const uint8_t id128[128], int rank, i
     return mlp_set_shard(ctx, rank, world);
 }
 
+// QuickProbs cells are (column < 65536, code / 65535.0f with a 16-bit code): they cross NVLink as 4 bytes instead of 8.
+__global__ void k_xpack(const int2* __restrict__ cells, unsigned* __restrict__ q, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int2 c = cells[i];
+        q[i] = ((unsigned)c.x & 0xffffu) | (__float2uint_rn(__fmul_rn(__int_as_float(c.y), 65535.0f)) << 16);
+    }
+}
+__global__ void k_xunpack(const unsigned* __restrict__ q, int2* __restrict__ cells, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned v = q[i];
+        cells[i] = make_int2((int)(v & 0xffffu), __float_as_int(__fdiv_rn((float)(v >> 16), 65535.0f)));   // SparseEntry.h:31
+    }
+}
+
 // Second half of an exchange started with mlp_exchange_begin: wait for the copies and fill the statistics.
 extern "C" int mlp_exchange_end(mlp_ctx* ctx) {
     if (!ctx) return MLP_E_ARG;
@@ -151,12 +167,30 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     NK(g_nccl.AllReduce(ctx->set[cur].rp_pool, ctx->set[cur].rp_pool, (size_t)ctx->rp_total, ncclInt32, ncclSum, comm, st));
     NK(g_nccl.AllReduce(ctx->set[cur].nz_cnt, ctx->set[cur].nz_cnt, (size_t)n * n, ncclInt32, ncclSum, comm, st));
     NK(g_nccl.AllReduce(ctx->set[cur].nz_off, ctx->set[cur].nz_off, (size_t)n * n, ncclInt64, ncclSum, comm, st));
-    // 4. cells: every rank broadcasts its slab into the common pool (8-byte cells sent as uint64)
-    NK(g_nccl.GroupStart());
-    for (int r = 0; r < W; ++r)
-        if (used[r])
-            NK(g_nccl.Broadcast(ctx->set[cur].cells, ctx->set[oth].cells + base[r], (size_t)used[r], ncclUint64, r, comm, st));
-    NK(g_nccl.GroupEnd());
+    // 4. cells: every rank broadcasts its slab into the common pool
+    if (ctx->flavour_of_set == MLP_QP && !getenv("MLP_XCHG_RAW")) {
+        // packed: 4 bytes per cell on the wire (pack own slab -> broadcast in place -> unpack the whole pool)
+        if ((size_t)total + 8 > ctx->xq_cap) {
+            free_dev(ctx->d_xq); ctx->d_xq = nullptr; ctx->xq_cap = 0;
+            CK(cudaMalloc(&ctx->d_xq, ((size_t)total + total / 8 + 64) * sizeof(unsigned)));
+            ctx->xq_cap = (size_t)total + total / 8 + 56;
+        }
+        unsigned* q = ctx->d_xq;
+        const int grid = ctx->num_sms * 8;
+        if (used[R]) { k_xpack<<<grid, 256, 0, st>>>(ctx->set[cur].cells, q + base[R], (long long)used[R]); CK(cudaGetLastError()); }
+        NK(g_nccl.GroupStart());
+        for (int r = 0; r < W; ++r)
+            if (used[r]) NK(g_nccl.Broadcast(q + base[r], q + base[r], (size_t)used[r], ncclUint32, r, comm, st));
+        NK(g_nccl.GroupEnd());
+        if (total) { k_xunpack<<<grid, 256, 0, st>>>(q, ctx->set[oth].cells, total); CK(cudaGetLastError()); }
+    } else {
+        // 8-byte cells sent as uint64 (cpnp: full floats)
+        NK(g_nccl.GroupStart());
+        for (int r = 0; r < W; ++r)
+            if (used[r])
+                NK(g_nccl.Broadcast(ctx->set[cur].cells, ctx->set[oth].cells + base[r], (size_t)used[r], ncclUint64, r, comm, st));
+        NK(g_nccl.GroupEnd());
+    }
     ctx->exch_total = (unsigned long long)total;     // lives in the context: the copy below may read it after this call returns
     CK(cudaMemcpyAsync(ctx->set[cur].cursor, &ctx->exch_total, sizeof(ctx->exch_total), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[1], st));
