@@ -168,8 +168,13 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     NK(g_nccl.AllReduce(ctx->set[cur].nz_cnt, ctx->set[cur].nz_cnt, (size_t)n * n, ncclInt32, ncclSum, comm, st));
     NK(g_nccl.AllReduce(ctx->set[cur].nz_off, ctx->set[cur].nz_off, (size_t)n * n, ncclInt64, ncclSum, comm, st));
     // 4. cells: every rank broadcasts its slab into the common pool
-    if (ctx->flavour_of_set == MLP_QP && !getenv("MLP_XCHG_RAW")) {
-        // packed: 4 bytes per cell on the wire (pack own slab -> broadcast in place -> unpack the whole pool)
+    // Packed cells halve the wire bytes but add a pass over the whole pool (k_xunpack).  Measured per step at 1000 x 300: 2 GPUs
+    // 52 -> 40 ms, 8 GPUs (NVSwitch, 1/8 of the set per sender) 55 -> 72 ms.  So: packed on two GPUs, raw otherwise;
+    // MLP_XCHG_PACKED=0/1 overrides.
+    const char* xenv = getenv("MLP_XCHG_PACKED");
+    const bool packed = ctx->flavour_of_set == MLP_QP && (xenv ? atoi(xenv) != 0 : W == 2);
+    if (packed) {
+        // 4 bytes per cell on the wire (pack own slab -> broadcast in place -> unpack the whole pool)
         if ((size_t)total + 8 > ctx->xq_cap) {
             free_dev(ctx->d_xq); ctx->d_xq = nullptr; ctx->xq_cap = 0;
             CK(cudaMalloc(&ctx->d_xq, ((size_t)total + total / 8 + 64) * sizeof(unsigned)));
