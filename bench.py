@@ -152,7 +152,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="A")
-    ap.add_argument("--ref-sample", type=int, default=64)
+    ap.add_argument("--ref-sample", type=int, default=144,
+                    help="sequences of the workload the reference CPU arm aligns per step (144 -> 10,296 pairs, about 10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -266,6 +267,7 @@ def main():
                              # profiles/r1c_all_kernels_ncu_full.txt: 14.57 B per cell (k_hmm_fwd + k_hmm_bwd) against
                              # 12 algorithmic, scaled to this workload's cells per launch
                              "traffic": cells_rank * NCU_DRAM_BYTES_PER_CELL_HMM5,
+                             "traffic_unit": "DRAM bytes per step on this rank, both kernels, all of the step's launches (same scope as `achieved`)",
                              "traffic_source": "ncu dram bytes per cell measured at 192 x 300 (profiles/r1c_all_kernels_ncu_full.txt) x cells per step",
                              "hbm": {"bound": "hbm", "achieved": cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
                                      "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
