@@ -151,6 +151,21 @@ int mlp_cpnp_finish_alignment_host(int n, const int32_t* len, const uint8_t* res
                                    char** rows_out, int32_t* aln_len, int32_t* order_out);
 int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, const int32_t* left, const int32_t* right,
                               int refine_reps, int pid, char** rows_out, int32_t* aln_len, int32_t* order_out);
+/* c_p_np_aln -p 1 (the non-progressive strategy), everything after the relaxation of MSA::npdoAlign (MSA.cpp:1084-1160):
+ * MSA::ComputeGraph (MSA.cpp:1777-1845) with the alignment graph of AlignGraph.h (cells of the a<b matrices sorted by its own
+ * quicksort, greedy insertion strongest first with its cycle tests, Graph2Align) and MSA::DoRefinement (MSA.cpp:1852-1980:
+ * FindSimilar's two-means sets, each sequence re-aligned to its similar set and the set to the rest, unweighted profile
+ * posteriors; skipped above 150 sequences).  The sparse set must come from mlp_posterior_all_pairs(MLP_CPNP_P1, ...) +
+ * mlp_relax; distances = its distance matrix (read only).  refine_reps = -ir (reference default 100).
+ * The reference calls srand(time(0)) before every refinement sweep, so its output depends on the wall clock; seed < 0 does
+ * the same, seed >= 0 uses that value instead of the clock (what `oracle/_ref/ref_cpnp msa --p1 --fixtime T` pins).
+ * rows_out: malloc'ed n x aln_len matrix, rows in input order (AlignAlignments re-sorts by label); mlp_free_host releases it.
+ *   _host: sparse set given as a host copy in the pooled layout of mlp_csr_layout / mlp_get_csr_raw (no GPU work);
+ *   device: the graph is built on the host from a read-back of the set, the refinement runs on the resident set. */
+int mlp_cpnp_np_finish_alignment_host(int n, const int32_t* len, const uint8_t* residues, const float* distances,
+                                      const int64_t* rp_off, const int64_t* nz_off, const int32_t* rp_pool, const void* cells,
+                                      int refine_reps, int64_t seed, char** rows_out, int32_t* aln_len);
+int mlp_cpnp_np_finish_alignment(mlp_ctx* ctx, int refine_reps, int64_t seed, char** rows_out, int32_t* aln_len);
 /* MLProbs' Python-side column scores of an alignment (utils/calculate_column_scores.py:37-82 calculateColScore, :123-137
  * getSD / getPeakLengthRatio): rows = n x columns bytes.  col_score (may be NULL) receives the per-column values; the mean
  * over columns, the standard deviation and the fraction of columns >= 1 go to the three outputs.  Host only; same doubles
@@ -158,6 +173,8 @@ int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, const int32
 int mlp_column_scores(int n, int columns, const char* rows, double* col_score, double* mean, double* sd, double* peak_ratio);
 /* test hook: first `count` outputs of the private glibc rand() replica */
 int mlp_debug_glibc_rand(int count, int32_t* out);
+/* the same after srand(seed) */
+int mlp_debug_glibc_rand_seeded(uint32_t seed, int count, int32_t* out);
 
 /* Sparse posterior read-back. Ordered pair (a,b), a != b; rows 1..len[a]; row_ptr has len[a]+2 entries
  * (row_ptr[i]..row_ptr[i+1] = row i, row 0 empty).  val is the dequantised value for MLP_QP

@@ -228,6 +228,26 @@ def cpnp_finish_alignment_host(seqs, iweights, left, right, rp_off, nz_off, rp_p
     return _take_rows(n, rows_p, alen), order
 
 
+def cpnp_np_finish_alignment_host(seqs, distances, rp_off, nz_off, rp_pool, cells, refine_reps=100, seed=-1):
+    """c_p_np_aln -p 1 tail (alignment graph + similar-set refinement) from a HOST copy of the pooled set -> rows in input order.
+    seed < 0 reseeds from the wall clock before every sweep like the reference; seed >= 0 pins it."""
+    n = len(seqs)
+    lens = np.array([len(x) for x in seqs], np.int32)
+    cat = np.frombuffer(b"".join(seqs), np.uint8)
+    keep = [np.ascontiguousarray(distances, np.float32), np.ascontiguousarray(rp_off, np.int64), np.ascontiguousarray(nz_off, np.int64),
+            np.ascontiguousarray(rp_pool, np.int32), np.ascontiguousarray(cells)]
+    rows_p = C.c_void_p(0)
+    alen = C.c_int32(0)
+    lib = load()
+    lib.mlp_cpnp_np_finish_alignment_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_int64,
+                                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    rc = lib.mlp_cpnp_np_finish_alignment_host(n, _ptr(lens), _ptr(cat), *[_ptr(k) for k in keep], int(refine_reps), int(seed),
+                                               C.byref(rows_p), C.byref(alen))
+    if rc:
+        raise MlpError(rc)
+    return _take_rows(n, rows_p, alen)
+
+
 def column_scores(rows):
     """calculateColScore of MLProbs' Python driver for an alignment given as equal-length byte rows ->
     (col_score float64 array, mean, sd, peak_length_ratio)."""
@@ -249,6 +269,16 @@ def debug_glibc_rand(count):
     lib = load()
     lib.mlp_debug_glibc_rand.argtypes = [C.c_int, C.c_void_p]
     rc = lib.mlp_debug_glibc_rand(count, _ptr(out))
+    if rc:
+        raise MlpError(rc)
+    return out
+
+
+def debug_glibc_rand_seeded(seed, count):
+    out = np.zeros(count, np.int32)
+    lib = load()
+    lib.mlp_debug_glibc_rand_seeded.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+    rc = lib.mlp_debug_glibc_rand_seeded(int(seed) & 0xffffffff, count, _ptr(out))
     if rc:
         raise MlpError(rc)
     return out
@@ -498,6 +528,14 @@ class Engine:
         self._ck(self._lib.mlp_cpnp_finish_alignment(self._ctx, *[_ptr(k) for k in keep], int(refine_reps), int(pid),
                                                      C.byref(rows_p), C.byref(alen), _ptr(order)))
         return _take_rows(self.n, rows_p, alen), order
+
+    def cpnp_np_finish_alignment(self, refine_reps=100, seed=-1):
+        """c_p_np_aln -p 1 tail on the resident set (graph on the host from a read-back, refinement on the device)."""
+        rows_p = C.c_void_p(0)
+        alen = C.c_int32(0)
+        self._lib.mlp_cpnp_np_finish_alignment.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+        self._ck(self._lib.mlp_cpnp_np_finish_alignment(self._ctx, int(refine_reps), int(seed), C.byref(rows_p), C.byref(alen)))
+        return _take_rows(self.n, rows_p, alen)
 
     def csr_packed(self, out=None):
         """Pooled read-back in QuickProbs' packed cell format (QP flavour only). `out` = PinnedPackedBuffers to reuse."""

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <random>
+#include <ctime>
 
 namespace qptail {
 
@@ -204,12 +205,16 @@ double WeightSpec::total(const Profile& A, const Profile& B) const {
 struct GlibcRand {
     std::vector<uint32_t> state;
     size_t pos;
-    GlibcRand() {
+    explicit GlibcRand(uint32_t seed = 1) {
+        // srandom_r: seed 0 means 1; Schrage's form of 16807 * x mod (2^31 - 1) on 32-bit words, as glibc writes it
         std::vector<int64_t> s(34);
-        s[0] = 1;
+        int32_t word = seed == 0 ? 1 : (int32_t)seed;
+        s[0] = word;
         for (int i = 1; i < 31; ++i) {
-            s[i] = (16807 * s[i - 1]) % 2147483647;
-            if (s[i] < 0) s[i] += 2147483647;
+            const int32_t hi = word / 127773, lo = word % 127773;
+            word = 16807 * lo - 2836 * hi;
+            if (word < 0) word += 2147483647;
+            s[i] = word;
         }
         for (int i = 31; i < 34; ++i) s[i] = s[i - 31];
         state.resize(34);
@@ -329,6 +334,121 @@ int run_cpnp_tail(int n, const int32_t* len, const uint8_t* residues, const int3
                 }
                 if (ineffectiveness > 2 * n && it > cutoff_iter) break;
             } else if (n > 200) reps = 10;
+        }
+    }
+    out = std::move(*aln);
+    return 0;
+}
+
+// MSA::FindSimilar (MSA.cpp:1988-2078): for every sequence x a two-means split of the others by their distance to x; S_x is
+// the cluster seeded with the farthest sequence, and always holds x itself
+static void find_similar(int n, const float* distances, std::vector<std::vector<int>>& sim) {
+    std::vector<float> d(distances, distances + (size_t)n * n);
+    for (int i = 0; i < n; ++i) d[(size_t)i * n + i] = 1.0f;
+    sim.assign(n, std::vector<int>());
+    std::vector<char> in1(n);
+    std::vector<int> changes(n);
+    for (int i = 0; i < n; ++i) {
+        const float* di = d.data() + (size_t)i * n;
+        float min_d = 1, max_d = 0;
+        int at_min = 0, at_max = 0;
+        for (int j = 0; j < n; ++j) {                         // ties: the last index wins
+            if (di[j] <= min_d) { at_min = j; min_d = di[j]; }
+            if (di[j] >= max_d) { at_max = j; max_d = di[j]; }
+        }
+        std::fill(in1.begin(), in1.end(), 0);
+        // both seeds are inserted into sets: when they coincide the sequence sits in both clusters, and the membership
+        // tests below look at the first cluster first
+        std::vector<char> in2(n, 0);
+        in1[at_max] = 1;
+        in2[at_min] = 1;
+        for (int j = 0; j < n; ++j)
+            if (j != at_min && j != at_max) {
+                const float v = d[(size_t)j * n + i];
+                if (std::fabs(v - max_d) < std::fabs(v - min_d)) in1[j] = 1; else in2[j] = 1;
+            }
+        if (!in1[i]) { in2[i] = 0; in1[i] = 1; }
+        bool changed = true;
+        for (int pass = 0; pass < 100 && changed; ++pass) {
+            changed = false;
+            std::fill(changes.begin(), changes.end(), 0);
+            float m1 = 0, m2 = 0;
+            size_t c1 = 0, c2 = 0;
+            for (int j = 0; j < n; ++j) if (in1[j]) { m1 += di[j]; ++c1; }
+            for (int j = 0; j < n; ++j) if (in2[j]) { m2 += di[j]; ++c2; }
+            m1 /= (float)c1;
+            m2 /= (float)c2;
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const float v = d[(size_t)j * n + i];
+                if (in1[j]) { if (std::fabs(v - m1) > std::fabs(v - m2)) { changes[j] = 1; changed = true; } }
+                else if (std::fabs(v - m2) > std::fabs(v - m1)) { changes[j] = -1; changed = true; }
+            }
+            if (changed)
+                for (int j = 0; j < n; ++j) {
+                    if (changes[j] == 1) { in1[j] = 0; in2[j] = 1; }
+                    else if (changes[j] == -1) { in2[j] = 0; in1[j] = 1; }
+                }
+        }
+        for (int j = 0; j < n; ++j) if (in1[j]) sim[i].push_back(j);
+    }
+}
+
+int run_cpnp_np_tail(const HostCsrView& graph_set, const uint8_t* residues, const float* distances, ProfilePosterior& prov,
+                     int refine_reps, long long seed, Profile& out, std::string& err) {
+    const int n = graph_set.n;
+    std::unique_ptr<Profile> aln(new Profile());
+    int rc = build_graph_alignment(graph_set, residues, *aln, err);
+    if (rc < 0) return rc;
+    // MSA::DoRefinement (MSA.cpp:1852-1980): every sequence x in a random order: re-align x against the rest of S_x, then the
+    // updated S_x against everything else.  AlignAlignments re-sorts the rows by label, so row k is always sequence k.
+    int reps = refine_reps;
+    if (n > 150) reps = 0;
+    if (reps > 0 && !distances) { err = "distances required for the refinement"; return MLP_E_ARG; }
+    std::vector<std::vector<int>> sim;
+    if (reps > 0) find_similar(n, distances, sim);
+    WeightSpec flat;
+    flat.mode = WeightSpec::UNWEIGHTED;
+    // AlignAlignments(…, nflag = false) = unweighted profile posterior, MEA path, rows merged by label: align_profiles().
+    // The reference also tracks the MEA scores (`nalignscore < oalignscore` extends the pass budget), but oalignscore starts
+    // at 0 and a sum of posteriors is never negative, so that branch cannot fire and the scores are not computed here.
+    int cnt = 0;
+    Profile one, two, self, rest, updated;
+    std::vector<int> others, pick(1), remaining;
+    while (cnt < reps) {
+        GlibcRand rng(seed >= 0 ? (uint32_t)seed : (uint32_t)time(nullptr));     // srand(time(0)) before every sweep
+        std::vector<int> pool(n), visit;
+        for (int i = 0; i < n; ++i) pool[i] = i;
+        while (!pool.empty()) {
+            const int at = rng.next() % (int)pool.size();
+            visit.push_back(pool[at]);
+            pool.erase(pool.begin() + at);
+        }
+        for (int step = 0; step < n; ++step) {
+            const int x = visit[step];
+            const std::vector<int>& g1 = sim[x];
+            others.clear();
+            for (int j = 0, k = 0; j < n; ++j) { if (k < (int)g1.size() && g1[k] == j) ++k; else others.push_back(j); }
+            ++cnt;
+            if (g1.empty() || others.empty()) continue;
+            extract_subset(*aln, g1, one);
+            extract_subset(*aln, others, two);
+            if (one.count() > 1) {
+                const int at = (int)(std::find(g1.begin(), g1.end(), x) - g1.begin());
+                pick[0] = at;
+                remaining.clear();
+                for (int k = 0; k < one.count(); ++k) if (k != at) remaining.push_back(k);
+                extract_subset(one, pick, self);
+                extract_subset(one, remaining, rest);
+                rc = align_profiles(self, rest, flat, prov, updated);
+                if (rc < 0) { err = "profile posterior failed"; return rc; }
+                ++cnt;
+                std::swap(one, updated);
+            }
+            std::unique_ptr<Profile> next(new Profile());
+            rc = align_profiles(one, two, flat, prov, *next);
+            if (rc < 0) { err = "profile posterior failed"; return rc; }
+            aln = std::move(next);
         }
     }
     out = std::move(*aln);
@@ -483,6 +603,34 @@ extern "C" int mlp_cpnp_finish_alignment_host(int n, const int32_t* len, const u
     }
     *rows_out = buf;
     *aln_len = L;
+    return MLP_OK;
+}
+
+extern "C" int mlp_cpnp_np_finish_alignment_host(int n, const int32_t* len, const uint8_t* residues, const float* distances,
+                                                 const int64_t* rp_off, const int64_t* nz_off, const int32_t* rp_pool,
+                                                 const void* cells, int refine_reps, int64_t seed, char** rows_out, int32_t* aln_len) {
+    if (n < 1 || !len || !residues || !rows_out || !aln_len) return MLP_E_ARG;
+    if (n > 1 && (!rp_off || !nz_off || !rp_pool || !cells)) return MLP_E_ARG;
+    qptail::HostCsrView v{n, len, rp_off, nz_off, rp_pool, cells};
+    std::unique_ptr<qptail::ProfilePosterior> prov(qptail::make_host_provider(v));
+    qptail::Profile out;
+    std::string err;
+    const int rc = qptail::run_cpnp_np_tail(v, residues, distances, *prov, refine_reps, (long long)seed, out, err);
+    if (rc < 0) return rc;
+    const int L = out.length();
+    char* buf = (char*)std::malloc((size_t)n * (size_t)std::max(L, 1));
+    if (!buf) return MLP_E_NOMEM;
+    for (int i = 0; i < n; ++i) std::memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+    *rows_out = buf;
+    *aln_len = L;
+    return MLP_OK;
+}
+
+// test hook: the first `count` values of the private glibc rand() replica after srand(seed)
+extern "C" int mlp_debug_glibc_rand_seeded(uint32_t seed, int count, int32_t* out) {
+    if (count < 0 || !out) return MLP_E_ARG;
+    qptail::GlibcRand g(seed);
+    for (int i = 0; i < count; ++i) out[i] = g.next();
     return MLP_OK;
 }
 

@@ -78,6 +78,14 @@ int run_tail(int n, const int32_t* len, const uint8_t* residues, const float* we
 int run_cpnp_tail(int n, const int32_t* len, const uint8_t* residues, const int32_t* iweights, const int32_t* left, const int32_t* right,
                   ProfilePosterior& prov, int refine_reps, int pid, Profile& out, std::string& err);
 
+// c_p_np_aln -p 1 (non-progressive, MSA::npdoAlign MSA.cpp:1084-1160 after the relaxation): the alignment graph over the
+// a<b matrices of `graph_set` (cpnp_graph.cpp), then MSA::DoRefinement's similar-set re-alignments through `prov`.
+// distances: n x n (needed when refine_reps > 0 and n <= 150); seed < 0: time(0) before every sweep, as the reference does;
+// seed >= 0: that value instead (what the tests and `ref_cpnp --fixtime` use).  Rows of `out` are in input order.
+int build_graph_alignment(const HostCsrView& graph_set, const uint8_t* residues, Profile& out, std::string& err);
+int run_cpnp_np_tail(const HostCsrView& graph_set, const uint8_t* residues, const float* distances, ProfilePosterior& prov,
+                     int refine_reps, long long seed, Profile& out, std::string& err);
+
 // MEA traceback over a dense profile posterior (ProbabilisticModel::computeAlignment, ProbabilisticModel.cpp:345-421);
 // *score (may be NULL) receives the maximum sum, i.e. the last cell of the last row
 std::string mea_path(int l1, int l2, const float* dense, float* score = nullptr);

@@ -477,3 +477,44 @@ extern "C" int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, 
     *aln_len = L;
     return MLP_OK;
 }
+
+// c_p_np_aln -p 1: the alignment graph is host work on a copy of the relaxed set (a scalar, order-dependent greedy over the
+// sorted cells), the similar-set refinement after it runs its profile posteriors and MEA sweeps on the resident set.
+extern "C" int mlp_cpnp_np_finish_alignment(mlp_ctx* ctx, int refine_reps, int64_t seed, char** rows_out, int32_t* aln_len) {
+    if (!ctx) return MLP_E_ARG;
+    if (!rows_out || !aln_len) { ctx->err = "null output"; return MLP_E_ARG; }
+    if (ctx->n < 2) { ctx->err = "no sequences"; return MLP_E_STATE; }
+    if (!ctx->have_sets || (ctx->flavour_of_set != MLP_CPNP_P0 && ctx->flavour_of_set != MLP_CPNP_P1)) { ctx->err = "no c_p_np_aln sparse set on the device"; return MLP_E_STATE; }
+    if (ctx->world > 1 && !ctx->nccl_comm) { ctx->err = "sharded set: call mlp_exchange first"; return MLP_E_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n;
+    const size_t nn = (size_t)n * n;
+    std::vector<int64_t> rp_off(nn), nz_off(nn);
+    int64_t rp_total = 0, cells_used = 0;
+    int rc = mlp_csr_layout(ctx, rp_off.data(), &rp_total, &cells_used);
+    if (rc != MLP_OK) return rc;
+    std::vector<int32_t> rp_pool((size_t)rp_total);
+    std::vector<int2> cells((size_t)cells_used + 1);
+    rc = mlp_get_csr_raw(ctx, nz_off.data(), nullptr, rp_pool.data(), cells.data());
+    if (rc != MLP_OK) return rc;
+    std::vector<float> dist(nn);
+    rc = mlp_get_distances(ctx, dist.data());
+    if (rc != MLP_OK) return rc;
+    ctx->stats = mlp_stage_stats{};
+    std::vector<uint8_t> letters(ctx->codes_h.size());
+    for (size_t k = 0; k < letters.size(); ++k) letters[k] = (uint8_t)('A' + ctx->codes_h[k]);
+    std::vector<int32_t> len(ctx->len.begin(), ctx->len.end());
+    const qptail::HostCsrView view{n, len.data(), rp_off.data(), nz_off.data(), rp_pool.data(), cells.data()};
+    DeviceProfilePosterior prov(ctx);
+    qptail::Profile out;
+    std::string err;
+    rc = qptail::run_cpnp_np_tail(view, letters.data(), dist.data(), prov, refine_reps, (long long)seed, out, err);
+    if (rc < 0) { if (ctx->err.empty() || rc != MLP_E_CUDA) ctx->err = err; return rc; }
+    const int L = out.length();
+    char* buf = (char*)malloc((size_t)n * (size_t)std::max(L, 1));
+    if (!buf) { ctx->err = "out of host memory"; return MLP_E_NOMEM; }
+    for (int i = 0; i < n; ++i) memcpy(buf + (size_t)i * L, out.rows[i].data(), (size_t)L);
+    *rows_out = buf;
+    *aln_len = L;
+    return MLP_OK;
+}

@@ -35,6 +35,17 @@ extern VF* ComputePostProbs(int a, int b, string seq1, string seq2);
 extern double sub_matrix[26][26];
 extern int subst_index[26];
 
+// `c_p_np_aln -p 1` reseeds rand() with time(0) before every refinement sweep (MSA.cpp:1896). Defining time() here takes
+// precedence over libc's for the reference objects linked into this executable, so `--fixtime T` makes that program
+// reproducible without touching its sources; without the flag the real clock is returned.
+static long long g_fixed_time = -1;
+extern "C" time_t time(time_t* out) {
+    time_t t = g_fixed_time >= 0 ? (time_t)g_fixed_time
+                                 : (time_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+    if (out) *out = t;
+    return t;
+}
+
 static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -68,6 +79,7 @@ int main(int argc, char** argv) {
     for (; ai < argc; ai++) {
         std::string a = argv[ai];
         if (a == "--ir") { ir = atoi(argv[++ai]); continue; }
+        if (a == "--fixtime") { g_fixed_time = atoll(argv[++ai]); continue; }
         if (a == "--pid") o.pid = atoi(argv[++ai]);
         else if (a == "--reps") o.reps = atoi(argv[++ai]);
         else if (a == "--threads") o.threads = atoi(argv[++ai]);
@@ -75,11 +87,11 @@ int main(int argc, char** argv) {
         else if (a == "--nodense") o.dense = 0;
     }
     if (o.mode == "msa") {
-        // the reference's complete program flow (MSA::MSA, MSA.cpp:123-187): `c_p_np_aln -p 0 [-ir R] -o out fasta`, with the
+        // the reference's complete program flow (MSA::MSA, MSA.cpp:123-187): `c_p_np_aln -p 0|1 [-ir R] -o out fasta`, with the
         // OpenMP team pinned to o.threads (1 = the deterministic summation order of BuildPosterior)
         numThreads = o.threads;
         std::string irs = std::to_string(ir);
-        std::vector<const char*> av = {"c_p_np_aln", "-p", "0", "-o", o.out.c_str()};
+        std::vector<const char*> av = {"c_p_np_aln", "-p", o.p1 ? "1" : "0", "-o", o.out.c_str()};
         if (ir >= 0) { av.push_back("-ir"); av.push_back(irs.c_str()); }
         av.push_back(o.fasta.c_str());
         MSA whole((int)av.size(), (char**)av.data());
