@@ -1,9 +1,11 @@
-// c_p_np_aln_b200: command-line drop-in for `c_p_np_aln` (baseMSA/C_P_NP_Aln, MSA::MSA MSA.cpp:123-187) for the two ways
+// c_p_np_aln_b200: command-line drop-in for `c_p_np_aln` (baseMSA/C_P_NP_Aln, MSA::MSA MSA.cpp:123-187) for the ways
 // MLProbs calls it (utils/prepare_features_4_classifier_1.py:12, utils/classifier_c_p_np_aln.py:14,37):
 //   c_p_np_aln -G file      -> the feature line of MSA::Alter_ModelAdjustmentTest on stdout
 //   c_p_np_aln -p 0 file    -> model selection, all-pairs posteriors, tree, consistency, progressive alignment, refinement
-// every O(N^2 L^2) stage on the GPU through the C ABI of include/mlprobs_b200.h.  `-p 1` (non-progressive strategy) is not
-// built: the reference seeds rand() with the wall clock there (MSA.cpp:1896), so it has no reproducible output to match.
+//   c_p_np_aln -p 1 file    -> model selection, all-pairs posteriors, consistency, alignment graph, similar-set refinement
+// every O(N^2 L^2) stage on the GPU through the C ABI of include/mlprobs_b200.h.  The reference reseeds rand() from the wall
+// clock before every refinement sweep of -p 1 (MSA.cpp:1896); so does this program, unless `--seed S` (an extension, also
+// read from the environment variable MLP_CPNP_SEED) pins the value the clock would have returned.
 // Options kept: -p, -G, -o/--outfile, -c/--consistency, -ir/--iterative-refinement, -v.  No CPU fallback.
 #include "../../include/mlprobs_b200.h"
 #include <algorithm>
@@ -75,7 +77,8 @@ int fail(mlp_ctx* ctx, const char* what, int rc) {
 }  // namespace
 
 // one input file; returns the exit status for it
-int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int getpid, int reps, int refine, int verbose) {
+int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int getpid, int reps, int refine, int verbose,
+             int program, long long seed) {
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     auto fail = [&](mlp_ctx* c, const char* what, int rc) {
@@ -131,10 +134,24 @@ int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile
     if ((rc = mlp_set_tables(ctx, &hmm, &part))) return fail(ctx, "mlp_set_tables", rc);
     const double t2 = now();
     const uint32_t mask = pid <= 1 ? (MLP_M_HMM5 | MLP_M_PART | MLP_M_LOCAL) : (pid == 2 ? MLP_M_LOCAL : MLP_M_PART);   // MSA.cpp:946-1010
-    rc = mlp_posterior_all_pairs(ctx, MLP_CPNP_P0, mask, 0.01f);
+    rc = mlp_posterior_all_pairs(ctx, program == 1 ? MLP_CPNP_P1 : MLP_CPNP_P0, mask, 0.01f);   // -p 1: ArrangePosteriorProbs, MSA.cpp:1635-1766
     if (rc == MLP_E_OVERFLOW) { std::printf("ERROR: huge val error for zM\n"); return 1; }            // MSAPartProbs.cpp:547-589
     if (rc) return fail(ctx, "mlp_posterior_all_pairs", rc);
     const double t3 = now();
+    if (program == 1) {
+        // MSA::npdoAlign, MSA.cpp:1117-1136: the same relaxation, then the alignment graph and DoRefinement; rows in input order
+        for (int r = 0; r < reps; ++r)
+            if ((rc = mlp_relax(ctx, MLP_CPNP_P0, nullptr, nullptr, 0.0f, 0.0f, 0.01f))) return fail(ctx, "mlp_relax", rc);
+        const double t4 = now();
+        char* rows = nullptr;
+        int32_t cols = 0;
+        if ((rc = mlp_cpnp_np_finish_alignment(ctx, refine, seed, &rows, &cols))) return fail(ctx, "mlp_cpnp_np_finish_alignment", rc);
+        for (int k = 0; k < n; ++k) write_mfa(out, in.headers[k], rows + (size_t)k * cols, cols);
+        if (verbose) std::fprintf(stderr, "c_p_np_aln_b200: %d sequences, model class %d, %d columns; ms: load+upload %.1f, viterbi %.1f, posterior %.1f, consistency %.1f, graph+refinement %.1f\n",
+                                  n, variance_mean, cols, t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
+        mlp_free_host(rows);
+        return 0;
+    }
     std::vector<float> dist((size_t)n * n);
     std::vector<int32_t> weights(n), left(2 * n - 1), right(2 * n - 1), order(n);
     if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
@@ -156,6 +173,8 @@ int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile
 int main(int argc, char** argv) {
     std::string infile, outfile;
     int program = 0, getpid = 0, reps = 2, refine = 100, device = 0, verbose = 0;
+    long long seed = -1;
+    if (const char* e = std::getenv("MLP_CPNP_SEED")) seed = std::atoll(e);
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char* name) -> const char* {
@@ -171,16 +190,13 @@ int main(int argc, char** argv) {
         else if (a == "-c" || a == "--consistency") reps = std::atoi(need("-c"));
         else if (a == "-ir" || a == "--iterative-refinement") refine = std::atoi(need("-ir"));
         else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
+        else if (a == "--seed") seed = std::atoll(need("--seed"));
         else if (a == "-v" || a == "--verbose") verbose = 1;
         else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "c_p_np_aln_b200: unsupported option %s\n", a.c_str()); return 2; }
         else if (infile.empty()) infile = a;
         else { std::fprintf(stderr, "c_p_np_aln_b200: more than one input file\n"); return 2; }
     }
-    if (infile.empty()) { std::fprintf(stderr, "usage: c_p_np_aln_b200 (-G | -p 0) [-o outfile] [-c reps] [-ir passes] <fasta>\n"); return 2; }
-    if (program == 1 && !getpid) {
-        std::fprintf(stderr, "c_p_np_aln_b200: -p 1 (non-progressive strategy) is not built; the reference seeds rand() with the clock there\n");
-        return 2;
-    }
+    if (infile.empty()) { std::fprintf(stderr, "usage: c_p_np_aln_b200 (-G | -p 0 | -p 1 [--seed S]) [-o outfile] [-c reps] [-ir passes] <fasta>\n"); return 2; }
     struct stat si, so;
     const bool dir_mode = !outfile.empty() && stat(infile.c_str(), &si) == 0 && S_ISDIR(si.st_mode) &&
                           stat(outfile.c_str(), &so) == 0 && S_ISDIR(so.st_mode);   // extension: a directory of families, one CUDA context
@@ -201,10 +217,10 @@ int main(int argc, char** argv) {
         }
         std::sort(names.begin(), names.end());
         for (const std::string& nm : names) {
-            const int r1 = run_file(ctx, infile + "/" + nm, outfile + "/" + nm, getpid, reps, refine, verbose);
+            const int r1 = run_file(ctx, infile + "/" + nm, outfile + "/" + nm, getpid, reps, refine, verbose, program, seed);
             if (r1) status = r1;
         }
-    } else status = run_file(ctx, infile, outfile, getpid, reps, refine, verbose);
+    } else status = run_file(ctx, infile, outfile, getpid, reps, refine, verbose, program, seed);
     mlp_destroy(ctx);
     return status;
 }

@@ -95,6 +95,34 @@ def run_cpnp(name, fasta, full, dense, pid=None, p1=False, reps=2):
     print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def run_cpnp_p1(name, fasta, fixtime):
+    """The reference's whole `c_p_np_aln -p 1` program (non-progressive: alignment graph + similar-set refinement) on one
+    OpenMP thread.  It reseeds rand() from time(0) before every refinement sweep; `--fixtime` makes the harness' own time()
+    return a constant, so the output is reproducible without touching the reference sources."""
+    def read_fasta(path):
+        rows = []
+        for line in open(path):
+            line = line.strip()
+            if line.startswith(">"): rows.append("")
+            elif line: rows[-1] += line
+        return rows
+    seqs = [r.replace("-", "").replace(".", "").upper() for r in read_fasta(fasta)]
+    out = {"n": np.array([len(seqs)], np.int32), "lens": np.array([len(x) for x in seqs], np.int32),
+           "residues": np.frombuffer("".join(seqs).encode(), np.uint8).copy(), "fixtime": np.array([fixtime], np.int64)}
+    with tempfile.TemporaryDirectory() as td:
+        tmpfa = os.path.join(td, "in.fa")
+        with open(tmpfa, "w") as f:
+            for i, x in enumerate(seqs): f.write(">s%d\n%s\n" % (i, x))
+        for key, ir in (("msa", None), ("msa_ir0", 0)):
+            o = os.path.join(td, key + ".fa")
+            subprocess.check_call([CPNP, "msa", tmpfa, o, "--p1", "--threads", "1", "--fixtime", str(fixtime)] + ([] if ir is None else ["--ir", str(ir)]),
+                                  stdout=subprocess.DEVNULL)
+            out[key] = read_rows(o)
+            assert [l.strip() for l in open(o) if l.startswith(">")] == [">s%d" % i for i in range(len(seqs))]     # input order
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
 def run_qp(name, fasta, full, dense):
     with tempfile.TemporaryDirectory() as td:
         dump = os.path.join(td, "d.bin")
@@ -127,3 +155,7 @@ if __name__ == "__main__":
     run_cpnp("cpnp_676s4_ref", f("oxx", "_676s4"), False, False)
     run_qp("qp_676s4", f("oxx", "_676s4"), False, False)                       # N=51 -> 1 consistency iteration, cutoff 1e-5
     run_qp("qp_75t2", f("oxx", "__75t2"), False, False)                        # N=204 -> selectivity excludes some z
+    # whole-program `-p 1` outputs (inputs + final alignments only)
+    run_cpnp_p1("cpnp_p1_sup139", f("sabre", "sup_139"), 777)
+    run_cpnp_p1("cpnp_p1_BB12003", f("bali3", "BB12003"), 777)               # the refinement order changes the result here
+    run_cpnp_p1("cpnp_p1_676s4", f("oxx", "_676s4"), 1792000000)             # N=51, non-standard letters

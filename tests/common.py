@@ -73,3 +73,32 @@ def cpnp_tail_from_csrset(S, seqs, distances, variance_mean, refine_reps=100):
     cells["v"] = S.val
     return M.cpnp_finish_alignment_host(seqs, t["weights"], t["left"], t["right"], S.rp_off, S.nz_off, S.rowptr, cells,
                                         refine_reps, int(variance_mean) % 10)
+
+
+def cpnp_p1_sparse_set(seqs, threads=4):
+    """What `c_p_np_aln -p 1` holds before its alignment graph, computed with the ORACLE: Viterbi statistics -> model class and
+    initDistrib[2] (MSA.cpp:775-882), all-pairs posteriors of that class with the -p 1 merge and distance
+    (ArrangePosteriorProbs, MSA.cpp:1635-1766), two relaxations.  Returns (distances, CsrSet, variance_mean)."""
+    import oracle_lib as O
+    n = len(seqs)
+    ht0 = O.hmm_tables()
+    ids, lens = [], []
+    for a, b in pairs(n):
+        _, i, l, _ = O.viterbi(ht0, seqs[a], seqs[b])
+        ids.append(i); lens.append(l)
+    vm, _, _, i2 = O.model_adjustment(ids, lens)
+    ht = O.hmm_tables(float(np.float32(i2))); pt = O.part_tables(O.CPNP_P0)
+    dist, S, rc = O.posterior_stage(O.CPNP_P1, cpnp_mask(vm), ht, pt, seqs, threads=threads)
+    assert rc == 0
+    for _ in range(2):
+        S = O.relax_cpnp(S, 0.01, threads=threads)
+    return dist, S, vm
+
+
+def cpnp_np_tail_from_csrset(S, seqs, distances, refine_reps=100, seed=-1):
+    """c_p_np_aln -p 1 tail on the host (mlp_cpnp_np_finish_alignment_host) from an oracle_lib.CsrSet."""
+    import mlprobs_b200 as M
+    cells = np.zeros(len(S.col), dtype=[("c", np.int32), ("v", np.float32)])
+    cells["c"] = S.col
+    cells["v"] = S.val
+    return M.cpnp_np_finish_alignment_host(seqs, distances, S.rp_off, S.nz_off, S.rowptr, cells, refine_reps, seed)

@@ -88,15 +88,32 @@ def test_cli_single_sequence_is_echoed(tmp_path):
 CPNP = os.path.join(os.path.dirname(HERE), "mlprobs_b200", "bin", "c_p_np_aln_b200")
 
 
-def test_cpnp_cli_is_built_and_refuses_without_gpu_or_for_p1(tmp_path):
+def test_cpnp_cli_is_built_and_refuses_without_gpu(tmp_path):
     assert os.path.exists(CPNP), "run __graft_entry__.build()"
     fa, _ = write_input(tmp_path, [b"ACDEFGHIK", b"ACDEFGHIK"])
-    r = subprocess.run([CPNP, "-p", "1", fa], capture_output=True, text=True)
-    assert r.returncode == 2 and "not built" in r.stderr
+    r = subprocess.run([CPNP, "-p", "2", fa], capture_output=True, text=True)
+    assert r.returncode == 1 and "integer must be 0 or 1" in r.stderr and r.stdout == ""
     import torch
     if not torch.cuda.is_available():
-        r = subprocess.run([CPNP, "-p", "0", fa], capture_output=True, text=True)
-        assert r.returncode != 0 and "CUDA device is required" in r.stderr and r.stdout == ""
+        for prog in ("0", "1"):
+            r = subprocess.run([CPNP, "-p", prog, fa], capture_output=True, text=True)
+            assert r.returncode != 0 and "CUDA device is required" in r.stderr and r.stdout == ""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cpnp_p1_BB12003", "cpnp_p1_676s4"])
+def test_cpnp_cli_non_progressive_reproduces_the_reference(tmp_path, name):
+    """`c_p_np_aln -p 1 file`; --seed stands in for the wall clock the reference seeds its refinement sweeps with."""
+    d = load_golden(name)
+    seqs = split_seqs(d)
+    fa, heads = write_input(tmp_path, seqs)
+    want = fasta_text(heads, [r.tobytes().decode() for r in d["msa"]])
+    r = subprocess.run([CPNP, "-p", "1", "--seed", str(int(d["fixtime"][0])), fa], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == want and r.stderr == ""
+    want0 = fasta_text(heads, [r_.tobytes().decode() for r_ in d["msa_ir0"]])
+    r = subprocess.run([CPNP, "-p", "1", "-ir", "0", fa], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == want0
 
 
 @pytest.mark.gpu

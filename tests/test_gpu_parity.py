@@ -240,6 +240,44 @@ def test_cpnp_p1_mix_against_reference_fixture():
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["cpnp_p1_sup139", "cpnp_p1_BB12003", "cpnp_p1_676s4"])
+def test_cpnp_non_progressive_program_on_the_device(name):
+    """`c_p_np_aln -p 1` end to end through the C ABI (Viterbi statistics, -p 1 posteriors, two relaxations, alignment graph from
+    the read-back set, similar-set refinement on the resident set) against the reference program's output."""
+    d = load_golden(name)
+    seqs = split_seqs(d)
+    eng = engine(M.CPNP_P0, seqs, 0.700645)
+    ident, ln = eng.viterbi_all_pairs()
+    vm, _, _, i2 = M.cpnp_model_adjustment(ident, ln)
+    h, p = M.default_tables(M.CPNP_P0, i2)
+    eng.set_tables(h, p)
+    eng.posterior_all_pairs(M.CPNP_P1, cpnp_mask(vm), 0.01)
+    for _ in range(2):
+        eng.relax(M.CPNP_P0, cutoff=0.01)
+    seed = int(d["fixtime"][0])
+    for key, ir in (("msa_ir0", 0), ("msa", 100)):
+        assert eng.cpnp_np_finish_alignment(ir, seed) == [r.tobytes() for r in d[key]], key
+    eng.close()
+
+
+def test_cpnp_non_progressive_tail_device_equals_host_on_a_synthetic_family():
+    """40 sequences x 120: the device refinement (k_profile_posterior + k_mea_wavefront) and the host provider walk the same
+    set and must give the same rows; every row degaps to its input."""
+    from common import cpnp_np_tail_from_csrset
+    seqs = synth.family(40, 120, seed=91)
+    n = len(seqs)
+    eng = engine(M.CPNP_P1, seqs, 0.4)
+    eng.posterior_all_pairs(M.CPNP_P1, 4, 0.01)
+    eng.relax(M.CPNP_P0, cutoff=0.01)
+    dist, S, _ = O.posterior_stage(O.CPNP_P1, 4, O.hmm_tables(0.4), O.part_tables(O.CPNP_P0), seqs, threads=8)
+    S = O.relax_cpnp(S, 0.01, threads=8)
+    np.testing.assert_array_equal(eng.distances(), dist)
+    got = eng.cpnp_np_finish_alignment(100, 12345)
+    assert got == cpnp_np_tail_from_csrset(S, seqs, dist, 100, 12345)
+    assert len({len(r) for r in got}) == 1 and [r.replace(b"-", b"") for r in got] == seqs
+    eng.close()
+
+
 def test_cpnp_partition_beyond_fp64_range_is_rescaled():
     """Similar sequences of length 1500: Z ~ 1e600, beyond FP64 but inside the reference's 80-bit range.  The device runs
     FP64 with per-row power-of-two rescaling and must agree with the long-double oracle to 1e-5 relative."""

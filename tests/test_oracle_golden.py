@@ -112,6 +112,25 @@ def test_cpnp_stage_and_relaxation(name, flav):
             assert rows == [r.tobytes() for r in d[key]], key
 
 
+@pytest.mark.parametrize("name", ["cpnp_p1_sup139", "cpnp_p1_BB12003", "cpnp_p1_676s4"])
+def test_cpnp_non_progressive_program(name):
+    """`c_p_np_aln -p 1` to the end (MSA::npdoAlign, MSA.cpp:1084-1160): the oracle's sparse set fed to the host alignment
+    graph (AlignGraph.h) and the similar-set refinement (MSA::DoRefinement) reproduces the reference program's output, both
+    without refinement and with the default 100 passes under the clock value the fixture was generated with."""
+    from common import cpnp_p1_sparse_set, cpnp_np_tail_from_csrset
+    d = load_golden(name)
+    seqs = split_seqs(d)
+    dist, S, _ = cpnp_p1_sparse_set(seqs)
+    seed = int(d["fixtime"][0])
+    for key, ir in (("msa_ir0", 0), ("msa", 100)):
+        rows = cpnp_np_tail_from_csrset(S, seqs, dist, ir, seed)
+        assert rows == [r.tobytes() for r in d[key]], key
+    for r, s in zip(rows, seqs):
+        assert r.replace(b"-", b"") == s
+    if name == "cpnp_p1_BB12003":           # the sweep order matters on this family: another clock value, another alignment
+        assert cpnp_np_tail_from_csrset(S, seqs, dist, 100, seed + 1) != rows
+
+
 @pytest.mark.parametrize("name", ["qp_sup139", "qp_sup002", "qp_676s4", "qp_75t2"])
 def test_qp_stage_and_consistency(name):
     d = load_golden(name)

@@ -80,3 +80,13 @@ def test_private_glibc_rand_replica_matches_libc():
     libc.srand(1)
     want = [libc.rand() for _ in range(5000)]
     assert M.debug_glibc_rand(5000).tolist() == want
+
+
+@pytest.mark.parametrize("seed", [0, 1, 777, 1792000000, 2**31 - 1, 2**31 + 5, 2**32 - 1])
+def test_private_glibc_rand_replica_matches_libc_after_srand(seed):
+    """`c_p_np_aln -p 1` calls srand(time(0)) before every refinement sweep (MSA.cpp:1896)."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(ctypes.c_uint(seed))
+    want = [libc.rand() for _ in range(2000)]
+    assert M.debug_glibc_rand_seeded(seed, 2000).tolist() == want

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Drop-in executables vs the reference programs on the bundled benchmark families (tests/golden/suites: inputs + SHA-256 of
-the reference outputs, written by oracle/gen_suite_golden.py).  Runs quickprobs_b200 and c_p_np_aln_b200 -p 0 in directory
-mode (one CUDA context per suite and tool) and compares every output byte for byte.  Prints one summary line per suite/tool
+the reference outputs, written by oracle/gen_suite_golden.py and gen_suite_golden_p1.py).  Runs quickprobs_b200,
+c_p_np_aln_b200 -p 0 and c_p_np_aln_b200 -p 1 --seed <the clock value the reference was pinned to> in directory mode (one CUDA
+context per suite and tool) and compares every output byte for byte.  Prints one summary line per suite/tool
 and writes the full report as JSON (default gpurun_out/suite_parity.json)."""
 import os, sys, json, hashlib, subprocess, tarfile, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,8 +10,10 @@ SUITES = os.path.join(ROOT, "tests", "golden", "suites")
 BIN = os.path.join(ROOT, "mlprobs_b200", "bin")
 
 
-def run(report_path=None, suites=None):
-    man = json.load(open(os.path.join(SUITES, "manifest.json")))["families"]
+def run(report_path=None, suites=None, tools=None):
+    manifest = json.load(open(os.path.join(SUITES, "manifest.json")))
+    man = manifest["families"]
+    seed = str(manifest.get("p1_fixtime", 777))
     tmp = tempfile.mkdtemp()
     with tarfile.open(os.path.join(SUITES, "inputs.tar.gz")) as tar:
         tar.extractall(tmp, filter="data")
@@ -19,11 +22,23 @@ def run(report_path=None, suites=None):
         if suites and suite not in suites:
             continue
         fams = [m for m in man if m["suite"] == suite]
-        for tool, exe, args, key in (("quickprobs", "quickprobs_b200", [], "qp_sha"), ("c_p_np_aln -p 0", "c_p_np_aln_b200", ["-p", "0"], "cpnp_sha")):
+        for tool, exe, args, key in (("quickprobs", "quickprobs_b200", [], "qp_sha"), ("c_p_np_aln -p 0", "c_p_np_aln_b200", ["-p", "0"], "cpnp_sha"),
+                                     ("c_p_np_aln -p 1", "c_p_np_aln_b200", ["-p", "1", "--seed", seed], "cpnp1_sha")):
+            if tools and key not in tools:
+                continue
+            fams = [m for m in man if m["suite"] == suite and key in m]
+            if not fams:
+                continue
             outdir = os.path.join(tmp, "out_%s_%s" % (suite, key))
             os.makedirs(outdir)
+            indir = os.path.join(tmp, suite)
+            if len(fams) != sum(1 for m in man if m["suite"] == suite):      # this tool has reference outputs for a subset only
+                indir = os.path.join(tmp, "in_%s_%s" % (suite, key))
+                os.makedirs(indir)
+                for m in fams:
+                    os.symlink(os.path.join(tmp, suite, m["name"]), os.path.join(indir, m["name"]))
             t0 = time.time()
-            r = subprocess.run([os.path.join(BIN, exe)] + args + [os.path.join(tmp, suite), "-o", outdir], capture_output=True, text=True)
+            r = subprocess.run([os.path.join(BIN, exe)] + args + [indir, "-o", outdir], capture_output=True, text=True)
             dt = time.time() - t0
             same = diff = missing = skipped = 0
             for m in fams:
@@ -52,4 +67,7 @@ def run(report_path=None, suites=None):
 
 
 if __name__ == "__main__":
-    run(os.path.join(ROOT, "gpurun_out", "suite_parity.json"), sys.argv[1:] or None)
+    # arguments: suite names and/or tool keys (qp_sha, cpnp_sha, cpnp1_sha)
+    keys = [x for x in sys.argv[1:] if x.endswith("_sha")]
+    names = [x for x in sys.argv[1:] if not x.endswith("_sha")]
+    run(os.path.join(ROOT, "gpurun_out", "suite_parity%s.json" % ("_" + "_".join(keys) if keys else "")), names or None, keys or None)
