@@ -173,6 +173,8 @@ int mlp_cpnp_np_finish_alignment(mlp_ctx* ctx, int refine_reps, int64_t seed, ch
 int mlp_column_scores(int n, int columns, const char* rows, double* col_score, double* mean, double* sd, double* peak_ratio);
 /* test hook: first `count` outputs of the private glibc rand() replica */
 int mlp_debug_glibc_rand(int count, int32_t* out);
+/* test hook: permutation produced by the alignment graph's sort (AlignGraph.h:62-113 restated; tasks != 0: OpenMP tasks) */
+int mlp_debug_reference_sort(int64_t n, const float* keys, int32_t* idx_out, int tasks);
 /* the same after srand(seed) */
 int mlp_debug_glibc_rand_seeded(uint32_t seed, int count, int32_t* out);
 

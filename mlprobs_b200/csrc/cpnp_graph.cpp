@@ -15,6 +15,9 @@
 #include "../../include/mlprobs_b200.h"
 #include <algorithm>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace qptail {
 
@@ -42,28 +45,55 @@ inline void delete_bit(Bits& b, int pos) {
     for (size_t k = w + 1; k < n; ++k) b[k] = (b[k] >> 1) | (k + 1 < n ? (b[k + 1] & 1) << 63 : 0);
 }
 
-// AlignGraph::Quick_sort with its hole-moving partition around the first element; an explicit stack replaces the recursion
-// (the sub-ranges are disjoint, so the order in which they are finished does not change the result)
-void reference_sort(std::vector<float>& key, std::vector<int>& idx) {
+// AlignGraph::Partition: hole-moving partition around the first element of [low, high]; returns the pivot's final position
+long long reference_partition(float* key, int* idx, long long low, long long high) {
+    const float pivot = key[low];
+    const int pivot_idx = idx[low];
+    while (high > low) {
+        while (pivot <= key[high] && high > low) --high;
+        key[low] = key[high]; idx[low] = idx[high];
+        while (pivot >= key[low] && high > low) ++low;
+        key[high] = key[low]; idx[high] = idx[low];
+    }
+    key[low] = pivot; idx[low] = pivot_idx;
+    return low;
+}
+
+// AlignGraph::Quick_sort.  The two sub-ranges of a partition are disjoint, so neither the order in which they are finished
+// nor the thread that finishes them changes the result: an explicit stack replaces the recursion, and large sub-ranges
+// become OpenMP tasks.
+void reference_sort_serial(float* key, int* idx, long long lo, long long hi) {
     std::vector<std::pair<long long, long long>> todo;
-    todo.emplace_back(0, (long long)key.size() - 1);
+    todo.emplace_back(lo, hi);
     while (!todo.empty()) {
-        long long low = todo.back().first, high = todo.back().second;
+        const long long low = todo.back().first, high = todo.back().second;
         todo.pop_back();
         if (low >= high) continue;
-        const long long first = low, last = high;
-        const float pivot = key[low];
-        const int pivot_idx = idx[low];
-        while (high > low) {
-            while (pivot <= key[high] && high > low) --high;
-            key[low] = key[high]; idx[low] = idx[high];
-            while (pivot >= key[low] && high > low) ++low;
-            key[high] = key[low]; idx[high] = idx[low];
-        }
-        key[low] = pivot; idx[low] = pivot_idx;
-        todo.emplace_back(first, low - 1);
-        todo.emplace_back(low + 1, last);
+        const long long p = reference_partition(key, idx, low, high);
+        todo.emplace_back(low, p - 1);
+        todo.emplace_back(p + 1, high);
     }
+}
+
+void reference_sort_tasks(float* key, int* idx, long long lo, long long hi) {
+    const long long grain = 1 << 16;
+    while (hi - lo > grain) {
+        const long long p = reference_partition(key, idx, lo, hi);
+#pragma omp task default(none) firstprivate(key, idx, lo, p)
+        reference_sort_tasks(key, idx, lo, p - 1);
+        lo = p + 1;
+    }
+    reference_sort_serial(key, idx, lo, hi);
+}
+
+void reference_sort(std::vector<float>& key, std::vector<int>& idx) {
+    if (key.empty()) return;
+    float* k = key.data();
+    int* i = idx.data();
+    const long long last = (long long)key.size() - 1;
+#pragma omp parallel
+#pragma omp single nowait
+    reference_sort_tasks(k, i, 0, last);
 }
 
 class Graph {
@@ -82,9 +112,9 @@ public:
         if (!fx && !fy) add_node(x, y);
         else if (fx != fy) {
             if (fy) { std::swap(x, y); std::swap(cx, cy); }
-            if (!contains(node_of_[y.seq], cx)) extend_column(y, cx);       // cx already holds a residue of y's sequence
+            if (!test(members_[cx], y.seq)) extend_column(y, cx);           // unless cx already holds a residue of y's sequence
         } else if (cx != cy) {
-            if (!contains(node_of_[y.seq], cx) && !contains(node_of_[x.seq], cy)) {
+            if (!test(members_[cx], y.seq) && !test(members_[cy], x.seq)) {
                 if (cx > cy) std::swap(cx, cy);
                 merge_columns(cx, cy);
             }
@@ -173,6 +203,9 @@ private:
         for (int p : parents) for (int c : children) drop(child_[p], c);
         node_of_[x.seq][x.pos] = g;
         node_of_[y.seq][y.pos] = g;
+        members_.push_back(Bits(((size_t)n_ + 63) / 64, 0));
+        set(members_[g], x.seq);
+        set(members_[g], y.seq);
         Bits a(words_, 0), d(words_, 0);
         if (!parents.empty()) a = anc_[parents[0]];
         if (parents.size() == 2) or_into(a, anc_[parents[1]]);
@@ -200,6 +233,7 @@ private:
         if (child != -1 && test(desc_[cx], child) && !cx_had) drop(child_[cx], child);
         if (parent != -1 && child != -1) drop(child_[parent], child);
         node_of_[y.seq][y.pos] = cx;
+        set(members_[cx], y.seq);
         if (parent != -1) { or_into(anc_[cx], anc_[parent]); set(anc_[cx], parent); }
         if (child != -1) { or_into(desc_[cx], desc_[child]); set(desc_[cx], child); }
         const Bits a = anc_[cx], d = desc_[cx];
@@ -243,6 +277,8 @@ private:
         for (int c : child_[cy]) if (test(dx, c) && !contains(child_[cx], c)) drop(next[cx], renum(c));
         for (std::vector<int>& row : node_of_) for (int& v : row) v = renum(v);
         child_.swap(next);
+        or_into(members_[cx], members_[cy]);
+        members_.erase(members_.begin() + cy);
         Bits a = anc_[cx], d = desc_[cx];
         or_into(a, anc_[cy]);
         or_into(d, desc_[cy]);
@@ -294,6 +330,7 @@ private:
     std::vector<std::vector<int>> child_;          // G
     std::vector<std::vector<int>> node_of_;        // IsPresent
     std::vector<Bits> anc_, desc_;                 // Ancs, Descs
+    std::vector<Bits> members_;                    // per node: which sequences have a residue in it (the reference scans IsPresent rows)
 };
 
 }  // namespace
@@ -308,6 +345,15 @@ int build_graph_alignment(const HostCsrView& v, const uint8_t* residues, Profile
     std::vector<float> key;
     std::vector<Residue> left, right;
     const Cell* cells = (const Cell*)v.cells;
+    {
+        size_t total = 0;
+        for (int a = 0; a < n; ++a)
+            for (int b = a + 1; b < n; ++b) {
+                const int32_t* rp = v.rp_pool + v.rp_off[(int64_t)a * n + b];
+                total += (size_t)std::max(0, rp[v.len[a] + 1] - rp[1]);
+            }
+        key.reserve(total); left.reserve(total); right.reserve(total);
+    }
     for (int a = 0; a < n; ++a)
         for (int b = a + 1; b < n; ++b) {
             const int64_t slot = (int64_t)a * n + b;
@@ -324,11 +370,29 @@ int build_graph_alignment(const HostCsrView& v, const uint8_t* residues, Profile
     if (key.size() > 0x7fffffffull) { err = "too many sparse cells for the alignment graph"; return MLP_E_UNSUPPORTED; }
     std::vector<int> order(key.size());
     for (size_t k = 0; k < order.size(); ++k) order[k] = (int)k;
+    const bool times = getenv("MLP_GRAPH_TIMES") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     reference_sort(key, order);
+    const double t1 = now();
     Graph g(n, v.len);
     for (size_t k = order.size(); k-- > 0;) g.offer(left[order[k]], right[order[k]]);
+    const double t2 = now();
     g.alignment(residues, off, out);
+    if (times) fprintf(stderr, "graph: %zu cells, sort %.2f s, insert %.2f s, columns %.2f s\n", order.size(), t1 - t0, t2 - t1, now() - t2);
     return 0;
 }
 
 }  // namespace qptail
+
+// test hook: the permutation the graph's sort produces (tasks = 1: the OpenMP task version used in production, 0: one thread)
+extern "C" int mlp_debug_reference_sort(int64_t n, const float* keys, int32_t* idx_out, int tasks) {
+    if (n < 0 || !keys || !idx_out) return MLP_E_ARG;
+    std::vector<float> key(keys, keys + n);
+    std::vector<int> idx((size_t)n);
+    for (int64_t k = 0; k < n; ++k) idx[(size_t)k] = (int)k;
+    if (tasks) qptail::reference_sort(key, idx);
+    else if (n > 0) qptail::reference_sort_serial(key.data(), idx.data(), 0, n - 1);
+    for (int64_t k = 0; k < n; ++k) idx_out[k] = idx[(size_t)k];
+    return MLP_OK;
+}

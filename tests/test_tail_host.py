@@ -90,3 +90,43 @@ def test_private_glibc_rand_replica_matches_libc_after_srand(seed):
     libc.srand(ctypes.c_uint(seed))
     want = [libc.rand() for _ in range(2000)]
     assert M.debug_glibc_rand_seeded(seed, 2000).tolist() == want
+
+
+def _quick_sort_reference(arr, ind, low, high):
+    """AlignGraph::Quick_sort / Partition (AlignGraph.h:62-113), restated in Python for small inputs."""
+    stack = [(low, high)]
+    while stack:
+        low, high = stack.pop()
+        if low >= high:
+            continue
+        lo, hi = low, high
+        pivot, ip = arr[lo], ind[lo]
+        while hi > lo:
+            while pivot <= arr[hi] and hi > lo:
+                hi -= 1
+            arr[lo], ind[lo] = arr[hi], ind[hi]
+            while pivot >= arr[lo] and hi > lo:
+                lo += 1
+            arr[hi], ind[hi] = arr[lo], ind[lo]
+        arr[lo], ind[lo] = pivot, ip
+        stack.append((low, lo - 1)); stack.append((lo + 1, high))
+
+
+def test_alignment_graph_sort_keeps_the_reference_order_of_ties():
+    """The graph takes cells strongest first from an UNSTABLE quicksort, so equal posteriors come out in that algorithm's order;
+    the production version runs large sub-ranges as OpenMP tasks and must give the same permutation."""
+    import ctypes as C
+    lib = M.load()
+    lib.mlp_debug_reference_sort.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(3)
+    def run(keys, tasks):
+        out = np.zeros(len(keys), np.int32)
+        assert lib.mlp_debug_reference_sort(len(keys), keys.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), tasks) == 0
+        return out
+    small = (rng.integers(0, 40, 3000) / 40).astype(np.float32)           # heavy ties
+    arr, ind = small.tolist(), list(range(len(small)))
+    _quick_sort_reference(arr, ind, 0, len(arr) - 1)
+    assert run(small, 0).tolist() == ind and run(small, 1).tolist() == ind
+    big = np.round(rng.random(600000), 3).astype(np.float32)              # 1000 distinct values: ties everywhere, task path
+    a, b = run(big, 0), run(big, 1)
+    assert np.array_equal(a, b) and np.all(np.diff(big[a]) >= 0) and sorted(a.tolist()) == list(range(len(big)))
