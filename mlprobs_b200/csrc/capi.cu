@@ -23,6 +23,7 @@ static void release_sets(mlp_ctx* ctx) {
     }
     free_dev(ctx->d_rp_off); ctx->d_rp_off = nullptr;
     free_dev(ctx->d_dist); ctx->d_dist = nullptr;
+    ctx->rp_cap = ctx->nn_cap = 0;
     ctx->have_sets = false;
 }
 
@@ -70,6 +71,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     release_sets(ctx);
     release_launch_scratch(ctx);
+    if (ctx->tail_prov && ctx->tail_prov_free) ctx->tail_prov_free(ctx->tail_prov);
     free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
@@ -177,7 +179,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     cudaSetDevice(ctx->device);
     // same family shape as before (same n and lengths): the pooled layout is unchanged, keep the device pools
     const bool same_layout = ctx->have_sets && ctx->n == n && std::equal(len, len + n, ctx->len.begin());
-    if (!same_layout) release_sets(ctx);
+    if (!same_layout) ctx->have_sets = false;        // the pools themselves stay: ensure_sets re-uses them when the new family fits
     ctx->flavour_of_set = -1;
     ctx->n = n;
     ctx->len.assign(len, len + n);
@@ -195,9 +197,18 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
         codes[k] = (uint8_t)(ch - 'A');
     }
     ctx->codes_h = codes;
-    free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
-    CK(cudaMalloc(&ctx->d_res, tot + 16));
-    CK(cudaMalloc(&ctx->d_seq_off, n * sizeof(long long)));
+    if (tot + 16 > ctx->res_cap) {
+        free_dev(ctx->d_res); ctx->d_res = nullptr; ctx->res_cap = 0;
+        const long long cap = tot + tot / 2 + 4096;
+        CK(cudaMalloc(&ctx->d_res, cap));
+        ctx->res_cap = cap;
+    }
+    if (n > ctx->seqoff_cap) {
+        free_dev(ctx->d_seq_off); ctx->d_seq_off = nullptr; ctx->seqoff_cap = 0;
+        const int cap = n + n / 2 + 64;
+        CK(cudaMalloc(&ctx->d_seq_off, (size_t)cap * sizeof(long long)));
+        ctx->seqoff_cap = cap;
+    }
     CK(cudaMemcpy(ctx->d_res, codes.data(), tot + 16, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_seq_off, ctx->seq_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
     ctx->stats.h2d_bytes += tot + 16 + n * (int64_t)sizeof(long long);
@@ -236,24 +247,38 @@ static int ensure_sets(mlp_ctx* ctx) {
         for (const PairTask& t : ctx->all_pairs) s += std::min(t.L1, t.L2);
         cap = 16 * s + (1 << 20);   // both orientations, ~8 cells per row of head-room
     }
-    CK(cudaMalloc(&ctx->d_rp_off, (size_t)n * n * sizeof(long long)));
+    const long long nn = (long long)n * n;
+    if (!ctx->d_rp_off || nn > ctx->nn_cap || ctx->rp_total + 8 > ctx->rp_cap) {
+        // first family, or one that does not fit the pools kept from the previous families: re-allocate with head-room
+        release_sets(ctx);
+        const long long nn_cap = nn + nn / 4 + 64, rp_cap = ctx->rp_total + ctx->rp_total / 4 + 64;   // rp_cap includes the 8 ints a 16-byte aligned bulk copy may read past the end
+        CK(cudaMalloc(&ctx->d_rp_off, (size_t)nn_cap * sizeof(long long)));
+        for (int s = 0; s < 2; ++s) {
+            CK(cudaMalloc(&ctx->set[s].rp_pool, (size_t)rp_cap * sizeof(int)));
+            CK(cudaMalloc(&ctx->set[s].nz_off, (size_t)nn_cap * sizeof(long long)));
+            CK(cudaMalloc(&ctx->set[s].nz_cnt, (size_t)nn_cap * sizeof(int)));
+            CK(cudaMalloc(&ctx->set[s].cursor, sizeof(unsigned long long)));
+        }
+        CK(cudaMalloc(&ctx->d_dist, (size_t)nn_cap * sizeof(float)));
+        ctx->nn_cap = nn_cap;
+        ctx->rp_cap = rp_cap;
+    }
     CK(cudaMemcpy(ctx->d_rp_off, ctx->rp_off_h.data(), (size_t)n * n * sizeof(long long), cudaMemcpyHostToDevice));
     ctx->stats.h2d_bytes += (int64_t)n * n * 8;
     for (int s = 0; s < 2; ++s) {
-        CK(cudaMalloc(&ctx->set[s].rp_pool, ((size_t)ctx->rp_total + 8) * sizeof(int)));     // +8: 16-byte aligned bulk copies may read past the end
-        CK(cudaMalloc(&ctx->set[s].nz_off, (size_t)n * n * sizeof(long long)));
-        CK(cudaMalloc(&ctx->set[s].nz_cnt, (size_t)n * n * sizeof(int)));
         const long long this_cap = (s == 0) ? cap : 1024;   // the relax output pool is sized when mlp_relax runs
-        CK(cudaMalloc(&ctx->set[s].cells, ((size_t)this_cap + 4) * sizeof(int2)));
-        CK(cudaMalloc(&ctx->set[s].cursor, sizeof(unsigned long long)));
-        CK(cudaMemset(ctx->set[s].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int)));
-        CK(cudaMemset(ctx->set[s].nz_off, 0, (size_t)n * n * sizeof(long long)));
-        CK(cudaMemset(ctx->set[s].nz_cnt, 0, (size_t)n * n * sizeof(int)));
-        CK(cudaMemset(ctx->set[s].cursor, 0, sizeof(unsigned long long)));
-        ctx->set[s].cap = this_cap;
+        if (!ctx->set[s].cells || ctx->set[s].cap < this_cap) {
+            free_dev(ctx->set[s].cells); ctx->set[s].cells = nullptr; ctx->set[s].cap = 0;
+            CK(cudaMalloc(&ctx->set[s].cells, ((size_t)this_cap + 4) * sizeof(int2)));
+            ctx->set[s].cap = this_cap;
+        }
+        CK(cudaMemsetAsync(ctx->set[s].rp_pool, 0, (size_t)ctx->rp_total * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->set[s].nz_off, 0, (size_t)n * n * sizeof(long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->set[s].nz_cnt, 0, (size_t)n * n * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->set[s].cursor, 0, sizeof(unsigned long long), ctx->stream));
     }
-    CK(cudaMalloc(&ctx->d_dist, (size_t)n * n * sizeof(float)));
-    CK(cudaMemset(ctx->d_dist, 0, (size_t)n * n * sizeof(float)));
+    CK(cudaMemsetAsync(ctx->d_dist, 0, (size_t)n * n * sizeof(float), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_sets = true;
     ctx->cur = 0;
     return MLP_OK;

@@ -49,6 +49,11 @@ struct mlp_ctx {
     long long rp_total = 0;
     long long* d_rp_off = nullptr;
     CsrSetDev set[2] = {};
+    long long rp_cap = 0, nn_cap = 0;    // allocated sizes of the pooled arrays (ints per rp_pool, entries per n*n array): a context
+                                         // that sees many families keeps its pools and only re-allocates when one does not fit
+    long long res_cap = 0; int seqoff_cap = 0;
+    void* tail_prov = nullptr;           // the tail's profile-posterior provider with its staging buffers (qp_tail_dev.cu), kept across families
+    void (*tail_prov_free)(void*) = nullptr;
     int cur = 0;
     bool have_sets = false;
     int flavour_of_set = -1;

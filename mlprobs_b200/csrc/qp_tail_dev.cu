@@ -414,6 +414,16 @@ private:
     unsigned char* d_gx = nullptr; unsigned char* h_gx = nullptr; size_t gx_cap = 0;   // score + gathered values (cpnp refinement)
 };
 
+// One provider per context: its pinned / device staging buffers only ever grow, so a context that aligns many families
+// (directory mode of the two executables) does not pay cudaHostAlloc / cudaMalloc again for every family.
+DeviceProfilePosterior& provider_of(mlp_ctx* ctx) {
+    if (!ctx->tail_prov) {
+        ctx->tail_prov = new DeviceProfilePosterior(ctx);
+        ctx->tail_prov_free = [](void* p) { delete static_cast<DeviceProfilePosterior*>(p); };
+    }
+    return *static_cast<DeviceProfilePosterior*>(ctx->tail_prov);
+}
+
 }  // namespace
 
 extern "C" int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const int32_t* left, const int32_t* right,
@@ -431,7 +441,7 @@ extern "C" int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const
     std::vector<uint8_t> letters(ctx->codes_h.size());
     for (size_t k = 0; k < letters.size(); ++k) letters[k] = (uint8_t)('A' + ctx->codes_h[k]);
     std::vector<int32_t> len(ctx->len.begin(), ctx->len.end());
-    DeviceProfilePosterior prov(ctx);
+    DeviceProfilePosterior& prov = provider_of(ctx);
     qptail::TailOptions opt;
     opt.ref_iters = ref_iters;
     opt.ref_seed = ref_seed;
@@ -461,7 +471,7 @@ extern "C" int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, 
     std::vector<uint8_t> letters(ctx->codes_h.size());
     for (size_t k = 0; k < letters.size(); ++k) letters[k] = (uint8_t)('A' + ctx->codes_h[k]);
     std::vector<int32_t> len(ctx->len.begin(), ctx->len.end());
-    DeviceProfilePosterior prov(ctx);
+    DeviceProfilePosterior& prov = provider_of(ctx);
     qptail::Profile out;
     std::string err;
     const int rc = qptail::run_cpnp_tail(ctx->n, len.data(), letters.data(), iweights, left, right, prov, refine_reps, pid, out, err);
@@ -505,7 +515,7 @@ extern "C" int mlp_cpnp_np_finish_alignment(mlp_ctx* ctx, int refine_reps, int64
     for (size_t k = 0; k < letters.size(); ++k) letters[k] = (uint8_t)('A' + ctx->codes_h[k]);
     std::vector<int32_t> len(ctx->len.begin(), ctx->len.end());
     const qptail::HostCsrView view{n, len.data(), rp_off.data(), nz_off.data(), rp_pool.data(), cells.data()};
-    DeviceProfilePosterior prov(ctx);
+    DeviceProfilePosterior& prov = provider_of(ctx);
     qptail::Profile out;
     std::string err;
     rc = qptail::run_cpnp_np_tail(view, letters.data(), dist.data(), prov, refine_reps, (long long)seed, out, err);
