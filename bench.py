@@ -99,7 +99,7 @@ def run_reference(args, wl):
     ms = 1e3 * float(np.mean(times))
     gcups = cells / (ms * 1e-3) / 1e9
     line = {"impl": "reference", "metric": "pair_hmm_cell_updates_per_second", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": wl["name"], "flavour": "quickprobs", "models_per_cell": 2},
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
