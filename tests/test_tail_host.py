@@ -130,3 +130,49 @@ def test_alignment_graph_sort_keeps_the_reference_order_of_ties():
     big = np.round(rng.random(600000), 3).astype(np.float32)              # 1000 distinct values: ties everywhere, task path
     a, b = run(big, 0), run(big, 1)
     assert np.array_equal(a, b) and np.all(np.diff(big[a]) >= 0) and sorted(a.tolist()) == list(range(len(big)))
+
+
+def _fake_pooled_set(seqs, rng, per_row=3):
+    """A pooled sparse set with `per_row` cells around the length-scaled diagonal of every ordered pair; values on a coarse grid so
+    that many cells tie.  The pairs contradict each other on purpose: the graph has to refuse cells that would close a cycle."""
+    n = len(seqs); lens = [len(s) for s in seqs]
+    rp_off = np.zeros(n * n, np.int64); nz_off = np.zeros(n * n, np.int64)
+    rps, cols, vals = [], [], []
+    rp_at = nz_at = 0
+    for a in range(n):
+        for b in range(n):
+            if a == b:
+                continue
+            la, lb = lens[a], lens[b]
+            rp = np.zeros(la + 2, np.int32); c = []
+            for i in range(1, la + 1):
+                k = min(per_row, lb)
+                j0 = max(1, min(lb - k + 1, int(i * lb / la) - 1))
+                c += list(range(j0, j0 + k))
+                rp[i + 1] = rp[i] + k
+            rp_off[a * n + b] = rp_at; nz_off[a * n + b] = nz_at
+            rps.append(rp); cols.append(np.array(c, np.int32)); vals.append((rng.integers(1, 21, len(c)) / 20).astype(np.float32))
+            rp_at += len(rp); nz_at += len(c)
+    cells = np.zeros(nz_at, dtype=[("c", np.int32), ("v", np.float32)])
+    cells["c"] = np.concatenate(cols); cells["v"] = np.concatenate(vals)
+    return rp_off, nz_off, np.concatenate(rps), cells
+
+
+@pytest.mark.parametrize("n,length,seed", [(2, 1, 1), (3, 7, 2), (9, 60, 3), (25, 40, 4), (12, 300, 5)])
+def test_alignment_graph_always_yields_a_valid_alignment(n, length, seed):
+    """Whatever the cells say, AlignGraph's output is an alignment: equal-length rows that degap to the inputs, no all-gap column,
+    and the same rows when the call is repeated (c_p_np_aln -p 1 without refinement is deterministic)."""
+    from mlprobs_b200 import synth
+    rng = np.random.default_rng(seed)
+    seqs = [synth.family(1, max(1, length + int(rng.integers(-length // 3, length // 3 + 1))), seed=seed * 100 + k)[0] for k in range(n)]
+    rp_off, nz_off, rp_pool, cells = _fake_pooled_set(seqs, rng)
+    dist = rng.random((n, n)).astype(np.float32)
+    rows = M.cpnp_np_finish_alignment_host(seqs, dist, rp_off, nz_off, rp_pool, cells, 0, 1)
+    assert len({len(r) for r in rows}) == 1
+    assert [r.replace(b"-", b"") for r in rows] == seqs
+    assert all(any(r[c] != ord("-") for r in rows) for c in range(len(rows[0])))
+    assert M.cpnp_np_finish_alignment_host(seqs, dist, rp_off, nz_off, rp_pool, cells, 0, 99) == rows
+    # with refinement the result depends on the seed only through the visiting order; it stays a valid alignment
+    ref = M.cpnp_np_finish_alignment_host(seqs, dist, rp_off, nz_off, rp_pool, cells, 20, 7)
+    assert len({len(r) for r in ref}) == 1 and [r.replace(b"-", b"") for r in ref] == seqs
+    assert M.cpnp_np_finish_alignment_host(seqs, dist, rp_off, nz_off, rp_pool, cells, 20, 7) == ref
