@@ -421,3 +421,58 @@ def test_properties_on_a_large_family():
     nnz3, rp3, col3, val3 = eng.csr_bulk()
     assert (nnz3 <= nnz).all() and nnz3.sum() > 0
     eng.close()
+
+
+def test_full_size_family_properties():
+    """BASELINE config A at full size (1,000 sequences x 300, the family bench.py times; 499,500 pairs, 4.7e10 cells per model):
+    size-independent properties plus oracle spot checks.  Pairs are independent in the posterior stage, so any sub-family
+    processed on its own must give the same bytes as the same pairs inside the full run."""
+    seqs = synth.family_fast(1000, 300, seed=20220148 + 2)
+    n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    d = eng.distances()
+    assert d.shape == (n, n) and np.array_equal(d, d.T) and (np.diag(d) == 0).all()
+    off = d[np.triu_indices(n, 1)]
+    assert np.isfinite(off).all() and (off > 0).all() and (off <= 1).all()
+    # a sub-family on its own context: same distances, same matrices (both orientations)
+    pick = [0, 1, 2, 3, 499, 500, 501, 997, 998, 999]
+    sub = engine(M.QP, [seqs[k] for k in pick])
+    sub.posterior_all_pairs(M.QP, 3, 0.01)
+    assert np.array_equal(sub.distances(), d[np.ix_(pick, pick)])
+    for x in range(len(pick)):
+        for y in range(len(pick)):
+            if x != y:
+                r1, c1, v1 = sub.csr(x, y)
+                r2, c2, v2 = eng.csr(pick[x], pick[y])
+                assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and np.array_equal(v1, v2), (x, y)
+    sub.close()
+    # oracle on three pairs spread over the (cost-sorted, batched) task list
+    ht, pt = O.hmm_tables(), O.part_tables(O.QP)
+    for a, b in [(0, 999), (123, 456), (998, 999)]:
+        post, dist, _ = O.pair_posterior(O.QP, 3, ht, pt, seqs[a], seqs[b])
+        assert dist == d[a, b]
+        rp, c, v = eng.csr(a, b)
+        keep = np.argwhere(post >= np.float32(0.01))
+        assert len(keep) == len(c) and np.array_equal(keep[:, 1], c)
+        codes = np.floor(post[keep[:, 0], keep[:, 1]].astype(np.float32) * np.float32(65535)).astype(np.float32)
+        assert np.array_equal(codes / np.float32(65535), v)
+    cells_before = eng.total_cells()
+    before = {p: eng.csr(*p) for p in [(0, 999), (999, 0), (123, 456), (700, 40)]}
+    # consistency (one repetition with the final cut-off, as QuickProbs runs it above 50 sequences): patterns only shrink,
+    # the stored transpose stays the transpose, values stay uint16 codes
+    w, sd, _, _ = M.qp_guide_tree(d)
+    eng.relax(M.QP, np.maximum(w, np.float32(1e-6)), sd, 200.0, 3.0, float(np.float32(1e-5)))
+    assert 0 < eng.total_cells() <= cells_before
+    for (a, b), (rp0, c0, v0) in before.items():
+        rp1, c1, v1 = eng.csr(a, b)
+        La = len(seqs[a])
+        for i in range(1, La + 1):
+            assert set(c1[rp1[i]:rp1[i + 1]].tolist()) <= set(c0[rp0[i]:rp0[i + 1]].tolist())
+        assert np.array_equal(np.round(v1.astype(np.float64) * 65535).astype(np.float32) / np.float32(65535), v1)
+    rp_ab, c_ab, v_ab = eng.csr(123, 456)
+    rp_ba, c_ba, v_ba = eng.csr(456, 123)
+    fwd = {(i, int(c)): float(v) for i in range(1, len(seqs[123]) + 1) for c, v in zip(c_ab[rp_ab[i]:rp_ab[i + 1]], v_ab[rp_ab[i]:rp_ab[i + 1]])}
+    rev = {(int(c), j): float(v) for j in range(1, len(seqs[456]) + 1) for c, v in zip(c_ba[rp_ba[j]:rp_ba[j + 1]], v_ba[rp_ba[j]:rp_ba[j + 1]])}
+    assert fwd == rev and len(fwd) > 0
+    eng.close()
