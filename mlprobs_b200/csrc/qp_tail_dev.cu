@@ -220,17 +220,20 @@ public:
         if (h_dense) cudaFreeHost(h_dense);
         if (d_tb) cudaFree(d_tb);
         if (h_tb) cudaFreeHost(h_tb);
-        if (d_gx) cudaFree(d_gx);
-        if (h_gx) cudaFreeHost(h_gx);
     }
-    int launch_profile(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws) {
+    // `offsets` (optional): element offsets into the dense matrix that k_gather_dense will read; they ride in the same
+    // host->device copy as the mappings (d_offsets points at them afterwards)
+    int launch_profile(const qptail::Profile& A, const qptail::Profile& B, const qptail::WeightSpec& ws,
+                       const std::vector<long long>* offsets = nullptr) {
         const int nA = A.count(), nB = B.count(), l1 = A.length(), l2 = B.length();
         int ldB = 1;
         for (int j = 0; j < nB; ++j) ldB = std::max(ldB, ctx->len[B.ids[j]] + 1);
         // blob layout: doubles first, then ints
         const size_t n_dbl = (size_t)nA + nB;
         const size_t n_inv = (size_t)(l1 + 1) * nA, n_map = (size_t)nB * ldB;
-        const size_t bytes = n_dbl * 8 + (n_inv + n_map + nA + nB) * 4;
+        const size_t ng = offsets ? offsets->size() : 0;
+        const size_t off_at = (n_dbl * 8 + (n_inv + n_map + nA + nB) * 4 + 7) & ~(size_t)7;
+        const size_t bytes = off_at + ng * 8;
         if (bytes > blob_cap) {
             if (d_blob) cudaFree(d_blob);
             if (h_blob) cudaFreeHost(h_blob);
@@ -279,6 +282,8 @@ public:
             CK(cudaFuncSetAttribute(k_profile_posterior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             smem_set = smem;
         }
+        if (ng) memcpy((char*)h_blob + off_at, offsets->data(), ng * 8);
+        d_offsets = reinterpret_cast<const long long*>((const char*)d_blob + off_at);
         CK(cudaMemcpyAsync(d_blob, h_blob, bytes, cudaMemcpyHostToDevice, ctx->stream));
         PPArgs a;
         a.wA = (const double*)d_blob; a.wB = a.wA + nA;
@@ -335,57 +340,45 @@ public:
         const int Bb = (C + 3) / 4;
         const size_t smem = ((size_t)T * C + 4 * (size_t)T) * 4;
         if (smem > 200 * 1024) return 1;
-        int rc = launch_profile(A, B, ws);
+        int rc = launch_profile(A, B, ws, offsets);
         if (rc < 0) return rc;
+        // result buffer: [2-bit choices, tbn bytes][pad to 16][score, 16 bytes][ng gathered values]: one device->host copy
         const size_t tbn = (size_t)l1 * T * Bb;
-        if (tbn > tb_cap) {
+        const size_t ng = offsets ? offsets->size() : 0;
+        const bool extras = score || ng;
+        const size_t xoff = (tbn + 15) & ~(size_t)15;
+        const size_t out_bytes = extras ? xoff + 16 + ng * 4 : tbn;
+        if (out_bytes > tb_cap) {
             if (d_tb) cudaFree(d_tb);
             if (h_tb) cudaFreeHost(h_tb);
-            d_tb = nullptr; h_tb = nullptr;
-            tb_cap = tbn + tbn / 2;
-            CK(cudaMalloc(&d_tb, tb_cap));
-            CK(cudaHostAlloc(&h_tb, tb_cap, cudaHostAllocDefault));
+            d_tb = nullptr; h_tb = nullptr; tb_cap = 0;
+            const size_t cap = out_bytes + out_bytes / 2 + 4096;
+            CK(cudaMalloc(&d_tb, cap));
+            CK(cudaHostAlloc(&h_tb, cap, cudaHostAllocDefault));
+            tb_cap = cap;
         }
         if (smem > mea_smem_set) {
             CK(cudaFuncSetAttribute(k_mea_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             mea_smem_set = smem;
         }
         MeaArgs m;
-        const size_t ng = offsets ? offsets->size() : 0;
-        if (score || ng) {                                        // extras: score word + gathered posterior values
-            const size_t need = 16 + ng * 12;
-            if (need > gx_cap) {
-                if (d_gx) cudaFree(d_gx);
-                if (h_gx) cudaFreeHost(h_gx);
-                d_gx = nullptr; h_gx = nullptr;
-                gx_cap = need + need / 2 + 4096;
-                CK(cudaMalloc(&d_gx, gx_cap));
-                CK(cudaHostAlloc(&h_gx, gx_cap, cudaHostAllocDefault));
-            }
-        }
-        // extras buffer layout: [score float, pad to 16] [ng offsets (8 B)] [ng values (4 B)]
-        float* d_score = score ? reinterpret_cast<float*>(d_gx) : nullptr;
-        long long* d_off = ng ? reinterpret_cast<long long*>(d_gx + 16) : nullptr;
-        float* d_val = ng ? reinterpret_cast<float*>(d_gx + 16 + ng * 8) : nullptr;
-        m.dense = d_dense; m.l1 = l1; m.l2 = l2; m.C = C; m.T = T; m.B = Bb; m.tb = d_tb; m.score = d_score;
+        float* d_score = extras ? reinterpret_cast<float*>(d_tb + xoff) : nullptr;
+        float* d_val = reinterpret_cast<float*>(d_tb + xoff + 16);
+        m.dense = d_dense; m.l1 = l1; m.l2 = l2; m.C = C; m.T = T; m.B = Bb; m.tb = d_tb; m.score = score ? d_score : nullptr;
         k_mea_wavefront<<<1, T, smem, ctx->stream>>>(m);
         CK(cudaGetLastError());
         ctx->stats.launches += 1;
         if (ng) {
-            memcpy(h_gx + 16, offsets->data(), ng * 8);
-            CK(cudaMemcpyAsync(d_off, h_gx + 16, ng * 8, cudaMemcpyHostToDevice, ctx->stream));
-            k_gather_dense<<<(unsigned)((ng + 255) / 256), 256, 0, ctx->stream>>>(d_dense, d_off, d_val, (int)ng);
+            k_gather_dense<<<(unsigned)((ng + 255) / 256), 256, 0, ctx->stream>>>(d_dense, d_offsets, d_val, (int)ng);
             CK(cudaGetLastError());
             ctx->stats.launches += 1;
-            CK(cudaMemcpyAsync(h_gx + 16 + ng * 8, d_val, ng * 4, cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if (score) CK(cudaMemcpyAsync(h_gx, d_score, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h_tb, d_tb, tbn, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_tb, d_tb, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         rc = finish_timing();
         if (rc < 0) return rc;
-        ctx->stats.d2h_bytes += (int64_t)tbn + (int64_t)ng * 4;
-        if (score) *score = *reinterpret_cast<float*>(h_gx);
-        if (values) { values->resize(ng); if (ng) memcpy(values->data(), h_gx + 16 + ng * 8, ng * 4); }
+        ctx->stats.d2h_bytes += (int64_t)out_bytes;
+        if (score) *score = *reinterpret_cast<const float*>(h_tb + xoff);
+        if (values) { values->resize(ng); if (ng) memcpy(values->data(), h_tb + xoff + 16, ng * 4); }
         path.clear();
         path.reserve((size_t)l1 + l2);
         int r = l1, c = l2;
@@ -410,8 +403,8 @@ private:
     void* d_blob = nullptr; void* h_blob = nullptr; size_t blob_cap = 0;
     float* d_dense = nullptr; float* h_dense = nullptr; size_t dense_cap = 0;
     size_t smem_set = 48 * 1024, mea_smem_set = 48 * 1024;
-    unsigned char* d_tb = nullptr; unsigned char* h_tb = nullptr; size_t tb_cap = 0;
-    unsigned char* d_gx = nullptr; unsigned char* h_gx = nullptr; size_t gx_cap = 0;   // score + gathered values (cpnp refinement)
+    unsigned char* d_tb = nullptr; unsigned char* h_tb = nullptr; size_t tb_cap = 0;   // traceback choices + score + gathered values (cpnp refinement)
+    const long long* d_offsets = nullptr;                                              // inside d_blob, set by launch_profile
 };
 
 // One provider per context: its pinned / device staging buffers only ever grow, so a context that aligns many families
