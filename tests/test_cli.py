@@ -129,3 +129,24 @@ def test_cpnp_cli_reproduces_the_reference(tmp_path, name):
     if name == "cpnp_sup002_ref":           # the -G feature line (20 standard letters only)
         r = subprocess.run([CPNP, "-G", fa], capture_output=True, text=True)
         assert r.returncode == 0 and r.stdout == d["gline"].tobytes().decode() + "\n"
+
+
+def test_cpnp_cli_input_errors_match_the_reference_messages(tmp_path):
+    """Sequence::Sequence / MSA::ParseParams error behaviour (Sequence.h:96-112, MSA.cpp:248-435, SURVEY 8b): exit status 1,
+    `ERROR:` on stderr, nothing on stdout -- MLProbs treats the non-zero status as failure.  These paths end before any CUDA
+    call, so they are checked without a GPU too."""
+    missing = str(tmp_path / "nope.fa")
+    r = subprocess.run([CPNP, "-p", "0", missing], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout == "" and r.stderr == "ERROR: Could not open file '%s' for reading.\n" % missing
+    bad = tmp_path / "bad.fa"
+    bad.write_text(">a\nACD1EF\n>b\nACDEF\n")
+    r = subprocess.run([CPNP, "-p", "1", str(bad)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout == "" and r.stderr == "ERROR: Unknown character encountered: 1\n"
+    empty = tmp_path / "empty.fa"
+    empty.write_text("\n\n")
+    r = subprocess.run([CPNP, "-G", str(empty)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout == "" and r.stderr == "ERROR: No sequences read.\n"
+    r = subprocess.run([CPNP, "-p"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Must specify a value after option" in r.stderr
+    r = subprocess.run([CPNP], capture_output=True, text=True)
+    assert r.returncode != 0 and r.stdout == ""
