@@ -76,9 +76,10 @@ int fail(mlp_ctx* ctx, const char* what, int rc) {
 
 }  // namespace
 
-// one input file; returns the exit status for it
-int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile, int getpid, int reps, int refine, int verbose,
+// one family (the reference loads every positional file into the same sequence set, MSA.cpp:133-137); returns the exit status
+int run_file(mlp_ctx* ctx, const std::vector<std::string>& infiles, const std::string& outfile, int getpid, int reps, int refine, int verbose,
              int program, long long seed) {
+    const std::string& infile = infiles[0];
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     auto fail = [&](mlp_ctx* c, const char* what, int rc) {
@@ -86,7 +87,8 @@ int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile
         return 1;
     };
     Input in;
-    if (!load_mfa(infile, in)) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
+    for (const std::string& f : infiles) load_mfa(f, in);
+    if (in.seqs.empty()) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
     const int n = (int)in.seqs.size();
     std::ofstream fout;
     if (!outfile.empty()) {
@@ -171,7 +173,8 @@ int run_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfile
 }
 
 int main(int argc, char** argv) {
-    std::string infile, outfile;
+    std::string outfile;
+    std::vector<std::string> infiles;
     int program = 0, getpid = 0, reps = 2, refine = 100, device = 0, verbose = 0;
     long long seed = -1;
     if (const char* e = std::getenv("MLP_CPNP_SEED")) seed = std::atoll(e);
@@ -192,15 +195,25 @@ int main(int argc, char** argv) {
         else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
         else if (a == "--seed") seed = std::atoll(need("--seed"));
         else if (a == "-v" || a == "--verbose") verbose = 1;
-        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "c_p_np_aln_b200: unsupported option %s\n", a.c_str()); return 2; }
-        else if (infile.empty()) infile = a;
-        else { std::fprintf(stderr, "c_p_np_aln_b200: more than one input file\n"); return 2; }
+        else if (a == "-clustalw" || a == "-timeon" || a == "-timeoff") {}            // parsed and without effect on the output in the reference too (MSA.cpp:182,404-409)
+        else if (a == "-version") { std::cerr << "c_p_np_aln_b200 (drop-in for PNPProbs c_p_np_aln)" << std::endl; return 1; }   // MSA.cpp:417-420: stderr, exit 1
+        else if (a == "-a" || a == "--alignment-order" || a == "-annot" || a == "-co" || a == "--cutoff") {
+            std::cerr << "ERROR: option " << a << " is not supported by c_p_np_aln_b200" << std::endl;
+            return 1;
+        }
+        else if (!a.empty() && a[0] == '-') { std::cerr << "ERROR: Unrecognized option: " << a << std::endl; return 1; }   // MSA.cpp:422-425
+        else infiles.push_back(a);
     }
-    if (infile.empty()) { std::fprintf(stderr, "usage: c_p_np_aln_b200 (-G | -p 0 | -p 1 [--seed S]) [-o outfile] [-c reps] [-ir passes] <fasta>\n"); return 2; }
+    if (infiles.empty()) { std::fprintf(stderr, "usage: c_p_np_aln_b200 (-G | -p 0 | -p 1 [--seed S]) [-o outfile] [-c reps] [-ir passes] <fasta>\n"); return 1; }   // the reference prints its usage on stderr and exits 1
     struct stat si, so;
-    const bool dir_mode = !outfile.empty() && stat(infile.c_str(), &si) == 0 && S_ISDIR(si.st_mode) &&
+    const std::string& infile = infiles[0];
+    const bool dir_mode = infiles.size() == 1 && !outfile.empty() && stat(infile.c_str(), &si) == 0 && S_ISDIR(si.st_mode) &&
                           stat(outfile.c_str(), &so) == 0 && S_ISDIR(so.st_mode);   // extension: a directory of families, one CUDA context
-    if (!dir_mode) { Input probe; if (!load_mfa(infile, probe)) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; } }
+    if (!dir_mode) {
+        Input probe;
+        for (const std::string& f : infiles) load_mfa(f, probe);
+        if (probe.seqs.empty()) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
+    }
     mlp_ctx* ctx = nullptr;
     int rc = mlp_create(device, &ctx);                 // no CUDA device -> stop: nothing falls back to the CPU
     if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
@@ -217,10 +230,10 @@ int main(int argc, char** argv) {
         }
         std::sort(names.begin(), names.end());
         for (const std::string& nm : names) {
-            const int r1 = run_file(ctx, infile + "/" + nm, outfile + "/" + nm, getpid, reps, refine, verbose, program, seed);
+            const int r1 = run_file(ctx, std::vector<std::string>(1, infile + "/" + nm), outfile + "/" + nm, getpid, reps, refine, verbose, program, seed);
             if (r1) status = r1;
         }
-    } else status = run_file(ctx, infile, outfile, getpid, reps, refine, verbose, program, seed);
+    } else status = run_file(ctx, infiles, outfile, getpid, reps, refine, verbose, program, seed);
     mlp_destroy(ctx);
     return status;
 }

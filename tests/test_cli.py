@@ -150,3 +150,15 @@ def test_cpnp_cli_input_errors_match_the_reference_messages(tmp_path):
     assert r.returncode == 1 and "Must specify a value after option" in r.stderr
     r = subprocess.run([CPNP], capture_output=True, text=True)
     assert r.returncode != 0 and r.stdout == ""
+    # option handling as MSA::ParseParams: unknown option and -version end with status 1, the options the reference parses
+    # without any effect on its output are accepted
+    ok = tmp_path / "ok.fa"
+    ok.write_text(">a\nACDEF\n>b\nACDEF\n")
+    r = subprocess.run([CPNP, "--bogus", str(ok)], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout == "" and r.stderr == "ERROR: Unrecognized option: --bogus\n"
+    r = subprocess.run([CPNP, "-version"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout == "" and r.stderr != ""
+    import torch
+    if not torch.cuda.is_available():       # accepted options and several input files get as far as the device check
+        r = subprocess.run([CPNP, "-clustalw", "-timeon", "-p", "0", str(ok), str(ok)], capture_output=True, text=True)
+        assert r.returncode != 0 and "CUDA device is required" in r.stderr and r.stdout == ""
