@@ -139,20 +139,28 @@ int main(int argc, char** argv) {
             if (i + 1 >= argc) { std::fprintf(stderr, "quickprobs_b200: option %s needs a value\n", name); std::exit(2); }
             return argv[++i];
         };
-        if (a == "-o" || a == "--outfile") outfile = need("-o");
-        else if (a == "-c" || a == "--con-iters") con_iters = std::atoi(need("-c"));
-        else if (a == "-r" || a == "--ref-count") ref_count = std::atoi(need("-r"));
-        else if (a == "--ref-seed") ref_seed = (unsigned)std::strtoul(need("--ref-seed"), nullptr, 10);
-        else if (a == "-t" || a == "--num-threads") (void)need("-t");
-        else if (a == "-d" || a == "--device") device = std::atoi(need("-d"));
-        else if (a == "-v" || a == "--verbose") verbose = 1;
-        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "quickprobs_b200: unsupported option %s\n", a.c_str()); return 2; }
-        else if (infile.empty()) infile = a;
-        else { std::fprintf(stderr, "quickprobs_b200: more than one input file\n"); return 2; }
+        // ProgramOptions::parse (Common/ProgramOptions.cpp:15-48): any number of leading dashes, long or short name
+        std::string name = a;
+        while (!name.empty() && name[0] == '-') name.erase(0, 1);
+        const bool dashed = !a.empty() && a[0] == '-';
+        if (!dashed) {
+            if (infile.empty()) infile = a;
+            else { std::fprintf(stderr, "quickprobs_b200: more than one input file\n"); return 2; }
+        }
+        else if (name == "o" || name == "outfile") outfile = need("-o");
+        else if (name == "c" || name == "con-iters") con_iters = std::atoi(need("-c"));
+        else if (name == "r" || name == "ref-count") ref_count = std::atoi(need("-r"));
+        else if (name == "ref-seed") ref_seed = (unsigned)std::strtoul(need("--ref-seed"), nullptr, 10);
+        else if (name == "t" || name == "num-threads" || name == "p" || name == "platform" || name == "mem-limit" || name == "ref-threads")
+            (void)need(a.c_str());                   // host threads, OpenCL platform, memory limit: no meaning here, value skipped
+        else if (name == "d" || name == "device") device = std::atoi(need("-d"));    // the reference's OpenCL device id; here the CUDA device
+        else if (name == "v" || name == "verbose") verbose = 1;
+        else { std::fprintf(stderr, "quickprobs_b200: unsupported option %s\n", a.c_str()); return 2; }   // incl. -n/--nucleotide, -l/--clustalw
     }
     if (infile.empty()) {
+        // the reference prints its usage on stderr and returns 0 when the positional argument is missing (Console/main.cpp:27-36)
         std::fprintf(stderr, "usage: quickprobs_b200 <infile | indir> [-o outfile | outdir] [-c con-iters] [-r ref-count] [--ref-seed S] [-d cuda-device]\n");
-        return 2;
+        return 0;
     }
     // directory mode (Configuration.cpp:248-267): every regular file of the input directory is aligned into a file of the same
     // name in the output directory -- one process, one CUDA context for all of them

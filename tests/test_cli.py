@@ -162,3 +162,16 @@ def test_cpnp_cli_input_errors_match_the_reference_messages(tmp_path):
     if not torch.cuda.is_available():       # accepted options and several input files get as far as the device check
         r = subprocess.run([CPNP, "-clustalw", "-timeon", "-p", "0", str(ok), str(ok)], capture_output=True, text=True)
         assert r.returncode != 0 and "CUDA device is required" in r.stderr and r.stdout == ""
+
+
+def test_quickprobs_cli_option_syntax(tmp_path):
+    """ProgramOptions::parse (Common/ProgramOptions.cpp:15-48): options take any number of leading dashes and a long or short
+    name; without the positional argument the reference returns 0 and writes nothing to stdout (Console/main.cpp:33-37)."""
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == ""
+    missing = str(tmp_path / "nope.fa")
+    for opt in ("-o", "--o", "---outfile", "-outfile"):
+        r = subprocess.run([CLI, opt, str(tmp_path / "out.fa"), "-t", "3", "--platform", "0", "--mem-limit", "100", missing], capture_output=True, text=True)
+        assert r.returncode == 255 and "unable to open input file" in r.stderr and r.stdout == "", opt
+    r = subprocess.run([CLI, "-l", missing], capture_output=True, text=True)
+    assert r.returncode == 2 and "unsupported option" in r.stderr
