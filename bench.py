@@ -259,7 +259,9 @@ def main():
                 "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "roofline": {"bound": "fp32_issue", "kernel": "k_hmm_fwd+k_hmm_bwd", "achieved": slot_rate / 1e12, "peak": FP32_ISSUE_PEAK / 1e12,
+                "roofline": {"bound": "fp32_issue",
+                             "bound_note": "north_star and SURVEY 8d name FP32 instruction issue as the roofline of this path (log-space compare/select/polynomial work, no contraction for tensor cores); the HBM view of the same kernels is under roofline.hbm",
+                             "kernel": "k_hmm_fwd+k_hmm_bwd", "achieved": slot_rate / 1e12, "peak": FP32_ISSUE_PEAK / 1e12,
                              "unit": "Tlane-op/s", "frac": slot_rate / FP32_ISSUE_PEAK,
                              "peak_source": "148 SMs x 128 FP32 lanes x 1.965 GHz (MEASURED_PEAKS.json sm_max_mhz); no measured FP32-issue peak exists in MEASURED_PEAKS.json",
                              "algorithmic_ops_per_cell": SLOTS_PER_CELL["hmm5"],
