@@ -80,7 +80,10 @@ int mlp_viterbi_all_pairs(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len
 int mlp_viterbi_all_pairs_ex(mlp_ctx* ctx, int32_t* n_identical, int32_t* align_len, char* aln, int64_t* aln_off);
 /* The `c_p_np_aln -G` feature line (MSA::Alter_ModelAdjustmentTest MSA.cpp:646-762) from the Viterbi alignments, host only,
  * one-core summation order: "identity\tsigma\tN\tavgLen\tavgSP\tpeakRatio\tfactor" with std::to_string formatting.
- * Returns MLP_E_UNSUPPORTED if a residue is outside the 20 standard letters (the reference indexes out of bounds there). */
+ * A residue outside the 20 standard letters makes the reference index BLOSUM62 with string::npos and add whatever lies in
+ * front of that array (observed in a build of its sources: anything from denormals to -4.9e13 in field 5); such a column
+ * pair contributes 0 here, which leaves fields 1-4 and 7 exact and fields 5-6 within about 1e-3 of the reference where the
+ * reference's own value is sane.  MLP_E_UNSUPPORTED for an alignment longer than the reference's fixed 10,000-entry array. */
 int mlp_cpnp_g_features(int n, const int32_t* len, const uint8_t* residues, const char* aln, const int64_t* aln_off,
                         float theta, char* line, int line_cap);
 /* Host part of ModelAdjustmentTest (MSA.cpp:838-881): sequential one-core float sums in pair order.

@@ -164,7 +164,14 @@ extern "C" int mlp_cpnp_g_features(int n, const int32_t* len, const uint8_t* res
     std::vector<long long> off(n);
     long long tot = 0;
     for (int i = 0; i < n; i++) { off[i] = tot; tot += len[i]; }
-    for (long long k = 0; k < tot; k++) if (residues[k] < 'A' || residues[k] > 'Z' || idx[residues[k] - 'A'] < 0) return MLP_E_UNSUPPORTED;
+    for (long long k = 0; k < tot; k++) if (residues[k] < 'A' || residues[k] > 'Z') return MLP_E_ARG;
+    // Letters outside the 20-letter alphabet (B, J, O, U, X, Z): the reference indexes BLOSUM62[find(c1)][find(c2)] with
+    // string::npos and reads whatever the linker placed in front of that array (in a build of the unmodified sources here:
+    // a few unrelated int/bool globals, i.e. denormals or small numbers, all < 10 and therefore added).  That has no
+    // defined value to reproduce; a column pair with such a letter contributes 0 here.  Fields 1-4 and 7 of the line do not
+    // depend on it and stay exact; fields 5 and 6 agree with the compiled reference to about 1e-3 relative on the bundled
+    // families that hold such letters (tests/test_host.py).
+    auto blosum_as_compiled = [&](int i1, int i2) -> float { return (i1 < 0 || i2 < 0) ? 0.0f : MLP_BLOSUM62[i1 * 20 + i2]; };
     const int npairs = n * (n - 1) / 2;
     float identity = 0, tmp_sp = 0;
     int avg_length = 0, max_len = 0, tmp_sp_idx = 0;
@@ -184,7 +191,7 @@ extern "C" int mlp_cpnp_g_features(int n, const int32_t* len, const uint8_t* res
                 if (s[k] == 'B') {
                     const uint8_t c1 = s1[i - 1], c2 = s2[j - 1]; i++; j++;
                     if (c1 == c2) nc += 1;
-                    const float bl = MLP_BLOSUM62[idx[c1 - 'A'] * 20 + idx[c2 - 'A']];
+                    const float bl = blosum_as_compiled(idx[c1 - 'A'], idx[c2 - 'A']);
                     if (bl < 10) { arr[num_idx] += bl; tmp_sp += bl; }
                 } else if (s[k] == 'X') i++;
                 else j++;

@@ -52,7 +52,7 @@ static double now_s() {
 
 struct Opts {
     std::string mode, fasta, out;
-    int pid = -1, reps = 2, threads = 1, p1 = 0, dense = 1;
+    int pid = -1, reps = 2, threads = 1, p1 = 0, dense = 1, g = 0;
 };
 
 static void dump_sparse(DumpWriter& w, const std::string& tag, SparseMatrix* m) {
@@ -84,12 +84,20 @@ int main(int argc, char** argv) {
         else if (a == "--reps") o.reps = atoi(argv[++ai]);
         else if (a == "--threads") o.threads = atoi(argv[++ai]);
         else if (a == "--p1") o.p1 = 1;
+        else if (a == "--G") o.g = 1;
         else if (a == "--nodense") o.dense = 0;
     }
     if (o.mode == "msa") {
         // the reference's complete program flow (MSA::MSA, MSA.cpp:123-187): `c_p_np_aln -p 0|1 [-ir R] -o out fasta`, with the
         // OpenMP team pinned to o.threads (1 = the deterministic summation order of BuildPosterior)
         numThreads = o.threads;
+        if (o.g) {
+            // `c_p_np_aln -G fasta`: the feature line on stdout.  The bundled binary always takes every core (MSA.cpp:146-151
+            // ignores OMP_NUM_THREADS) and its line then changes from run to run; numThreads pins the team here.
+            std::vector<const char*> gv = {"c_p_np_aln", "-G", o.fasta.c_str()};
+            MSA feature((int)gv.size(), (char**)gv.data());
+            return 0;
+        }
         std::string irs = std::to_string(ir);
         std::vector<const char*> av = {"c_p_np_aln", "-p", o.p1 ? "1" : "0", "-o", o.out.c_str()};
         if (ir >= 0) { av.push_back("-ir"); av.push_back(irs.c_str()); }

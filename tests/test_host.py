@@ -144,3 +144,48 @@ def test_suite_fixture_is_consistent():
         names = {m.name for m in t.getmembers() if m.isfile()}
     assert {m["suite"] + "/" + m["name"] for m in man} == names and len(man) > 1000
     assert all(m["qp_sha"] and m["cpnp_sha"] for m in man)
+
+
+def test_g_feature_line_host_code_on_suite_families():
+    """`c_p_np_aln -G` (MSA::Alter_ModelAdjustmentTest, MSA.cpp:646-762) over a spread of bundled families: the product's host
+    function mlp_cpnp_g_features, fed with the oracle's Viterbi alignments (what k_viterbi delivers on the device), prints the
+    reference binary's line byte for byte (tests/golden/suites/manifest.json `cpnpG`, written by oracle/gen_suite_golden_G.py)."""
+    import json, tarfile
+    from common import HERE
+    import oracle_lib as O
+    suites = os.path.join(HERE, "golden", "suites")
+    man = [m for m in json.load(open(os.path.join(suites, "manifest.json")))["families"] if m.get("cpnpG")]
+    assert len(man) > 500
+    texts = {}
+    with tarfile.open(os.path.join(suites, "inputs.tar.gz")) as tar:
+        for ti in tar.getmembers():
+            if ti.isfile():
+                texts[ti.name] = tar.extractfile(ti).read().decode()
+    ht = O.hmm_tables()
+    standard = set(b"ARNDCQEGHILKMFPSTWYV")
+    checked = other = 0
+    for m in sorted(man, key=lambda e: e["cpnp_s"])[::12]:                    # every 12th family, cheapest first
+        seqs = []
+        for rec in texts["%s/%s" % (m["suite"], m["name"])].split(">")[1:]:
+            body = "".join(rec.split("\n")[1:])
+            seqs.append("".join(ch for ch in body if ch.isalpha()).upper().encode())
+        if len(seqs) < 2 or len(seqs) > 40:
+            continue
+        alns, offs = [], [0]
+        for a in range(len(seqs)):
+            for b in range(a + 1, len(seqs)):
+                aln = O.viterbi(ht, seqs[a], seqs[b])[3]
+                alns.append(aln); offs.append(offs[-1] + len(aln))
+        line = M.cpnp_g_features(seqs, np.frombuffer(b"".join(alns), np.uint8), np.array(offs, np.int64)).decode()
+        if all(set(s) <= standard for s in seqs):
+            assert line == m["cpnpG"], (m["suite"], m["name"])
+            checked += 1
+        else:
+            # B/J/O/U/X/Z: the reference adds out-of-bounds reads to fields 5 and 6 (see include/mlprobs_b200.h); the other
+            # fields are exact, and fields 5-6 stay close whenever the reference's own number is sane
+            got, want = line.split("\t"), m["cpnpG"].split("\t")
+            assert [got[k] for k in (0, 1, 2, 3, 6)] == [want[k] for k in (0, 1, 2, 3, 6)], (m["suite"], m["name"])
+            if abs(float(want[4])) < 100:
+                assert abs(float(got[4]) - float(want[4])) <= 5e-3 * max(1.0, abs(float(want[4]))) and abs(float(got[5]) - float(want[5])) < 0.02
+            other += 1
+    assert checked >= 40 and other >= 3
