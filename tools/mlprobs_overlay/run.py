@@ -40,7 +40,7 @@ def assemble(mlprobs, binaries):
     return work
 
 
-def run(mlprobs, binaries, fasta, out, seed=None, keep=False, quiet=False):
+def run(mlprobs, binaries, fasta, out, seed=None, keep=False, quiet=False, one_core=False):
     work = assemble(os.path.abspath(mlprobs), binaries)
     env = dict(os.environ)
     env["PYTHONPATH"] = HERE + os.pathsep + env.get("PYTHONPATH", "")
@@ -48,7 +48,10 @@ def run(mlprobs, binaries, fasta, out, seed=None, keep=False, quiet=False):
         env["MLP_CPNP_SEED"] = str(seed)          # c_p_np_aln_b200 -p 1: stands in for the clock the reference seeds with
     try:
         # the driver passes file names through a shell unquoted: use plain absolute paths
-        r = subprocess.run([sys.executable, "MLProbs.py", os.path.abspath(fasta), os.path.abspath(out)], cwd=work, env=env,
+        # one_core: the reference c_p_np_aln sizes its OpenMP team from the cores it may run on (it overrides OMP_NUM_THREADS)
+        # and both its -G line and its refinement change from run to run with more than one thread; taskset makes it repeatable
+        pin = ["taskset", "-c", "0"] if one_core and shutil.which("taskset") else []
+        r = subprocess.run(pin + [sys.executable, "MLProbs.py", os.path.abspath(fasta), os.path.abspath(out)], cwd=work, env=env,
                            capture_output=quiet, text=True)
         return r.returncode, (r.stdout if quiet else "")
     finally:
@@ -62,8 +65,9 @@ if __name__ == "__main__":
     ap.add_argument("--binaries", choices=("b200", "reference"), default="b200")
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--one-core", action="store_true", help="pin the run to one core (repeatable output with the reference programs)")
     ap.add_argument("fasta")
     ap.add_argument("out")
     a = ap.parse_args()
-    rc, _ = run(a.mlprobs, a.binaries, a.fasta, a.out, a.seed, a.keep)
+    rc, _ = run(a.mlprobs, a.binaries, a.fasta, a.out, a.seed, a.keep, one_core=a.one_core)
     sys.exit(rc)
