@@ -37,5 +37,8 @@ if __name__ == "__main__":
         k = (m["suite"], m["name"])
         if k in res:
             m["cpnpG_sha"], m["cpnpG"] = res[k]
+            # exact = only the 20 standard letters occur (otherwise fields 5-6 of the reference's line are out-of-bounds reads)
+            letters = set(ch.upper() for line in open(os.path.join(REF, m["suite"], "in", m["name"])) if not line.startswith(">") for ch in line if ch.isalpha())
+            m["cpnpG_exact"] = bool(letters <= set("ARNDCQEGHILKMFPSTWYV"))
     json.dump(man, open(MAN, "w"), indent=0)
     print("done: %d families, %d without a line, %.0f s" % (len(res), sum(1 for v in res.values() if v[0] is None), time.time() - t0))

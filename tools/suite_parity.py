@@ -23,10 +23,13 @@ def run(report_path=None, suites=None, tools=None):
             continue
         fams = [m for m in man if m["suite"] == suite]
         for tool, exe, args, key in (("quickprobs", "quickprobs_b200", [], "qp_sha"), ("c_p_np_aln -p 0", "c_p_np_aln_b200", ["-p", "0"], "cpnp_sha"),
-                                     ("c_p_np_aln -p 1", "c_p_np_aln_b200", ["-p", "1", "--seed", seed], "cpnp1_sha")):
+                                     ("c_p_np_aln -p 1", "c_p_np_aln_b200", ["-p", "1", "--seed", seed], "cpnp1_sha"),
+                                     ("c_p_np_aln -G", "c_p_np_aln_b200", ["-G"], "cpnpG_sha")):
             if tools and key not in tools:
                 continue
-            fams = [m for m in man if m["suite"] == suite and key in m]
+            if key == "cpnpG_sha" and not (tools and key in tools):
+                continue                  # the feature-line run is opt-in (added at the end of round 1, not yet run on a GPU)
+            fams = [m for m in man if m["suite"] == suite and key in m and (key != "cpnpG_sha" or m.get("cpnpG_exact"))]
             if not fams:
                 continue
             outdir = os.path.join(tmp, "out_%s_%s" % (suite, key))
