@@ -99,8 +99,10 @@ int run_file(mlp_ctx* ctx, const std::vector<std::string>& infiles, const std::s
 
     int rc = 0;
     if (n < 2) {
-        if (!getpid) write_mfa(out, in.headers[0], in.seqs[0].data(), (int)in.seqs[0].size());
-        return getpid ? 1 : 0;
+        // one sequence: the reference crashes (-p 0/1: SIGSEGV, -G: SIGFPE) with nothing on stdout, and MLProbs reads the
+        // non-zero status as "fall back to quickprobs" (utils/classifier_c_p_np_aln.py:40-41): same contract here
+        std::cerr << "ERROR: at least two sequences are required." << std::endl;
+        return 1;
     }
     std::vector<int32_t> len(n);
     std::string cat;
@@ -213,6 +215,7 @@ int main(int argc, char** argv) {
         Input probe;
         for (const std::string& f : infiles) load_mfa(f, probe);
         if (probe.seqs.empty()) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
+        if (probe.seqs.size() < 2) { std::cerr << "ERROR: at least two sequences are required." << std::endl; return 1; }   // see run_file
     }
     mlp_ctx* ctx = nullptr;
     int rc = mlp_create(device, &ctx);                 // no CUDA device -> stop: nothing falls back to the CPU

@@ -150,6 +150,11 @@ def test_cpnp_cli_input_errors_match_the_reference_messages(tmp_path):
     assert r.returncode == 1 and "Must specify a value after option" in r.stderr
     r = subprocess.run([CPNP], capture_output=True, text=True)
     assert r.returncode != 0 and r.stdout == ""
+    single = tmp_path / "single.fa"
+    single.write_text(">a\nACDEFGHIK\n")
+    for mode in (["-p", "0"], ["-p", "1"], ["-G"]):      # the reference crashes here (exit 139 / 136, empty stdout); MLProbs falls back
+        r = subprocess.run([CPNP] + mode + [str(single)], capture_output=True, text=True)
+        assert r.returncode == 1 and r.stdout == "" and "at least two sequences" in r.stderr
     # option handling as MSA::ParseParams: unknown option and -version end with status 1, the options the reference parses
     # without any effect on its output are accepted
     ok = tmp_path / "ok.fa"
