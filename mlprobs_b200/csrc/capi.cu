@@ -284,6 +284,15 @@ static int ensure_sets(mlp_ctx* ctx) {
     return MLP_OK;
 }
 
+// The context's stream is cudaStreamNonBlocking: a legacy-stream cudaMemcpy is NOT ordered against work queued on it.
+// Every host read of a set's cursor goes through the stream itself.
+int read_cursor(mlp_ctx* ctx, int which, unsigned long long* out) {
+    CK(cudaMemcpyAsync(out, ctx->set[which].cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MLP_OK;
+}
+#define END_EXCHANGE(ctx) do { if ((ctx)->exch_pending) { const int rce__ = mlp_exchange_end(ctx); if (rce__ != MLP_OK) return rce__; } } while (0)
+
 // Re-allocate the cell pool of one set to new_cap cells, keeping the first `keep` cells.
 int grow_cells(mlp_ctx* ctx, int which, long long new_cap, unsigned long long keep) {
     int2* fresh = nullptr;
@@ -434,7 +443,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         CK(cudaMemsetAsync(ctx->d_pout, 0, batch.size() * sizeof(PairOut), ctx->stream));
 
         unsigned long long cursor_before = 0;
-        CK(cudaMemcpy(&cursor_before, ctx->set[ctx->cur].cursor, sizeof(cursor_before), cudaMemcpyDeviceToHost));
+        { int rcc = read_cursor(ctx, ctx->cur, &cursor_before); if (rcc != MLP_OK) return rcc; }
         for (int attempt = 0;; ++attempt) {
         KArgs a = {};
         a.tasks = ctx->d_tasks; a.ntasks = (int)batch.size(); a.counter = ctx->d_counter; a.pout = ctx->d_pout;
@@ -499,18 +508,19 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         }
         if (err & 2) {
             unsigned long long used = 0;
-            CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+            { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
             const double done_frac = (double)(pos) / (double)tasks_in.size();
             long long want = (long long)((double)used / std::max(done_frac, 1e-3) * 1.15) + (1 << 20);
             want = std::max(want, ctx->set[ctx->cur].cap * 2);
             int rc2 = grow_cells(ctx, ctx->cur, want, cursor_before);
             if (rc2 != MLP_OK) return rc2;
         }
-        CK(cudaMemcpy(ctx->set[ctx->cur].cursor, &cursor_before, sizeof(cursor_before), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(ctx->set[ctx->cur].cursor, &cursor_before, sizeof(cursor_before), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         }
         if (!planned && pos < tasks_in.size()) {
             unsigned long long used = 0;
-            CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+            { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
             double done_cost = 0, all_cost = 0;
             for (size_t k = 0; k < tasks_in.size(); ++k) { const double c = (double)std::min(tasks_in[k].L1, tasks_in[k].L2); all_cost += c; if (k < pos) done_cost += c; }   // kept cells scale with the shorter length
             const long long want = (long long)((double)(used - cursor_before) * (all_cost / std::max(done_cost, 1.0)) * 1.25) + (long long)cursor_before + (1 << 20);
@@ -669,7 +679,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     ctx->stats.ms_total = ms;
     unsigned long long cur = 0;
-    CK(cudaMemcpy(&cur, ctx->set[0].cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+    { int rcc = read_cursor(ctx, 0, &cur); if (rcc != MLP_OK) return rcc; }
     ctx->stats.nnz = (int64_t)(cur / 2);
     ctx->flavour_of_set = flavour;
     return MLP_OK;
@@ -692,7 +702,7 @@ extern "C" int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_ma
     std::vector<PairTask> one;
     for (const PairTask& t : ctx->all_pairs) if (t.a == a && t.b == b) one.push_back(t);
     unsigned long long cursor_save = 0;
-    CK(cudaMemcpy(&cursor_save, ctx->set[ctx->cur].cursor, sizeof(cursor_save), cudaMemcpyDeviceToHost));
+    { int rcc = read_cursor(ctx, ctx->cur, &cursor_save); if (rcc != MLP_OK) return rcc; }
     mlp_stage_stats keep = ctx->stats;
     rc = run_posterior_tasks(ctx, flavour == MLP_CPNP_P1 ? MLP_CPNP_P1 : flavour, model_mask, 0.01f, one, d, d + cells, d + 2 * cells, d + 3 * cells);
     ctx->stats = keep;
@@ -748,6 +758,7 @@ extern "C" int mlp_get_csr(mlp_ctx* ctx, int a, int b, int32_t* row_ptr, int32_t
 
 extern "C" int mlp_total_cells(mlp_ctx* ctx, int64_t* cells) {
     if (!ctx || !cells) return MLP_E_ARG;
+    END_EXCHANGE(ctx);
     if (!ctx->have_sets) return MLP_E_STATE;
     cudaSetDevice(ctx->device);
     std::vector<int> cnt((size_t)ctx->n * ctx->n);
@@ -760,6 +771,7 @@ extern "C" int mlp_total_cells(mlp_ctx* ctx, int64_t* cells) {
 
 extern "C" int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* row_ptr, int32_t* col, float* val) {
     if (!ctx) return MLP_E_ARG;
+    END_EXCHANGE(ctx);
     if (!ctx->have_sets) return MLP_E_STATE;
     cudaSetDevice(ctx->device);
     const int n = ctx->n;
@@ -778,7 +790,7 @@ extern "C" int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* ro
     std::vector<int2> cells;
     unsigned long long used = 0;
     if (col || val) {
-        CK(cudaMemcpy(&used, s.cursor, sizeof(used), cudaMemcpyDeviceToHost));
+        { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
         used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
         cells.resize(used);
         if (used) CK(cudaMemcpy(cells.data(), s.cells, used * sizeof(int2), cudaMemcpyDeviceToHost));
@@ -803,13 +815,14 @@ extern "C" int mlp_get_csr_bulk(mlp_ctx* ctx, int64_t* nnz_per_pair, int32_t* ro
 
 extern "C" int mlp_csr_layout(mlp_ctx* ctx, int64_t* rp_off, int64_t* rp_total, int64_t* cells_used) {
     if (!ctx) return MLP_E_ARG;
+    END_EXCHANGE(ctx);
     if (!ctx->have_sets) return MLP_E_STATE;
     cudaSetDevice(ctx->device);
     if (rp_off) for (size_t k = 0; k < ctx->rp_off_h.size(); ++k) rp_off[k] = ctx->rp_off_h[k];
     if (rp_total) *rp_total = ctx->rp_total;
     if (cells_used) {
         unsigned long long used = 0;
-        CK(cudaMemcpy(&used, ctx->set[ctx->cur].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+        { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
         *cells_used = (int64_t)std::min<unsigned long long>(used, (unsigned long long)ctx->set[ctx->cur].cap);
     }
     return MLP_OK;
@@ -823,7 +836,7 @@ extern "C" int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, i
     const CsrSetDev& s = ctx->set[ctx->cur];
     const size_t nn = (size_t)ctx->n * ctx->n;
     unsigned long long used = 0;
-    CK(cudaMemcpy(&used, s.cursor, sizeof(used), cudaMemcpyDeviceToHost));
+    { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
     used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
     if (nz_off) { CK(cudaMemcpyAsync(nz_off, s.nz_off, nn * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)nn * 8; }
     if (nz_cnt) { CK(cudaMemcpyAsync(nz_cnt, s.nz_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += (int64_t)nn * 4; }
@@ -861,7 +874,7 @@ extern "C" int mlp_get_csr_packed(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt
     const int other = 1 - ctx->cur;
     const size_t nn = (size_t)ctx->n * ctx->n;
     unsigned long long used = 0;
-    CK(cudaMemcpy(&used, s.cursor, sizeof(used), cudaMemcpyDeviceToHost));
+    { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
     used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
     // scratch: the cell pool of the set that is not current (dead after a relaxation, unused before one)
     const unsigned long long used_even = (used + 1) & ~1ull;
@@ -956,7 +969,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     }
     {   // the relaxed set can only shrink: size the output pool to what the input set holds
         unsigned long long used = 0;
-        CK(cudaMemcpy(&used, ctx->set[in].cursor, sizeof(used), cudaMemcpyDeviceToHost));
+        { int rcc = read_cursor(ctx, in, &used); if (rcc != MLP_OK) return rcc; }
         if ((long long)used + 1024 > ctx->set[out].cap) { rc = grow_cells(ctx, out, (long long)used + 1024, 0); if (rc != MLP_OK) return rc; }
     }
     CK(cudaMemcpyAsync(ctx->d_tasks, tasks.data(), tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
@@ -1004,7 +1017,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     ctx->cur = out;
     ctx->stats.pairs = (int64_t)tasks.size();
     unsigned long long cur = 0;
-    CK(cudaMemcpy(&cur, ctx->set[out].cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+    { int rcc = read_cursor(ctx, out, &cur); if (rcc != MLP_OK) return rcc; }
     ctx->stats.nnz = (int64_t)(cur / 2);
     return MLP_OK;
 }

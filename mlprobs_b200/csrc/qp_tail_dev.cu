@@ -422,6 +422,7 @@ DeviceProfilePosterior& provider_of(mlp_ctx* ctx) {
 extern "C" int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const int32_t* left, const int32_t* right,
                                        int ref_iters, uint32_t ref_seed, char** rows_out, int32_t* aln_len) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }   // a split exchange must have landed before the set is read
     if (!rows_out || !aln_len) { ctx->err = "null output"; return MLP_E_ARG; }
     if (ctx->n < 1) { ctx->err = "no sequences"; return MLP_E_STATE; }
     if (ctx->n > 1) {
@@ -454,6 +455,7 @@ extern "C" int mlp_qp_finish_alignment(mlp_ctx* ctx, const float* weights, const
 extern "C" int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, const int32_t* left, const int32_t* right,
                                          int refine_reps, int pid, char** rows_out, int32_t* aln_len, int32_t* order_out) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }   // a split exchange must have landed before the set is read
     if (!rows_out || !aln_len) { ctx->err = "null output"; return MLP_E_ARG; }
     if (ctx->n < 2) { ctx->err = "no sequences"; return MLP_E_STATE; }
     if (!iweights || !left || !right) { ctx->err = "weights and tree required"; return MLP_E_ARG; }
@@ -485,6 +487,7 @@ extern "C" int mlp_cpnp_finish_alignment(mlp_ctx* ctx, const int32_t* iweights, 
 // sorted cells), the similar-set refinement after it runs its profile posteriors and MEA sweeps on the resident set.
 extern "C" int mlp_cpnp_np_finish_alignment(mlp_ctx* ctx, int refine_reps, int64_t seed, char** rows_out, int32_t* aln_len) {
     if (!ctx) return MLP_E_ARG;
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }   // a split exchange must have landed before the set is read
     if (!rows_out || !aln_len) { ctx->err = "null output"; return MLP_E_ARG; }
     if (ctx->n < 2) { ctx->err = "no sequences"; return MLP_E_STATE; }
     if (!ctx->have_sets || (ctx->flavour_of_set != MLP_CPNP_P0 && ctx->flavour_of_set != MLP_CPNP_P1)) { ctx->err = "no c_p_np_aln sparse set on the device"; return MLP_E_STATE; }

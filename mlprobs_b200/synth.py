@@ -58,3 +58,28 @@ def family_fast(n, length, seed=20220148, p_sub=0.5, p_del=0.02, p_ins=0.02):
             vals = root[:1]
         seqs.append(al[vals].tobytes())
     return seqs
+
+
+def family_clustered(n_clusters, per_cluster, length, seed=20220148, p_sub_root=0.45, p_sub_leaf=0.25, p_del=0.02, p_ins=0.02):
+    """A family with sub-families: every cluster root is a mutated copy of the family root and every member a mutated copy of
+    its cluster root, so the UPGMA guide tree has real subtrees (QuickProbs' consistency selectivity, ConsistencyStage.cpp:181-216,
+    accepts a third sequence only inside a <= 200-leaf subtree shared with both sequences of the pair).  Members are interleaved
+    (member k of cluster c is sequence k * n_clusters + c) so that input order carries no cluster structure."""
+    rng = np.random.default_rng(seed)
+    bg = BACKGROUND / BACKGROUND.sum()
+    al = np.frombuffer(ALPHABET, np.uint8)
+
+    def mutate(src, p_sub):
+        out = []
+        for r in src:
+            if rng.random() < p_del:
+                continue
+            out.append(int(rng.choice(20, p=bg)) if rng.random() < p_sub else int(r))
+            if rng.random() < p_ins:
+                out.extend(int(x) for x in rng.choice(20, size=int(rng.geometric(0.5)), p=bg))
+        return out or [int(src[0])]
+
+    root = [int(x) for x in rng.choice(20, size=length, p=bg)]
+    croots = [mutate(root, p_sub_root) for _ in range(n_clusters)]
+    members = [[mutate(croots[c], p_sub_leaf) for _ in range(per_cluster)] for c in range(n_clusters)]
+    return [al[np.array(members[c][k])].tobytes() for k in range(per_cluster) for c in range(n_clusters)]

@@ -140,8 +140,69 @@ def run_qp(name, fasta, full, dense):
     print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def run_qp_compact(name, seqs):
+    """Large synthetic family (mlprobs_b200.synth.family_clustered) where QuickProbs' selectivity really filters third
+    sequences: the dump (gigabytes) is streamed once and only per-pair nnz + ONE combined CRC32 (row pointers | columns |
+    values, in that order) per tag is kept, for the tags s0 (after the posterior stage), sF and tF (after consistency,
+    both orientations), plus distances, weights and subtree distances."""
+    import struct
+    from _dumpfmt import _DT
+    n = len(seqs)
+    P = {ab: p for p, ab in enumerate(pairs(n))}
+    out = {"n": np.array([n], np.int32), "lens": np.array([len(x) for x in seqs], np.int32),
+           "residues": np.frombuffer(b"".join(seqs), np.uint8).copy()}
+    tags = ("s0", "sF", "tF")
+    nnz = {t: np.zeros(len(P), np.int32) for t in tags}
+    part = {t: {} for t in tags}
+    comb = {t: np.zeros(len(P), np.uint32) for t in tags}
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "in.fa"); dump = os.path.join(td, "d.bin")
+        with open(fa, "w") as f:
+            for i, x in enumerate(seqs): f.write(">s%05d\n%s\n" % (i, x.decode()))
+        subprocess.check_call([QP, "dump", fa, dump, "--threads", "8", "--nodense"], stdout=subprocess.DEVNULL)
+        with open(dump, "rb") as f:
+            while True:
+                h = f.read(4)
+                if len(h) < 4: break
+                (nl,) = struct.unpack("<I", h)
+                key = f.read(nl).decode(); dt = _DT[f.read(1)]
+                (nd,) = struct.unpack("<I", f.read(4))
+                dims = struct.unpack("<%dQ" % nd, f.read(8 * nd))
+                cnt = int(np.prod(dims)) if nd else 1
+                arr = np.frombuffer(f.read(cnt * np.dtype(dt).itemsize), dtype=dt).reshape(dims)
+                if key in ("distances", "weights", "seldist", "cons.iterations", "cons.selfweight"):
+                    out[key] = arr.copy()
+                elif key.startswith("pair."):
+                    parts = key.split(".")
+                    if len(parts) != 5: continue                       # pair.a.b.dist: already in `distances`
+                    _, a, b, tag, what = parts
+                    if tag not in tags or what == "code": continue     # the value already is code / 65535
+                    p = P[(int(a), int(b))]
+                    part[tag].setdefault(p, {})[what] = arr.astype(np.int32) if what == "col" else arr
+                    got = part[tag][p]
+                    if len(got) == 3:
+                        nnz[tag][p] = len(got["col"])
+                        c = zlib.crc32(np.ascontiguousarray(got["rowptr"]).tobytes())
+                        c = zlib.crc32(np.ascontiguousarray(got["col"]).tobytes(), c)
+                        comb[tag][p] = zlib.crc32(np.ascontiguousarray(got["val"]).tobytes(), c) & 0xffffffff
+                        del part[tag][p]
+    for t in tags:
+        out["digest.%s.nnz" % t] = nnz[t]; out["digest.%s.crc" % t] = comb[t]
+    sd = out["seldist"].reshape(n, n)
+    acc = [(np.maximum(sd[a], sd[b]) <= 200).sum() - 2 for a, b in list(P)[::97]]
+    print("accepted third sequences per pair (sample): min %d max %d mean %.1f of %d" % (min(acc), max(acc), float(np.mean(acc)), n - 2))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["qp_syn400"]:
+        # N = 400 x L ~ 120, eight sub-families of 50: most third sequences are rejected by the selectivity filter
+        sys.path.insert(0, ROOT)
+        from mlprobs_b200 import synth
+        run_qp_compact("qp_syn400", synth.family_clustered(8, 50, 120, seed=20220148 + 7))
+        sys.exit(0)
     f = lambda b, x: os.path.join(REF, b, "in", x)
     # tiny, everything stored (dense posteriors of all three models)
     run_cpnp("cpnp_sup139_mix", f("sabre", "sup_139"), True, True, pid=0)

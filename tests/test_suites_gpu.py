@@ -27,3 +27,22 @@ def test_ox_families_non_progressive_program_is_byte_identical():
     assert rep["mismatches"] == [] and rep["failures"] == []
     for key, v in rep["suites"].items():
         assert v["identical"] == v["families"] - v["reference_failed"] > 0, (key, v)
+
+
+def test_feature_line_G_is_byte_identical_on_the_standard_letter_families():
+    """c_p_np_aln -G (the line classifier 1 consumes, MSA.cpp:646-762) against the one-thread reference harness, ox + oxx."""
+    import suite_parity
+    rep = suite_parity.run(None, suites=("ox", "oxx"), tools=("cpnpG_sha",))
+    assert rep["suites"], "no -G reference lines in the manifest"
+    assert rep["mismatches"] == [] and rep["failures"] == []
+    for key, v in rep["suites"].items():
+        assert v["identical"] == v["families"] - v["reference_failed"] > 0, (key, v)
+
+
+def test_realignment_regions_are_byte_identical_to_the_reference_quickprobs():
+    """BASELINE config #4: the 112 region files MLProbs' unmodified driver handed to quickprobs (utils/do_realign.py:52-63),
+    realigned by quickprobs_b200 in directory mode (one CUDA context)."""
+    import region_parity
+    rep = region_parity.run(None)
+    assert rep["different"] == [] and rep["no_output"] == [], rep
+    assert rep["identical"] == rep["regions"] - rep["reference_failed"] > 0
