@@ -75,7 +75,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
-    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq);
+    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -177,25 +177,28 @@ extern "C" int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, i
 extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* residues) {
     if (!ctx || n < 2 || !len || !residues) return MLP_E_ARG;
     cudaSetDevice(ctx->device);
+    // validate everything before touching the context: a rejected family must leave the previous one intact
+    long long tot = 0;
+    for (int i = 0; i < n; ++i) {
+        if (len[i] < 1 || len[i] > 65535) { ctx->err = "sequence length must be in 1..65535"; return MLP_E_ARG; }
+        tot += len[i];
+    }
+    for (long long k = 0; k < tot; ++k)
+        if (residues[k] < 'A' || residues[k] > 'Z') { ctx->err = "residues must be upper-case letters"; return MLP_E_ARG; }
+    if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     // same family shape as before (same n and lengths): the pooled layout is unchanged, keep the device pools
     const bool same_layout = ctx->have_sets && ctx->n == n && std::equal(len, len + n, ctx->len.begin());
     if (!same_layout) ctx->have_sets = false;        // the pools themselves stay: ensure_sets re-uses them when the new family fits
     ctx->flavour_of_set = -1;
+    ctx->set_partial = ctx->dist_partial = false;
     ctx->n = n;
     ctx->len.assign(len, len + n);
     ctx->seq_off.resize(n);
-    long long tot = 0;
-    for (int i = 0; i < n; ++i) {
-        if (len[i] < 1 || len[i] > 65535) { ctx->err = "sequence length must be in 1..65535"; return MLP_E_ARG; }
-        ctx->seq_off[i] = tot; tot += len[i];
-    }
+    tot = 0;
+    for (int i = 0; i < n; ++i) { ctx->seq_off[i] = tot; tot += len[i]; }
     ctx->total_res = tot;
     std::vector<uint8_t> codes(tot + 16, 0);
-    for (long long k = 0; k < tot; ++k) {
-        const uint8_t ch = residues[k];
-        if (ch < 'A' || ch > 'Z') { ctx->err = "residues must be upper-case letters"; return MLP_E_ARG; }
-        codes[k] = (uint8_t)(ch - 'A');
-    }
+    for (long long k = 0; k < tot; ++k) codes[k] = (uint8_t)(residues[k] - 'A');
     ctx->codes_h = codes;
     if (tot + 16 > ctx->res_cap) {
         free_dev(ctx->d_res); ctx->d_res = nullptr; ctx->res_cap = 0;
@@ -222,10 +225,9 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
             if (a != b) rp += len[a] + 2;
         }
     ctx->rp_total = rp;
-    ctx->rank = 0; ctx->world = 1;
-    ctx->owned = ctx->all_pairs;
-    ctx->relax_tasks.clear();
-    return MLP_OK;
+    // a context that belongs to a communicator (or was sharded by hand) keeps its shard for the next family
+    if (ctx->nccl_comm) { ctx->rank = ctx->comm_rank; ctx->world = ctx->comm_world; }
+    return mlp_set_shard(ctx, ctx->rank, ctx->world);
 }
 
 extern "C" int mlp_set_shard(mlp_ctx* ctx, int rank, int world) {
@@ -361,9 +363,28 @@ struct KernelTimer {
 };
 
 static int launch_one(mlp_ctx* ctx, int kernel, KArgs a, int ntasks, KernelTimer& kt, int stat_slot,
-                      cudaStream_t st = nullptr, int bps_cap = 0) {
+                      cudaStream_t st = nullptr, int bps_cap = 0, const std::vector<std::pair<int, int>>* cgroups = nullptr) {
     if (!st) st = ctx->stream;
     const int warps_per_cta = MLP_BLOCK / 32;
+    a.counter = ctx->d_counter + (kernel & 15);      // every kernel id has its own work-queue head (kernels may overlap)
+    if (cgroups && posterior_c_available(kernel, a)) {
+        // register-band kernels: one launch per run of tasks with the same columns-per-lane value (the batch is sorted by C)
+        kt.begin(stat_slot, st);
+        for (const auto& g : *cgroups) {
+            const int begin = g.second;
+            const int end = (&g == &cgroups->back()) ? ntasks : (&g)[1].second;
+            const int C = g.first;
+            int bps = std::min(posterior_c_max_blocks_per_sm(kernel, C), 16);
+            if (bps_cap > 0) bps = std::min(bps, bps_cap);
+            int grid = std::max(1, std::min(ctx->num_sms * bps, (end - begin + warps_per_cta - 1) / warps_per_cta));
+            CK(cudaMemsetAsync(a.counter, 0, sizeof(int), st));
+            a.task_begin = begin; a.ntasks = end;
+            CK(posterior_c_launch(kernel, C, a, grid, st));
+            ctx->stats.launches += 1;
+        }
+        kt.end(st);
+        return MLP_OK;
+    }
     const size_t smem = posterior_smem_bytes(kernel, a.Cmax, warps_per_cta);
     int bps = posterior_max_blocks_per_sm(kernel, smem);
     bps = std::min(bps, 16);
@@ -371,7 +392,6 @@ static int launch_one(mlp_ctx* ctx, int kernel, KArgs a, int ntasks, KernelTimer
     int grid = ctx->num_sms * bps;
     grid = std::min(grid, (ntasks + warps_per_cta - 1) / warps_per_cta);
     grid = std::max(grid, 1);
-    a.counter = ctx->d_counter + (kernel & 15);      // every kernel id has its own work-queue head (kernels may overlap)
     CK(cudaMemsetAsync(a.counter, 0, sizeof(int), st));
     kt.begin(stat_slot, st);
     CK(posterior_launch(kernel, a, grid, smem, st));
@@ -405,7 +425,9 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         max_elems = std::max(max_elems, (long long)t.nb * (t.L1 + 32) * t.C * 32);
     }
     if ((size_t)max_elems * bpe > budget) budget = (size_t)max_elems * bpe;   // a single pair must fit
-    const long long max_warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
+    // resident warps of the largest grid launch_one can choose (num_sms * 16 CTAs), never more than one warp per task
+    const long long max_warps = std::min<long long>((long long)ctx->num_sms * 16 * (MLP_BLOCK / 32),
+                                                    (((long long)tasks_in.size() + MLP_BLOCK / 32 - 1) / (MLP_BLOCK / 32)) * (MLP_BLOCK / 32));
     int stage_mult = 32;
     {
         int rc = ensure_warp_buffers(ctx, max_warps, maxL1, maxL2, need_edge, stage_mult);
@@ -423,6 +445,17 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             if (!batch.empty() && (size_t)(elems + e) * bpe > budget) break;
             t.off = elems; elems += e; Cmax = std::max(Cmax, t.C);
             batch.push_back(t); ++pos;
+        }
+        // the register-band kernels are compiled per columns-per-lane value: order the batch by C (stable, so the cost order
+        // survives inside a group) and remember where every group starts
+        std::stable_sort(batch.begin(), batch.end(), [](const PairTask& x, const PairTask& y) { return x.C > y.C; });
+        std::vector<std::pair<int, int>> cgroups;   // (C, first task)
+        {
+            long long o = 0;
+            for (size_t k = 0; k < batch.size(); ++k) {
+                batch[k].off = o; o += (long long)batch[k].nb * (batch[k].L1 + 32) * batch[k].C * 32;
+                if (cgroups.empty() || cgroups.back().first != batch[k].C) cgroups.push_back({batch[k].C, (int)k});
+            }
         }
         const size_t need = (size_t)elems * bpe + 256;
         if (need > ctx->scratch_bytes) {
@@ -478,8 +511,8 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         const int capP = fork ? (ctx->bps_part > 0 ? ctx->bps_part : 2) : 0;
         const int capH = fork ? (ctx->bps_hmm > 0 ? ctx->bps_hmm : 4) : 0;
         if (useP) {
-            if ((rc = launch_one(ctx, MLP_K_PART_FWD, a, nt, kt, MLP_K_PART_FWD, sp, capP)) != MLP_OK) return rc;
-            if ((rc = launch_one(ctx, MLP_K_PART_REV, a, nt, kt, MLP_K_PART_REV, sp, capP)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_PART_FWD, a, nt, kt, MLP_K_PART_FWD, sp, capP, &cgroups)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_PART_REV, a, nt, kt, MLP_K_PART_REV, sp, capP, &cgroups)) != MLP_OK) return rc;
         }
         if (useL) {
             // the local model's Z terms alias the partition layer: it must wait for the partition posterior
@@ -488,11 +521,11 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             if ((rc = launch_one(ctx, MLP_K_LOCAL_BWD, a, nt, kt, MLP_K_LOCAL_BWD)) != MLP_OK) return rc;
         }
         if (use5) {
-            if ((rc = launch_one(ctx, MLP_K_HMM_FWD, a, nt, kt, MLP_K_HMM_FWD, nullptr, useL ? 0 : capH)) != MLP_OK) return rc;
-            if ((rc = launch_one(ctx, MLP_K_HMM_BWD, a, nt, kt, MLP_K_HMM_BWD, nullptr, useL ? 0 : capH)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_HMM_FWD, a, nt, kt, MLP_K_HMM_FWD, nullptr, useL ? 0 : capH, &cgroups)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_HMM_BWD, a, nt, kt, MLP_K_HMM_BWD, nullptr, useL ? 0 : capH, &cgroups)) != MLP_OK) return rc;
         }
         if (fork && !useL) { CK(cudaEventRecord(ctx->ev_join, ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
-        if ((rc = launch_one(ctx, MLP_K_FINAL, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
+        if ((rc = launch_one(ctx, MLP_K_FINAL, a, nt, kt, MLP_K_FINAL, nullptr, 0, &cgroups)) != MLP_OK) return rc;
         if ((rc = launch_one(ctx, MLP_K_TRANSPOSE, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
         CK(cudaStreamSynchronize(ctx->stream));
         int err = 0;
@@ -500,6 +533,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         if (!err) break;
         // capacity miss: grow what overflowed and redo this batch (batches are idempotent once the cursor is rewound)
         cudaMemset(ctx->d_err, 0, sizeof(int));
+        if (err & 8) { ctx->err = "transpose met a column index outside its matrix (corrupt cell pool)"; return MLP_E_CUDA; }
         if (attempt >= 6) { ctx->err = "sparse capacity still exhausted after 6 growth attempts"; return MLP_E_CAPACITY; }
         if (err & 1) {
             stage_mult *= 4;
@@ -682,6 +716,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     { int rcc = read_cursor(ctx, 0, &cur); if (rcc != MLP_OK) return rcc; }
     ctx->stats.nnz = (int64_t)(cur / 2);
     ctx->flavour_of_set = flavour;
+    ctx->set_partial = ctx->dist_partial = (ctx->world > 1);
     return MLP_OK;
 }
 
@@ -701,17 +736,40 @@ extern "C" int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_ma
     CK(cudaMemset(d, 0, cells * 4 * sizeof(float)));
     std::vector<PairTask> one;
     for (const PairTask& t : ctx->all_pairs) if (t.a == a && t.b == b) one.push_back(t);
+    // The run goes through the live set: save what it overwrites (cursor, the pair's table entries, row pointers and distance)
+    // and put it back afterwards, so that a relaxed set survives a debug call.
     unsigned long long cursor_save = 0;
     { int rcc = read_cursor(ctx, ctx->cur, &cursor_save); if (rcc != MLP_OK) return rcc; }
+    const int n = ctx->n;
+    const size_t sAB = (size_t)a * n + b, sBA = (size_t)b * n + a;
+    CsrSetDev& S = ctx->set[ctx->cur];
+    long long off_save[2]; int cnt_save[2]; float dist_save[2];
+    std::vector<int> rpA(L1 + 2), rpB(L2 + 2);
+    CK(cudaMemcpy(&off_save[0], S.nz_off + sAB, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&off_save[1], S.nz_off + sBA, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&cnt_save[0], S.nz_cnt + sAB, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&cnt_save[1], S.nz_cnt + sBA, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&dist_save[0], ctx->d_dist + sAB, 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&dist_save[1], ctx->d_dist + sBA, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rpA.data(), S.rp_pool + ctx->rp_off_h[sAB], rpA.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rpB.data(), S.rp_pool + ctx->rp_off_h[sBA], rpB.size() * 4, cudaMemcpyDeviceToHost));
     mlp_stage_stats keep = ctx->stats;
     rc = run_posterior_tasks(ctx, flavour == MLP_CPNP_P1 ? MLP_CPNP_P1 : flavour, model_mask, 0.01f, one, d, d + cells, d + 2 * cells, d + 3 * cells);
     ctx->stats = keep;
+    float dist_new = 0.0f;
+    if (rc == MLP_OK) cudaMemcpy(&dist_new, ctx->d_dist + sAB, sizeof(float), cudaMemcpyDeviceToHost);
+    {
+        CsrSetDev& R = ctx->set[ctx->cur];   // the cell pool may have been re-allocated; the tables are the same arrays
+        cudaMemcpy(R.cursor, &cursor_save, 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(R.nz_off + sAB, &off_save[0], 8, cudaMemcpyHostToDevice); cudaMemcpy(R.nz_off + sBA, &off_save[1], 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(R.nz_cnt + sAB, &cnt_save[0], 4, cudaMemcpyHostToDevice); cudaMemcpy(R.nz_cnt + sBA, &cnt_save[1], 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_dist + sAB, &dist_save[0], 4, cudaMemcpyHostToDevice); cudaMemcpy(ctx->d_dist + sBA, &dist_save[1], 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(R.rp_pool + ctx->rp_off_h[sAB], rpA.data(), rpA.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(R.rp_pool + ctx->rp_off_h[sBA], rpB.data(), rpB.size() * 4, cudaMemcpyHostToDevice);
+    }
     if (rc == MLP_OK) {
         cudaMemcpy(merged, d, cells * sizeof(float), cudaMemcpyDeviceToHost);
         if (p_hmm5) cudaMemcpy(p_hmm5, d + cells, cells * sizeof(float), cudaMemcpyDeviceToHost);
         if (p_part) cudaMemcpy(p_part, d + 2 * cells, cells * sizeof(float), cudaMemcpyDeviceToHost);
         if (p_local) cudaMemcpy(p_local, d + 3 * cells, cells * sizeof(float), cudaMemcpyDeviceToHost);
-        if (distance) cudaMemcpy(distance, ctx->d_dist + (size_t)a * ctx->n + b, sizeof(float), cudaMemcpyDeviceToHost);
+        if (distance) *distance = dist_new;
     }
     cudaFree(d);
     return rc;
@@ -1015,6 +1073,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
         return MLP_E_CAPACITY;
     }
     ctx->cur = out;
+    ctx->set_partial = (ctx->world > 1);
     ctx->stats.pairs = (int64_t)tasks.size();
     unsigned long long cur = 0;
     { int rcc = read_cursor(ctx, out, &cur); if (rcc != MLP_OK) return rcc; }

@@ -70,7 +70,9 @@ struct mlp_ctx {
     float* d_weights = nullptr; float* d_seldist = nullptr; int weights_cap = 0;
     // nccl
     void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+    unsigned long long* d_xused = nullptr;               // per-rank cell counts of an exchange
     unsigned* d_xq = nullptr; size_t xq_cap = 0;          // packed wire buffer of the QuickProbs exchange
+    bool set_partial = false, dist_partial = false;       // sharded stage output not yet exchanged (set by posterior / relax, cleared by mlp_exchange)
     cudaEvent_t ev_dist = nullptr; bool exch_pending = false; unsigned long long exch_total = 0;   // split exchange (mlp_exchange_begin / _end)
     // stats
     mlp_stage_stats stats = {};

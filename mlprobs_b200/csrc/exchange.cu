@@ -127,6 +127,9 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     if (ctx->comm_world <= 1) return MLP_OK;
     if (ctx->exch_pending) { const int rc0 = mlp_exchange_end(ctx); if (rc0 != MLP_OK) return rc0; }
     if (!ctx->nccl_comm || !ctx->have_sets) { ctx->err = "mlp_comm_init and a posterior/relax stage must come first"; return MLP_E_STATE; }
+    // The merge is a SUM over ranks of tables whose foreign slots are zero: it is only correct on a set a sharded stage has
+    // just produced.  A set that is already complete (second call without a stage in between) is left alone.
+    if (!ctx->set_partial) return MLP_OK;
     cudaSetDevice(ctx->device);
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const int W = ctx->comm_world, R = ctx->comm_rank, n = ctx->n;
@@ -134,13 +137,13 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     cudaStream_t st = ctx->stream;
     CK(cudaEventRecord(ctx->ev[0], st));
     // 1. how many cells does every rank hold?
-    unsigned long long* d_used = nullptr;
-    CK(cudaMalloc(&d_used, (size_t)W * sizeof(unsigned long long)));
+    if (!ctx->d_xused) CK(cudaMalloc(&ctx->d_xused, 64 * sizeof(unsigned long long)));   // kept for the life of the context
+    if (W > 64) { ctx->err = "more than 64 ranks"; return MLP_E_ARG; }
+    unsigned long long* d_used = ctx->d_xused;
     NK(g_nccl.AllGather(ctx->set[cur].cursor, d_used, 1, ncclUint64, comm, st));
     std::vector<unsigned long long> used(W);
     CK(cudaMemcpyAsync(used.data(), d_used, (size_t)W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    cudaFree(d_used);
+    CK(cudaStreamSynchronize(st));   // the slab sizes decide the broadcast arguments: one host round trip per exchange
     std::vector<long long> base(W + 1, 0);
     for (int r = 0; r < W; ++r) base[r + 1] = base[r] + (long long)used[r];
     const long long total = base[W];
@@ -162,7 +165,11 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
         CK(cudaGetLastError());
     }
     // 3. fixed-layout tables: sum == union
-    NK(g_nccl.AllReduce(ctx->d_dist, ctx->d_dist, (size_t)n * n, ncclFloat32, ncclSum, comm, st));
+    // distances: only the posterior stage writes them (owned pairs, zeros elsewhere); after a relaxation every rank still holds
+    // the complete matrix from the first exchange and summing it again would multiply it by the world size
+    if (ctx->dist_partial) NK(g_nccl.AllReduce(ctx->d_dist, ctx->d_dist, (size_t)n * n, ncclFloat32, ncclSum, comm, st));
+    ctx->dist_partial = false;
+    ctx->set_partial = false;
     CK(cudaEventRecord(ctx->ev_dist, st));
     NK(g_nccl.AllReduce(ctx->set[cur].rp_pool, ctx->set[cur].rp_pool, (size_t)ctx->rp_total, ncclInt32, ncclSum, comm, st));
     NK(g_nccl.AllReduce(ctx->set[cur].nz_cnt, ctx->set[cur].nz_cnt, (size_t)n * n, ncclInt32, ncclSum, comm, st));

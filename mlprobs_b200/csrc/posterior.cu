@@ -928,7 +928,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_final_t(KArgs a) {
         if (lane == 0) {
             basecell = (long long)atomicAdd(a.out.cursor, (unsigned long long)nnz);
             a.out.nz_off[slotAB] = basecell;
-            a.out.nz_cnt[slotAB] = nnz;
+            a.out.nz_cnt[slotAB] = (staged <= a.stage_cap && basecell + nnz <= a.out.cap) ? nnz : 0;   // nothing written -> nothing published
             if (staged > a.stage_cap) atomicOr(a.err, 1);
             if (basecell + nnz > a.out.cap) atomicOr(a.err, 2);
         }
@@ -954,6 +954,10 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_transpose(KArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    // A capacity miss in the producing kernel (k_final / k_relax_blk) leaves pairs whose cells were never written: their
+    // columns are stale memory and must not be used as indices.  The host re-runs the batch after growing the pools, so
+    // the whole transpose is skipped as soon as the error word is set.
+    if (*reinterpret_cast<volatile int*>(a.err) != 0) return;
     for (long long ti = gw; ti < a.ntasks; ti += nw) {
         const PairTask t = a.tasks[ti];
         const long long sAB = (long long)t.a * a.n + t.b, sBA = (long long)t.b * a.n + t.a;
@@ -973,7 +977,9 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_transpose(KArgs a) {
         for (int j = lane; j <= t.L2 + 1; j += 32) trp[j] = 0;
         __syncwarp();
         for (int k = lane; k < nnz; k += 32) {
-            atomicAdd(&trp[a.out.cells[src + k].x + 1], 1);
+            const int col = a.out.cells[src + k].x;
+            if ((unsigned)col > (unsigned)t.L2) { atomicOr(a.err, 8); continue; }   // never index with a column outside the matrix
+            atomicAdd(&trp[col + 1], 1);
         }
         __syncwarp();
         // 2. inclusive scan over trp[2..L2+1] -> trp[j+1] = end of row j ; trp[j] = start of row j
@@ -998,7 +1004,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_transpose(KArgs a) {
             const bool ok = k < nnz;
             int col = 0, r = 0; int2 cf = make_int2(0, 0);
             if (ok) {
-                cf = a.out.cells[src + k]; col = cf.x;
+                cf = a.out.cells[src + k]; col = min(max(cf.x, 0), t.L2);
                 // binary search the row containing k: largest r with rp[r] <= k
                 int lo = row, hi = t.L1;
                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rp[mid] <= k) lo = mid; else hi = mid - 1; }
@@ -1039,7 +1045,56 @@ size_t posterior_smem_bytes(int kernel, int Cmax, int warps) {
 }
 
 cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
-    return cudaMemcpyToSymbolAsync(c_sc, &s, sizeof(DevScalars), 0, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_sc, &s, sizeof(DevScalars), 0, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = part_c_set_scalars(s, st);
+    if (e == cudaSuccess) e = hmm_c_set_scalars(s, st);
+    return e;
+}
+
+// ---- register-band kernels (one instantiation per columns-per-lane value)
+// developer knob: MLP_OLD_SWEEP = bit mask of kernels that use the round-1 shared-memory-band version (1 part_fwd, 2 part_rev, 4 hmm_fwd,
+// 8 hmm_bwd, 16 final), read at every launch so that a test can A/B inside one process
+static int old_sweeps() { const char* e = getenv("MLP_OLD_SWEEP"); return e ? atoi(e) : 0; }
+bool posterior_c_available(int kernel, const KArgs& a) {
+    if (a.dense) return false;
+    const int old = old_sweeps();
+    if ((kernel == MLP_K_PART_FWD && (old & 1)) || (kernel == MLP_K_PART_REV && (old & 2)) || (kernel == MLP_K_HMM_FWD && (old & 4)) ||
+        (kernel == MLP_K_HMM_BWD && (old & 8)) || (kernel == MLP_K_FINAL && (old & 16))) return false;
+    switch (kernel) {
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return a.flavour == 0;
+        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return true;
+        case MLP_K_FINAL: return a.flavour == 0 && a.mask == 3u;
+        default: return false;
+    }
+}
+size_t posterior_c_smem(int kernel) {
+    const int warps = MLP_BLOCK / 32;
+    switch (kernel) {
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES;
+        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return MLP_HMM_TABLE_BYTES + warps * 32;
+        case MLP_K_FINAL: return MLP_FINAL_TABLE_BYTES + warps * 16;
+        default: return 0;
+    }
+}
+static void (*c_kernel(int kernel, int C))(KArgs) {
+    switch (kernel) {
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return part_c_kernel(kernel, C);
+        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return hmm_c_kernel(kernel, C);
+        case MLP_K_FINAL: return final_c_kernel(C);
+        default: return nullptr;
+    }
+}
+int posterior_c_max_blocks_per_sm(int kernel, int C) {
+    void (*fn)(KArgs) = c_kernel(kernel, C);
+    int nb = 0;
+    if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, MLP_BLOCK, posterior_c_smem(kernel)) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+cudaError_t posterior_c_launch(int kernel, int C, const KArgs& a, int grid, cudaStream_t st) {
+    void (*fn)(KArgs) = c_kernel(kernel, C);
+    if (!fn) return cudaErrorInvalidValue;
+    fn<<<grid, MLP_BLOCK, posterior_c_smem(kernel), st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, cudaStream_t st) {

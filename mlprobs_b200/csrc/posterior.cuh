@@ -29,6 +29,7 @@ struct CsrSetDev {
 
 struct KArgs {
     const PairTask* tasks; int ntasks; int* counter;
+    int task_begin;        // register-band kernels (sweep_c.cuh) process tasks[task_begin .. ntasks): one launch per columns-per-lane value
     PairOut* pout;
     const uint8_t* residues; const long long* seq_off; int n;
     int flavour; unsigned mask; float cutoff;
@@ -75,3 +76,13 @@ size_t posterior_smem_bytes(int kernel, int Cmax, int warps);
 cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st);
 cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, cudaStream_t st);
 int posterior_max_blocks_per_sm(int kernel, size_t smem);
+// Register-band kernels, compiled per columns-per-lane value C (part_c.cu, hmm_c.cu, final_c.cu)
+bool posterior_c_available(int kernel, const KArgs& a);          // is there a C-specialised kernel for this launch?
+size_t posterior_c_smem(int kernel);
+int posterior_c_max_blocks_per_sm(int kernel, int C);
+cudaError_t posterior_c_launch(int kernel, int C, const KArgs& a, int grid, cudaStream_t st);
+cudaError_t part_c_set_scalars(const DevScalars& s, cudaStream_t st);
+cudaError_t hmm_c_set_scalars(const DevScalars& s, cudaStream_t st);
+void (*part_c_kernel(int kernel, int C))(KArgs);
+void (*hmm_c_kernel(int kernel, int C))(KArgs);
+void (*final_c_kernel(int C))(KArgs);

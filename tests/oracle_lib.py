@@ -149,11 +149,11 @@ def _seqs(seqs):
     return lens, off, b"".join(seqs)
 
 
-def posterior_stage(flavour, mask, ht, pt, seqs, cutoff=0.01, threads=1):
+def posterior_stage(flavour, mask, ht, pt, seqs, cutoff=0.01, threads=1, nz_cap=None):
     lens, off, cat = _seqs(seqs)
     n = len(seqs)
     dist = np.zeros((n, n), np.float32)
-    out = CsrSet(lens)
+    out = CsrSet(lens, nz_cap)
     rc = lib().orc_posterior_stage(flavour, mask, C.byref(ht), C.byref(pt), n, _p(lens), cat, _p(off),
                                    C.c_float(cutoff), _p(dist), C.byref(out.c), threads)
     return dist, out, rc

@@ -476,3 +476,99 @@ def test_full_size_family_properties():
     rev = {(int(c), j): float(v) for j in range(1, len(seqs[456]) + 1) for c, v in zip(c_ba[rp_ba[j]:rp_ba[j + 1]], v_ba[rp_ba[j]:rp_ba[j + 1]])}
     assert fwd == rev and len(fwd) > 0
     eng.close()
+
+
+# ------------------------------------------------------------------ capacity misses, reused contexts
+def _same_sets(eng, S, n):
+    for a in range(n):
+        for b in range(n):
+            if a != b:
+                rp, c, v = eng.csr(a, b)
+                orp, oc, ov = S.get(a, b)
+                assert np.array_equal(rp, orp) and np.array_equal(c, oc) and np.array_equal(v, ov), (a, b)
+
+
+def test_capacity_misses_are_retried_and_leave_earlier_families_intact():
+    """cutoff = 0 keeps every inner cell, so a pair stages far more hits than the per-warp staging buffer holds (error bit 1)
+    and the cell pool, configured tiny, overflows as well (error bit 2): k_final must publish nothing for the pairs it could
+    not write, k_transpose must not index with stale columns, and the re-run after growing must equal the oracle -- on a
+    context that has already served another family (directory mode re-uses the pools)."""
+    ht, pt = O.hmm_tables(), O.part_tables(O.QP)
+    first = synth.family(5, 60, seed=5)
+    eng = engine(M.QP, first)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    d1, S1, _ = O.posterior_stage(O.QP, 3, ht, pt, first)
+    _same_sets(eng, S1, len(first))
+    seqs = synth.family(7, 90, seed=9)
+    n = len(seqs)
+    eng.configure(0, 64)                       # 64 cells: every batch overflows the pool at least once
+    eng.set_sequences(seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.0)
+    all_cells = 2 * sum(len(a) * len(b) for i, a in enumerate(seqs) for b in seqs[i + 1:]) + 1024
+    dist, S, rc = O.posterior_stage(O.QP, 3, ht, pt, seqs, cutoff=0.0, nz_cap=all_cells)
+    assert rc == 0
+    np.testing.assert_array_equal(eng.distances(), dist)
+    _same_sets(eng, S, n)
+    # and the normal cutoff afterwards on the same context (pools now larger than needed)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    dist, S, _ = O.posterior_stage(O.QP, 3, ht, pt, seqs)
+    _same_sets(eng, S, n)
+    eng.close()
+
+
+def test_debug_pair_dense_leaves_a_relaxed_set_untouched():
+    seqs = synth.family(6, 70, seed=21)
+    n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    t = M.qp_guide_tree_ex(eng.distances())
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, 0.01)
+    before = [[eng.csr(a, b) for b in range(n) if b != a] for a in range(n)]
+    dist_before = eng.distances().copy()
+    eng.debug_pair_dense(M.QP, 3, 1, 4)
+    after = [[eng.csr(a, b) for b in range(n) if b != a] for a in range(n)]
+    for ra, rb in zip(before, after):
+        for x, y in zip(ra, rb):
+            assert all(np.array_equal(p, q) for p, q in zip(x, y))
+    np.testing.assert_array_equal(eng.distances(), dist_before)
+    eng.close()
+
+
+def test_qp_selectivity_fixture_400_sequences():
+    """Reference-pinned relaxation where QuickProbs' selectivity really rejects third sequences (ConsistencyStage.cpp:181-216):
+    400 synthetic sequences in eight sub-families, ref_qp dump reduced to per-pair nnz + CRC32(row pointers | columns | values)."""
+    import zlib
+    d = load_golden("qp_syn400")
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    np.testing.assert_array_equal(eng.distances(), d["distances"].reshape(n, n))
+    t = M.qp_guide_tree_ex(eng.distances())
+    np.testing.assert_array_equal(t["weights"], d["weights"])
+    np.testing.assert_array_equal(t["seldist"].reshape(-1), d["seldist"].reshape(-1))
+    sd = t["seldist"].reshape(n, n)
+    accepted = np.array([(np.maximum(sd[a], sd[b]) <= 200).sum() - 2 for a, b in pairs(n)])
+    assert (accepted < n - 2).mean() > 0.5
+
+    def digest(tag, transposed):
+        raw = eng.csr_raw()
+        try:
+            for p, (a, b) in enumerate(pairs(n)):
+                x, y = (b, a) if transposed else (a, b)
+                slot = x * n + y
+                cnt = int(raw.nz_cnt[slot]); off = int(raw.nz_off[slot]); ro = int(raw.rp_off[slot])
+                assert cnt == int(d["digest.%s.nnz" % tag][p]), (tag, a, b)
+                cells = raw.cells[off:off + cnt]
+                c = zlib.crc32(np.ascontiguousarray(raw.rp_pool[ro:ro + int(eng.lens[x]) + 2]).tobytes())
+                c = zlib.crc32(np.ascontiguousarray(cells["col"].astype(np.int32)).tobytes(), c)
+                c = zlib.crc32(np.ascontiguousarray(cells["val"]).tobytes(), c) & 0xffffffff
+                assert c == int(d["digest.%s.crc" % tag][p]), (tag, a, b)
+        finally:
+            raw.close()
+    digest("s0", False)
+    w = np.maximum(t["weights"], np.float32(1e-6))
+    eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, float(np.float32(1e-5)))    # N > 50: one repetition
+    digest("sF", False)
+    digest("tF", True)
+    eng.close()

@@ -191,3 +191,37 @@ def test_g_feature_line_refuses_non_standard_letters():
     d = load_golden("cpnp_676s4_ref")       # holds X/B/Z: the reference indexes its tables out of bounds there
     rc, _ = O.g_features(O.hmm_tables(), split_seqs(d))
     assert rc == 1
+
+
+def _combined_crc(S, n, p_ab, transposed):
+    import zlib
+    nnz = np.zeros(len(p_ab), np.int32); crc = np.zeros(len(p_ab), np.uint32)
+    for p, (a, b) in enumerate(p_ab):
+        x, y = (b, a) if transposed else (a, b)
+        rp, c, v = S.get(x, y)
+        nnz[p] = len(c)
+        k = zlib.crc32(np.ascontiguousarray(rp).tobytes())
+        k = zlib.crc32(np.ascontiguousarray(c, np.int32).tobytes(), k)
+        crc[p] = zlib.crc32(np.ascontiguousarray(v).tobytes(), k) & 0xffffffff
+    return nnz, crc
+
+
+def test_qp_selectivity_fixture_400_sequences():
+    """N = 400 in eight sub-families: QuickProbs' selectivity (ConsistencyStage.cpp:181-216) rejects most third sequences.
+    The oracle must reproduce the reference's per-pair digests before and after the consistency repetition."""
+    d = load_golden("qp_syn400")
+    seqs = split_seqs(d); n = len(seqs)
+    ht, pt = O.hmm_tables(), O.part_tables(O.QP)
+    dist, S, rc = O.posterior_stage(O.QP, 3, ht, pt, seqs, threads=8)
+    assert rc == 0
+    np.testing.assert_array_equal(dist, d["distances"].reshape(n, n))
+    p_ab = list(pairs(n))
+    nnz, crc = _combined_crc(S, n, p_ab, False)
+    np.testing.assert_array_equal(nnz, d["digest.s0.nnz"]); np.testing.assert_array_equal(crc, d["digest.s0.crc"])
+    sd = d["seldist"].reshape(n, n)
+    acc = np.array([(np.maximum(sd[a], sd[b]) <= 200).sum() for a, b in p_ab])
+    assert (acc < n).mean() > 0.5                                 # the filter bites
+    S = O.relax_qp(S, d["weights"], d["seldist"], float(np.float32(1e-5)), 200.0, float(d["cons.selfweight"][0]), threads=8)
+    for tag, tr in (("sF", False), ("tF", True)):
+        nnz, crc = _combined_crc(S, n, p_ab, tr)
+        np.testing.assert_array_equal(nnz, d["digest.%s.nnz" % tag]); np.testing.assert_array_equal(crc, d["digest.%s.crc" % tag])
