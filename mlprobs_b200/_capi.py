@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmlprobs_b200.so")
+LIB_PATH = os.environ.get("MLP_B200_LIB") or os.path.join(_HERE, "libmlprobs_b200.so")   # MLP_B200_LIB: developer override (A/B builds)
 
 QP, CPNP_P0, CPNP_P1 = 0, 1, 2
 M_HMM5, M_PART, M_LOCAL = 1, 2, 4

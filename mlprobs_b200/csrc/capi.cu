@@ -367,6 +367,7 @@ static int launch_one(mlp_ctx* ctx, int kernel, KArgs a, int ntasks, KernelTimer
     if (!st) st = ctx->stream;
     const int warps_per_cta = MLP_BLOCK / 32;
     a.counter = ctx->d_counter + (kernel & 15);      // every kernel id has its own work-queue head (kernels may overlap)
+    if (const char* e = getenv("MLP_BPS_CAP")) { const int v = atoi(e); if (v > 0) bps_cap = bps_cap > 0 ? std::min(bps_cap, v) : v; }   // developer knob: resident CTAs per SM
     if (cgroups && posterior_c_available(kernel, a)) {
         // register-band kernels: one launch per run of tasks with the same columns-per-lane value (the batch is sorted by C)
         kt.begin(stat_slot, st);

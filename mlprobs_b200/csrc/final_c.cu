@@ -10,6 +10,9 @@
 // warp step when none of its lanes has a posterior that can be non-zero.
 #include "posterior.cuh"
 #include "sweep_c.cuh"
+#ifndef MLP_MINB_FINAL
+#define MLP_MINB_FINAL 6   // minimum resident CTAs per SM the register allocation is held to (measured)
+#endif
 
 namespace {
 
@@ -23,7 +26,8 @@ template <int C>
 struct FinalQ {
     typedef float T;
     typedef float TIN;
-    enum { NS = 2, NIN = 2, REV = 0, ROW_LO = 1 };
+    enum { NS = 2, NIN = 2, REV = 0, ROW_LO = 1, USES_S1 = 0 };
+    __device__ __forceinline__ int row_residue(int) const { return -1; }
     const float* S5; const float* P; const ExpLut* elut;
     float total5, cutoff; int L1, L2;
     int* rowcnt; int4* stage; int stage_cap; int* stage_n;
@@ -43,7 +47,7 @@ struct FinalQ {
     }
     __device__ __forceinline__ void band_init(T (&st)[NS], int) const { st[0] = 0.0f; st[1] = 0.0f; }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = 0.0f; e[1] = 0.0f; }
-    __device__ __forceinline__ void begin_row(int) { hitmask = 0u; }
+    __device__ __forceinline__ void begin_row(int, int) { hitmask = 0u; }
     __device__ __forceinline__ void cell(int c, int, int, long long, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS],
                                          const TIN (&in)[2], T (&nw)[NS]) {
         const float x = fminf(0.0f, __fsub_rn(in[0], total5));      // ProbabilisticModel.h:483 / ParallelProbabilisticModel.cpp:262
@@ -52,7 +56,10 @@ struct FinalQ {
         // v5 is exactly 0 for x <= -16 (ScoreType.h EXP) and sqrt((0 + 0) * 0.5) is +0: skip the whole evaluation when no lane of the warp needs it
         if (__any_sync(__activemask(), (x > -16.0f) || (vp != 0.0f))) {
             const float v5 = dev_exp_lut(x, elut);
-            p = __fsqrt_rn(__fmul_rn(__fadd_rn(__fmul_rn(v5, v5), __fmul_rn(vp, vp)), 0.5f));   // PosteriorStage.cpp:169-177
+            // sqrt.rn of 0 (most lanes of a step) would take the compiler's out-of-line special-operand path: feed it 1 and select 0
+            const float s2 = __fmul_rn(__fadd_rn(__fmul_rn(v5, v5), __fmul_rn(vp, vp)), 0.5f);   // PosteriorStage.cpp:169-177
+            const float rt = __fsqrt_rn(s2 == 0.0f ? 1.0f : s2);
+            p = (s2 == 0.0f) ? 0.0f : rt;
         }
         if (c == 0 && col0) p = 0.0f;                                  // column 0 is forced to 0
         if (c == 0) cnt_in = col0 ? 0.0f : carry[1];
@@ -86,7 +93,7 @@ struct FinalQ {
 };
 
 template <int C>
-__global__ void __launch_bounds__(MLP_BLOCK) k_final_c(KArgs a) {
+__global__ void __launch_bounds__(MLP_BLOCK, MLP_MINB_FINAL) k_final_c(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     ExpLut* elut = reinterpret_cast<ExpLut*>(smem);
     exp_lut_fill(elut, threadIdx.x);
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_final_c(KArgs a) {
         m.total5 = a.pout[ti].total5; m.cutoff = a.cutoff; m.L1 = t.L1; m.L2 = t.L2;
         m.rowcnt = rowptr; m.stage = stage; m.stage_cap = a.stage_cap; m.stage_n = stage_n;
         m.has_score = false; m.score = 0.0f; m.hitmask = 0u; m.cnt_in = 0.0f;
-        run_sweep_c<FinalQ<C>, C>(m, cx, edge);
+        run_sweep_c<FinalQ<C>, C>(m, cx, edge, smem + MLP_FINAL_TABLE_BYTES + 64 + warp * MLP_SWEEP_RING_BYTES(2, 4));
         if (m.has_score) {
             const float dist = __fsub_rn(1.0f, __fdiv_rn(m.score, (float)min(t.L1, t.L2)));   // PosteriorStage.cpp:194
             a.pout[ti].mea = m.score;

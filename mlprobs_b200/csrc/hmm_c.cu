@@ -7,6 +7,14 @@
 // LOG_ZEROs is LOG_ZERO: the padding stays LOG_ZERO by itself).
 #include "posterior.cuh"
 #include "sweep_c.cuh"
+// minimum resident CTAs per SM the register allocation is held to (measured at 1000 x 300: the forward sweep wants its 128
+// registers, the backward sweep runs best at 96)
+#ifndef MLP_MINB_HMM_FWD
+#define MLP_MINB_HMM_FWD 4
+#endif
+#ifndef MLP_MINB_HMM_BWD
+#define MLP_MINB_HMM_BWD 5
+#endif
 
 __constant__ DevScalars c_sc_hmm;
 
@@ -36,7 +44,8 @@ template <int C>
 struct HmmFwdC {
     typedef float T;
     typedef float TIN;
-    enum { NS = 5, NIN = 0, REV = 0, ROW_LO = 0 };
+    enum { NS = 5, NIN = 0, REV = 0, ROW_LO = 0, USES_S1 = 1 };
+    __device__ __forceinline__ int row_residue(int i) const { return i - 1; }
     const float* match; const float* ins; unsigned lutb;
     float* F; const uint8_t* s1; const uint8_t* s2; int L1, L2;
     float t0q[5], tqq[5], tq0[5];
@@ -65,8 +74,7 @@ struct HmmFwdC {
 #pragma unroll
         for (int s = 0; s < NS; ++s) e[s] = MLP_LOG_ZERO;
     }
-    __device__ __forceinline__ void begin_row(int i) {
-        const int r1 = (i >= 1) ? s1[i - 1] : 0;
+    __device__ __forceinline__ void begin_row(int i, int r1) {
         ins1 = ins[r1]; mrow = match + r1 * 26;
         init_row = (i <= 1);
     }
@@ -107,7 +115,7 @@ struct HmmFwdC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd_c(KArgs a) {
+__global__ void __launch_bounds__(MLP_BLOCK, MLP_MINB_HMM_FWD) k_hmm_fwd_c(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* match; float* ins; LogAddLut* lut;
     load_hmm_tables_c(smem, a, match, ins, lut);
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_fwd_c(KArgs a) {
         cx.s1 = a.residues + a.seq_off[t.a]; cx.s2 = a.residues + a.seq_off[t.b];
         cx.lane = lane; cx.L1 = t.L1; cx.L2 = t.L2; cx.nb = t.nb;
         m.F = a.layerS5 + t.off; m.s1 = cx.s1; m.s2 = cx.s2; m.L1 = t.L1; m.L2 = t.L2; m.has_fin = false;
-        run_sweep_c<HmmFwdC<C>, C>(m, cx, edge);
+        run_sweep_c<HmmFwdC<C>, C>(m, cx, edge, smem + MLP_HMM_TABLE_BYTES + 128 + warp * MLP_SWEEP_RING_BYTES(5, 4));
         if (m.has_fin) {   // total forward probability, ProbabilisticModel.h:415-419
             float tF = MLP_LOG_ZERO;
 #pragma unroll
@@ -139,7 +147,8 @@ template <int C>
 struct HmmBwdC {
     typedef float T;
     typedef float TIN;
-    enum { NS = 5, NIN = 1, REV = 1, ROW_LO = 0 };
+    enum { NS = 5, NIN = 1, REV = 1, ROW_LO = 0, USES_S1 = 1 };
+    __device__ __forceinline__ int row_residue(int i) const { return i; }     // residue i+1 of the row sequence
     const float* match; const float* ins; unsigned lutb;
     float* F;      // in: forward M, out: F + B (ProbabilisticModel.h:483 evaluates (F+B)-total)
     float* cap;    // [0]=B_M(1,1) [1]=B_X1(1,0) [2]=B_Y1(0,1) [3]=B_X2(1,0) [4]=B_Y2(0,1)
@@ -169,8 +178,7 @@ struct HmmBwdC {
 #pragma unroll
         for (int s = 0; s < NS; ++s) e[s] = MLP_LOG_ZERO;
     }
-    __device__ __forceinline__ void begin_row(int i) {
-        const int r1 = (i + 1 <= L1) ? s1[i] : 0;          // residue i+1 of the row sequence
+    __device__ __forceinline__ void begin_row(int i, int r1) {
         ins1 = ins[r1]; mrow = match + r1 * 26;
         special_row = (i <= 1) || (i == L1);
     }
@@ -210,7 +218,7 @@ struct HmmBwdC {
 };
 
 template <int C>
-__global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd_c(KArgs a) {
+__global__ void __launch_bounds__(MLP_BLOCK, MLP_MINB_HMM_BWD) k_hmm_bwd_c(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* match; float* ins; LogAddLut* lut;
     load_hmm_tables_c(smem, a, match, ins, lut);
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_hmm_bwd_c(KArgs a) {
         cx.s1 = a.residues + a.seq_off[t.a]; cx.s2 = a.residues + a.seq_off[t.b];
         cx.lane = lane; cx.L1 = t.L1; cx.L2 = t.L2; cx.nb = t.nb;
         m.F = a.layerS5 + t.off; m.s1 = cx.s1; m.s2 = cx.s2; m.L1 = t.L1; m.L2 = t.L2;
-        run_sweep_c<HmmBwdC<C>, C>(m, cx, edge);
+        run_sweep_c<HmmBwdC<C>, C>(m, cx, edge, smem + MLP_HMM_TABLE_BYTES + 128 + warp * MLP_SWEEP_RING_BYTES(5, 4));
         __syncwarp();
         if (lane == 0) {   // ProbabilisticModel.h:421-432 / ParallelProbabilisticModel.cpp:226-231, then :453 and PosteriorStage.cpp:142
             const int r1 = cx.s1[0], r2 = cx.s2[0];

@@ -15,6 +15,9 @@
 //     reverse pass (everything that flows into them is zero) and are garbage nobody reads in the forward pass.
 #include "posterior.cuh"
 #include "sweep_c.cuh"
+#ifndef MLP_MINB_PART
+#define MLP_MINB_PART 5   // minimum resident CTAs per SM the register allocation is held to (measured)
+#endif
 
 __constant__ DevScalars c_sc_part;
 
@@ -34,7 +37,8 @@ template <int C>
 struct PartFwdQ {
     typedef double T;
     typedef double TIN;
-    enum { NS = 3, NIN = 0, REV = 0, ROW_LO = 1 };
+    enum { NS = 3, NIN = 0, REV = 0, ROW_LO = 1, USES_S1 = 1 };
+    __device__ __forceinline__ int row_residue(int i) const { return i - 1; }
     const double* sub; double* Z; const uint8_t* s1; const uint8_t* s2; int L1, L2;
     double go, ge;
     int roff[C]; double gov[C], gev[C];
@@ -55,8 +59,8 @@ struct PartFwdQ {
         st[0] = (j == 0) ? 1.0 : 0.0; st[1] = (j >= 1 && j <= L2) ? 1.0 : 0.0; st[2] = 0.0;
     }
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const { e[0] = e[1] = e[2] = 0.0; }
-    __device__ __forceinline__ void begin_row(int i) {
-        srow = sub + s1[i - 1] * 26;
+    __device__ __forceinline__ void begin_row(int i, int r1) {
+        srow = sub + r1 * 26;
         o0 = (i == L1) ? 1.0 : go; e0 = (i == L1) ? 1.0 : ge;      // H-type gap is terminal in the last row
     }
     __device__ __forceinline__ void cell(int c, int, int, long long idx, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS],
@@ -66,7 +70,11 @@ struct PartFwdQ {
         const double v = __dadd_rn(__dmul_rn(old[0], gov[c]), __dmul_rn(old[2], gev[c]));
         const double zm = __dmul_rn(__dadd_rn(__dadd_rn(diag[0], diag[1]), diag[2]), score);   // (Zm+H)+V, PartitionFunction.cpp:137
         nw[0] = zm; nw[1] = h; nw[2] = v;
+#ifndef MLP_EXP_NOSTORE
         Z[idx] = zm;
+#else
+        if (zm == -1.2345) Z[idx] = zm;   // timing experiment only
+#endif
     }
     __device__ __forceinline__ void end_row(int i, int jbase, const T (&band)[C][NS], T (&)[NS]) {
         if (i == L1) {
@@ -78,7 +86,7 @@ struct PartFwdQ {
 };
 
 template <int C>
-__global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd_c(KArgs a) {
+__global__ void __launch_bounds__(MLP_BLOCK, MLP_MINB_PART) k_part_fwd_c(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* sub = reinterpret_cast<double*>(smem);
     for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_fwd_c(KArgs a) {
         PartFwdQ<C> m;
         m.sub = sub; m.Z = a.layerZ + t.off; m.s1 = cx.s1; m.s2 = cx.s2; m.L1 = t.L1; m.L2 = t.L2;
         m.go = c_sc_part.go; m.ge = c_sc_part.ge; m.has_zz = false; m.zz = 0.0;
-        run_sweep_c<PartFwdQ<C>, C>(m, cx, edge);
+        run_sweep_c<PartFwdQ<C>, C>(m, cx, edge, smem + MLP_PART_TABLE_BYTES + warp * MLP_SWEEP_RING_BYTES(3, 8));
         if (m.has_zz) { a.pout[ti].Zpart = m.zz; a.pout[ti].zexp = 0; }
     }
 }
@@ -105,7 +113,8 @@ template <int C>
 struct PartRevQ {
     typedef double T;
     typedef double TIN;
-    enum { NS = 3, NIN = 1, REV = 1, ROW_LO = 1 };
+    enum { NS = 3, NIN = 1, REV = 1, ROW_LO = 1, USES_S1 = 1 };
+    __device__ __forceinline__ int row_residue(int i) const { return i - 1; }
     const double* sub; const double* Z; float* P; const uint8_t* s1; const uint8_t* s2; int L1, L2, ncols;
     double go, ge, Ztot;
     int roff[C]; double gov[C], gev[C];
@@ -129,8 +138,8 @@ struct PartRevQ {
     __device__ __forceinline__ void edge_init(T (&e)[NS], int) const {      // column 32*C*nb: the virtual column L2+1 only if it lies outside the strips
         e[0] = 0.0; e[1] = 0.0; e[2] = (ncols == L2 + 1) ? 1.0 : 0.0;
     }
-    __device__ __forceinline__ void begin_row(int i) {
-        srow = sub + s1[i - 1] * 26;
+    __device__ __forceinline__ void begin_row(int i, int r1) {
+        srow = sub + r1 * 26;
         o0 = (i == 1) ? 1.0 : go; e0 = (i == 1) ? 1.0 : ge;        // H-type gap is terminal at the first row
     }
     __device__ __forceinline__ void cell(int c, int, int, long long idx, const T (&old)[NS], const T (&carry)[NS], const T (&diag)[NS],
@@ -160,7 +169,7 @@ struct PartRevQ {
 };
 
 template <int C>
-__global__ void __launch_bounds__(MLP_BLOCK) k_part_rev_c(KArgs a) {
+__global__ void __launch_bounds__(MLP_BLOCK, MLP_MINB_PART) k_part_rev_c(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* sub = reinterpret_cast<double*>(smem);
     for (int k = threadIdx.x; k < 676; k += blockDim.x) sub[k] = a.sub[k];
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_part_rev_c(KArgs a) {
         for (int cb = 0; cb < t.nb; ++cb)
 #pragma unroll
             for (int c = 0; c < C; ++c) m.P[((long long)(cb * (t.L1 + 32) + lane) * C + c) * 32 + lane] = 0.0f;
-        run_sweep_c<PartRevQ<C>, C>(m, cx, edge);
+        run_sweep_c<PartRevQ<C>, C>(m, cx, edge, smem + MLP_PART_TABLE_BYTES + warp * MLP_SWEEP_RING_BYTES(3, 8));
     }
 }
 

@@ -6,6 +6,7 @@
 //   k_transpose               second orientation of each CSR matrix (PackedSparseMatrix.cpp:93-140, SparseMatrix.h:205-248)
 #include "posterior.cuh"
 #include "sweep.cuh"
+#include "sweep_c.cuh"
 
 __constant__ DevScalars c_sc;
 
@@ -1070,9 +1071,10 @@ bool posterior_c_available(int kernel, const KArgs& a) {
 size_t posterior_c_smem(int kernel) {
     const int warps = MLP_BLOCK / 32;
     switch (kernel) {
-        case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES;
-        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return MLP_HMM_TABLE_BYTES + warps * 32;
-        case MLP_K_FINAL: return MLP_FINAL_TABLE_BYTES + warps * 16;
+        // tables | small per-warp words (backward caps / stage counters) | per-warp edge + residue ring (sweep_c.cuh)
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES + warps * MLP_SWEEP_RING_BYTES(3, 8);
+        case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(5, 4);
+        case MLP_K_FINAL: return MLP_FINAL_TABLE_BYTES + 64 + warps * MLP_SWEEP_RING_BYTES(2, 4);
         default: return 0;
     }
 }

@@ -15,13 +15,15 @@
 //   void begin_block(int cb, int cbi, int jbase)        per-column constants for columns jbase .. jbase+C-1
 //   void band_init(T (&st)[NS], int j)                  virtual row before the first computed one (ROW_LO-1 / L1+1)
 //   void edge_init(T (&e)[NS], int i)                   virtual column before the first one (-1 / 32*C*nb)
-//   void begin_row(int i)                               per-row setup
+//   int  row_residue(int i)                             0-based index into the row sequence of the residue row i needs (-1: none)
+//   void begin_row(int i, int r1)                       per-row setup; r1 = that residue (fetched one step ahead), enum USES_S1
 //   TIN  load_in(int k, long long idx)                  dense input layer k at element idx of this pair's layer
 //   void cell<c>(i, j, idx, old, carry, diag, in, nw)   one cell; idx = element index of the cell in the pair's layers
 //   void end_row(int i, int jbase, const T (&band)[C][NS], T (&carry)[NS])   after the row's cells; may adjust what the next lane receives
 //   void step_sync()                                    called by all lanes at the top of every step
 #pragma once
 #include "dev_common.cuh"
+#define MLP_SWEEP_RING_BYTES(NS, TSIZE) (128 * (NS) * (TSIZE) + 128)
 
 struct SweepCtx2 {
     const uint8_t* s1;     // residues (letter - 'A') of the row sequence, 0-based
@@ -30,7 +32,8 @@ struct SweepCtx2 {
 };
 
 template <class M, int C>
-__device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename M::T* edgebuf /* [(L1+1)][NS] per warp, nb > 1 only */) {
+__device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename M::T* edgebuf /* [(L1+1)][NS] per warp, nb > 1 only */,
+                                            unsigned char* wsm /* per-warp shared memory, MLP_SWEEP_RING_BYTES(NS, sizeof(T)) */) {
     typedef typename M::T T;
     typedef typename M::TIN TIN;
     constexpr int NS = M::NS, NIN = M::NIN, ROW_LO = M::ROW_LO;
@@ -58,6 +61,29 @@ __device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename 
         for (int s = 0; s < NS; ++s) diag_in[s] = myout[s];
         // element index of (slot, c = 0, this lane) inside the pair's layers: ((cb*T + slot)*C + c)*32 + lane
         const long long blk0 = (long long)cb * T_slots * (C * 32) + lane;
+        // The hand-off column of the previous column block (edgebuf, global memory) and the residue of the row are needed at the
+        // very start of a step, and by then the store stream of the sweep has pushed them out of L2 (round-2 profile: these
+        // dependent loads were 20-36 % of all stall samples).  They go through a per-warp shared-memory ring of 128 rows that
+        // the warp refills 32 rows at a time, 32 steps before the first of them is needed: lane l fetches the row the head
+        // lane reaches l steps into the chunk.  A row's slot (row & 127) is rewritten only after every lane has left it.
+        T* ering = reinterpret_cast<T*>(wsm);
+        uint8_t* rring = wsm + 128 * NS * sizeof(T);
+        auto fill = [&](int t0) {          // rows the head lane visits at steps t0 .. t0+31
+            const int r = REV ? (cx.L1 - (t0 + lane)) : (ROW_LO + t0 + lane);
+            if (r >= ROW_LO && r <= cx.L1) {
+                if (cbi > 0) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) ering[(r & 127) * NS + s] = edgebuf[(long long)r * NS + s];
+                }
+                if (M::USES_S1) {
+                    const int ri = m.row_residue(r);
+                    rring[r & 127] = (ri >= 0 && ri < cx.L1) ? cx.s1[ri] : (uint8_t)0;
+                }
+            }
+        };
+        __syncwarp();
+        fill(0); fill(32);
+        __syncwarp();
         TIN nxt[NIN > 0 ? NIN : 1][C];
         if (NIN > 0) {
             const int i0 = REV ? (cx.L1 + 31 - lane) : (ROW_LO - lane);
@@ -76,6 +102,7 @@ __device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename 
             const bool in_rows = (i >= ROW_LO && i <= cx.L1);
             const bool active = in_rows && lane_has_cols;
             m.step_sync();
+            if ((t & 31) == 0 && t > 0) { fill(t + 32); __syncwarp(); }   // rows of steps t+32 .. t+63 (t .. t+31 were fetched 32 steps ago)
             TIN cur[NIN > 0 ? NIN : 1][C];
             if (NIN > 0) {
 #pragma unroll
@@ -98,7 +125,7 @@ __device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename 
                 if (cbi == 0) m.edge_init(in, i);
                 else {
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) in[s] = edgebuf[(long long)i * NS + s];
+                    for (int s = 0; s < NS; ++s) in[s] = ering[(i & 127) * NS + s];
                 }
             }
             if (active) {
@@ -111,7 +138,7 @@ __device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename 
                 }
 #pragma unroll
                 for (int s = 0; s < NS; ++s) carry[s] = in[s];
-                m.begin_row(i);
+                m.begin_row(i, M::USES_S1 ? (int)rring[i & 127] : 0);
                 const long long idx0 = blk0 + (long long)slot * (C * 32);
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc) {
