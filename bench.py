@@ -7,9 +7,15 @@ orientations), host UPGMA tree, one consistency repetition (N > 50, as the refer
 `value` = pair-HMM cell updates per second (1 cell update = one (i,j) cell through forward+backward+posterior of ONE
 model; the QuickProbs flavour runs 2 models per cell) over the whole step, inputs resident; `e2e` = same with the
 host->device copy of the family and the device->host read-back of distances and CSR inside the timed region.
+At N > 1 the pairs are sharded; after the tree every rank imports only the matrices QuickProbs' selectivity lets a
+relaxation read (mlp_exchange_needed), the relaxed set stays sharded and every rank reads its own shard back.
+`parity_digest` pins the result: CRC32 of the distance matrix and of the per-matrix device digests (summed over ranks)
+against the committed single-GPU value (tests/golden/bench_digest.json).
 `--impl reference` times the compiled reference (oracle/_ref/ref_qp) on the host cores on a bounded sample.
+The line also carries `cpnp` (the c_p_np_aln flavour on the same family, measured at N = 1) and `families_per_sec`
+(FASTA -> FASTA through the drop-in executables).
 """
-import argparse, json, os, subprocess, sys, threading, time
+import argparse, json, os, subprocess, sys, tarfile, tempfile, threading, time, zlib
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -21,7 +27,15 @@ WORKLOADS = {
     "small": dict(n=200, length=300, name="synthetic 200 protein seqs x len 300 (development size)"),
 }
 FP32_ISSUE_PEAK = 148 * 128 * 1.965e9          # lane-instructions / s
-SLOTS_PER_CELL = {"hmm5": 358.0, "part": 62.0, "merge": 10.0}   # algorithmic FP32-slot equivalents per cell
+# algorithmic FP32-slot equivalents per grid cell: 5-state forward+backward+posterior, partition function
+# (FP64 ops counted as 2 slots), merge + MEA + threshold; the whole QuickProbs stage = 430, cpnp's local model 270
+SLOTS_PER_CELL = {"hmm5": 358.0, "part": 62.0, "merge": 10.0, "stage_qp": 430.0, "local": 270.0, "stage_cpnp3": 700.0}
+DIGEST_FILE = os.path.join(ROOT, "tests", "golden", "bench_digest.json")
+# ncu --set full of tools/prof_run.py 192 300, main batch (17,254 pairs, 1.6237e9 cells, all C = 5), round-2 kernels
+# (profiles/r2_posterior_kernels_ncu_full.txt): k_hmm_fwd_c 1.136 + 6.994 GB, k_hmm_bwd_c 7.557 + 6.985 GB of DRAM traffic
+# -> 13.96 B per DP cell against 12 algorithmic (the slot layout pads 301 x 301 cells to 332 x 320 elements)
+NCU_DRAM_BYTES_PER_CELL_HMM5 = (1.13579 + 6.99383 + 7.55665 + 6.98525) * 1e9 / 1.6237e9
+NCU_TRAFFIC_SOURCE = "profiles/r2_posterior_kernels_ncu_full.txt"
 
 
 def measured_peaks():
@@ -61,6 +75,23 @@ def make_family(wl, rank=0):
     return synth.family_fast(wl["n"], wl["length"], seed=20220148 + 2)
 
 
+def write_fasta(path, seqs):
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">s%05d\n%s\n" % (i, s.decode()))
+
+
+def ref_qp_sample(seqs, n_s, cores):
+    """The UNMODIFIED QuickProbs CPU stage objects (oracle/_ref/ref_qp) on the first n_s sequences, all host cores."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_qp")
+    tmp = os.path.join("/tmp", "mlp_ref_sample_%d.fa" % os.getpid())
+    write_fasta(tmp, seqs[:n_s])
+    out = subprocess.run([exe, "bench", tmp, "--threads", str(cores)], capture_output=True, text=True).stdout
+    os.unlink(tmp)
+    j = json.loads(out.strip().splitlines()[-1])
+    return j["t_posterior_s"] + j["t_tree_s"] + j["t_relax_s"], j["cells"] * j["models"], j
+
+
 def run_reference(args, wl):
     """Reference arm: the UNMODIFIED QuickProbs CPU code (oracle/_ref/ref_qp) on all host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -69,33 +100,23 @@ def run_reference(args, wl):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_qp")
     cores = os.cpu_count() or 1
     seqs = make_family(wl)
-    # bounded sample of the same workload: the first n_s sequences, sized for ~10-20 s of CPU work per step
-    n_s = int(args.ref_sample)
-    sample = seqs[:n_s]
-    tmp = os.path.join("/tmp", "mlp_ref_sample_%d.fa" % os.getpid())
-    with open(tmp, "w") as f:
-        for i, s in enumerate(sample):
-            f.write(">s%05d\n%s\n" % (i, s.decode()))
-    kind = "reference"
-    if not os.path.exists(exe):
-        kind = "port"
+    n_s = int(args.ref_sample)      # bounded sample of the same workload: the first n_s sequences (~10-20 s of CPU work per step)
+    kind = "reference" if os.path.exists(exe) else "port"
     times, cells = [], 0
     for it in range(args.warmup + args.steps):
         if kind == "reference":
-            out = subprocess.run([exe, "bench", tmp, "--threads", str(cores)], capture_output=True, text=True).stdout
-            j = json.loads(out.strip().splitlines()[-1])
-            t = j["t_posterior_s"] + j["t_tree_s"] + j["t_relax_s"]; cells = j["cells"] * j["models"]
+            t, cells, _ = ref_qp_sample(seqs, n_s, cores)
         else:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as O
             ht, pt = O.hmm_tables(), O.part_tables(O.QP)
+            sample = seqs[:n_s]
             t0 = time.time()
             dist, S, _ = O.posterior_stage(O.QP, 3, ht, pt, sample, threads=cores)
             t = time.time() - t0
             cells = 2 * sum((len(a) + 1) * (len(b) + 1) for i, a in enumerate(sample) for b in sample[i + 1:])
         if it >= args.warmup:
             times.append(t)
-    os.unlink(tmp)
     ms = 1e3 * float(np.mean(times))
     gcups = cells / (ms * 1e-3) / 1e9
     line = {"impl": "reference", "metric": "pair_hmm_cell_updates_per_second", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
@@ -109,40 +130,102 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
-# ncu --set full, main batch of tools/prof_run.py 192 300 (17,073 of the 18,336 pairs; the first 1,263 go to the small
-# density-measuring batch): k_hmm_fwd 1.394 + 6.868 GB, k_hmm_bwd 7.421 + 6.852 GB of DRAM traffic -> 14.57 B per DP cell against
-# 12 algorithmic (the slot layout pads 301 x 301 cells to 332 x 320 elements, x1.17)
-NCU_DRAM_BYTES_PER_CELL_HMM5 = (1.393716 + 6.868421 + 7.421081 + 6.852403) * 1e9 / (17073 * 301 * 301)
-
-
-def one_step(eng, M, n, e2e, seqs=None, world=1, read_back=True, host_out=None):
-    """posterior stage [+ exchange] + host tree + consistency [+ exchange]. Returns the per-stage stats."""
+def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
+    """posterior stage -> [distances all-reduce] -> host tree -> [selective import] -> consistency [-> read-back of the own shard]."""
     if e2e:
-        eng.set_sequences(seqs)                       # host -> device copy of the family inside the timed region
-        if world > 1:
-            eng.set_shard(int(os.environ.get("RANK", "0")), world)
+        eng.set_sequences(seqs)                       # host -> device copy of the family inside the timed region (keeps the shard)
     stats = []
     eng.posterior_all_pairs(M.QP, 3, 0.01)
     stats.append(("posterior", eng.stats()))
     if world > 1:
-        eng.exchange_begin()                          # cell broadcasts run over NVLink while the host builds the tree
+        eng.exchange_distances()
     d = eng.distances()                               # the guide tree is host work between the stages, as in the reference
     w, sd, _, _ = M.qp_guide_tree(d)
     w = np.maximum(w, np.float32(1e-6))
     if world > 1:
-        eng.exchange_end(); stats.append(("exchange", eng.stats()))
+        eng.exchange_needed(sd, 200.0); stats.append(("exchange", eng.stats()))
     iters = 1 if n > 50 else 2
     for it in range(iters):
         cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))
         eng.relax(M.QP, w, sd, 200.0, 3.0, cutoff)
         stats.append(("relax", eng.stats()))
-        if world > 1:
+        if world > 1 and it < iters - 1:
             eng.exchange(); stats.append(("exchange", eng.stats()))
     out = None
-    if e2e and read_back:
-        out = eng.csr_packed(host_out)                # device -> host read of the step's result (QuickProbs' own packed cell
-                                                      # format, PackedSparseMatrix) into caller-owned page-locked buffers
-    return stats, out
+    if e2e:
+        out = eng.csr_packed(host_out)                # device -> host read of this rank's part of the result (QuickProbs' own packed
+                                                      # cell format, PackedSparseMatrix) into caller-owned page-locked buffers
+    return stats, out, d
+
+
+def cpnp_step(eng, M, mask):
+    """c_p_np_aln flavour: posterior stage (models by `mask`), two unselective consistency repetitions (MSA.cpp:1172-1281)."""
+    stats = []
+    eng.posterior_all_pairs(M.CPNP_P0, mask, 0.01)
+    stats.append(("posterior", eng.stats()))
+    for _ in range(2):
+        eng.relax(M.CPNP_P0, cutoff=0.01)
+        stats.append(("relax", eng.stats()))
+    return stats
+
+
+def cpnp_object(M, dev, seqs, total_cells, n_sub):
+    """Second object of the line: the c_p_np_aln flavour.  Posterior stage on the whole family for model class 0 (three models)
+    and class 2 (local model only); the unselective consistency (every third sequence, two repetitions) is cubic in N, so it
+    is timed on the first n_sub sequences and reported as MAC/s and per (pair, z) -- the reference does the same work."""
+    out = {}
+    npairs = len(seqs) * (len(seqs) - 1) // 2
+    for label, mask, models, slots in (("class0_three_models", 7, 3, SLOTS_PER_CELL["stage_cpnp3"]), ("class2_local_only", 4, 1, SLOTS_PER_CELL["local"])):
+        eng = M.Engine(dev)
+        h, p = M.default_tables(M.CPNP_P0, 0.100675); eng.set_tables(h, p); eng.set_sequences(seqs)
+        eng.posterior_all_pairs(M.CPNP_P0, mask, 0.01)            # warm-up (pool sizing)
+        eng.posterior_all_pairs(M.CPNP_P0, mask, 0.01)
+        st = eng.stats()
+        ms = st["ms_total"]
+        out[label] = {"posterior_ms": ms, "gcups": total_cells * models / (ms * 1e-3) / 1e9, "models_per_cell": models,
+                      "kernel_ms": {k: v for k, v in st["ms_kernel"].items() if v},
+                      "stage_frac_fp32_issue": total_cells * slots / (ms * 1e-3) / FP32_ISSUE_PEAK}
+        eng.close()
+    sub = seqs[:n_sub]
+    eng = M.Engine(dev)
+    h, p = M.default_tables(M.CPNP_P0, 0.100675); eng.set_tables(h, p); eng.set_sequences(sub)
+    for rep in range(2):                                         # first pass warms the pools
+        eng.posterior_all_pairs(M.CPNP_P0, 7, 0.01)
+        cells_in = eng.total_cells()
+        eng.relax(M.CPNP_P0, cutoff=0.01); r1 = eng.stats()
+        eng.relax(M.CPNP_P0, cutoff=0.01); r2 = eng.stats()
+    ns = len(sub); pz = ns * (ns - 1) // 2 * (ns - 2)
+    out["relax_unselective"] = {"n_sub": ns, "ms_rep1": r1["ms_total"], "ms_rep2": r2["ms_total"], "pair_z_per_sec": pz / (r1["ms_total"] * 1e-3),
+                                "cells_in": int(cells_in), "extrapolated_ms_per_rep_at_n": r1["ms_total"] * (npairs * (len(seqs) - 2)) / pz,
+                                "note": "first %d sequences; cost is proportional to pairs x (N-2), the extrapolation to N = %d is labelled as such" % (ns, len(seqs))}
+    eng.close()
+    return out
+
+
+def families_per_sec(seqs):
+    """FASTA -> FASTA through the drop-in executables (process start, CUDA context, tail and file output included)."""
+    out = {}
+    exe = os.path.join(ROOT, "mlprobs_b200", "bin", "quickprobs_b200")
+    tmp = tempfile.mkdtemp()
+    fa = os.path.join(tmp, "A.fa"); write_fasta(fa, seqs)
+    t0 = time.time()
+    r = subprocess.run([exe, fa, "-o", os.path.join(tmp, "A.out")], capture_output=True, text=True)
+    dt = time.time() - t0
+    ok = r.returncode == 0 and os.path.getsize(os.path.join(tmp, "A.out")) > 0 if os.path.exists(os.path.join(tmp, "A.out")) else False
+    out["quickprobs_b200_config_A"] = {"families": 1, "seconds": dt, "families_per_sec": 1.0 / dt, "ok": bool(ok)}
+    reg = os.path.join(ROOT, "tests", "golden", "regions", "inputs.tar.gz")
+    if os.path.exists(reg):
+        indir, outdir = os.path.join(tmp, "reg_in"), os.path.join(tmp, "reg_out")
+        os.makedirs(indir); os.makedirs(outdir)
+        with tarfile.open(reg) as tar:
+            tar.extractall(indir, filter="data")
+        nf = len(os.listdir(indir))
+        t0 = time.time()
+        r = subprocess.run([exe, indir, "-o", outdir], capture_output=True, text=True)
+        dt = time.time() - t0
+        out["quickprobs_b200_realignment_regions"] = {"families": nf, "seconds": dt, "families_per_sec": nf / dt, "ok": r.returncode == 0,
+                                                      "note": "the 112 region files MLProbs' driver hands to quickprobs (BASELINE config #4), one process / one CUDA context"}
+    return out
 
 
 def main():
@@ -155,6 +238,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=144,
                     help="sequences of the workload the reference CPU arm aligns per step (144 -> 10,296 pairs, about 10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cpnp object and the FASTA->FASTA runs (development)")
+    ap.add_argument("--write-digest", action="store_true", help="record this run's parity digest as the committed expectation (N = 1 only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -198,7 +283,7 @@ def main():
     ms_dev, launches, kms = [], 0, {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        stats, _ = one_step(eng, M, n, False, world=world)
+        stats, _, _ = one_step(eng, M, n, False, world=world)
         ms_dev.append(sum(s["ms_total"] for _, s in stats))
         launches += sum(s["launches"] for _, s in stats)
         for name, s_ in stats:
@@ -210,18 +295,23 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     dev_ms = float(np.mean(ms_dev))
-    # ---- end-to-end arm (host buffers in, host buffers out through the C ABI)
+    # ---- parity digest of the step's result (untimed): distances + every matrix of the relaxed set
+    _, _, d_last = one_step(eng, M, n, False, world=world)
+    dg = torch.from_numpy(eng.set_digest().view(np.int64)).cuda()
+    if dist is not None:
+        dist.all_reduce(dg)                           # int64 wrap-around sum == sum mod 2^64 of the ranks' disjoint parts
+    digest = {"distances_crc32": zlib.crc32(np.ascontiguousarray(d_last).tobytes()) & 0xffffffff,
+              "set_crc32": zlib.crc32(dg.cpu().numpy().tobytes()) & 0xffffffff}
+    # ---- end-to-end arm (host buffers in, host buffers out through the C ABI; every rank reads its own shard back)
     h2d = d2h = 0
-    host_out = None
-    if rank == 0:   # caller-owned page-locked result buffers, allocated once outside the timed region
-        lay = eng.csr_layout()
-        host_out = M.PinnedPackedBuffers(n, lay[1], int(lay[2] * 1.05))
+    lay = eng.csr_layout()
+    host_out = M.PinnedPackedBuffers(n, lay[1], int(lay[2] * 1.05))   # caller-owned page-locked result buffers, allocated once outside the timed region
     for _ in range(min(args.warmup, 2)):   # untimed: first use of the host->device / read-back path (allocations, page-locking)
-        one_step(eng, M, n, True, seqs, world=world, read_back=(rank == 0), host_out=host_out)
+        one_step(eng, M, n, True, seqs, world=world, host_out=host_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        stats, out = one_step(eng, M, n, True, seqs, world=world, read_back=(rank == 0), host_out=host_out)
+        stats, out, _ = one_step(eng, M, n, True, seqs, world=world, host_out=host_out)
         h2d = sum(s["h2d_bytes"] for _, s in stats) + sum(len(s) for s in seqs)
         d2h = n * n * 4 + (out.nbytes() if out is not None else 0)
     barrier()
@@ -231,9 +321,13 @@ def main():
         t = torch.tensor([wall_ms, e2e_ms, dev_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall_ms, e2e_ms, dev_ms = [float(x) for x in t.tolist()]
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        lt = torch.tensor([launches, h2d, d2h], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
-        launches = int(lt.item())
+        launches, h2d, d2h = [int(x) for x in lt.tolist()]
+        km = torch.tensor([kms.get(k, 0.0) for k in M.K_NAMES + ["exchange"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        kms = {k: float(v) for k, v in zip(M.K_NAMES + ["exchange"], km.tolist())}
+    eng.close()
     if rank == 0:
         models = 2
         value = total_cells * models / (wall_ms * 1e-3) / 1e9
@@ -245,41 +339,65 @@ def main():
         hmm_ms = per_kernel_ms.get("hmm_fwd", 0) + per_kernel_ms.get("hmm_bwd", 0)
         cells_rank = total_cells / max(world, 1)
         slot_rate = cells_rank * SLOTS_PER_CELL["hmm5"] / (hmm_ms * 1e-3) if hmm_ms else 0.0
+        post_ms = sum(v for k, v in per_kernel_ms.items() if k not in ("relax", "exchange"))
+        expected = None
+        try:
+            expected = json.load(open(DIGEST_FILE)).get(args.workload)
+        except Exception:
+            pass
+        if args.write_digest and world == 1:
+            allx = {}
+            try:
+                allx = json.load(open(DIGEST_FILE))
+            except Exception:
+                pass
+            allx[args.workload] = digest
+            json.dump(allx, open(DIGEST_FILE, "w"), indent=1)
+            expected = digest
         line = {"metric": "pair_hmm_cell_updates_per_second", "value": value, "unit": "GCUPS", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
                 "config": {"workload": wl["name"], "flavour": "quickprobs (5-state pair-HMM f32 + partition function f64, 1 consistency rep)",
                            "models_per_cell": models, "n": n, "pairs": npairs, "cells": total_cells,
                            "generator": "mlprobs_b200.synth.family_fast(p_sub=0.5): expected pairwise identity ~0.29",
-                           "l2_policy": "inputs larger than L2: each batch streams >10 GB of dense DP layers (L2 = 126 MB)"},
+                           "l2_policy": "inputs larger than L2: each batch streams >10 GB of dense DP layers (L2 = 126 MB)",
+                           "multi_gpu": "pairs sharded round-robin over the cost-sorted list; distances all-reduced, then only the matrices within QuickProbs' selectivity are imported (mlp_exchange_needed); the relaxed set stays sharded" if world > 1 else "single GPU"},
                 "device_ms_per_step": dev_ms, "kernel_ms_per_step": per_kernel_ms,
                 "alignments_per_sec": npairs / (wall_ms * 1e-3),
-                "gcups_posterior_stage": total_cells * models / max(world, 1) / (sum(v for k, v in per_kernel_ms.items() if k not in ("relax", "exchange")) * 1e-3) / 1e9,
+                "gcups_posterior_stage": total_cells * models / max(world, 1) / (post_ms * 1e-3) / 1e9 if post_ms else None,
                 "gcups_hmm5_fwd_bwd_per_gpu": cells_rank / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
-                "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+                "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                        "note": "bytes summed over ranks; every rank copies the family in and reads its own shard of the result back over its own PCIe link"},
                 "gpu_launches": int(launches),
+                "parity_digest": {"value": digest, "expected": expected, "match": (digest == expected) if expected else None,
+                                  "what": "CRC32 of the n x n distance matrix; CRC32 of the n x n per-matrix device digests (row pointers + cells of every matrix after the consistency repetition, summed over ranks)",
+                                  "expected_source": "tests/golden/bench_digest.json (single-GPU run, bench.py --write-digest)"},
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "fp32_issue",
                              "bound_note": "north_star and SURVEY 8d name FP32 instruction issue as the roofline of this path (log-space compare/select/polynomial work, no contraction for tensor cores); the HBM view of the same kernels is under roofline.hbm",
-                             "kernel": "k_hmm_fwd+k_hmm_bwd", "achieved": slot_rate / 1e12, "peak": FP32_ISSUE_PEAK / 1e12,
+                             "kernel": "k_hmm_fwd_c+k_hmm_bwd_c", "achieved": slot_rate / 1e12, "peak": FP32_ISSUE_PEAK / 1e12,
                              "unit": "Tlane-op/s", "frac": slot_rate / FP32_ISSUE_PEAK,
                              "peak_source": "148 SMs x 128 FP32 lanes x 1.965 GHz (MEASURED_PEAKS.json sm_max_mhz); no measured FP32-issue peak exists in MEASURED_PEAKS.json",
                              "algorithmic_ops_per_cell": SLOTS_PER_CELL["hmm5"],
-                             # DRAM bytes (dram__bytes_read + write) of the two launches per step, from the ncu --set full capture
-                             # profiles/r1c_all_kernels_ncu_full.txt: 14.57 B per cell (k_hmm_fwd + k_hmm_bwd) against
-                             # 12 algorithmic, scaled to this workload's cells per launch
+                             # the quantity north_star's 50 % target is stated on: the whole all-pairs posterior + consistency stage
+                             "stage_frac": total_cells * SLOTS_PER_CELL["stage_qp"] / max(world, 1) / (wall_ms * 1e-3) / FP32_ISSUE_PEAK,
+                             "stage_frac_note": "430 algorithmic slots per cell (SURVEY 8d: 358 HMM + 62 partition + 10 merge) x cells per GPU / wall time of the step (consistency, host tree and exchange included) / peak",
+                             "posterior_kernels_frac": cells_rank * SLOTS_PER_CELL["stage_qp"] / (post_ms * 1e-3) / FP32_ISSUE_PEAK if post_ms else None,
                              "traffic": cells_rank * NCU_DRAM_BYTES_PER_CELL_HMM5,
                              "traffic_unit": "DRAM bytes per step on this rank, both kernels, all of the step's launches (same scope as `achieved`)",
-                             "traffic_source": "ncu dram bytes per cell measured at 192 x 300 (profiles/r1c_all_kernels_ncu_full.txt) x cells per step",
+                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per cell measured at 192 x 300 (%s) x cells per step" % NCU_TRAFFIC_SOURCE,
                              "hbm": {"bound": "hbm", "achieved": cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9 if hmm_ms else None,
                                      "peak": peaks["hbm_gbs"] if peaks else 6650.0, "unit": "GB/s",
                                      "frac": (cells_rank * 12.0 / (hmm_ms * 1e-3) / 1e9) / (peaks["hbm_gbs"] if peaks else 6650.0) if hmm_ms else None,
                                      "peak_source": "measured" if peaks else "fallback", "algorithmic_bytes_per_cell": 12}}}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl, seqs, args.ref_sample)
+        if not args.no_extras and world == 1:
+            line["cpnp"] = cpnp_object(M, dev, seqs, total_cells, 144)
+            line["families_per_sec"] = families_per_sec(seqs)
         print(json.dumps(line))
-    eng.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -288,15 +406,8 @@ def cpu_baseline(wl, seqs, n_s):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_qp")
     sample = seqs[:n_s]
     if os.path.exists(exe):
-        tmp = os.path.join("/tmp", "mlp_cpu_sample_%d.fa" % os.getpid())
-        with open(tmp, "w") as f:
-            for i, s in enumerate(sample):
-                f.write(">s%05d\n%s\n" % (i, s.decode()))
-        out = subprocess.run([exe, "bench", tmp, "--threads", str(cores)], capture_output=True, text=True).stdout
-        os.unlink(tmp)
-        j = json.loads(out.strip().splitlines()[-1])
-        t = j["t_posterior_s"] + j["t_tree_s"] + j["t_relax_s"]
-        return {"value": j["cells"] * j["models"] / t / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
+        t, cells, _ = ref_qp_sample(seqs, n_s, cores)
+        return {"value": cells / t / 1e9, "unit": "GCUPS", "cores": cores, "kind": "reference",
                 "sample": "first %d of %d sequences of the same family (%d pairs): reference PosteriorStage+tree+ConsistencyStage, %.2f s" % (n_s, len(seqs), n_s * (n_s - 1) // 2, t)}
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O

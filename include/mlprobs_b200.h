@@ -225,6 +225,18 @@ int mlp_exchange(mlp_ctx* ctx);
  * all-reduce, so the host guide tree overlaps the cell broadcasts; _end (or any later stage call) waits for the rest. */
 int mlp_exchange_begin(mlp_ctx* ctx);
 int mlp_exchange_end(mlp_ctx* ctx);
+/* Selective exchange for the QuickProbs flavour.  QuickProbs' consistency reads S_xz only when the subtree distance d[x][z] is
+ * within the selectivity (ConsistencyStage.cpp:181-216), so once the guide tree exists each rank ships only those matrices:
+ *   mlp_exchange_distances   all-reduce of the distance matrix (the tree needs all of it; no-op when already complete)
+ *   mlp_exchange_needed      imports, on every rank, the matrices with seldist[a*n+b] <= selectivity that other ranks own
+ * The following mlp_relax works on the rank's own pairs; its result stays sharded (mlp_get_csr* return the owned pairs,
+ * mlp_exchange gathers everything where a tail needs the whole set). */
+/* Device-side digest of the current set: per ordered matrix (a,b) of the pairs this rank owns, a 64-bit position-weighted
+ * hash of its row pointers and cells (0 for matrices of other ranks), n*n values.  Summed over the ranks of a sharded run it
+ * equals the single-GPU vector: bench.py and tools/multigpu_check.py use it as the N-GPU parity check. */
+int mlp_set_digest(mlp_ctx* ctx, uint64_t* per_matrix_nn);
+int mlp_exchange_distances(mlp_ctx* ctx);
+int mlp_exchange_needed(mlp_ctx* ctx, const float* seldist_nxn, float selectivity);
 
 /* timing / accounting of the last stage call, measured with CUDA events on the library's stream */
 typedef struct {

@@ -24,7 +24,8 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_alloc_pinned", "mlp_free_pinned", "mlp_viterbi_all_pairs", "mlp_cpnp_model_adjustment", "mlp_viterbi_all_pairs_ex",
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
-           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end"]
+           "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end",
+           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_set_digest"]
 
 
 class HmmTables(C.Structure):
@@ -80,6 +81,9 @@ def load():
         lib.mlp_nccl_unique_id.argtypes = [C.c_void_p]
         lib.mlp_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.mlp_exchange.argtypes = [C.c_void_p]
+        lib.mlp_exchange_distances.argtypes = [C.c_void_p]
+        lib.mlp_exchange_needed.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        lib.mlp_set_digest.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_csr_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.mlp_get_csr_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -459,6 +463,21 @@ class Engine:
     def exchange(self):
         """All-gather the sparse posteriors + distances of every rank's shard (NCCL)."""
         self._ck(self._lib.mlp_exchange(self._ctx))
+
+    def exchange_distances(self):
+        """All-reduce of the distance matrix only (the guide tree needs all of it)."""
+        self._ck(self._lib.mlp_exchange_distances(self._ctx))
+
+    def exchange_needed(self, seldist, selectivity=200.0):
+        """Import the matrices QuickProbs' consistency can read (seldist <= selectivity) from the ranks that own them."""
+        sd = np.ascontiguousarray(seldist, np.float32)
+        self._ck(self._lib.mlp_exchange_needed(self._ctx, _ptr(sd), C.c_float(selectivity)))
+
+    def set_digest(self):
+        """Per-matrix 64-bit digests (n*n, zeros for matrices other ranks own), computed on the device."""
+        out = np.zeros(self.n * self.n, np.uint64)
+        self._ck(self._lib.mlp_set_digest(self._ctx, _ptr(out)))
+        return out
 
     def exchange_begin(self):
         """Start the exchange; distances() then only waits for the distance all-reduce (the tree overlaps the cell broadcasts)."""

@@ -75,7 +75,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
-    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused);
+    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -718,6 +718,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     ctx->stats.nnz = (int64_t)(cur / 2);
     ctx->flavour_of_set = flavour;
     ctx->set_partial = ctx->dist_partial = (ctx->world > 1);
+    ctx->imported = false;
     return MLP_OK;
 }
 
@@ -963,6 +964,65 @@ extern "C" int mlp_get_csr_packed(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt
     return MLP_OK;
 }
 
+// Per-matrix digest of the current set, computed on the device: one warp per owned pair and orientation, a polynomial hash
+// mod 2^64 over the row pointers followed by the (column, value bits) of every cell.  Position-weighted, so it pins order as
+// well as content, and independent of where the cells sit in the pool -- the same value on one GPU and on any sharding.
+__global__ void k_set_digest(const PairTask* __restrict__ tasks, int ntasks, int n, const int* __restrict__ len, const long long* __restrict__ rp_off,
+                             const int* __restrict__ rp_pool, const long long* __restrict__ nz_off, const int* __restrict__ nz_cnt,
+                             const int2* __restrict__ cells, unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long B = 0x9E3779B97F4A7C15ull;
+    unsigned long long B32 = 1, Bl = 1;
+    for (int k = 0; k < 32; ++k) { B32 *= B; if (k < lane) Bl *= B; }
+    for (long long w = gw; w < 2LL * ntasks; w += nw) {
+        const PairTask t = tasks[w >> 1];
+        const int a = (w & 1) ? t.b : t.a, b = (w & 1) ? t.a : t.b;
+        const long long slot = (long long)a * n + b;
+        const int rows = len[a] + 2, cnt = nz_cnt[slot];
+        const int* rp = rp_pool + rp_off[slot];
+        const int2* c = cells + nz_off[slot];
+        unsigned long long h = 0, pw = Bl;
+        const long long words = rows + 2LL * cnt;
+        for (long long k = lane; k < words; k += 32) {
+            unsigned v;
+            if (k < rows) v = (unsigned)rp[k];
+            else { const long long q = k - rows; const int2 e = c[q >> 1]; v = (q & 1) ? (unsigned)e.y : (unsigned)e.x; }
+            h += ((unsigned long long)v + 1ull) * pw;
+            pw *= B32;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+        if (lane == 0) out[slot] = h + (unsigned long long)cnt;
+    }
+}
+
+extern "C" int mlp_set_digest(mlp_ctx* ctx, uint64_t* per_matrix_nn) {
+    if (!ctx || !per_matrix_nn) return MLP_E_ARG;
+    END_EXCHANGE(ctx);
+    if (!ctx->have_sets) return MLP_E_STATE;
+    cudaSetDevice(ctx->device);
+    const int n = ctx->n;
+    const size_t nn = (size_t)n * n;
+    int rc = ensure_tasks(ctx, ctx->owned.size());
+    if (rc != MLP_OK) return rc;
+    unsigned long long* d_out = nullptr; int* d_len = nullptr;
+    CK(cudaMalloc(&d_out, nn * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d_len, n * sizeof(int)));
+    CK(cudaMemsetAsync(d_out, 0, nn * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemcpyAsync(d_len, ctx->len.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tasks, ctx->owned.data(), ctx->owned.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
+    const CsrSetDev& s = ctx->set[ctx->cur];
+    if (!ctx->owned.empty()) {
+        k_set_digest<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d_tasks, (int)ctx->owned.size(), n, d_len, ctx->d_rp_off, s.rp_pool, s.nz_off, s.nz_cnt, s.cells, d_out);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(per_matrix_nn, d_out, nn * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_out); cudaFree(d_len);
+    return MLP_OK;
+}
+
 extern "C" int mlp_alloc_pinned(int64_t bytes, void** out) {
     if (!out || bytes <= 0) return MLP_E_ARG;
     return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? MLP_OK : MLP_E_CUDA;
@@ -1075,6 +1135,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     }
     ctx->cur = out;
     ctx->set_partial = (ctx->world > 1);
+    ctx->imported = false;
     ctx->stats.pairs = (int64_t)tasks.size();
     unsigned long long cur = 0;
     { int rcc = read_cursor(ctx, out, &cur); if (rcc != MLP_OK) return rcc; }

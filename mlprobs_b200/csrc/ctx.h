@@ -70,6 +70,9 @@ struct mlp_ctx {
     float* d_weights = nullptr; float* d_seldist = nullptr; int weights_cap = 0;
     // nccl
     void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
+    int* d_xcnt = nullptr; size_t xcnt_cap = 0;          // gathered per-matrix cell counts (selective exchange)
+    void* d_ximp = nullptr; size_t ximp_cap = 0;         // import list of the selective exchange
+    bool imported = false;                               // set holds foreign matrices imported by mlp_exchange_needed (only the owned pairs are this rank's result)
     unsigned long long* d_xused = nullptr;               // per-rank cell counts of an exchange
     unsigned* d_xq = nullptr; size_t xq_cap = 0;          // packed wire buffer of the QuickProbs exchange
     bool set_partial = false, dist_partial = false;       // sharded stage output not yet exchanged (set by posterior / relax, cleared by mlp_exchange)

@@ -211,3 +211,150 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     ctx->exch_pending = true;
     return MLP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ selective exchange (QuickProbs flavour)
+// QuickProbs' consistency only ever reads S_xz with subtree distance d[x][z] <= selectivity (ConsistencyStage.cpp:181-216): about a
+// fifth of the matrices at N = 1000.  Once the guide tree is known, every rank ships just those of its matrices to the others:
+//   1. mlp_exchange_distances: all-reduce of the distance matrix (the host tree needs all of it);
+//   2. mlp_exchange_needed(seldist, selectivity): the per-matrix cell counts are gathered (sum over ranks of a zero-padded table),
+//      every rank derives the SAME import list on the host (owner-major, pair order of the cost-sorted list, (a,b) then (b,a)),
+//      packs its own needed matrices into its slice of an import region behind its local cells, and one grouped in-place
+//      ncclBroadcast per rank fills the region everywhere; row pointers travel the same way and are scattered into the fixed
+//      row-pointer layout.  Matrices nobody can read stay where they were computed.
+// The relaxation then runs on the owned pairs; its output is again sharded (mlp_exchange gathers it when a tail needs the whole set).
+namespace {
+struct XImport { long long slot; long long cell_off; long long rp_off; int cnt; int rows; };   // one needed ordered matrix
+
+__global__ void k_xgather(const XImport* __restrict__ imp, int n_imp, const long long* __restrict__ nz_off, const long long* __restrict__ rp_off,
+                          const int2* __restrict__ cells_src, int2* __restrict__ region, const int* __restrict__ rp_pool, int* __restrict__ rp_region) {
+    for (int m = blockIdx.x; m < n_imp; m += gridDim.x) {           // one CTA per matrix I own
+        const XImport e = imp[m];
+        const int2* src = cells_src + nz_off[e.slot];
+        for (int k = threadIdx.x; k < e.cnt; k += blockDim.x) region[e.cell_off + k] = src[k];
+        const int* rsrc = rp_pool + rp_off[e.slot];
+        for (int k = threadIdx.x; k < e.rows; k += blockDim.x) rp_region[e.rp_off + k] = rsrc[k];
+    }
+}
+__global__ void k_ximport(const XImport* __restrict__ imp, int n_imp, long long* __restrict__ nz_off, int* __restrict__ nz_cnt,
+                          const long long* __restrict__ rp_off, long long region_base, int* __restrict__ rp_pool, const int* __restrict__ rp_region) {
+    for (int m = blockIdx.x; m < n_imp; m += gridDim.x) {           // one CTA per matrix another rank owns
+        const XImport e = imp[m];
+        if (threadIdx.x == 0) { nz_off[e.slot] = region_base + e.cell_off; nz_cnt[e.slot] = e.cnt; }
+        int* rdst = rp_pool + rp_off[e.slot];
+        for (int k = threadIdx.x; k < e.rows; k += blockDim.x) rdst[k] = rp_region[e.rp_off + k];
+    }
+}
+}  // namespace
+
+extern "C" int mlp_exchange_distances(mlp_ctx* ctx) {
+    if (!ctx) return MLP_E_ARG;
+    if (ctx->comm_world <= 1) return MLP_OK;
+    if (ctx->exch_pending) { const int rc0 = mlp_exchange_end(ctx); if (rc0 != MLP_OK) return rc0; }
+    if (!ctx->nccl_comm || !ctx->have_sets) { ctx->err = "mlp_comm_init and the posterior stage must come first"; return MLP_E_STATE; }
+    if (!ctx->dist_partial) return MLP_OK;
+    cudaSetDevice(ctx->device);
+    NK(g_nccl.AllReduce(ctx->d_dist, ctx->d_dist, (size_t)ctx->n * ctx->n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dist_partial = false;
+    return MLP_OK;
+}
+
+extern "C" int mlp_exchange_needed(mlp_ctx* ctx, const float* seldist_nxn, float selectivity) {
+    if (!ctx || !seldist_nxn) return MLP_E_ARG;
+    if (ctx->comm_world <= 1) return MLP_OK;
+    if (ctx->exch_pending) { const int rc0 = mlp_exchange_end(ctx); if (rc0 != MLP_OK) return rc0; }
+    if (!ctx->nccl_comm || !ctx->have_sets) { ctx->err = "mlp_comm_init and the posterior stage must come first"; return MLP_E_STATE; }
+    if (!ctx->set_partial) return MLP_OK;
+    { const int rcd = mlp_exchange_distances(ctx); if (rcd != MLP_OK) return rcd; }
+    cudaSetDevice(ctx->device);
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int W = ctx->comm_world, R = ctx->comm_rank, n = ctx->n;
+    const size_t nn = (size_t)n * n;
+    const int cur = ctx->cur;
+    cudaStream_t st = ctx->stream;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    // 1. every rank's cell counts (foreign slots are zero: sum == union), into a scratch table
+    if (nn > ctx->xcnt_cap) {
+        free_dev(ctx->d_xcnt); ctx->d_xcnt = nullptr;
+        CK(cudaMalloc(&ctx->d_xcnt, (nn + 64) * sizeof(int)));
+        ctx->xcnt_cap = nn + 64;
+    }
+    NK(g_nccl.AllReduce(ctx->set[cur].nz_cnt, ctx->d_xcnt, nn, ncclInt32, ncclSum, comm, st));
+    std::vector<int> cnt(nn);
+    unsigned long long used_local = 0;
+    CK(cudaMemcpyAsync(cnt.data(), ctx->d_xcnt, nn * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&used_local, ctx->set[cur].cursor, sizeof(used_local), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // 2. the import list, identical on every rank: owner-major, cost-sorted pair order, (a,b) before (b,a)
+    std::vector<XImport> mine, theirs;
+    std::vector<long long> cbase(W + 1, 0), rbase(W + 1, 0);
+    long long coff = 0, roff = 0;
+    for (int q = 0; q < W; ++q) {
+        cbase[q] = coff; rbase[q] = roff;
+        for (size_t k = q; k < ctx->all_pairs.size(); k += W) {
+            const PairTask& t = ctx->all_pairs[k];
+            for (int o = 0; o < 2; ++o) {
+                const int a = o ? t.b : t.a, b = o ? t.a : t.b;
+                const size_t slot = (size_t)a * n + b;
+                if (!(seldist_nxn[slot] <= selectivity)) continue;
+                XImport e; e.slot = (long long)slot; e.cell_off = coff; e.rp_off = roff; e.cnt = cnt[slot]; e.rows = ctx->len[a] + 2;
+                (q == R ? mine : theirs).push_back(e);
+                coff += (e.cnt + 1) & ~1;          // matrices stay 16-byte aligned inside the region (bulk copies of the relaxation)
+                roff += (e.rows + 3) & ~3;
+            }
+        }
+    }
+    cbase[W] = coff; rbase[W] = roff;
+    // 3. room: import region behind the local cells (even base), row-pointer region in the wire buffer
+    const long long region_base = (long long)((used_local + 1) & ~1ull);
+    if (region_base + coff + 1024 > ctx->set[cur].cap) { int rc = grow_cells(ctx, cur, region_base + coff + coff / 16 + 1024, used_local); if (rc != MLP_OK) return rc; }
+    if ((size_t)roff + 64 > ctx->xq_cap) {
+        free_dev(ctx->d_xq); ctx->d_xq = nullptr; ctx->xq_cap = 0;
+        CK(cudaMalloc(&ctx->d_xq, ((size_t)roff + roff / 8 + 64) * sizeof(unsigned)));
+        ctx->xq_cap = (size_t)roff + roff / 8 + 56;
+    }
+    const size_t n_list = mine.size() + theirs.size();
+    if (n_list > ctx->ximp_cap) {
+        free_dev(ctx->d_ximp); ctx->d_ximp = nullptr;
+        CK(cudaMalloc(&ctx->d_ximp, (n_list + n_list / 4 + 64) * sizeof(XImport)));
+        ctx->ximp_cap = n_list + n_list / 4 + 64;
+    }
+    XImport* d_mine = reinterpret_cast<XImport*>(ctx->d_ximp);
+    XImport* d_theirs = d_mine + mine.size();
+    if (!mine.empty()) CK(cudaMemcpyAsync(d_mine, mine.data(), mine.size() * sizeof(XImport), cudaMemcpyHostToDevice, st));
+    if (!theirs.empty()) CK(cudaMemcpyAsync(d_theirs, theirs.data(), theirs.size() * sizeof(XImport), cudaMemcpyHostToDevice, st));
+    int2* region = ctx->set[cur].cells + region_base;
+    int* rp_region = reinterpret_cast<int*>(ctx->d_xq);
+    if (!mine.empty()) {
+        k_xgather<<<std::min<int>((int)mine.size(), ctx->num_sms * 8), 128, 0, st>>>(d_mine, (int)mine.size(), ctx->set[cur].nz_off, ctx->d_rp_off,
+                                                                                   ctx->set[cur].cells, region, ctx->set[cur].rp_pool, rp_region);
+        CK(cudaGetLastError());
+    }
+    // 4. one grouped in-place broadcast per rank: cells (as uint64) and row pointers
+    NK(g_nccl.GroupStart());
+    for (int q = 0; q < W; ++q) {
+        const size_t nc = (size_t)(cbase[q + 1] - cbase[q]), nr = (size_t)(rbase[q + 1] - rbase[q]);
+        if (nc) NK(g_nccl.Broadcast(region + cbase[q], region + cbase[q], nc, ncclUint64, q, comm, st));
+        if (nr) NK(g_nccl.Broadcast(rp_region + rbase[q], rp_region + rbase[q], nr, ncclInt32, q, comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    // 5. point the foreign slots at the region, scatter their row pointers into the fixed layout
+    if (!theirs.empty()) {
+        k_ximport<<<std::min<int>((int)theirs.size(), ctx->num_sms * 8), 128, 0, st>>>(d_theirs, (int)theirs.size(), ctx->set[cur].nz_off, ctx->set[cur].nz_cnt,
+                                                                                     ctx->d_rp_off, region_base, ctx->set[cur].rp_pool, rp_region);
+        CK(cudaGetLastError());
+    }
+    ctx->exch_total = (unsigned long long)(region_base + coff);
+    CK(cudaMemcpyAsync(ctx->set[cur].cursor, &ctx->exch_total, sizeof(ctx->exch_total), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats = mlp_stage_stats{};
+    ctx->stats.ms_total = ms;
+    ctx->stats.nnz = coff;                         // cells in the import region (all ranks' needed matrices)
+    ctx->stats.pairs = (int64_t)n_list;
+    ctx->stats.launches = 2;
+    ctx->set_partial = false;                      // every matrix a relaxation of the owned pairs can read is now present
+    ctx->imported = true;
+    return MLP_OK;
+}
