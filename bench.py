@@ -130,20 +130,35 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+TRACE = {} if os.environ.get("MLP_BENCH_TRACE") else None    # developer: wall time of every phase of a step, printed to stderr
+
+
+def _tr(name, t0):
+    if TRACE is not None:
+        TRACE[name] = TRACE.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+    return time.perf_counter()
+
+
 def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
     """posterior stage -> [distances all-reduce] -> host tree -> [selective import] -> consistency [-> read-back of the own shard]."""
+    t0 = time.perf_counter()
     if e2e:
         eng.set_sequences(seqs)                       # host -> device copy of the family inside the timed region (keeps the shard)
+        t0 = _tr("e2e.set_sequences", t0)
     stats = []
     eng.posterior_all_pairs(M.QP, 3, 0.01)
     stats.append(("posterior", eng.stats()))
+    t0 = _tr("posterior", t0)
     if world > 1:
         eng.exchange_distances()
     d = eng.distances()                               # the guide tree is host work between the stages, as in the reference
+    t0 = _tr("distances", t0)
     w, sd, _, _ = M.qp_guide_tree(d)
     w = np.maximum(w, np.float32(1e-6))
+    t0 = _tr("tree", t0)
     if world > 1:
         eng.exchange_needed(sd, 200.0); stats.append(("exchange", eng.stats()))
+        t0 = _tr("exchange_needed", t0)
     iters = 1 if n > 50 else 2
     for it in range(iters):
         cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))
@@ -151,10 +166,12 @@ def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
         stats.append(("relax", eng.stats()))
         if world > 1 and it < iters - 1:
             eng.exchange(); stats.append(("exchange", eng.stats()))
+    t0 = _tr("relax", t0)
     out = None
     if e2e:
         out = eng.csr_packed(host_out)                # device -> host read of this rank's part of the result (QuickProbs' own packed
                                                       # cell format, PackedSparseMatrix) into caller-owned page-locked buffers
+        t0 = _tr("e2e.read_back", t0)
     return stats, out, d
 
 
@@ -316,6 +333,8 @@ def main():
         d2h = n * n * 4 + (out.nbytes() if out is not None else 0)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if TRACE is not None and rank == 0:
+        print("trace (ms, summed over all steps of both arms):", {k: round(v, 1) for k, v in TRACE.items()}, file=sys.stderr)
     sampler.stop_flag = True; sampler.join(timeout=2)
     if dist is not None:
         t = torch.tensor([wall_ms, e2e_ms, dev_ms], device="cuda", dtype=torch.float64)

@@ -75,7 +75,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
-    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp);
+    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp); free_dev(ctx->d_relax_tasks);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -153,8 +153,10 @@ static void build_sorted_pairs(int n, const int32_t* len, std::vector<PairTask>&
             t.pidx = pidx++; t.flags = 0; t.off = 0;
             out.push_back(t);
         }
-    // cost-sorted (largest first) for load balance; stable, so ties keep row-major pair order
+    // grouped by columns per lane (the register-band kernels are compiled per C: one launch per group), cost-sorted (largest
+    // first) inside a group for load balance; stable, so ties keep row-major pair order
     std::stable_sort(out.begin(), out.end(), [](const PairTask& x, const PairTask& y) {
+        if (x.C != y.C) return x.C > y.C;
         const long long cx = (long long)x.nb * (x.L1 + 32) * x.C, cy = (long long)y.nb * (y.L1 + 32) * y.C;
         return cx > cy;
     });
@@ -189,6 +191,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     // same family shape as before (same n and lengths): the pooled layout is unchanged, keep the device pools
     const bool same_layout = ctx->have_sets && ctx->n == n && std::equal(len, len + n, ctx->len.begin());
     if (!same_layout) ctx->have_sets = false;        // the pools themselves stay: ensure_sets re-uses them when the new family fits
+    const bool same_shape = ctx->n == n && (int)ctx->len.size() == n && std::equal(len, len + n, ctx->len.begin()) && !ctx->all_pairs.empty();
     ctx->flavour_of_set = -1;
     ctx->set_partial = ctx->dist_partial = false;
     ctx->n = n;
@@ -215,6 +218,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     CK(cudaMemcpy(ctx->d_res, codes.data(), tot + 16, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_seq_off, ctx->seq_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
     ctx->stats.h2d_bytes += tot + 16 + n * (int64_t)sizeof(long long);
+    if (same_shape) return MLP_OK;    // same lengths as the family before (a re-submitted family): pair list, shard and layout stand
     build_sorted_pairs(n, len, ctx->all_pairs);
     // fixed row-pointer layout: ordered pair (a,b) owns len[a]+2 ints
     ctx->rp_off_h.assign((size_t)n * n, 0);
@@ -237,6 +241,7 @@ extern "C" int mlp_set_shard(mlp_ctx* ctx, int rank, int world) {
     for (size_t k = 0; k < ctx->all_pairs.size(); ++k)
         if ((int)(k % world) == rank) ctx->owned.push_back(ctx->all_pairs[k]);
     ctx->relax_tasks.clear();
+    ctx->relax_tasks_on_device = false;
     return MLP_OK;
 }
 
@@ -449,7 +454,8 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         }
         // the register-band kernels are compiled per columns-per-lane value: order the batch by C (stable, so the cost order
         // survives inside a group) and remember where every group starts
-        std::stable_sort(batch.begin(), batch.end(), [](const PairTask& x, const PairTask& y) { return x.C > y.C; });
+        if (!std::is_sorted(batch.begin(), batch.end(), [](const PairTask& x, const PairTask& y) { return x.C > y.C; }))   // the pair list already is
+            std::stable_sort(batch.begin(), batch.end(), [](const PairTask& x, const PairTask& y) { return x.C > y.C; });
         std::vector<std::pair<int, int>> cgroups;   // (C, first task)
         {
             long long o = 0;
@@ -1065,22 +1071,26 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
             return x.pidx < y.pidx;
         });
         ctx->relax_tasks_n = n;
+        ctx->relax_tasks_on_device = false;
     }
     const std::vector<PairTask>& tasks = ctx->relax_tasks;
-    int rc = ensure_tasks(ctx, tasks.size());
-    if (rc != MLP_OK) return rc;
+    int rc = MLP_OK;
+    if (tasks.size() > ctx->relax_tasks_cap) {       // the tile-ordered list has its own device copy: it only changes with the family or the shard
+        free_dev(ctx->d_relax_tasks); ctx->d_relax_tasks = nullptr;
+        ctx->relax_tasks_cap = tasks.size() + tasks.size() / 4 + 64;
+        CK(cudaMalloc(&ctx->d_relax_tasks, ctx->relax_tasks_cap * sizeof(PairTask)));
+        ctx->relax_tasks_on_device = false;
+    }
     int maxL1 = 0, maxL2 = 0;
     for (const PairTask& t : tasks) { maxL1 = std::max(maxL1, t.L1); maxL2 = std::max(maxL2, t.L2); }
-    static const bool use_warp_kernel = getenv("MLP_RELAX_WARP") != nullptr;   // developer knob: the older warp-per-pair kernel
-    int bps = use_warp_kernel ? std::min(relax_max_blocks_per_sm(), 16) : relax_blk_max_blocks_per_sm();
-    int grid = use_warp_kernel ? std::max(1, std::min(ctx->num_sms * bps, (int)((tasks.size() + 3) / 4)))
-                               : std::max(1, std::min(ctx->num_sms * bps, (int)tasks.size()));
+    const int bps = relax_blk_max_blocks_per_sm();
+    const int grid = std::max(1, std::min(ctx->num_sms * bps, (int)tasks.size()));
     const long long warps = (long long)ctx->num_sms * 16 * (MLP_BLOCK / 32);
     rc = ensure_warp_buffers(ctx, warps, maxL1, maxL2, false, 1);
     if (rc != MLP_OK) return rc;
-    // per-warp (old kernel: n weights + n indices) or per-CTA (weights, indices, slice descriptors) scratch
-    const long long wk_stride = use_warp_kernel ? 2LL * n : relax_blk_scratch_words(n);
-    const long long wk_units = use_warp_kernel ? warps : (long long)ctx->num_sms * bps;
+    // per-CTA scratch: weights and indices of the accepted third sequences, slice descriptors of the current band
+    const long long wk_stride = relax_blk_scratch_words(n);
+    const long long wk_units = (long long)ctx->num_sms * bps;
     if (wk_units * wk_stride > ctx->wk_warps) {
         free_dev(ctx->d_wk); ctx->d_wk = nullptr;
         CK(cudaMalloc(&ctx->d_wk, (size_t)(wk_units * wk_stride) * sizeof(float)));
@@ -1091,8 +1101,11 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
         { int rcc = read_cursor(ctx, in, &used); if (rcc != MLP_OK) return rcc; }
         if ((long long)used + 1024 > ctx->set[out].cap) { rc = grow_cells(ctx, out, (long long)used + 1024, 0); if (rc != MLP_OK) return rc; }
     }
-    CK(cudaMemcpyAsync(ctx->d_tasks, tasks.data(), tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += (int64_t)(tasks.size() * sizeof(PairTask));
+    if (!ctx->relax_tasks_on_device) {
+        CK(cudaMemcpyAsync(ctx->d_relax_tasks, tasks.data(), tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (int64_t)(tasks.size() * sizeof(PairTask));
+        ctx->relax_tasks_on_device = true;
+    }
     CK(cudaMemsetAsync(ctx->set[out].cursor, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->set[out].nz_cnt, 0, (size_t)n * n * sizeof(int), ctx->stream));
     if (ctx->world > 1) {
@@ -1101,7 +1114,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     }
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
     RelaxArgs ra = {};
-    ra.tasks = ctx->d_tasks; ra.ntasks = (int)tasks.size(); ra.counter = ctx->d_counter;
+    ra.tasks = ctx->d_relax_tasks; ra.ntasks = (int)tasks.size(); ra.counter = ctx->d_counter;
     ra.n = n; ra.flavour = flavour; ra.cutoff = cutoff; ra.rp_off = ctx->d_rp_off;
     ra.in = ctx->set[in]; ra.out = ctx->set[out];
     ra.weights = ctx->d_weights; ra.seldist = ctx->d_seldist; ra.selectivity = selectivity; ra.selfweight = selfweight;
@@ -1110,12 +1123,12 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     KernelTimer kt;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     kt.begin(MLP_K_RELAX_ID, ctx->stream);
-    CK(use_warp_kernel ? relax_launch(ra, grid, ctx->stream) : relax_blk_launch(ra, grid, ctx->stream));
+    CK(relax_blk_launch(ra, grid, ctx->stream));
     kt.end(ctx->stream);
     ctx->stats.launches += 1;
     // second orientation of every new matrix
     KArgs a = {};
-    a.tasks = ctx->d_tasks; a.ntasks = (int)tasks.size(); a.counter = ctx->d_counter; a.n = n; a.flavour = flavour;
+    a.tasks = ctx->d_relax_tasks; a.ntasks = (int)tasks.size(); a.counter = ctx->d_counter; a.n = n; a.flavour = flavour;
     a.rp_off = ctx->d_rp_off; a.out = ctx->set[out]; a.tfill = ctx->d_tfill; a.tfill_stride = ctx->tfill_stride; a.err = ctx->d_err;
     a.Cmax = 1;
     rc = launch_one(ctx, MLP_K_TRANSPOSE, a, (int)tasks.size(), kt, MLP_K_RELAX_ID);

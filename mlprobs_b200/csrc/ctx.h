@@ -43,6 +43,7 @@ struct mlp_ctx {
     std::vector<PairTask> owned;         // this shard
     std::vector<PairTask> relax_tasks;   // owned pairs in the tile order mlp_relax processes them (cached)
     int relax_tasks_n = 0;
+    PairTask* d_relax_tasks = nullptr; size_t relax_tasks_cap = 0; bool relax_tasks_on_device = false;
     int rank = 0, world = 1;
     // sparse sets (double buffered for relax)
     std::vector<long long> rp_off_h;

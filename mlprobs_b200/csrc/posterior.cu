@@ -488,7 +488,7 @@ struct LocFwd {
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 3, REV = 0, COLMASK = 0x7, NIN = 0, UNROLLC = 0 };
-    const float* match; const float* ins; const LogAddLut* lut; float* F; int L1, L2;
+    const float* match; const float* ins; const LogAddLut* lut; unsigned lutb; float* F; int L1, L2;
     float* RM;   // row-major copy of F_M for the sequential Z replay (lives in the not-yet-used Z-term layer)
     float ins1; const float* mrow;
     __device__ __forceinline__ void prefetch(int, int, int) const {}
@@ -502,12 +502,12 @@ struct LocFwd {
         // ProbabilisticModel.h:210-211,222-227: base = ((m - a) - b); M = (base - 2r) (+) sum_k ((base + F_k) + lt[k][0]) - 2r
         const float base = __fsub_rn(__fsub_rn(mrow[r2], ins1), ins[r2]);
         float m = __fsub_rn(base, c_sc.r2);
-        m = dev_log_add_lut(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[0]), c_sc.lt00), c_sc.r2), lut);
-        m = dev_log_add_lut(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[1]), c_sc.lt10), c_sc.r2), lut);
-        m = dev_log_add_lut(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[2]), c_sc.lt20), c_sc.r2), lut);
+        m = dev_log_add_lutb(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[0]), c_sc.lt00), c_sc.r2), lutb);
+        m = dev_log_add_lutb(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[1]), c_sc.lt10), c_sc.r2), lutb);
+        m = dev_log_add_lutb(m, __fsub_rn(__fadd_rn(__fadd_rn(base, diag[2]), c_sc.lt20), c_sc.r2), lutb);
         // :238-241, :252-255
-        float x = dev_log_add_lut(__fsub_rn(__fadd_rn(old[0], c_sc.lt01), c_sc.r), __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r), lut);
-        float y = dev_log_add_lut(__fsub_rn(__fadd_rn(carry[0], c_sc.lt02), c_sc.r), __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r), lut);
+        float x = dev_log_add_lutb(__fsub_rn(__fadd_rn(old[0], c_sc.lt01), c_sc.r), __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r), lutb);
+        float y = dev_log_add_lutb(__fsub_rn(__fadd_rn(carry[0], c_sc.lt02), c_sc.r), __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r), lutb);
         if (i == 0 || j == 0) m = MLP_LOG_ZERO;
         if (i == 0) x = MLP_LOG_ZERO;
         if (j == 0) y = MLP_LOG_ZERO;
@@ -527,7 +527,7 @@ struct LocBwd {
     __device__ __forceinline__ void end_row() const {}
     typedef float T;
     enum { NS = 3, REV = 1, COLMASK = 0x3, NIN = 1, UNROLLC = 0 };   // keep B_M and X of row i+1; Y travels along the row
-    const float* match; const float* ins; const LogAddLut* lut; float* F; float* VB; int L1, L2;
+    const float* match; const float* ins; const LogAddLut* lut; unsigned lutb; float* F; float* VB; int L1, L2;
     float* stage; int Cmax, lane;
     __device__ __forceinline__ void prefetch(int slotbase, int C, int buf) const {
         for (int c = 0; c < C; ++c) cp_async4(stage + (buf * Cmax + c) * 32 + lane, F + slotbase + c * 32);
@@ -551,17 +551,17 @@ struct LocBwd {
         float bm = 0.0f, x = MLP_LOG_ZERO, y = MLP_LOG_ZERO;
         if (i < L1 && j < L2) {
             const float pxy = __fsub_rn(__fsub_rn(__fadd_rn(diag[0], mrown[r2]), ins1n), ins[r2]);
-            bm = dev_log_add_lut(bm, __fsub_rn(__fadd_rn(pxy, c_sc.lt00), c_sc.r2), lut);
+            bm = dev_log_add_lutb(bm, __fsub_rn(__fadd_rn(pxy, c_sc.lt00), c_sc.r2), lutb);
             x = __fsub_rn(__fadd_rn(pxy, c_sc.lt10), c_sc.r2);
             y = __fsub_rn(__fadd_rn(pxy, c_sc.lt20), c_sc.r2);
         }
         if (i < L1) {
-            bm = dev_log_add_lut(bm, __fsub_rn(__fadd_rn(old[1], c_sc.lt01), c_sc.r), lut);
-            x = dev_log_add_lut(x, __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r), lut);
+            bm = dev_log_add_lutb(bm, __fsub_rn(__fadd_rn(old[1], c_sc.lt01), c_sc.r), lutb);
+            x = dev_log_add_lutb(x, __fsub_rn(__fadd_rn(old[1], c_sc.lt11), c_sc.r), lutb);
         }
         if (j < L2) {
-            bm = dev_log_add_lut(bm, __fsub_rn(__fadd_rn(carry[2], c_sc.lt02), c_sc.r), lut);
-            y = dev_log_add_lut(y, __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r), lut);
+            bm = dev_log_add_lutb(bm, __fsub_rn(__fadd_rn(carry[2], c_sc.lt02), c_sc.r), lutb);
+            y = dev_log_add_lutb(y, __fsub_rn(__fadd_rn(carry[2], c_sc.lt22), c_sc.r), lutb);
         }
         nw[0] = bm; nw[1] = x; nw[2] = y;
         // Z term of this cell, ProbabilisticModel.h:445-446: (((B_M + m) - a) - b) - 2r with the cell's own residues
@@ -583,23 +583,35 @@ __device__ float replay_rowmajor(const float* __restrict__ rm /* row-major (L1+1
     float sum = MLP_LOG_ZERO;
     const int lane = cx.lane;
     const int W = cx.L2 + 1;
-    for (int i = 1; i <= cx.L1; ++i) {
-        const float* row = rm + (long long)i * W;
-        for (int j0 = 1; j0 <= cx.L2; j0 += 32) {
-            const int j = j0 + lane;
-            const bool in = (j <= cx.L2);
-            const float v = in ? row[j] : MLP_LOG_ZERO;
-            int pos = 0;
-            for (;;) {
-                // the cell changes the sum unless sum >= v and (v == LOG_ZERO or sum - v >= 7.5)
-                const bool fires = (lane >= pos) && in && !(sum >= v && (v == MLP_LOG_ZERO || __fsub_rn(sum, v) >= 7.5f));
-                const unsigned mask = __ballot_sync(MLP_FULL, fires);
-                if (mask == 0) break;
-                const int l0 = __ffs(mask) - 1;
-                const float vv = __shfl_sync(MLP_FULL, v, l0);
-                sum = dev_log_add(sum, vv);
-                pos = l0 + 1;
-            }
+    // The chain is serial, the loads are not: the 32-column chunks of rows 1..L1 are visited in row-major order and the next
+    // four chunks are always in flight (round 1 issued one dependent global load per chunk: ~3000 exposed latencies per pair).
+    const int nch = (cx.L2 + 31) >> 5;
+    const long long total = (long long)cx.L1 * nch;
+    int pi = 1, pk = 0;                       // row / chunk of the next chunk to fetch
+    auto fetch = [&]() -> float {
+        float v = MLP_LOG_ZERO;
+        if (pi <= cx.L1) {
+            const int j = 1 + (pk << 5) + lane;
+            if (j <= cx.L2) v = rm[(long long)pi * W + j];
+            if (++pk == nch) { pk = 0; ++pi; }
+        }
+        return v;
+    };
+    float b0 = fetch(), b1 = fetch(), b2 = fetch(), b3 = fetch();
+    for (long long q = 0; q < total; ++q) {
+        const float v = b0;
+        b0 = b1; b1 = b2; b2 = b3; b3 = fetch();
+        int pos = 0;
+        for (;;) {
+            // the cell changes the sum unless sum >= v and (v == LOG_ZERO or sum - v >= 7.5); padding lanes hold LOG_ZERO and never fire
+            // (the running sum starts at LOG_ZERO and only grows)
+            const bool fires = (lane >= pos) && !(sum >= v && (v == MLP_LOG_ZERO || __fsub_rn(sum, v) >= 7.5f));
+            const unsigned mask = __ballot_sync(MLP_FULL, fires);
+            if (mask == 0) break;
+            const int l0 = __ffs(mask) - 1;
+            const float vv = __shfl_sync(MLP_FULL, v, l0);
+            sum = dev_log_add(sum, vv);
+            pos = l0 + 1;
         }
     }
     return sum;
@@ -612,6 +624,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* band; float* stage; uint8_t* colres; float* cap;
     warp_smem<float, 3, 0>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
+    const unsigned lutb = log_add_lut_bias(lut);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -620,7 +633,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_fwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         LocFwd m;
-        m.match = match; m.ins = ins; m.lut = lut; m.F = a.layerSL + t.off; m.RM = a.layerVB + t.off; m.L1 = t.L1; m.L2 = t.L2;
+        m.match = match; m.ins = ins; m.lut = lut; m.lutb = lutb; m.F = a.layerSL + t.off; m.RM = a.layerVB + t.off; m.L1 = t.L1; m.L2 = t.L2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();
         __threadfence_block();
@@ -636,6 +649,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* band; float* stage; uint8_t* colres; float* cap;
     warp_smem<float, 2, 1>(smem, MLP_HMM_TABLE_BYTES, a.Cmax, warp, band, stage, colres, cap);
+    const unsigned lutb = log_add_lut_bias(lut);
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     float* edge = a.edge_f ? a.edge_f + gw * a.edge_stride : nullptr;
     for (;;) {
@@ -644,7 +658,7 @@ __global__ void __launch_bounds__(MLP_BLOCK) k_loc_bwd(KArgs a) {
         const PairTask t = a.tasks[ti];
         SweepCtx cx = make_ctx(t, a, lane);
         LocBwd m;
-        m.stage = stage; m.Cmax = a.Cmax; m.lane = lane; m.lut = lut;
+        m.stage = stage; m.Cmax = a.Cmax; m.lane = lane; m.lut = lut; m.lutb = lutb;
         m.match = match; m.ins = ins; m.F = a.layerSL + t.off; m.VB = a.layerVB + t.off; m.L1 = t.L1; m.L2 = t.L2; m.s1 = cx.s1; m.s2 = cx.s2;
         run_sweep(m, cx, band, colres, a.Cmax, edge);
         __syncwarp();

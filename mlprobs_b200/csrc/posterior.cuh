@@ -53,7 +53,7 @@ struct KArgs {
     float* dense; float* dense5; float* denseP; float* denseL;
 };
 
-// relax.cu
+// relax_blk.cu
 struct RelaxArgs {
     const PairTask* tasks; int ntasks; int* counter;
     int n; int flavour; float cutoff;
@@ -65,8 +65,6 @@ struct RelaxArgs {
     int* err;
     int wide_span;                            // S_yz rows spanning more q than this are merged instead of getting a dense strip
 };
-cudaError_t relax_launch(const RelaxArgs& a, int grid, cudaStream_t st);
-int relax_max_blocks_per_sm();
 // CTA-per-pair relaxation with TMA-staged slices (relax_blk.cu)
 cudaError_t relax_blk_launch(const RelaxArgs& a, int grid, cudaStream_t st);
 int relax_blk_max_blocks_per_sm();

@@ -25,6 +25,11 @@
 #define RB_RMAX 256         // rows of S_xy per band
 #define RB_CWMAX 320        // columns of S_xy per band (= rows of S_yz staged)
 #define RB_WCAP 6144        // floats in the strip pool
+// Cell -> thread mapping inside a band: a warp owns 128 consecutive cells and lane l takes cells l, l+32, l+64, l+96 of them,
+// so the 32 cells a warp works on at a time are consecutive (about three rows of S_xy: similar row lengths of S_xz, the row
+// walks of the lanes end together).  Round 1 gave every thread 4 consecutive cells: a warp then spanned a dozen rows and ran
+// at 19 of 32 lanes.
+#define RB_CELL(tid, g) ((((tid) >> 5) << 7) + ((g) << 5) + ((tid) & 31))
 
 struct __align__(16) RbDesc {          // one accepted third sequence for the current band (80 bytes, in global scratch)
     long long a_src, b_src;            // first cell of the staged slices in the cell pool (even index = 16-byte aligned)
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
             float acc[RB_G];
 #pragma unroll
             for (int g = 0; g < RB_G; ++g) {
-                const int cidx = c0 + tid * RB_G + g;
+                const int cidx = c0 + RB_CELL(tid, g);
                 rr[g] = 1; cc[g] = 0; acc[g] = 0.0f;
                 if (cidx < c0 + nb) {
                     const int2 cell = c_ij[cidx];
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
                 int v0 = 0x7fffffff, v1 = 0, v2 = 0x7fffffff, v3 = 0;
 #pragma unroll
                 for (int g = 0; g < RB_G; ++g)
-                    if (c0 + tid * RB_G + g < c0 + nb) { v0 = min(v0, rr[g]); v1 = max(v1, rr[g]); v2 = min(v2, cc[g]); v3 = max(v3, cc[g]); }
+                    if (RB_CELL(tid, g) < nb) { v0 = min(v0, rr[g]); v1 = max(v1, rr[g]); v2 = min(v2, cc[g]); v3 = max(v3, cc[g]); }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) {
                     v0 = min(v0, __shfl_xor_sync(MLP_FULL, v0, d)); v1 = max(v1, __shfl_xor_sync(MLP_FULL, v1, d));
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
             const bool band_fits = (R <= RB_RMAX && CW <= RB_CWMAX);
             bool okc[RB_G];
 #pragma unroll
-            for (int g = 0; g < RB_G; ++g) okc[g] = (c0 + tid * RB_G + g) < c0 + nb;
+            for (int g = 0; g < RB_G; ++g) okc[g] = RB_CELL(tid, g) < nb;
 
             // ---- slice descriptors of every accepted z for this band (one thread per z: the dependent loads overlap)
             for (int m = tid; m < nk; m += RB_THREADS) {
@@ -342,29 +347,31 @@ __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
 
             // ---- normalise, threshold, ordered compaction of the band
             float vv[RB_G];
-            int cnt = 0;
             bool keep[RB_G];
 #pragma unroll
             for (int g = 0; g < RB_G; ++g) {
                 vv[g] = __fdiv_rn(acc[g], norm);
                 keep[g] = okc[g] && (vv[g] >= a.cutoff);
-                cnt += keep[g] ? 1 : 0;
             }
-            int inc = cnt;
+            // cells of a warp in row-major order: pass g = 0..3, lane ascending inside a pass
+            int rank[RB_G], wtot = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(MLP_FULL, inc, d); if (lane >= d) inc += o; }
+            for (int g = 0; g < RB_G; ++g) {
+                const unsigned bm = __ballot_sync(MLP_FULL, keep[g]);
+                rank[g] = wtot + __popc(bm & ((1u << lane) - 1u));
+                wtot += __popc(bm);
+            }
             __syncthreads();
-            if (lane == 31) sm.scan[warp] = inc;
+            if (lane == 0) sm.scan[warp] = wtot;
             __syncthreads();
             int before = 0, band_total = 0;
 #pragma unroll
             for (int w8 = 0; w8 < RB_THREADS / 32; ++w8) { const int s8 = sm.scan[w8]; if (w8 < warp) before += s8; band_total += s8; }
             if (room) {
-                long long dpos = obase + kept_total + before + inc - cnt;
 #pragma unroll
                 for (int g = 0; g < RB_G; ++g)
                     if (keep[g]) {
-                        a.out.cells[dpos++] = make_int2(cc[g], __float_as_int(weighted ? dev_quantize_u16(vv[g]) : vv[g]));
+                        a.out.cells[obase + kept_total + before + rank[g]] = make_int2(cc[g], __float_as_int(weighted ? dev_quantize_u16(vv[g]) : vv[g]));
                         atomicAdd(&orp[rr[g] + 1], 1);
                     }
             }
