@@ -230,6 +230,15 @@ def families_per_sec(seqs):
     dt = time.time() - t0
     ok = r.returncode == 0 and os.path.getsize(os.path.join(tmp, "A.out")) > 0 if os.path.exists(os.path.join(tmp, "A.out")) else False
     out["quickprobs_b200_config_A"] = {"families": 1, "seconds": dt, "families_per_sec": 1.0 / dt, "ok": bool(ok)}
+    # persistent-process mode (csrc/serve.h, MLP_B200_SERVER=1): the second call finds the server and its CUDA context warm
+    env = dict(os.environ, MLP_B200_SERVER="1", MLP_B200_SERVER_IDLE="20")
+    subprocess.run([exe, fa, "-o", os.path.join(tmp, "A.out1")], capture_output=True, text=True, env=env)
+    t0 = time.time()
+    r = subprocess.run([exe, fa, "-o", os.path.join(tmp, "A.out2")], capture_output=True, text=True, env=env)
+    dt = time.time() - t0
+    same = os.path.exists(os.path.join(tmp, "A.out2")) and open(os.path.join(tmp, "A.out2"), "rb").read() == open(os.path.join(tmp, "A.out"), "rb").read()
+    out["quickprobs_b200_config_A_persistent_process"] = {"families": 1, "seconds": dt, "families_per_sec": 1.0 / dt, "ok": r.returncode == 0,
+                                                          "same_output_as_stand_alone": bool(same)}
     reg = os.path.join(ROOT, "tests", "golden", "regions", "inputs.tar.gz")
     if os.path.exists(reg):
         indir, outdir = os.path.join(tmp, "reg_in"), os.path.join(tmp, "reg_out")

@@ -8,6 +8,7 @@
 // read from the environment variable MLP_CPNP_SEED) pins the value the clock would have returned.
 // Options kept: -p, -G, -o/--outfile, -c/--consistency, -ir/--iterative-refinement, -v.  No CPU fallback.
 #include "../../include/mlprobs_b200.h"
+#include "serve.h"
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
@@ -28,7 +29,7 @@ struct Input { std::vector<std::string> headers, seqs; };
 // Sequence::Sequence(FileBuffer&, stripGaps = true), Sequence.h:52-122
 bool load_mfa(const std::string& path, Input& in) {
     std::ifstream f(path.c_str(), std::ios::binary);
-    if (!f.is_open()) { std::cerr << "ERROR: Could not open file '" << path << "' for reading." << std::endl; std::exit(1); }
+    if (!f.is_open()) { std::cerr << "ERROR: Could not open file '" << path << "' for reading." << std::endl; throw mlpserve::Exit{1}; }
     std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     size_t p = 0;
     while (p < all.size()) {
@@ -51,7 +52,7 @@ bool load_mfa(const std::string& path, Input& in) {
             if (ch == '.' || ch == '-') continue;               // stripGaps
             if (!((ch >= 'A' && ch <= 'Z') || (ch >= 'a' && ch <= 'z'))) {
                 std::cerr << "ERROR: Unknown character encountered: " << ch << std::endl;
-                std::exit(1);
+                throw mlpserve::Exit{1};
             }
             if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 'a' + 'A');
             data.push_back(ch);
@@ -70,8 +71,7 @@ void write_mfa(std::ostream& out, const std::string& header, const char* row, in
 
 int fail(mlp_ctx* ctx, const char* what, int rc) {
     std::fprintf(stderr, "c_p_np_aln_b200: %s failed (%d)%s%s\n", what, rc, ctx ? ": " : "", ctx ? mlp_last_error(ctx) : "");
-    if (ctx) mlp_destroy(ctx);
-    return 1;
+    return 1;                                          // the context belongs to main (or to the server): never destroyed here
 }
 
 }  // namespace
@@ -174,7 +174,8 @@ int run_file(mlp_ctx* ctx, const std::vector<std::string>& infiles, const std::s
     return 0;
 }
 
-int main(int argc, char** argv) {
+// the program proper; `shared` (persistent-process mode, serve.h) points to a context that outlives the call
+static int tool_main(int argc, char** argv, mlp_ctx** shared) {
     std::string outfile;
     std::vector<std::string> infiles;
     int program = 0, getpid = 0, reps = 2, refine = 100, device = 0, verbose = 0;
@@ -183,7 +184,7 @@ int main(int argc, char** argv) {
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char* name) -> const char* {
-            if (i + 1 >= argc) { std::cerr << "ERROR: Must specify a value after option " << name << "." << std::endl; std::exit(1); }
+            if (i + 1 >= argc) { std::cerr << "ERROR: Must specify a value after option " << name << "." << std::endl; throw mlpserve::Exit{1}; }
             return argv[++i];
         };
         if (a == "-o" || a == "--outfile") outfile = need("-o");
@@ -217,9 +218,10 @@ int main(int argc, char** argv) {
         if (probe.seqs.empty()) { std::cerr << "ERROR: No sequences read." << std::endl; return 1; }
         if (probe.seqs.size() < 2) { std::cerr << "ERROR: at least two sequences are required." << std::endl; return 1; }   // see run_file
     }
-    mlp_ctx* ctx = nullptr;
-    int rc = mlp_create(device, &ctx);                 // no CUDA device -> stop: nothing falls back to the CPU
+    mlp_ctx* ctx = shared ? *shared : nullptr;
+    int rc = ctx ? 0 : mlp_create(device, &ctx);                 // no CUDA device -> stop: nothing falls back to the CPU
     if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
+    if (shared) *shared = ctx;
     int status = 0;
     if (dir_mode) {
         std::vector<std::string> names;
@@ -237,6 +239,8 @@ int main(int argc, char** argv) {
             if (r1) status = r1;
         }
     } else status = run_file(ctx, infiles, outfile, getpid, reps, refine, verbose, program, seed);
-    mlp_destroy(ctx);
+    if (!shared) mlp_destroy(ctx);
     return status;
 }
+
+int main(int argc, char** argv) { return mlpserve::run("c_p_np_aln_b200", argc, argv, tool_main); }

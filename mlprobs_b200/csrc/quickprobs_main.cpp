@@ -7,6 +7,7 @@
 // ignored: there is no thread team), -v.  Anything else the reference offers (nucleotide mode, other trees, OpenCL
 // device selection, ClustalW output) is refused loudly rather than approximated.  There is no CPU fallback.
 #include "../../include/mlprobs_b200.h"
+#include "serve.h"
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
@@ -65,8 +66,7 @@ void write_fasta(std::ostream& out, const std::vector<std::string>& headers, con
 
 int fail(mlp_ctx* ctx, const char* what, int rc) {
     std::fprintf(stderr, "quickprobs_b200: %s failed (%d)%s%s\n", what, rc, ctx ? ": " : "", ctx ? mlp_last_error(ctx) : "");
-    if (ctx) mlp_destroy(ctx);
-    return 1;
+    return 1;                                          // the context belongs to main (or to the server): never destroyed here
 }
 
 }  // namespace
@@ -129,14 +129,15 @@ int align_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfi
     return 0;
 }
 
-int main(int argc, char** argv) {
+// the program proper; `shared` (persistent-process mode, serve.h) points to a context that outlives the call
+static int tool_main(int argc, char** argv, mlp_ctx** shared) {
     std::string infile, outfile;
     int con_iters = -1, ref_count = -1, device = 0, verbose = 0;
     unsigned ref_seed = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char* name) -> const char* {
-            if (i + 1 >= argc) { std::fprintf(stderr, "quickprobs_b200: option %s needs a value\n", name); std::exit(2); }
+            if (i + 1 >= argc) { std::fprintf(stderr, "quickprobs_b200: option %s needs a value\n", name); throw mlpserve::Exit{2}; }
             return argv[++i];
         };
         // ProgramOptions::parse (Common/ProgramOptions.cpp:15-48): any number of leading dashes, long or short name
@@ -172,9 +173,10 @@ int main(int argc, char** argv) {
         std::string err;
         if (!load_fasta(infile, probe, err)) { std::fprintf(stderr, "quickprobs_b200: %s\n", err.c_str()); return 255; }
     }
-    mlp_ctx* ctx = nullptr;
-    int rc = mlp_create(device, &ctx);                 // no CUDA device -> MLP_E_NO_DEVICE: stop here, nothing falls back to the CPU
+    mlp_ctx* ctx = shared ? *shared : nullptr;
+    int rc = ctx ? 0 : mlp_create(device, &ctx);                 // no CUDA device -> MLP_E_NO_DEVICE: stop here, nothing falls back to the CPU
     if (rc) return fail(nullptr, "mlp_create (a CUDA device is required)", rc);
+    if (shared) *shared = ctx;
     int status = 0;
     if (dir_mode) {
         std::vector<std::string> names;
@@ -192,6 +194,8 @@ int main(int argc, char** argv) {
             if (r1) status = r1;
         }
     } else status = align_file(ctx, infile, outfile, con_iters, ref_count, ref_seed, verbose);
-    mlp_destroy(ctx);
+    if (!shared) mlp_destroy(ctx);
     return status;
 }
+
+int main(int argc, char** argv) { return mlpserve::run("quickprobs_b200", argc, argv, tool_main); }

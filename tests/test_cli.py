@@ -6,6 +6,8 @@ import pytest
 from common import load_golden, split_seqs, HERE
 
 CLI = os.path.join(os.path.dirname(HERE), "mlprobs_b200", "bin", "quickprobs_b200")
+QP_EXE = CLI
+CPNP_EXE = os.path.join(os.path.dirname(HERE), "mlprobs_b200", "bin", "c_p_np_aln_b200")
 
 
 def fasta_text(headers, rows):
@@ -180,3 +182,25 @@ def test_quickprobs_cli_option_syntax(tmp_path):
         assert r.returncode == 255 and "unable to open input file" in r.stderr and r.stdout == "", opt
     r = subprocess.run([CLI, "-l", missing], capture_output=True, text=True)
     assert r.returncode == 2 and "unsupported option" in r.stderr
+
+
+@pytest.mark.gpu
+def test_persistent_process_mode_gives_the_stand_alone_output(tmp_path):
+    """MLP_B200_SERVER=1 (csrc/serve.h): the executable hands its command line to a server process of the same program that
+    keeps one CUDA context; outputs, exit status and error messages are those of the stand-alone run."""
+    from mlprobs_b200 import synth
+    seqs = synth.family(7, 60, seed=31)
+    fa = tmp_path / "in.fa"
+    fa.write_text("".join(">s%d\n%s\n" % (i, s.decode()) for i, s in enumerate(seqs)))
+    env = dict(os.environ, MLP_B200_SERVER="1", MLP_B200_SERVER_IDLE="3")
+    for exe, args in ((QP_EXE, []), (CPNP_EXE, ["-p", "0"]), (CPNP_EXE, ["-G"]), (CPNP_EXE, ["-p", "1", "--seed", "5"])):
+        alone = subprocess.run([exe] + args + [str(fa)], capture_output=True)
+        for _ in range(2):                                  # first call starts the server, second re-uses it
+            served = subprocess.run([exe] + args + [str(fa)], capture_output=True, env=env)
+            assert served.returncode == alone.returncode == 0
+            assert served.stdout == alone.stdout and len(alone.stdout) > 0
+    # errors travel too: unknown option and a missing file keep their message and status
+    for exe, args in ((CPNP_EXE, ["-zzz", str(fa)]), (QP_EXE, [str(tmp_path / "missing.fa")])):
+        alone = subprocess.run([exe] + args, capture_output=True)
+        served = subprocess.run([exe] + args, capture_output=True, env=env)
+        assert served.returncode == alone.returncode != 0 and served.stderr == alone.stderr

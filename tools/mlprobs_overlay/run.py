@@ -40,10 +40,12 @@ def assemble(mlprobs, binaries):
     return work
 
 
-def run(mlprobs, binaries, fasta, out, seed=None, keep=False, quiet=False, one_core=False):
+def run(mlprobs, binaries, fasta, out, seed=None, keep=False, quiet=False, one_core=False, server=False):
     work = assemble(os.path.abspath(mlprobs), binaries)
     env = dict(os.environ)
     env["PYTHONPATH"] = HERE + os.pathsep + env.get("PYTHONPATH", "")
+    if server:
+        env["MLP_B200_SERVER"] = "1"              # persistent-process mode of the drop-ins (csrc/serve.h): one CUDA context for all the driver's calls
     if seed is not None:
         env["MLP_CPNP_SEED"] = str(seed)          # c_p_np_aln_b200 -p 1: stands in for the clock the reference seeds with
     try:
@@ -65,9 +67,10 @@ if __name__ == "__main__":
     ap.add_argument("--binaries", choices=("b200", "reference"), default="b200")
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--server", action="store_true", help="b200 binaries in persistent-process mode (MLP_B200_SERVER=1)")
     ap.add_argument("--one-core", action="store_true", help="pin the run to one core (repeatable output with the reference programs)")
     ap.add_argument("fasta")
     ap.add_argument("out")
     a = ap.parse_args()
-    rc, _ = run(a.mlprobs, a.binaries, a.fasta, a.out, a.seed, a.keep, one_core=a.one_core)
+    rc, _ = run(a.mlprobs, a.binaries, a.fasta, a.out, a.seed, a.keep, one_core=a.one_core, server=a.server)
     sys.exit(rc)
