@@ -15,8 +15,10 @@ def run(report_path=None, suites=None, tools=None):
     man = manifest["families"]
     seed = str(manifest.get("p1_fixtime", 777))
     tmp = tempfile.mkdtemp()
-    with tarfile.open(os.path.join(SUITES, "inputs.tar.gz")) as tar:
-        tar.extractall(tmp, filter="data")
+    for arc in ("inputs.tar.gz", "inputs_rest.tar.gz"):          # the second archive: the large families pinned in round 2
+        if os.path.exists(os.path.join(SUITES, arc)):
+            with tarfile.open(os.path.join(SUITES, arc)) as tar:
+                tar.extractall(tmp, filter="data")
     report = {"suites": {}, "mismatches": [], "failures": []}
     for suite in sorted({m["suite"] for m in man}):
         if suites and suite not in suites:
