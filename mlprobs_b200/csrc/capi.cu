@@ -344,7 +344,7 @@ static int ensure_warp_buffers(mlp_ctx* ctx, long long warps, int maxL1, int max
             free_dev(ctx->d_edge); ctx->d_edge = nullptr;
             ctx->edge_stride = std::max(want_edge, ctx->edge_stride);
             ctx->edge_warps = std::max(warps, ctx->edge_warps);
-            CK(cudaMalloc(&ctx->d_edge, (size_t)ctx->edge_warps * ctx->edge_stride * sizeof(double)));
+            CK(cudaMalloc(&ctx->d_edge, (size_t)2 * ctx->edge_warps * ctx->edge_stride * sizeof(double)));   // second half: the partition sweeps when they run beside the HMM sweeps (MLP_OVERLAP)
         }
     }
     return MLP_OK;
@@ -518,8 +518,10 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         const int capP = fork ? (ctx->bps_part > 0 ? ctx->bps_part : 2) : 0;
         const int capH = fork ? (ctx->bps_hmm > 0 ? ctx->bps_hmm : 4) : 0;
         if (useP) {
-            if ((rc = launch_one(ctx, MLP_K_PART_FWD, a, nt, kt, MLP_K_PART_FWD, sp, capP, &cgroups)) != MLP_OK) return rc;
-            if ((rc = launch_one(ctx, MLP_K_PART_REV, a, nt, kt, MLP_K_PART_REV, sp, capP, &cgroups)) != MLP_OK) return rc;
+            KArgs ap = a;
+            if (fork && need_edge) ap.edge_d = (double*)ctx->d_edge + (size_t)ctx->edge_warps * ctx->edge_stride;   // own hand-off buffer: the HMM sweeps run at the same time
+            if ((rc = launch_one(ctx, MLP_K_PART_FWD, ap, nt, kt, MLP_K_PART_FWD, sp, capP, &cgroups)) != MLP_OK) return rc;
+            if ((rc = launch_one(ctx, MLP_K_PART_REV, ap, nt, kt, MLP_K_PART_REV, sp, capP, &cgroups)) != MLP_OK) return rc;
         }
         if (useL) {
             // the local model's Z terms alias the partition layer: it must wait for the partition posterior
