@@ -136,14 +136,18 @@ def test_column_scores_equal_the_reference_python_function():
 
 
 def test_suite_fixture_is_consistent():
-    """tests/golden/suites: every family of the manifest has its input in the archive and both reference digests."""
+    """tests/golden/suites: every family of the manifest has its input in one of the two archives (inputs_rest.tar.gz: the large
+    families pinned in round 2) and a quickprobs digest; the round-1 families also have the c_p_np_aln one."""
     import json, tarfile
     base = os.path.join(os.path.dirname(__file__), "golden", "suites")
     man = json.load(open(os.path.join(base, "manifest.json")))["families"]
-    with tarfile.open(os.path.join(base, "inputs.tar.gz")) as t:
-        names = {m.name for m in t.getmembers() if m.isfile()}
-    assert {m["suite"] + "/" + m["name"] for m in man} == names and len(man) > 1000
-    assert all(m["qp_sha"] and m["cpnp_sha"] for m in man)
+    names = set()
+    for arc in ("inputs.tar.gz", "inputs_rest.tar.gz"):
+        with tarfile.open(os.path.join(base, arc)) as t:
+            names |= {m.name for m in t.getmembers() if m.isfile()}
+    assert {m["suite"] + "/" + m["name"] for m in man} == names and len(man) > 1500
+    assert all(m["qp_sha"] for m in man)
+    assert all(m["cpnp_sha"] for m in man if not m.get("rest"))
 
 
 def test_g_feature_line_host_code_on_suite_families():
@@ -154,7 +158,7 @@ def test_g_feature_line_host_code_on_suite_families():
     from common import HERE
     import oracle_lib as O
     suites = os.path.join(HERE, "golden", "suites")
-    man = [m for m in json.load(open(os.path.join(suites, "manifest.json")))["families"] if m.get("cpnpG")]
+    man = [m for m in json.load(open(os.path.join(suites, "manifest.json")))["families"] if m.get("cpnpG") and not m.get("rest")]   # the round-1 (small) families
     assert len(man) > 500
     texts = {}
     with tarfile.open(os.path.join(suites, "inputs.tar.gz")) as tar:
