@@ -207,6 +207,13 @@ int mlp_get_csr_raw(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, int32_t* rp_
  * after the last row are 0), so rowIndices are their running sum.  Any pointer may be NULL.  Packing runs on the device
  * into the idle half of the double-buffered cell pool. */
 int mlp_get_csr_packed(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells);
+/* The same read-back in two halves: _begin packs the current set and enqueues the copies on a stream of its own, _end waits
+ * for them.  In between the caller may submit the next family (mlp_set_sequences of the same shape) and run its
+ * mlp_posterior_all_pairs: the PCIe transfer of one result hides behind the next posterior stage.  Calls that would overwrite
+ * the set being read (mlp_relax, a gathering exchange, a family of another shape, ...) end the read-back themselves.
+ * The host buffers (page-locked for a truly asynchronous copy, mlp_alloc_pinned) must not be touched before _end. */
+int mlp_get_csr_packed_begin(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells);
+int mlp_get_csr_packed_end(mlp_ctx* ctx);
 int mlp_alloc_pinned(int64_t bytes, void** out);
 void mlp_free_pinned(void* p);
 

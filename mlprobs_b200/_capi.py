@@ -25,7 +25,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
            "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end",
-           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_set_digest"]
+           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
 
 
 class HmmTables(C.Structure):
@@ -88,6 +88,8 @@ def load():
         lib.mlp_csr_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.mlp_get_csr_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mlp_get_csr_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_get_csr_packed_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mlp_get_csr_packed_end.argtypes = [C.c_void_p]
         lib.mlp_qp_guide_tree_ex.argtypes = [C.c_int] + [C.c_void_p] * 6
         lib.mlp_alloc_pinned.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
         lib.mlp_free_pinned.argtypes = [C.c_void_p]
@@ -565,6 +567,18 @@ class Engine:
         self._ck(self._lib.mlp_get_csr_packed(self._ctx, _ptr(out.nz_off), _ptr(out.nz_cnt), _ptr(out.row_sizes), _ptr(out.cells)))
         out.rp_off, out.rp_total, out.used = rp_off, rp_total, used
         return out
+
+    def csr_packed_begin(self, out):
+        """Start the packed read-back into `out` (PinnedPackedBuffers); csr_packed_end() waits for it.  The next family's posterior
+        stage may run in between."""
+        rp_off, rp_total, used = self.csr_layout()
+        out.ensure(self.n, rp_total, used)
+        self._ck(self._lib.mlp_get_csr_packed_begin(self._ctx, _ptr(out.nz_off), _ptr(out.nz_cnt), _ptr(out.row_sizes), _ptr(out.cells)))
+        out.rp_off, out.rp_total, out.used = rp_off, rp_total, used
+        return out
+
+    def csr_packed_end(self):
+        self._ck(self._lib.mlp_get_csr_packed_end(self._ctx))
 
     def total_cells(self):
         c = C.c_int64(0)

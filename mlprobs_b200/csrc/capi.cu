@@ -37,6 +37,9 @@ static void release_launch_scratch(mlp_ctx* ctx) {
     free_dev(ctx->d_wk); ctx->d_wk = nullptr; ctx->wk_warps = 0;
 }
 
+// a split read-back must have finished before the set it reads (or any pool) is touched again
+#define END_READBACK(ctx) do { if ((ctx)->rb_set >= 0) { const int rcr__ = mlp_get_csr_packed_end(ctx); if (rcr__ != MLP_OK) return rcr__; } } while (0)
+
 extern "C" int mlp_create(int device, mlp_ctx** out) {
     if (!out) return MLP_E_ARG;
     *out = nullptr;
@@ -54,6 +57,7 @@ extern "C" int mlp_create(int device, mlp_ctx** out) {
     cudaEventCreate(&ctx->ev[0]); cudaEventCreate(&ctx->ev[1]);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_dist, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->stream_rb, cudaStreamNonBlocking); cudaEventCreateWithFlags(&ctx->ev_rb, cudaEventDisableTiming);
     if (const char* e = getenv("MLP_OVERLAP")) ctx->overlap = atoi(e);
     if (const char* e = getenv("MLP_BPS_PART")) ctx->bps_part = atoi(e);
     if (const char* e = getenv("MLP_BPS_HMM")) ctx->bps_hmm = atoi(e);
@@ -69,6 +73,9 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_rb) { cudaStreamSynchronize(ctx->stream_rb); cudaStreamDestroy(ctx->stream_rb); }
+    if (ctx->ev_rb) cudaEventDestroy(ctx->ev_rb);
+    free_dev(ctx->d_pack);
     release_sets(ctx);
     release_launch_scratch(ctx);
     if (ctx->tail_prov && ctx->tail_prov_free) ctx->tail_prov_free(ctx->tail_prov);
@@ -192,6 +199,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     const bool same_layout = ctx->have_sets && ctx->n == n && std::equal(len, len + n, ctx->len.begin());
     if (!same_layout) ctx->have_sets = false;        // the pools themselves stay: ensure_sets re-uses them when the new family fits
     const bool same_shape = ctx->n == n && (int)ctx->len.size() == n && std::equal(len, len + n, ctx->len.begin()) && !ctx->all_pairs.empty();
+    if (!same_shape) END_READBACK(ctx);              // a different family may re-allocate the pools a split read-back is copying from
     ctx->flavour_of_set = -1;
     ctx->set_partial = ctx->dist_partial = false;
     ctx->n = n;
@@ -692,6 +700,7 @@ extern "C" int mlp_viterbi_all_pairs_ex(mlp_ctx* ctx, int32_t* n_identical, int3
 extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model_mask, float cutoff) {
     if (!ctx) return MLP_E_ARG;
     if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
+    if (ctx->rb_set == 0) END_READBACK(ctx);         // this stage writes set 0; a read-back of set 1 (a relaxed set) may go on beside it
     cudaSetDevice(ctx->device);
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
@@ -733,6 +742,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
 extern "C" int mlp_debug_pair_dense(mlp_ctx* ctx, int flavour, uint32_t model_mask, int a, int b,
                                     float* merged, float* p_hmm5, float* p_part, float* p_local, float* distance) {
     if (!ctx || !merged) return MLP_E_ARG;
+    END_READBACK(ctx);
     cudaSetDevice(ctx->device);
     if (!ctx->have_tables || ctx->n < 2) return MLP_E_STATE;
     if (a < 0 || b <= a || b >= ctx->n) return MLP_E_ARG;
@@ -934,6 +944,7 @@ __global__ void k_row_sizes(const int* __restrict__ rp, unsigned short* __restri
 
 extern "C" int mlp_get_csr_packed(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells) {
     if (!ctx) return MLP_E_ARG;
+    END_READBACK(ctx);
     if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     if (!ctx->have_sets) return MLP_E_STATE;
     if (ctx->flavour_of_set != MLP_QP) { ctx->err = "packed cells are the QuickProbs format (uint16 fixed-point values)"; return MLP_E_UNSUPPORTED; }
@@ -1031,6 +1042,62 @@ extern "C" int mlp_set_digest(mlp_ctx* ctx, uint64_t* per_matrix_nn) {
     return MLP_OK;
 }
 
+// Split read-back: _begin packs the current set into the context's own pack buffer and enqueues the copies on a separate stream,
+// _end waits for them.  Between the two the caller may run the NEXT posterior stage (it writes set 0 and the dense scratch,
+// the relaxed set being read is set 1): the PCIe transfer of one step's result then hides behind the compute of the next.
+// Every call that would overwrite the set being read ends the read-back first.  The host buffers must stay untouched until _end.
+extern "C" int mlp_get_csr_packed_begin(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells) {
+    if (!ctx) return MLP_E_ARG;
+    END_EXCHANGE(ctx);
+    END_READBACK(ctx);
+    if (!ctx->have_sets) return MLP_E_STATE;
+    if (ctx->flavour_of_set != MLP_QP) { ctx->err = "packed cells are the QuickProbs format (uint16 fixed-point values)"; return MLP_E_UNSUPPORTED; }
+    cudaSetDevice(ctx->device);
+    const CsrSetDev& s = ctx->set[ctx->cur];
+    const size_t nn = (size_t)ctx->n * ctx->n;
+    unsigned long long used = 0;
+    { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
+    used = std::min<unsigned long long>(used, (unsigned long long)s.cap);
+    const unsigned long long used_even = (used + 1) & ~1ull;
+    const size_t need_bytes = (size_t)used_even * 4 + (size_t)ctx->rp_total * 2 + 64;
+    if (need_bytes > ctx->pack_bytes) {
+        free_dev(ctx->d_pack); ctx->d_pack = nullptr; ctx->pack_bytes = 0;
+        CK(cudaMalloc(&ctx->d_pack, need_bytes + need_bytes / 16));
+        ctx->pack_bytes = need_bytes + need_bytes / 16;
+    }
+    unsigned* d_cells = reinterpret_cast<unsigned*>(ctx->d_pack);
+    unsigned short* d_sizes = reinterpret_cast<unsigned short*>(d_cells + used_even);
+    cudaStream_t st = ctx->stream_rb;
+    CK(cudaEventRecord(ctx->ev_rb, ctx->stream));            // everything queued on the main stream so far (the stage that produced the set)
+    CK(cudaStreamWaitEvent(st, ctx->ev_rb, 0));
+    const int grid = ctx->num_sms * 2;                       // a thin grid: it shares the SMs with the next stage
+    if (nz_off) { CK(cudaMemcpyAsync(nz_off, s.nz_off, nn * sizeof(long long), cudaMemcpyDeviceToHost, st)); ctx->stats.d2h_bytes += (int64_t)nn * 8; }
+    if (nz_cnt) { CK(cudaMemcpyAsync(nz_cnt, s.nz_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, st)); ctx->stats.d2h_bytes += (int64_t)nn * 4; }
+    if (row_sizes) {
+        k_row_sizes<<<grid, 256, 0, st>>>(s.rp_pool, d_sizes, ctx->rp_total);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(row_sizes, d_sizes, (size_t)ctx->rp_total * 2, cudaMemcpyDeviceToHost, st));
+        ctx->stats.d2h_bytes += ctx->rp_total * 2; ctx->stats.launches += 1;
+    }
+    if (cells && used) {
+        k_pack_cells<<<grid, 256, 0, st>>>(s.cells, d_cells, (long long)used);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(cells, d_cells, (size_t)used * 4, cudaMemcpyDeviceToHost, st));
+        ctx->stats.d2h_bytes += (int64_t)used * 4; ctx->stats.launches += 1;
+    }
+    ctx->rb_set = ctx->cur;
+    return MLP_OK;
+}
+
+extern "C" int mlp_get_csr_packed_end(mlp_ctx* ctx) {
+    if (!ctx) return MLP_E_ARG;
+    if (ctx->rb_set < 0) return MLP_OK;
+    cudaSetDevice(ctx->device);
+    ctx->rb_set = -1;
+    CK(cudaStreamSynchronize(ctx->stream_rb));
+    return MLP_OK;
+}
+
 extern "C" int mlp_alloc_pinned(int64_t bytes, void** out) {
     if (!out || bytes <= 0) return MLP_E_ARG;
     return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? MLP_OK : MLP_E_CUDA;
@@ -1041,6 +1108,7 @@ extern "C" void mlp_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
                          float selectivity, float selfweight, float cutoff) {
     if (!ctx) return MLP_E_ARG;
+    END_READBACK(ctx);                               // the relaxation writes the set a split read-back may still be reading
     if (ctx->exch_pending) { const int rce = mlp_exchange_end(ctx); if (rce != MLP_OK) return rce; }
     if (!ctx->have_sets || ctx->flavour_of_set < 0) { ctx->err = "run mlp_posterior_all_pairs first"; return MLP_E_STATE; }
     cudaSetDevice(ctx->device);

@@ -77,6 +77,10 @@ struct mlp_ctx {
     unsigned long long* d_xused = nullptr;               // per-rank cell counts of an exchange
     unsigned* d_xq = nullptr; size_t xq_cap = 0;          // packed wire buffer of the QuickProbs exchange
     bool set_partial = false, dist_partial = false;       // sharded stage output not yet exchanged (set by posterior / relax, cleared by mlp_exchange)
+    // split read-back (mlp_get_csr_packed_begin / _end): own stream and pack buffers, so that the copy of one step's result runs
+    // beside the posterior stage of the next; rb_set = the set being read (-1: none)
+    cudaStream_t stream_rb = nullptr; cudaEvent_t ev_rb = nullptr; int rb_set = -1;
+    void* d_pack = nullptr; size_t pack_bytes = 0;
     cudaEvent_t ev_dist = nullptr; bool exch_pending = false; unsigned long long exch_total = 0;   // split exchange (mlp_exchange_begin / _end)
     // stats
     mlp_stage_stats stats = {};

@@ -126,6 +126,7 @@ extern "C" int mlp_exchange_begin(mlp_ctx* ctx) {
     if (!ctx) return MLP_E_ARG;
     if (ctx->comm_world <= 1) return MLP_OK;
     if (ctx->exch_pending) { const int rc0 = mlp_exchange_end(ctx); if (rc0 != MLP_OK) return rc0; }
+    if (ctx->rb_set >= 0) { const int rcr = mlp_get_csr_packed_end(ctx); if (rcr != MLP_OK) return rcr; }   // the gather lands in the other set's cell pool
     if (!ctx->nccl_comm || !ctx->have_sets) { ctx->err = "mlp_comm_init and a posterior/relax stage must come first"; return MLP_E_STATE; }
     // The merge is a SUM over ranks of tables whose foreign slots are zero: it is only correct on a set a sharded stage has
     // just produced.  A set that is already complete (second call without a stage in between) is left alone.

@@ -572,3 +572,36 @@ def test_qp_selectivity_fixture_400_sequences():
     digest("sF", False)
     digest("tF", True)
     eng.close()
+
+
+def test_split_read_back_overlapping_the_next_posterior_stage():
+    """mlp_get_csr_packed_begin / _end: the packed copy of a relaxed set runs on its own stream while the same family is
+    submitted again and its posterior stage runs; what arrives equals the synchronous read-back, and the second pass is
+    unharmed."""
+    seqs = synth.family(9, 110, seed=44)
+    eng = engine(M.QP, seqs)
+
+    def stage():
+        eng.posterior_all_pairs(M.QP, 3, 0.01)
+        t = M.qp_guide_tree_ex(eng.distances())
+        w = np.maximum(t["weights"], np.float32(1e-6))
+        return w, t["seldist"]
+
+    w, sd = stage()
+    eng.relax(M.QP, w, sd, 200.0, 3.0, 0.01)
+    ref = eng.csr_packed()
+    want = (ref.nz_off.copy(), ref.nz_cnt.copy(), ref.row_sizes[:ref.rp_total].copy(), ref.cells[:ref.used].copy())
+    lay = eng.csr_layout()
+    out = M.PinnedPackedBuffers(len(seqs), lay[1], lay[2])
+    eng.csr_packed_begin(out)
+    eng.set_sequences(seqs)                      # same shape: the pools stay, the read-back goes on
+    w2, sd2 = stage()                            # posterior of the "next family" beside the copy
+    eng.relax(M.QP, w2, sd2, 200.0, 3.0, 0.01)   # ends the read-back before it overwrites the set
+    got = (out.nz_off, out.nz_cnt, out.row_sizes[:out.rp_total], out.cells[:out.used])
+    for x, y in zip(want, got):
+        np.testing.assert_array_equal(x, y)
+    again = eng.csr_packed()
+    np.testing.assert_array_equal(again.cells[:again.used], want[3])
+    np.testing.assert_array_equal(again.nz_cnt, want[1])
+    eng.csr_packed_end()
+    eng.close()
