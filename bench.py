@@ -218,6 +218,26 @@ def cpnp_object(M, dev, seqs, total_cells, n_sub):
                                 "cells_in": int(cells_in), "extrapolated_ms_per_rep_at_n": r1["ms_total"] * (npairs * (len(seqs) - 2)) / pz,
                                 "note": "first %d sequences; cost is proportional to pairs x (N-2), the extrapolation to N = %d is labelled as such" % (ns, len(seqs))}
     eng.close()
+    # the reference's own code for this flavour on the host cores: unmodified c_p_np_aln sources behind oracle/_ref/ref_cpnp, all models
+    # (class 0), two consistency repetitions, on the first 64 sequences; the consistency part is cubic in N and is compared per (pair, z)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cpnp")
+    if os.path.exists(exe):
+        n_ref = 64
+        cores = os.cpu_count() or 1
+        tmp = os.path.join("/tmp", "mlp_cpnp_ref_%d.fa" % os.getpid())
+        write_fasta(tmp, seqs[:n_ref])
+        r = subprocess.run([exe, "bench", tmp, "--pid", "0", "--reps", "2", "--threads", str(cores)], capture_output=True, text=True).stdout
+        os.unlink(tmp)
+        try:
+            j = json.loads(r.strip().splitlines()[-1])
+            pz_ref = 2 * j["pairs"] * (j["n"] - 2) / j["t_relax_s"]
+            out["cpu_reference"] = {"kind": "reference", "cores": cores, "sample": "first %d sequences of the same family (%d pairs), model class 0, 2 consistency repetitions" % (n_ref, j["pairs"]),
+                                    "posterior_gcups": j["cells"] * j["models"] / j["t_posterior_s"] / 1e9, "posterior_s": j["t_posterior_s"],
+                                    "relax_pair_z_per_sec": pz_ref, "relax_s": j["t_relax_s"],
+                                    "extrapolated_relax_s_per_rep_at_n": (npairs * (len(seqs) - 2)) / pz_ref,
+                                    "note": "the extrapolation to N = %d assumes the cost stays proportional to pairs x (N-2); it is an extrapolation, not a measurement" % len(seqs)}
+        except Exception as e:
+            out["cpu_reference"] = {"error": str(e)[:200]}
     return out
 
 
@@ -342,7 +362,7 @@ def main():
     for _ in range(args.steps):
         stats, out, _ = one_step(eng, M, n, True, seqs, world=world, host_out=host_out)
         h2d = sum(s["h2d_bytes"] for _, s in stats) + sum(len(s) for s in seqs)
-        d2h = n * n * 4 + (out.nbytes() if out is not None else 0)
+        d2h = n * n * 4 + eng.stats()["d2h_bytes"]   # distances + what the read-back enqueued (nz_off, nz_cnt, row sizes of the owned matrices, cells)
     eng.csr_packed_end()                       # the last step's read-back, inside the timed region
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps

@@ -75,7 +75,8 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream_rb) { cudaStreamSynchronize(ctx->stream_rb); cudaStreamDestroy(ctx->stream_rb); }
     if (ctx->ev_rb) cudaEventDestroy(ctx->ev_rb);
-    free_dev(ctx->d_pack);
+    free_dev(ctx->d_pack); free_dev(ctx->d_rs_off); free_dev(ctx->d_rs_tasks);
+    if (ctx->h_rs_stage) cudaFreeHost(ctx->h_rs_stage);
     release_sets(ctx);
     release_launch_scratch(ctx);
     if (ctx->tail_prov && ctx->tail_prov_free) ctx->tail_prov_free(ctx->tail_prov);
@@ -1046,6 +1047,20 @@ extern "C" int mlp_set_digest(mlp_ctx* ctx, uint64_t* per_matrix_nn) {
 // _end waits for them.  Between the two the caller may run the NEXT posterior stage (it writes set 0 and the dense scratch,
 // the relaxed set being read is set 1): the PCIe transfer of one step's result then hides behind the compute of the next.
 // Every call that would overwrite the set being read ends the read-back first.  The host buffers must stay untouched until _end.
+// row sizes of the owned matrices only, concatenated in owned-list order ((a,b) then (b,a) of every task)
+__global__ void k_row_sizes_owned(const PairTask* __restrict__ tasks, int ntasks, int n, const long long* __restrict__ rp_off, const int* __restrict__ rp_pool,
+                                  const long long* __restrict__ rs_off, unsigned short* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = gw; w < 2LL * ntasks; w += nw) {
+        const PairTask t = tasks[w >> 1];
+        const int a = (w & 1) ? t.b : t.a, b = (w & 1) ? t.a : t.b, rows = ((w & 1) ? t.L2 : t.L1) + 2;
+        const int* rp = rp_pool + rp_off[(long long)a * n + b];
+        unsigned short* o = out + rs_off[w >> 1] + ((w & 1) ? t.L1 + 2 : 0);
+        for (int i = lane; i < rows; i += 32) { const int d = (i + 1 < rows) ? rp[i + 1] - rp[i] : 0; o[i] = (unsigned short)(d > 0 ? d : 0); }
+    }
+}
+
 extern "C" int mlp_get_csr_packed_begin(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uint16_t* row_sizes, uint32_t* cells) {
     if (!ctx) return MLP_E_ARG;
     END_EXCHANGE(ctx);
@@ -1073,7 +1088,40 @@ extern "C" int mlp_get_csr_packed_begin(mlp_ctx* ctx, int64_t* nz_off, int32_t* 
     const int grid = ctx->num_sms * 2;                       // a thin grid: it shares the SMs with the next stage
     if (nz_off) { CK(cudaMemcpyAsync(nz_off, s.nz_off, nn * sizeof(long long), cudaMemcpyDeviceToHost, st)); ctx->stats.d2h_bytes += (int64_t)nn * 8; }
     if (nz_cnt) { CK(cudaMemcpyAsync(nz_cnt, s.nz_cnt, nn * sizeof(int), cudaMemcpyDeviceToHost, st)); ctx->stats.d2h_bytes += (int64_t)nn * 4; }
-    if (row_sizes) {
+    ctx->rb_row_sizes = nullptr;
+    if (row_sizes && ctx->world > 1) {
+        // sharded set: this rank's matrices are an N-th of the fixed-layout table -- ship only those, scatter them on the host in _end
+        const std::vector<PairTask>& own = ctx->owned;
+        ctx->rs_off_h.resize(own.size() + 1);
+        long long tot = 0;
+        for (size_t k = 0; k < own.size(); ++k) { ctx->rs_off_h[k] = tot; tot += own[k].L1 + 2 + own[k].L2 + 2; }
+        ctx->rs_off_h[own.size()] = tot;
+        if ((size_t)tot + 64 > ctx->rs_stage_cap) {
+            if (ctx->h_rs_stage) cudaFreeHost(ctx->h_rs_stage);
+            ctx->h_rs_stage = nullptr; ctx->rs_stage_cap = 0;
+            CK(cudaHostAlloc((void**)&ctx->h_rs_stage, ((size_t)tot + tot / 8 + 64) * 2, cudaHostAllocDefault));
+            ctx->rs_stage_cap = (size_t)tot + tot / 8 + 64;
+        }
+        if (own.size() + 1 > ctx->rs_off_cap) {
+            free_dev(ctx->d_rs_off); ctx->d_rs_off = nullptr;
+            CK(cudaMalloc(&ctx->d_rs_off, (own.size() + own.size() / 4 + 64) * sizeof(long long)));
+            ctx->rs_off_cap = own.size() + own.size() / 4 + 64;
+        }
+        if (own.size() > ctx->rs_tasks_cap) {        // own copy of the task list: d_tasks belongs to the stages running beside this read-back
+            free_dev(ctx->d_rs_tasks); ctx->d_rs_tasks = nullptr;
+            CK(cudaMalloc(&ctx->d_rs_tasks, (own.size() + own.size() / 4 + 64) * sizeof(PairTask)));
+            ctx->rs_tasks_cap = own.size() + own.size() / 4 + 64;
+        }
+        CK(cudaMemcpyAsync(ctx->d_rs_tasks, own.data(), own.size() * sizeof(PairTask), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_rs_off, ctx->rs_off_h.data(), (own.size() + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        if (!own.empty()) {
+            k_row_sizes_owned<<<grid, 256, 0, st>>>(ctx->d_rs_tasks, (int)own.size(), ctx->n, ctx->d_rp_off, s.rp_pool, ctx->d_rs_off, d_sizes);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(ctx->h_rs_stage, d_sizes, (size_t)tot * 2, cudaMemcpyDeviceToHost, st));
+        }
+        ctx->stats.d2h_bytes += tot * 2; ctx->stats.launches += 1;
+        ctx->rb_row_sizes = row_sizes; ctx->rb_rs_total = tot;
+    } else if (row_sizes) {
         k_row_sizes<<<grid, 256, 0, st>>>(s.rp_pool, d_sizes, ctx->rp_total);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(row_sizes, d_sizes, (size_t)ctx->rp_total * 2, cudaMemcpyDeviceToHost, st));
@@ -1095,6 +1143,19 @@ extern "C" int mlp_get_csr_packed_end(mlp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->rb_set = -1;
     CK(cudaStreamSynchronize(ctx->stream_rb));
+    if (ctx->rb_row_sizes) {          // sharded set: the owned matrices' row sizes go to their places in the caller's fixed-layout table
+        const std::vector<PairTask>& own = ctx->owned;
+        uint16_t* dst = ctx->rb_row_sizes;
+        const int n = ctx->n;
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < (long long)own.size(); ++k) {
+            const PairTask& t = own[k];
+            const unsigned short* src = ctx->h_rs_stage + ctx->rs_off_h[k];
+            std::memcpy(dst + ctx->rp_off_h[(size_t)t.a * n + t.b], src, (size_t)(t.L1 + 2) * 2);
+            std::memcpy(dst + ctx->rp_off_h[(size_t)t.b * n + t.a], src + t.L1 + 2, (size_t)(t.L2 + 2) * 2);
+        }
+        ctx->rb_row_sizes = nullptr;
+    }
     return MLP_OK;
 }
 

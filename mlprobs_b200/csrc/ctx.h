@@ -81,6 +81,10 @@ struct mlp_ctx {
     // beside the posterior stage of the next; rb_set = the set being read (-1: none)
     cudaStream_t stream_rb = nullptr; cudaEvent_t ev_rb = nullptr; int rb_set = -1;
     void* d_pack = nullptr; size_t pack_bytes = 0;
+    // sharded sets: only the row sizes of the owned matrices cross PCIe (compact, in owned-list order) and are scattered into the
+    // caller's fixed-layout table by _end
+    unsigned short* h_rs_stage = nullptr; size_t rs_stage_cap = 0; long long* d_rs_off = nullptr; size_t rs_off_cap = 0; PairTask* d_rs_tasks = nullptr; size_t rs_tasks_cap = 0;
+    std::vector<long long> rs_off_h; uint16_t* rb_row_sizes = nullptr; long long rb_rs_total = 0;
     cudaEvent_t ev_dist = nullptr; bool exch_pending = false; unsigned long long exch_total = 0;   // split exchange (mlp_exchange_begin / _end)
     // stats
     mlp_stage_stats stats = {};

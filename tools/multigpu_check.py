@@ -57,6 +57,16 @@ def run_selective(sharded, fam):
     w = np.maximum(t["weights"], np.float32(1e-6))
     if sharded: eng.exchange_needed(t["seldist"], 200.0)
     eng.relax(M.QP, w, t["seldist"], 200.0, 3.0, float(np.float32(1e-5)))
+    # sharded packed read-back (split call): the owned matrices' row sizes are shipped compact and scattered into the fixed layout
+    lay = eng.csr_layout()
+    out = M.PinnedPackedBuffers(len(fam), lay[1], lay[2])
+    eng.csr_packed_begin(out); eng.csr_packed_end()
+    own = M.shard_pairs(eng.lens, rank if sharded else 0, world if sharded else 1)
+    for a, b in [tuple(x) for x in own[:: max(1, len(own) // 7)]]:
+        for x, y in ((a, b), (b, a)):
+            rp, col, val = eng.csr(x, y)
+            got_rp, got_col, got_val = out.matrix(x, y, eng.lens)
+            assert np.array_equal(rp, got_rp) and np.array_equal(col, got_col) and np.array_equal(val, got_val), (x, y)
     dg = torch.from_numpy(eng.set_digest().view(np.int64)).cuda()
     if sharded: dist.all_reduce(dg)                   # int64 wrap-around sum == sum mod 2^64
     dg = dg.cpu().numpy()
