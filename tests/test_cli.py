@@ -204,3 +204,24 @@ def test_persistent_process_mode_gives_the_stand_alone_output(tmp_path):
         alone = subprocess.run([exe] + args, capture_output=True)
         served = subprocess.run([exe] + args, capture_output=True, env=env)
         assert served.returncode == alone.returncode != 0 and served.stderr == alone.stderr
+
+
+def test_persistent_process_mode_protocol_without_a_gpu(tmp_path):
+    """The client/server plumbing of csrc/serve.h needs no device to be exercised: without a GPU the server's run ends in the same
+    'a CUDA device is required' error, input errors keep their message and exit status, and the server goes away when idle."""
+    import time
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu test")
+    fa, _ = write_input(tmp_path, [b"ACDEFGHIK", b"ACDEFGHIK", b"ACDEFGHIKL"])
+    env = dict(os.environ, MLP_B200_SERVER="1", MLP_B200_SERVER_IDLE="2")
+    sock = "/tmp/mlprobs_b200_%d_%s.sock" % (os.getuid(), "quickprobs_b200")
+    for exe, args in ((QP_EXE, [fa]), (CPNP_EXE, ["-p", "0", fa]), (CPNP_EXE, ["-zzz", fa]), (QP_EXE, [str(tmp_path / "missing.fa")])):
+        alone = subprocess.run([exe] + args, capture_output=True, text=True)
+        for _ in range(2):
+            served = subprocess.run([exe] + args, capture_output=True, text=True, env=env)
+            assert served.returncode == alone.returncode != 0
+            assert served.stderr == alone.stderr and served.stdout == alone.stdout
+    assert os.path.exists(sock)                      # a server was started and is listening
+    time.sleep(4)
+    assert not os.path.exists(sock)                  # idle for MLP_B200_SERVER_IDLE seconds: it removed its socket and left
