@@ -65,6 +65,8 @@ extern "C" int mlp_create(int device, mlp_ctx** out) {
         delete ctx; return MLP_E_CUDA;
     }
     cudaMemset(ctx->d_err, 0, sizeof(int));
+    if (cudaHostAlloc((void**)&ctx->h_flags, 4 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->d_hflags, ctx->h_flags, 0) != cudaSuccess) { delete ctx; return MLP_E_CUDA; }
     *out = ctx;
     return MLP_OK;
 }
@@ -83,6 +85,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_res); free_dev(ctx->d_seq_off);
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp); free_dev(ctx->d_relax_tasks);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -302,11 +305,21 @@ static int ensure_sets(mlp_ctx* ctx) {
 
 // The context's stream is cudaStreamNonBlocking: a legacy-stream cudaMemcpy is NOT ordered against work queued on it.
 // Every host read of a set's cursor goes through the stream itself.
-int read_cursor(mlp_ctx* ctx, int which, unsigned long long* out) {
-    CK(cudaMemcpyAsync(out, ctx->set[which].cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+__global__ void k_publish(const unsigned long long* cursor, const int* err, volatile unsigned long long* host_words) {
+    if (cursor) host_words[0] = *cursor;
+    if (err) host_words[1] = (unsigned long long)(unsigned)*err;
+    __threadfence_system();
+}
+// cursor of a set and / or the error word, through the host-mapped words (no DMA copy, see ctx.h)
+int read_words(mlp_ctx* ctx, int which, unsigned long long* cursor_out, int* err_out) {
+    k_publish<<<1, 1, 0, ctx->stream>>>(cursor_out ? ctx->set[which].cursor : nullptr, err_out ? ctx->d_err : nullptr, ctx->d_hflags);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    if (cursor_out) *cursor_out = ctx->h_flags[0];
+    if (err_out) *err_out = (int)ctx->h_flags[1];
     return MLP_OK;
 }
+int read_cursor(mlp_ctx* ctx, int which, unsigned long long* out) { return read_words(ctx, which, out, nullptr); }
 #define END_EXCHANGE(ctx) do { if ((ctx)->exch_pending) { const int rce__ = mlp_exchange_end(ctx); if (rce__ != MLP_OK) return rce__; } } while (0)
 
 // Re-allocate the cell pool of one set to new_cap cells, keeping the first `keep` cells.
@@ -545,9 +558,8 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         if (fork && !useL) { CK(cudaEventRecord(ctx->ev_join, ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
         if ((rc = launch_one(ctx, MLP_K_FINAL, a, nt, kt, MLP_K_FINAL, nullptr, 0, &cgroups)) != MLP_OK) return rc;
         if ((rc = launch_one(ctx, MLP_K_TRANSPOSE, a, nt, kt, MLP_K_FINAL)) != MLP_OK) return rc;
-        CK(cudaStreamSynchronize(ctx->stream));
         int err = 0;
-        CK(cudaMemcpy(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        { int rcw = read_words(ctx, ctx->cur, nullptr, &err); if (rcw != MLP_OK) return rcw; }   // syncs the stream
         if (!err) break;
         // capacity miss: grow what overflowed and redo this batch (batches are idempotent once the cursor is rewound)
         cudaMemset(ctx->d_err, 0, sizeof(int));

@@ -62,6 +62,9 @@ struct mlp_ctx {
     // per-launch scratch
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
     PairTask* d_tasks = nullptr; PairOut* d_pout = nullptr; size_t tasks_cap = 0;
+    // host-mapped words the device publishes the error word and a set's cursor into: the host reads them after a stream sync without
+    // a device->host copy (a small copy would queue behind a split read-back on the DMA engine and stall the stage for its whole length)
+    unsigned long long* h_flags = nullptr; unsigned long long* d_hflags = nullptr;
     int* d_counter = nullptr; int* d_err = nullptr;   // d_counter: 16 work-queue heads, one per kernel id
     int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
     int* d_rowexp = nullptr; size_t rowexp_cap = 0;
