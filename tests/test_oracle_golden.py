@@ -225,3 +225,38 @@ def test_qp_selectivity_fixture_400_sequences():
     for tag, tr in (("sF", False), ("tF", True)):
         nnz, crc = _combined_crc(S, n, p_ab, tr)
         np.testing.assert_array_equal(nnz, d["digest.%s.nnz" % tag]); np.testing.assert_array_equal(crc, d["digest.%s.crc" % tag])
+
+
+def test_cpnp_partition_cells_near_the_cutoff_are_counted():
+    """cpnp's partition function is 80-bit in the reference and FP64 on the device: the 1e-5 tolerance bounds values, not the
+    index set -- a merged posterior within rounding distance of the 0.01 cutoff could be kept by one and dropped by the other.
+    This counts, with the long-double oracle, the cells of three bali3 families (37 M cell evaluations: the three-model mix
+    MSA.cpp:1001 thresholds, and the partition posterior alone) that lie within 1 and within 4 float ulps of the cutoff.  They
+    exist (about 3e-8 of the cells within 4 ulps), so identical index sets are an empirical property of the families run, not
+    a guarantee; the test pins how rare the exposed cells are."""
+    import os, tarfile
+    from common import HERE
+    suites = os.path.join(HERE, "golden", "suites")
+    ht, pt = O.hmm_tables(), O.part_tables(O.CPNP_P0)
+    cut = np.float32(0.01)
+    lo1, hi1 = np.nextafter(cut, np.float32(0)), np.nextafter(cut, np.float32(1))
+    lo4, hi4 = cut, cut
+    for _ in range(4):
+        lo4, hi4 = np.nextafter(lo4, np.float32(0)), np.nextafter(hi4, np.float32(1))
+    near1 = near4 = cells = 0
+    with tarfile.open(os.path.join(suites, "inputs.tar.gz")) as tar:
+        for name in ("bali3/BB11036", "bali3/BB12026", "bali3/BBS11014"):
+            text = tar.extractfile(name).read().decode()
+            seqs = ["".join(ch for ch in "".join(rec.split("\n")[1:]) if ch.isalpha()).upper().encode() for rec in text.split(">")[1:]]
+            for a in range(len(seqs)):
+                for b in range(a + 1, len(seqs)):
+                    for mask in (7, 2):                                     # the three-model mix and the partition posterior alone
+                        post, _, rc = O.pair_posterior(O.CPNP_P0, mask, ht, pt, seqs[a], seqs[b])
+                        assert rc == 0
+                        inner = post[1:, 1:]
+                        near1 += int(((inner >= lo1) & (inner <= hi1)).sum())
+                        near4 += int(((inner >= lo4) & (inner <= hi4)).sum())
+                        cells += inner.size
+    print("cells %d, within 1 ulp of the cutoff %d, within 4 ulps %d" % (cells, near1, near4))
+    assert cells > 30_000_000
+    assert near1 <= 1 and near4 <= 4          # measured: 0 and 1
