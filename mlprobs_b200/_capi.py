@@ -571,7 +571,13 @@ class Engine:
     def csr_packed_begin(self, out):
         """Start the packed read-back into `out` (PinnedPackedBuffers); csr_packed_end() waits for it.  The next family's posterior
         stage may run in between."""
-        rp_off, rp_total, used = self.csr_layout()
+        key = self.lens.tobytes()
+        if getattr(self, "_layout_key", None) != key:          # the row-pointer layout depends on the lengths only
+            self._layout_rp_off, self._layout_rp_total, _ = self.csr_layout()
+            self._layout_key = key
+        rp_total = C.c_int64(0); used = C.c_int64(0)
+        self._ck(self._lib.mlp_csr_layout(self._ctx, None, C.byref(rp_total), C.byref(used)))
+        rp_off, rp_total, used = self._layout_rp_off, rp_total.value, used.value
         out.ensure(self.n, rp_total, used)
         self._ck(self._lib.mlp_get_csr_packed_begin(self._ctx, _ptr(out.nz_off), _ptr(out.nz_cnt), _ptr(out.row_sizes), _ptr(out.cells)))
         out.rp_off, out.rp_total, out.used = rp_off, rp_total, used
