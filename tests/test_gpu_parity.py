@@ -610,3 +610,37 @@ def test_split_read_back_overlapping_the_next_posterior_stage():
                     np.testing.assert_array_equal(x, y)
     eng.csr_packed_end()
     eng.close()
+
+
+@pytest.mark.parametrize("lens", [[40, 37, 52], [300, 290, 310, 305], [20, 170, 33, 400], [700, 650], [5, 31, 33, 64, 257, 511]])
+def test_register_band_kernels_equal_the_round1_kernels(lens, monkeypatch):
+    """Every register-band kernel (sweep_c.cuh: k_part_fwd_c, k_part_rev_c, k_hmm_fwd_c, k_hmm_bwd_c, k_final_c) in isolation and all
+    together against the round-1 shared-memory-band kernels they replaced (MLP_OLD_SWEEP = bit mask of kernels that fall back,
+    read at every launch): distances and every matrix bit for bit, on ragged families that mix columns-per-lane groups, one
+    and several column blocks, and sequences shorter than a warp."""
+    rng = np.random.default_rng(sum(lens))
+    al = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    base = al[rng.integers(0, 20, max(lens))]
+    seqs = []
+    for L in lens:
+        s = base[:L].copy(); m = rng.random(L) < 0.4; s[m] = al[rng.integers(0, 20, int(m.sum()))]; seqs.append(s.tobytes())
+    n = len(seqs)
+
+    def run(mask):
+        monkeypatch.setenv("MLP_OLD_SWEEP", str(mask))
+        eng = engine(M.QP, seqs)
+        eng.posterior_all_pairs(M.QP, 3, 0.01)
+        out = (eng.distances().copy(), [eng.csr(a, b) for a in range(n) for b in range(n) if a != b])
+        eng.close()
+        return out
+
+    ref = run(31)
+    for name, mask in (("part_fwd", 30), ("part_rev", 29), ("hmm_fwd", 27), ("hmm_bwd", 23), ("final", 15), ("all", 0)):
+        got = run(mask)
+        np.testing.assert_array_equal(ref[0], got[0], err_msg=name)
+        for r, g in zip(ref[1], got[1]):
+            for x, y in zip(r, g):
+                np.testing.assert_array_equal(x, y, err_msg=name)
+    # and against the oracle, for the new kernels alone
+    dist, S, _ = O.posterior_stage(O.QP, 3, O.hmm_tables(), O.part_tables(O.QP), seqs)
+    np.testing.assert_array_equal(run(0)[0], dist)
