@@ -436,7 +436,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
     int bpe = 0;
     if (useP) bpe += 12;
     if (use5) bpe += 4;
-    if (useL) bpe += useP ? 4 : 8;
+    if (useL) bpe += useP ? 4 : 12;   // SL | Z terms + candidate lists of the Z chain (loc_c.cu), which alias Z when the partition model is also run
     // Memory plan: the first batch is small and measures the sparse density; the cell pool is then grown once to the
     // extrapolated size, the same amount is left free for the relaxation output set, and the rest goes to dense scratch.
     size_t budget = (size_t)1 << 31;
@@ -517,7 +517,10 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         if (use5) { a.layerS5 = (float*)p; p += (size_t)elems * 4; }
         if (useL) {
             a.layerSL = (float*)p; p += (size_t)elems * 4;
-            if (useP) a.layerVB = (float*)a.layerZ; else { a.layerVB = (float*)p; p += (size_t)elems * 4; }
+            float* lc;
+            if (useP) { a.layerVB = (float*)a.layerZ; lc = (float*)a.layerZ + elems; }
+            else { a.layerVB = (float*)p; p += (size_t)elems * 4; lc = (float*)p; p += (size_t)elems * 4; }
+            a.layerLC = ctx->loc_old ? nullptr : lc;
         }
         a.layerTB = (int*)(a.layerS5 ? a.layerS5 : (a.layerP ? a.layerP : a.layerSL));
         a.rowexp = ctx->d_rowexp; a.rowexp_stride = rowexp_stride;
@@ -548,8 +551,23 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         if (useL) {
             // the local model's Z terms alias the partition layer: it must wait for the partition posterior
             if (fork) { CK(cudaEventRecord(ctx->ev_join, ctx->stream2)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
-            if ((rc = launch_one(ctx, MLP_K_LOCAL_FWD, a, nt, kt, MLP_K_LOCAL_FWD)) != MLP_OK) return rc;
-            if ((rc = launch_one(ctx, MLP_K_LOCAL_BWD, a, nt, kt, MLP_K_LOCAL_BWD)) != MLP_OK) return rc;
+            if (posterior_c_available(MLP_K_LOCAL_FWD, a)) {
+                // register-band sweeps; the sequential Z chain runs over row-major candidate lists, one thread per pair (loc_c.cu)
+                static const bool split = getenv("MLP_LOC_SPLIT") != nullptr;   // developer knob (local model alone): candidate pass -> slots 0 / 2, chain -> slots 1 / 3
+                for (int phase = 0; phase < 2; ++phase) {
+                    const int kid = phase == 0 ? MLP_K_LOCAL_FWD : MLP_K_LOCAL_BWD;
+                    KArgs al = a; al.loc_phase = phase; al.loc_debug = split ? 1 : 0;
+                    if ((rc = launch_one(ctx, kid, al, nt, kt, kid, nullptr, 0, &cgroups)) != MLP_OK) return rc;
+                    if ((rc = launch_one(ctx, MLP_K_LOCAL_CAND, al, nt, kt, split ? 2 * phase : kid, nullptr, 0, &cgroups)) != MLP_OK) return rc;
+                    kt.begin(split ? 2 * phase + 1 : kid, ctx->stream);
+                    CK(loc_replay_launch(al, ctx->stream));
+                    kt.end(ctx->stream);
+                    ctx->stats.launches += 1;
+                }
+            } else {
+                if ((rc = launch_one(ctx, MLP_K_LOCAL_FWD, a, nt, kt, MLP_K_LOCAL_FWD)) != MLP_OK) return rc;
+                if ((rc = launch_one(ctx, MLP_K_LOCAL_BWD, a, nt, kt, MLP_K_LOCAL_BWD)) != MLP_OK) return rc;
+            }
         }
         if (use5) {
             if ((rc = launch_one(ctx, MLP_K_HMM_FWD, a, nt, kt, MLP_K_HMM_FWD, nullptr, useL ? 0 : capH, &cgroups)) != MLP_OK) return rc;
@@ -564,6 +582,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         // capacity miss: grow what overflowed and redo this batch (batches are idempotent once the cursor is rewound)
         cudaMemset(ctx->d_err, 0, sizeof(int));
         if (err & 8) { ctx->err = "transpose met a column index outside its matrix (corrupt cell pool)"; return MLP_E_CUDA; }
+        if (err & 16) ctx->loc_old = true;   // the filtered Z chain of the local model met a running sum below its checked bound: redo the batch with the unfiltered kernels
         if (attempt >= 6) { ctx->err = "sparse capacity still exhausted after 6 growth attempts"; return MLP_E_CAPACITY; }
         if (err & 1) {
             stage_mult *= 4;
@@ -612,6 +631,15 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         ctx->stats.pairs += (int64_t)batch.size();
     }
     kt.collect(ctx->stats);
+    return MLP_OK;
+}
+
+// developer hook (tools/loc_ab.py with MLP_LOC_SPLIT=1): candidates / firing cells of the local model's forward and backward Z chains since the last call
+extern "C" int mlp_debug_loc_counters(mlp_ctx* ctx, unsigned long long* out4) {
+    if (!ctx || !out4) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(loc_debug_counters(out4));
     return MLP_OK;
 }
 

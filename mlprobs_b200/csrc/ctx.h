@@ -21,6 +21,7 @@ struct mlp_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: partition-function sweeps, overlapped with the HMM sweeps
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool loc_old = false;                                // local model: fall back to the round-1 kernels (set when loc_c.cu's checked bound fails)
     int overlap = 0, bps_part = 0, bps_hmm = 0;          // tuning knobs (MLP_OVERLAP, MLP_BPS_PART, MLP_BPS_HMM); measured: no gain, off
     std::string err;
     // configuration

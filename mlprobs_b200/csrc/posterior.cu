@@ -1063,21 +1063,24 @@ cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_sc, &s, sizeof(DevScalars), 0, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = part_c_set_scalars(s, st);
     if (e == cudaSuccess) e = hmm_c_set_scalars(s, st);
+    if (e == cudaSuccess) e = loc_c_set_scalars(s, st);
     return e;
 }
 
 // ---- register-band kernels (one instantiation per columns-per-lane value)
 // developer knob: MLP_OLD_SWEEP = bit mask of kernels that use the round-1 shared-memory-band version (1 part_fwd, 2 part_rev, 4 hmm_fwd,
-// 8 hmm_bwd, 16 final), read at every launch so that a test can A/B inside one process
+// 8 hmm_bwd, 16 final, 32 the local model's sweeps + Z chain), read at every launch so that a test can A/B inside one process
 static int old_sweeps() { const char* e = getenv("MLP_OLD_SWEEP"); return e ? atoi(e) : 0; }
 bool posterior_c_available(int kernel, const KArgs& a) {
     if (a.dense) return false;
     const int old = old_sweeps();
     if ((kernel == MLP_K_PART_FWD && (old & 1)) || (kernel == MLP_K_PART_REV && (old & 2)) || (kernel == MLP_K_HMM_FWD && (old & 4)) ||
         (kernel == MLP_K_HMM_BWD && (old & 8)) || (kernel == MLP_K_FINAL && (old & 16))) return false;
+    if ((kernel == MLP_K_LOCAL_FWD || kernel == MLP_K_LOCAL_BWD || kernel == MLP_K_LOCAL_CAND) && (old & 32)) return false;
     switch (kernel) {
         case MLP_K_PART_FWD: case MLP_K_PART_REV: return a.flavour == 0;
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return true;
+        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: case MLP_K_LOCAL_CAND: return a.layerLC != nullptr;
         case MLP_K_FINAL: return a.flavour == 0 && a.mask == 3u;
         default: return false;
     }
@@ -1089,6 +1092,8 @@ size_t posterior_c_smem(int kernel) {
         case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES + warps * MLP_SWEEP_RING_BYTES(3, 8);
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(5, 4);
         case MLP_K_FINAL: return MLP_FINAL_TABLE_BYTES + 64 + warps * MLP_SWEEP_RING_BYTES(2, 4);
+        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(3, 4);
+        case MLP_K_LOCAL_CAND: return 64 + warps * MLP_SWEEP_RING_BYTES(2, 4);
         default: return 0;
     }
 }
@@ -1097,6 +1102,7 @@ static void (*c_kernel(int kernel, int C))(KArgs) {
         case MLP_K_PART_FWD: case MLP_K_PART_REV: return part_c_kernel(kernel, C);
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return hmm_c_kernel(kernel, C);
         case MLP_K_FINAL: return final_c_kernel(C);
+        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: case MLP_K_LOCAL_CAND: return loc_c_kernel(kernel, C);
         default: return nullptr;
     }
 }

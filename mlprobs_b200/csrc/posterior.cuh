@@ -10,6 +10,8 @@
 #define MLP_K_VITERBI 9                // all-pairs 3-state Viterbi (model selection)
 #define MLP_K_TRANSPOSE 8              // extends the MLP_K_* kernel ids of mlprobs_b200.h
 #define MLP_K_RELAX_ID 7
+#define MLP_K_LOCAL_CAND 10            // candidate lists of the local model's Z chain (loc_c.cu)
+#define MLP_K_LOCAL_REPLAY 11          // the chain itself, one thread per pair
 
 
 // per-pair scalars handed from one sweep kernel to the next
@@ -38,6 +40,7 @@ struct KArgs {
     const float* match; const float* ins; const double* sub;
     // dense layers (slot layout)
     double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
+    float* layerLC; int loc_phase; int loc_debug;   // loc_c.cu: row-major candidate lists of the local model's Z chain; 0 = forward chain (over layerSL), 1 = backward chain (over layerVB)
     int* rowexp; long long rowexp_stride;   // per task: scale exponent of every row of the forward partition layer (cpnp)
     unsigned char* layerTB8; int* vit_ident; int* vit_len; float vit_init0, vit_init1;
     char* vit_aln; const long long* vit_aln_off;   // optional: reversed B/X/Y alignment string of every pair (by pidx)   // Viterbi: packed traceback bytes (slot layout), per-pair results by pidx
@@ -84,3 +87,7 @@ cudaError_t hmm_c_set_scalars(const DevScalars& s, cudaStream_t st);
 void (*part_c_kernel(int kernel, int C))(KArgs);
 void (*hmm_c_kernel(int kernel, int C))(KArgs);
 void (*final_c_kernel(int C))(KArgs);
+cudaError_t loc_c_set_scalars(const DevScalars& s, cudaStream_t st);
+void (*loc_c_kernel(int kernel, int C))(KArgs);
+cudaError_t loc_replay_launch(const KArgs& a, cudaStream_t st);
+cudaError_t loc_debug_counters(unsigned long long out[4]);

@@ -138,7 +138,8 @@ __device__ __forceinline__ void run_sweep_c(M& m, const SweepCtx2& cx, typename 
                 }
 #pragma unroll
                 for (int s = 0; s < NS; ++s) carry[s] = in[s];
-                m.begin_row(i, M::USES_S1 ? (int)rring[i & 127] : 0);
+                // USES_S1 == 2: the model also wants the residue the ring holds for row i-1 (bits 8..15; only meaningful for i > ROW_LO)
+                m.begin_row(i, M::USES_S1 == 2 ? ((int)rring[i & 127] | ((int)rring[(i - 1) & 127] << 8)) : (M::USES_S1 ? (int)rring[i & 127] : 0));
                 const long long idx0 = blk0 + (long long)slot * (C * 32);
 #pragma unroll
                 for (int cc = 0; cc < C; ++cc) {

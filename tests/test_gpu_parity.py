@@ -644,3 +644,36 @@ def test_register_band_kernels_equal_the_round1_kernels(lens, monkeypatch):
     # and against the oracle, for the new kernels alone
     dist, S, _ = O.posterior_stage(O.QP, 3, O.hmm_tables(), O.part_tables(O.QP), seqs)
     np.testing.assert_array_equal(run(0)[0], dist)
+
+
+@pytest.mark.parametrize("lens", [[40, 37, 52], [300, 290, 310, 305], [20, 170, 33, 400], [700, 650], [5, 31, 33, 64, 257, 511], [1, 1, 2, 3]])
+@pytest.mark.parametrize("mask", [4, 7])
+def test_local_model_register_band_kernels_equal_the_round1_kernels(lens, mask, monkeypatch):
+    """cpnp's 3-state local model on the register-band sweeps with the filtered, thread-per-pair Z chain (loc_c.cu: k_loc_fwd_c,
+    k_loc_bwd_c, k_loc_cand_c, k_loc_replay) against the round-1 kernels (MLP_OLD_SWEEP bit 32: warp-per-pair replay of the complete
+    row-major layer, no candidate filter): distances and every matrix bit for bit, alone (mask 4) and merged with the other two
+    models (mask 7, where the Z terms and the candidate lists alias the partition layer); mask 4 also against the oracle."""
+    rng = np.random.default_rng(sum(lens) + mask)
+    al = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    base = al[rng.integers(0, 20, max(lens))]
+    seqs = []
+    for L in lens:
+        s = base[:L].copy(); m = rng.random(L) < 0.4; s[m] = al[rng.integers(0, 20, int(m.sum()))]; seqs.append(s.tobytes())
+    n = len(seqs)
+
+    def run(old):
+        monkeypatch.setenv("MLP_OLD_SWEEP", str(old))
+        eng = engine(M.CPNP_P0, seqs)
+        eng.posterior_all_pairs(M.CPNP_P0, mask, 0.01)
+        out = (eng.distances().copy(), [eng.csr(a, b) for a in range(n) for b in range(a + 1, n)])
+        eng.close()
+        return out
+
+    ref, got = run(32), run(0)
+    np.testing.assert_array_equal(ref[0], got[0])
+    for r, g in zip(ref[1], got[1]):
+        for x, y in zip(r, g):
+            np.testing.assert_array_equal(x, y)
+    if mask == 4:
+        dist, S, _ = O.posterior_stage(O.CPNP_P0, 4, O.hmm_tables(), O.part_tables(O.CPNP_P0), seqs)
+        np.testing.assert_array_equal(got[0], dist)
