@@ -33,6 +33,7 @@ static void release_launch_scratch(mlp_ctx* ctx) {
     free_dev(ctx->d_stage); ctx->d_stage = nullptr; ctx->stage_warps = 0; ctx->stage_cap = 0;
     free_dev(ctx->d_tfill); ctx->d_tfill = nullptr; ctx->tfill_warps = 0;
     free_dev(ctx->d_rowexp); ctx->d_rowexp = nullptr; ctx->rowexp_cap = 0;
+    free_dev(ctx->d_rowaux); ctx->d_rowaux = nullptr; ctx->rowaux_cap = 0;
     free_dev(ctx->d_edge); ctx->d_edge = nullptr; ctx->edge_warps = 0;
     free_dev(ctx->d_wk); ctx->d_wk = nullptr; ctx->wk_warps = 0;
 }
@@ -402,7 +403,7 @@ static int launch_one(mlp_ctx* ctx, int kernel, KArgs a, int ntasks, KernelTimer
             const int begin = g.second;
             const int end = (&g == &cgroups->back()) ? ntasks : (&g)[1].second;
             const int C = g.first;
-            int bps = std::min(posterior_c_max_blocks_per_sm(kernel, C), 16);
+            int bps = std::min(posterior_c_max_blocks_per_sm(kernel, C, a), 16);
             if (bps_cap > 0) bps = std::min(bps, bps_cap);
             int grid = std::max(1, std::min(ctx->num_sms * bps, (end - begin + warps_per_cta - 1) / warps_per_cta));
             CK(cudaMemsetAsync(a.counter, 0, sizeof(int), st));
@@ -500,6 +501,12 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             ctx->rowexp_cap = batch.size() * (size_t)rowexp_stride + 1024;
             CK(cudaMalloc(&ctx->d_rowexp, ctx->rowexp_cap * sizeof(int)));
         }
+        const long long rowaux_stride = 3LL * (maxL1 + 2);
+        if (useL && !ctx->loc_old && batch.size() * (size_t)rowaux_stride > ctx->rowaux_cap) {
+            free_dev(ctx->d_rowaux); ctx->d_rowaux = nullptr;
+            ctx->rowaux_cap = batch.size() * (size_t)rowaux_stride + 1024;
+            CK(cudaMalloc(&ctx->d_rowaux, ctx->rowaux_cap * sizeof(float)));
+        }
         CK(cudaMemcpyAsync(ctx->d_tasks, batch.data(), batch.size() * sizeof(PairTask), cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += (int64_t)(batch.size() * sizeof(PairTask));
         CK(cudaMemsetAsync(ctx->d_pout, 0, batch.size() * sizeof(PairOut), ctx->stream));
@@ -524,6 +531,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
         }
         a.layerTB = (int*)(a.layerS5 ? a.layerS5 : (a.layerP ? a.layerP : a.layerSL));
         a.rowexp = ctx->d_rowexp; a.rowexp_stride = rowexp_stride;
+        a.rowaux = ctx->d_rowaux; a.rowaux_stride = rowaux_stride;
         a.edge_f = need_edge ? (float*)ctx->d_edge : nullptr;
         a.edge_d = need_edge ? (double*)ctx->d_edge : nullptr;
         a.edge_stride = ctx->edge_stride;   // in elements of the kernel's own type; the buffer is sized for doubles

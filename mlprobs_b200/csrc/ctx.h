@@ -69,6 +69,7 @@ struct mlp_ctx {
     int* d_counter = nullptr; int* d_err = nullptr;   // d_counter: 16 work-queue heads, one per kernel id
     int4* d_stage = nullptr; int stage_cap = 0; long long stage_warps = 0;
     int* d_rowexp = nullptr; size_t rowexp_cap = 0;
+    float* d_rowaux = nullptr; size_t rowaux_cap = 0;   // local model: per task row sums / prefix bounds / candidate counts of the Z chain (loc_c.cu)
     int* d_tfill = nullptr; long long tfill_stride = 0, tfill_warps = 0;
     void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
     float* d_wk = nullptr; long long wk_warps = 0;

@@ -1070,6 +1070,12 @@ cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
 // ---- register-band kernels (one instantiation per columns-per-lane value)
 // developer knob: MLP_OLD_SWEEP = bit mask of kernels that use the round-1 shared-memory-band version (1 part_fwd, 2 part_rev, 4 hmm_fwd,
 // 8 hmm_bwd, 16 final, 32 the local model's sweeps + Z chain), read at every launch so that a test can A/B inside one process
+// model mix of the C-specialised merge kernel (final_c.cu): 0 = QuickProbs default, a c_p_np_aln -p 0 model mask, -1 = general kernel
+static int final_c_mode(const KArgs& a) {
+    if (a.flavour == 0) return a.mask == 3u ? 0 : -1;
+    if (a.flavour == 1 && (a.mask == 1u || a.mask == 2u || a.mask == 4u || a.mask == 7u)) return (int)a.mask;
+    return -1;
+}
 static int old_sweeps() { const char* e = getenv("MLP_OLD_SWEEP"); return e ? atoi(e) : 0; }
 bool posterior_c_available(int kernel, const KArgs& a) {
     if (a.dense) return false;
@@ -1081,7 +1087,7 @@ bool posterior_c_available(int kernel, const KArgs& a) {
         case MLP_K_PART_FWD: case MLP_K_PART_REV: return a.flavour == 0;
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return true;
         case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: case MLP_K_LOCAL_CAND: return a.layerLC != nullptr;
-        case MLP_K_FINAL: return a.flavour == 0 && a.mask == 3u;
+        case MLP_K_FINAL: return final_c_mode(a) >= 0;
         default: return false;
     }
 }
@@ -1092,28 +1098,28 @@ size_t posterior_c_smem(int kernel) {
         case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES + warps * MLP_SWEEP_RING_BYTES(3, 8);
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(5, 4);
         case MLP_K_FINAL: return MLP_FINAL_TABLE_BYTES + 64 + warps * MLP_SWEEP_RING_BYTES(2, 4);
-        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(3, 4);
+        case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(4, 4);
         case MLP_K_LOCAL_CAND: return 64 + warps * MLP_SWEEP_RING_BYTES(2, 4);
         default: return 0;
     }
 }
-static void (*c_kernel(int kernel, int C))(KArgs) {
+static void (*c_kernel(int kernel, int C, const KArgs& a))(KArgs) {
     switch (kernel) {
         case MLP_K_PART_FWD: case MLP_K_PART_REV: return part_c_kernel(kernel, C);
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return hmm_c_kernel(kernel, C);
-        case MLP_K_FINAL: return final_c_kernel(C);
+        case MLP_K_FINAL: return final_c_kernel(C, final_c_mode(a));
         case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: case MLP_K_LOCAL_CAND: return loc_c_kernel(kernel, C);
         default: return nullptr;
     }
 }
-int posterior_c_max_blocks_per_sm(int kernel, int C) {
-    void (*fn)(KArgs) = c_kernel(kernel, C);
+int posterior_c_max_blocks_per_sm(int kernel, int C, const KArgs& a) {
+    void (*fn)(KArgs) = c_kernel(kernel, C, a);
     int nb = 0;
     if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, MLP_BLOCK, posterior_c_smem(kernel)) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 cudaError_t posterior_c_launch(int kernel, int C, const KArgs& a, int grid, cudaStream_t st) {
-    void (*fn)(KArgs) = c_kernel(kernel, C);
+    void (*fn)(KArgs) = c_kernel(kernel, C, a);
     if (!fn) return cudaErrorInvalidValue;
     fn<<<grid, MLP_BLOCK, posterior_c_smem(kernel), st>>>(a);
     return cudaGetLastError();

@@ -40,7 +40,8 @@ struct KArgs {
     const float* match; const float* ins; const double* sub;
     // dense layers (slot layout)
     double* layerZ; float* layerP; float* layerS5; float* layerSL; float* layerVB;
-    float* layerLC; int loc_phase; int loc_debug;   // loc_c.cu: row-major candidate lists of the local model's Z chain; 0 = forward chain (over layerSL), 1 = backward chain (over layerVB)
+    float* layerLC; int loc_phase; int loc_debug;
+    float* rowaux; long long rowaux_stride;   // loc_c.cu, per task: row sums R, prefix bounds PB and candidate counts of the Z chain (three arrays of rowaux_stride/3 floats)   // loc_c.cu: row-major candidate lists of the local model's Z chain; 0 = forward chain (over layerSL), 1 = backward chain (over layerVB)
     int* rowexp; long long rowexp_stride;   // per task: scale exponent of every row of the forward partition layer (cpnp)
     unsigned char* layerTB8; int* vit_ident; int* vit_len; float vit_init0, vit_init1;
     char* vit_aln; const long long* vit_aln_off;   // optional: reversed B/X/Y alignment string of every pair (by pidx)   // Viterbi: packed traceback bytes (slot layout), per-pair results by pidx
@@ -80,13 +81,13 @@ int posterior_max_blocks_per_sm(int kernel, size_t smem);
 // Register-band kernels, compiled per columns-per-lane value C (part_c.cu, hmm_c.cu, final_c.cu)
 bool posterior_c_available(int kernel, const KArgs& a);          // is there a C-specialised kernel for this launch?
 size_t posterior_c_smem(int kernel);
-int posterior_c_max_blocks_per_sm(int kernel, int C);
+int posterior_c_max_blocks_per_sm(int kernel, int C, const KArgs& a);
 cudaError_t posterior_c_launch(int kernel, int C, const KArgs& a, int grid, cudaStream_t st);
 cudaError_t part_c_set_scalars(const DevScalars& s, cudaStream_t st);
 cudaError_t hmm_c_set_scalars(const DevScalars& s, cudaStream_t st);
 void (*part_c_kernel(int kernel, int C))(KArgs);
 void (*hmm_c_kernel(int kernel, int C))(KArgs);
-void (*final_c_kernel(int C))(KArgs);
+void (*final_c_kernel(int C, int mode))(KArgs);
 cudaError_t loc_c_set_scalars(const DevScalars& s, cudaStream_t st);
 void (*loc_c_kernel(int kernel, int C))(KArgs);
 cudaError_t loc_replay_launch(const KArgs& a, cudaStream_t st);
