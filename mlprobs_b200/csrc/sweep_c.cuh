@@ -17,6 +17,7 @@
 //   void edge_init(T (&e)[NS], int i)                   virtual column before the first one (-1 / 32*C*nb)
 //   int  row_residue(int i)                             0-based index into the row sequence of the residue row i needs (-1: none)
 //   void begin_row(int i, int r1)                       per-row setup; r1 = that residue (fetched one step ahead), enum USES_S1
+//                                                       (USES_S1 == 2: bits 8..15 of r1 carry the residue fetched for row i-1 as well)
 //   TIN  load_in(int k, long long idx)                  dense input layer k at element idx of this pair's layer
 //   void cell<c>(i, j, idx, old, carry, diag, in, nw)   one cell; idx = element index of the cell in the pair's layers
 //   void end_row(int i, int jbase, const T (&band)[C][NS], T (&carry)[NS])   after the row's cells; may adjust what the next lane receives
