@@ -287,83 +287,46 @@ __global__ void __launch_bounds__(RB_THREADS, 2) k_relax_blk(RelaxArgs a) {
                     }
                     const int* rpB = sm.rpB[s] + dq.w;
                     const int2* Bs = sm.B[s];
-                    for (int x0 = 0; x0 < CW; x0 += RB_THREADS) {               // strips: one thread per staged row of S_yz
-                        const int x = x0 + tid;
-                        int b = 0, e = 0, first = 0, span = 0;
-                        if (x < CW) {
-                            b = rpB[x] - dq.y; e = rpB[x + 1] - dq.y;
-                            if (e > b) { first = Bs[b].x; span = Bs[e - 1].x - first + 1; }
+                    for (int x = tid; x < CW; x += RB_THREADS) {                // strips: one thread per staged row of S_yz
+                        const int b = rpB[x] - dq.y, e = rpB[x + 1] - dq.y;
+                        int4 me = make_int4(0, 0, 0, 0);
+                        if (e > b) {
+                            const int first = Bs[b].x, span = Bs[e - 1].x - first + 1;
+                            const int off = (span <= a.wide_span) ? atomicAdd(&sm.wtop, span) : RB_WCAP;
+                            if (off + span <= RB_WCAP) {
+                                float* strip = sm.W + off;
+                                for (int q = 0; q < span; ++q) strip[q] = 0.0f;
+                                for (int y = b; y < e; ++y) { const int2 cell = Bs[y]; strip[cell.x - first] = __int_as_float(cell.y); }
+                                me = make_int4(first, off, span, 0);
+                            } else me = make_int4(first, b, e, 1);
                         }
-                        // pool space: one shared-memory atomic per warp (a scan of the lanes' spans) instead of one per row -- 100+ atomics
-                        // on one word serialised the start of every third sequence
-                        const bool want = (e > b) && span <= a.wide_span;
-                        int inc = want ? span : 0;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(MLP_FULL, inc, d); if (lane >= d) inc += o; }
-                        const int tot = __shfl_sync(MLP_FULL, inc, 31);
-                        int base = 0;
-                        if (lane == 31 && tot > 0) base = atomicAdd(&sm.wtop, tot);
-                        base = __shfl_sync(MLP_FULL, base, 31);
-                        if (x < CW) {
-                            int4 me = make_int4(0, 0, 0, 0);
-                            if (e > b) {
-                                const int off = want ? base + inc - span : RB_WCAP;
-                                if (off + span <= RB_WCAP) {
-                                    float* strip = sm.W + off;
-                                    for (int q = 0; q < span; ++q) strip[q] = 0.0f;
-                                    for (int y = b; y < e; ++y) { const int2 cell = Bs[y]; strip[cell.x - first] = __int_as_float(cell.y); }
-                                    me = make_int4(first, off, span, 0);
-                                } else me = make_int4(first, b, e, 1);
-                            }
-                            sm.meta[x] = me;
-                        }
+                        sm.meta[x] = me;
                     }
                     __syncthreads();
                     if (tid == 0) sm.wtop = 0;
                     const int* rpA = sm.rpA[s] + dq.z;
                     const int2* As = sm.A[s];
-                    // The four cells of a thread walk their rows of S_xz together: every walk is a chain of dependent shared-memory
-                    // loads (cell -> strip element -> multiply -> add), four independent chains in flight hide each other's latency.
-                    // Each cell still sees its own q in ascending order, so the sums keep the reference's order.
-                    const int2* pa[RB_G]; const int2* ea[RB_G];
-                    const float* strip[RB_G]; unsigned span[RB_G]; int first[RB_G];
-                    bool merged = false;
 #pragma unroll
                     for (int g = 0; g < RB_G; ++g) {
-                        pa[g] = ea[g] = As; strip[g] = sm.W; span[g] = 0u; first[g] = 0;
                         if (!okc[g]) continue;
                         const int ra = rr[g] - rmin;
+                        const int2* pa = As + (rpA[ra] - dq.x);
+                        const int2* ea = As + (rpA[ra + 1] - dq.x);
                         const int4 me = sm.meta[cc[g] - cmin];
+                        float ac = acc[g];
                         if (me.w == 0) {
-                            pa[g] = As + (rpA[ra] - dq.x); ea[g] = As + (rpA[ra + 1] - dq.x);
-                            strip[g] = sm.W + me.y - me.x; span[g] = (unsigned)me.z; first[g] = me.x;
-                        } else merged = true;
-                    }
-                    for (;;) {
-                        bool any = false;
-#pragma unroll
-                        for (int g = 0; g < RB_G; ++g) {
-                            if (pa[g] < ea[g]) {
-                                any = true;
-                                const int2 e = *pa[g]++;
-                                if ((unsigned)(e.x - first[g]) < span[g]) {
-                                    const float v1 = __int_as_float(e.y), v2 = strip[g][e.x];
+                            const float* strip = sm.W + me.y - me.x;
+                            const unsigned span = (unsigned)me.z;
+                            for (; pa < ea; ++pa) {
+                                const int2 e = *pa;
+                                if ((unsigned)(e.x - me.x) < span) {
+                                    const float v1 = __int_as_float(e.y), v2 = strip[e.x];
                                     const float prod = weighted ? __fmul_rn(__fmul_rn(w, v1), v2) : __fmul_rn(v1, v2);   // ConsistencyStage.cpp:294 / MSA.cpp:1316
-                                    acc[g] = __fadd_rn(acc[g], prod);
+                                    ac = __fadd_rn(ac, prod);
                                 }
                             }
-                        }
-                        if (!any) break;
-                    }
-                    if (merged) {   // rows of S_yz without a strip: sorted merge against the staged cells
-#pragma unroll
-                        for (int g = 0; g < RB_G; ++g) {
-                            if (!okc[g]) continue;
-                            const int4 me = sm.meta[cc[g] - cmin];
-                            if (me.w == 0) continue;
-                            const int ra = rr[g] - rmin;
-                            acc[g] = rb_merge(As + (rpA[ra] - dq.x), As + (rpA[ra + 1] - dq.x), Bs + me.y, Bs + me.z, acc[g], w, weighted);
-                        }
+                        } else ac = rb_merge(pa, ea, Bs + me.y, Bs + me.z, ac, w, weighted);
+                        acc[g] = ac;
                     }
                     __syncthreads();
                 } else {
