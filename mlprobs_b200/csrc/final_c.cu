@@ -74,12 +74,23 @@ struct FinalQ {
             const float x5 = fminf(0.0f, __fsub_rn(in[0], total5));
             const float vp = in[NIN > 1 ? 1 : 0];
             const float xl = fminf(0.0f, __fsub_rn(in[NIN > 2 ? 2 : 0], totalL));
-            if (__any_sync(__activemask(), (x5 > -16.0f) || (vp != 0.0f) || (xl > -16.0f))) {
-                const float v5 = dev_exp_lut(x5, elut), vl = dev_exp_lut(xl, elut);
-                // MSA.cpp:997-1001: sqrt(((dbl^2 + glob^2) + loc^2) / 3) in the order the reference adds them: 5-state, partition, local
-                const float s3 = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(v5, v5), __fmul_rn(vp, vp)), __fmul_rn(vl, vl)), 3.0f);
+            // cpnp's partition posterior has no 0.001 filter (MSAPartProbs.cpp:294-298 is commented out), so vp is non-zero almost
+            // everywhere: each EXP is skipped on its own when no lane of the warp can have a non-zero value (x <= -16 gives exactly 0)
+            float q5 = 0.0f, ql = 0.0f;
+            if (__any_sync(__activemask(), x5 > -16.0f)) { const float v5 = dev_exp_lut(x5, elut); q5 = __fmul_rn(v5, v5); }
+            if (__any_sync(__activemask(), xl > -16.0f)) { const float vl = dev_exp_lut(xl, elut); ql = __fmul_rn(vl, vl); }
+            // MSA.cpp:997-1001: sqrt(((dbl^2 + glob^2) + loc^2) / 3) in the order the reference adds them: 5-state, partition, local
+            const float sq = __fadd_rn(__fadd_rn(q5, __fmul_rn(vp, vp)), ql);
+            // Far from the alignment vp is ~1e-20 and sq / 3 is a denormal float: div.rn and sqrt.rn then take their out-of-line
+            // special-operand paths, divergently -- 30 % of this kernel's instructions in the first profile.  Such a cell has
+            // p < 2^-60; the only reader of p besides the cutoff test is `p + S(i-1,j-1)`, and that sum IS S(i-1,j-1) whenever
+            // S(i-1,j-1) >= 2^-30 (p is below half an ulp of it).  There the cell is treated as p = 0 -- same bits everywhere;
+            // where the score so far is itself that small (first rows of unalignable ends) the exact value is computed.
+            const bool tiny = (sq < 0x1p-122f) && (diag[0] >= 0x1p-30f);
+            if (__any_sync(__activemask(), !tiny && sq != 0.0f)) {
+                const float s3 = __fdiv_rn(tiny ? 3.0f : sq, 3.0f);
                 const float rt = __fsqrt_rn(s3 == 0.0f ? 1.0f : s3);
-                p = (s3 == 0.0f) ? 0.0f : rt;
+                p = (tiny || s3 == 0.0f) ? 0.0f : rt;
             }
         } else if (MODE == 2) {
             p = in[0];
