@@ -3,7 +3,7 @@
 
 A step = one pass of the hot path over one synthetic protein family: posterior stage (QuickProbs flavour:
 5-state pair-HMM + FP64 partition function per cell -> merged posterior -> MEA distance -> CSR, both
-orientations), host UPGMA tree, one consistency repetition (N > 50, as the reference), run through the C ABI.
+orientations), UPGMA guide tree (built on the device from the resident distances), one consistency repetition (N > 50, as the reference), run through the C ABI.
 `value` = pair-HMM cell updates per second (1 cell update = one (i,j) cell through forward+backward+posterior of ONE
 model; the QuickProbs flavour runs 2 models per cell) over the whole step, inputs resident; `e2e` = same with the
 host->device copy of the family and the device->host read-back of distances and CSR inside the timed region.
@@ -140,7 +140,7 @@ def _tr(name, t0):
 
 
 def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
-    """posterior stage -> [distances all-reduce] -> host tree -> [selective import] -> consistency [-> read-back of the own shard]."""
+    """posterior stage -> [distances all-reduce] -> guide tree on the device -> [selective import] -> consistency [-> read-back of the own shard]."""
     t0 = time.perf_counter()
     if e2e:
         eng.set_sequences(seqs)                       # host -> device copy of the family inside the timed region (keeps the shard)
@@ -151,18 +151,17 @@ def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
     t0 = _tr("posterior", t0)
     if world > 1:
         eng.exchange_distances()
-    d = eng.distances()                               # the guide tree is host work between the stages, as in the reference
-    t0 = _tr("distances", t0)
-    w, sd, _, _ = M.qp_guide_tree(d)
-    w = np.maximum(w, np.float32(1e-6))
+    # guide tree on the device (tree_dev.cu): weights (saturated at 1e-6, ExtendedMSA.cpp:237-238) and selectivity distances stay resident
+    # for the consistency stage; only a sharded run needs the selectivity distances on the host (for its import list)
+    tree = eng.qp_guide_tree_device(1e-6, want_seldist=(world > 1))
     t0 = _tr("tree", t0)
     if world > 1:
-        eng.exchange_needed(sd, 200.0); stats.append(("exchange", eng.stats()))
+        eng.exchange_needed(tree["seldist"], 200.0); stats.append(("exchange", eng.stats()))
         t0 = _tr("exchange_needed", t0)
     iters = 1 if n > 50 else 2
     for it in range(iters):
         cutoff = float(np.float32(0.01)) if it < iters - 1 else float(np.float32(1e-5))
-        eng.relax(M.QP, w, sd, 200.0, 3.0, cutoff)
+        eng.relax(M.QP, None, None, 200.0, 3.0, cutoff)
         stats.append(("relax", eng.stats()))
         if world > 1 and it < iters - 1:
             eng.exchange(); stats.append(("exchange", eng.stats()))
@@ -433,7 +432,7 @@ def main():
                              "algorithmic_ops_per_cell": SLOTS_PER_CELL["hmm5"],
                              # the quantity north_star's 50 % target is stated on: the whole all-pairs posterior + consistency stage
                              "stage_frac": total_cells * SLOTS_PER_CELL["stage_qp"] / max(world, 1) / (wall_ms * 1e-3) / FP32_ISSUE_PEAK,
-                             "stage_frac_note": "430 algorithmic slots per cell (SURVEY 8d: 358 HMM + 62 partition + 10 merge) x cells per GPU / wall time of the step (consistency, host tree and exchange included) / peak",
+                             "stage_frac_note": "430 algorithmic slots per cell (SURVEY 8d: 358 HMM + 62 partition + 10 merge) x cells per GPU / wall time of the step (consistency, guide tree and exchange included) / peak",
                              "posterior_kernels_frac": cells_rank * SLOTS_PER_CELL["stage_qp"] / (post_ms * 1e-3) / FP32_ISSUE_PEAK if post_ms else None,
                              "traffic": cells_rank * NCU_DRAM_BYTES_PER_CELL_HMM5,
                              "traffic_unit": "DRAM bytes per step on this rank, both kernels, all of the step's launches (same scope as `achieved`)",

@@ -102,9 +102,22 @@ int mlp_get_distances(mlp_ctx* ctx, float* nxn);
 /* One consistency repetition over all owned pairs.
  * cpnp: MSA::DoRelaxation MSA.cpp:1172-1281 (weights/seldist NULL, unweighted, /N).
  * QP:   ConsistencyStage::doRelaxation ConsistencyStage.cpp:133-266 with the default Max/Deterministic
- *       selectivity (accept z iff max(seldist[i][z], seldist[j][z]) <= selectivity), weights from the guide tree. */
+ *       selectivity (accept z iff max(seldist[i][z], seldist[j][z]) <= selectivity), weights from the guide tree;
+ *       weights = seldist = NULL takes both from the preceding mlp_qp_guide_tree_device. */
 int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
               float selectivity, float selfweight, float cutoff);
+
+/* QuickProbs' guide tree ON THE DEVICE, from the distance matrix the posterior stage left in HBM (which stays untouched):
+ * UPGMA clustering (ClusterTree::build ClusterTree.cpp:17-124), normalised sequence weights (GuideTree::calculateSeqsWeights
+ * GuideTree.cpp:114-154) raised to at least min_weight (ExtendedMSA.cpp:237-238 saturates them at 1e-6; pass 0 for the raw
+ * weights) and the subtree-size selectivity distances (GuideTree::calculateSubtreeDistances GuideTree.cpp:189-221).
+ * Bit-identical to mlp_qp_guide_tree_ex on the same matrix.  The weights and the selectivity distances stay resident: a following
+ * mlp_relax(ctx, MLP_QP, NULL, NULL, ...) uses them without a host round trip.  weights_out: n floats; parent / left / right:
+ * 2n-1 ints (leaves 0..n-1, inner nodes in merge order, root last), optional; seldist_out: n*n floats, optional (mlp_exchange_needed
+ * wants them on the host).  After a sharded stage call mlp_exchange_distances first.  MLP_E_UNSUPPORTED beyond ~4,800 sequences
+ * (the row minima and tree arrays of the single-CTA clustering live in shared memory): use the host function there. */
+int mlp_qp_guide_tree_device(mlp_ctx* ctx, float min_weight, float* weights_out, int32_t* parent_out, int32_t* left_out,
+                             int32_t* right_out, float* seldist_out);
 
 /* Host utility of the QuickProbs flavour (no GPU work): UPGMA guide tree on the n*n distances (updated IN PLACE, as the
  * reference does), normalised sequence weights and subtree-size selectivity distances for mlp_relax.
@@ -216,6 +229,9 @@ int mlp_get_csr_packed_begin(mlp_ctx* ctx, int64_t* nz_off, int32_t* nz_cnt, uin
 int mlp_get_csr_packed_end(mlp_ctx* ctx);
 int mlp_alloc_pinned(int64_t bytes, void** out);
 void mlp_free_pinned(void* p);
+
+/* Test hook: overwrite the resident n*n distance matrix (the device guide tree is checked on tie-heavy matrices with it). */
+int mlp_debug_set_distances(mlp_ctx* ctx, const float* nxn);
 
 /* Dense per-pair debug read-back (tests): runs one pair and returns the merged dense posterior
  * (len[a]+1 x len[b]+1) and, if non-NULL, each model's posterior. */

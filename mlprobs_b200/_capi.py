@@ -25,7 +25,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
            "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end",
-           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
+           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
 
 
 class HmmTables(C.Structure):
@@ -83,6 +83,7 @@ def load():
         lib.mlp_exchange.argtypes = [C.c_void_p]
         lib.mlp_exchange_distances.argtypes = [C.c_void_p]
         lib.mlp_exchange_needed.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        lib.mlp_qp_guide_tree_device.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
         lib.mlp_set_digest.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_csr_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -457,6 +458,21 @@ class Engine:
         sd = np.ascontiguousarray(seldist, np.float32) if seldist is not None else None
         self._ck(self._lib.mlp_relax(self._ctx, flavour, _ptr(w), _ptr(sd), C.c_float(selectivity),
                                      C.c_float(selfweight), C.c_float(cutoff)))
+
+    def qp_guide_tree_device(self, min_weight=1e-6, want_seldist=False):
+        """QuickProbs' guide tree built on the device from the resident distance matrix (mlp_qp_guide_tree_device): the weights
+        (saturated at min_weight) and the selectivity distances stay on the device for relax(QP) with weights = seldist = None."""
+        n = self.n
+        w = np.zeros(n, np.float32)
+        par = np.zeros(2 * n - 1, np.int32); left = np.zeros(2 * n - 1, np.int32); right = np.zeros(2 * n - 1, np.int32)
+        sd = np.zeros((n, n), np.float32) if want_seldist else None
+        self._ck(self._lib.mlp_qp_guide_tree_device(self._ctx, C.c_float(min_weight), _ptr(w), _ptr(par), _ptr(left), _ptr(right), _ptr(sd)))
+        return {"weights": w, "parent": par, "left": left, "right": right, "seldist": sd}
+
+    def debug_set_distances(self, d):
+        d = np.ascontiguousarray(d, np.float32)
+        assert d.shape == (self.n, self.n)
+        self._ck(self._lib.mlp_debug_set_distances(self._ctx, _ptr(d)))
 
     def comm_init(self, id128: bytes, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(id128)

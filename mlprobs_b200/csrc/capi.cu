@@ -87,7 +87,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
-    free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp); free_dev(ctx->d_relax_tasks);
+    free_dev(ctx->d_tree); free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp); free_dev(ctx->d_relax_tasks);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -754,6 +754,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
     if (flavour == MLP_QP) model_mask = MLP_M_HMM5 | MLP_M_PART;
+    ctx->tree_resident = false;                      // a device guide tree belongs to the distance matrix it was built from
     if ((model_mask & MLP_M_PART) && flavour != MLP_QP) {
         // letters J, O, U index sub_matrix[-1] in the reference: refuse instead of guessing
         for (long long k = 0; k < ctx->total_res; ++k) {
@@ -1222,10 +1223,13 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     if (!ctx->have_sets || ctx->flavour_of_set < 0) { ctx->err = "run mlp_posterior_all_pairs first"; return MLP_E_STATE; }
     cudaSetDevice(ctx->device);
     const int n = ctx->n;
-    if (flavour == MLP_QP && (!weights || !seldist_nxn || !(selectivity > 0))) return MLP_E_ARG;
+    const bool resident_tree = (flavour == MLP_QP && !weights && !seldist_nxn && ctx->tree_resident);   // left on the device by mlp_qp_guide_tree_device
+    if (flavour == MLP_QP && !resident_tree && (!weights || !seldist_nxn)) return MLP_E_ARG;
+    if (flavour == MLP_QP && !(selectivity > 0)) return MLP_E_ARG;
     const int in = ctx->cur, out = 1 - ctx->cur;
     ctx->stats = mlp_stage_stats{};
-    if (flavour == MLP_QP) {
+    if (flavour == MLP_QP && !resident_tree) {
+        ctx->tree_resident = false;
         if (n > ctx->weights_cap) {                   // sized for the current family (a context may see many families)
             free_dev(ctx->d_weights); free_dev(ctx->d_seldist);
             ctx->d_weights = nullptr; ctx->d_seldist = nullptr; ctx->weights_cap = 0;

@@ -74,6 +74,8 @@ struct mlp_ctx {
     void* d_edge = nullptr; long long edge_stride = 0, edge_warps = 0;
     float* d_wk = nullptr; long long wk_warps = 0;
     float* d_weights = nullptr; float* d_seldist = nullptr; int weights_cap = 0;
+    void* d_tree = nullptr; int tree_cap = 0;            // device guide tree (tree_dev.cu): scratch matrix + tree arrays
+    bool tree_resident = false;                          // d_weights / d_seldist hold the tree of the current distance matrix (mlp_qp_guide_tree_device)
     // nccl
     void* nccl_comm = nullptr; int comm_rank = 0, comm_world = 1;
     int* d_xcnt = nullptr; size_t xcnt_cap = 0;          // gathered per-matrix cell counts (selective exchange)

@@ -106,16 +106,25 @@ int align_file(mlp_ctx* ctx, const std::string& infile, const std::string& outfi
     const double t1 = now();
     if ((rc = mlp_posterior_all_pairs(ctx, MLP_QP, MLP_M_HMM5 | MLP_M_PART, 0.01f))) return fail(ctx, "mlp_posterior_all_pairs", rc);
     const double t2 = now();
-    std::vector<float> dist((size_t)n * n), weights(n), seldist((size_t)n * n);
+    std::vector<float> weights(n), seldist;
     std::vector<int32_t> left(2 * n - 1), right(2 * n - 1);
-    if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
-    if ((rc = mlp_qp_guide_tree_ex(n, dist.data(), weights.data(), seldist.data(), nullptr, left.data(), right.data())))
-        return fail(ctx, "mlp_qp_guide_tree_ex", rc);
-    for (auto& w : weights) w = std::max(w, 1e-6f);    // consistency.saturation == finalSaturation == 1e-6
+    // guide tree on the device, weights saturated at 1e-6 (consistency.saturation == finalSaturation); families too large for the
+    // single-CTA clustering take the host tree on a read-back of the distances
+    bool resident = true;
+    rc = mlp_qp_guide_tree_device(ctx, 1e-6f, weights.data(), nullptr, left.data(), right.data(), nullptr);
+    if (rc == MLP_E_UNSUPPORTED) {
+        resident = false;
+        std::vector<float> dist((size_t)n * n);
+        seldist.resize((size_t)n * n);
+        if ((rc = mlp_get_distances(ctx, dist.data()))) return fail(ctx, "mlp_get_distances", rc);
+        if ((rc = mlp_qp_guide_tree_ex(n, dist.data(), weights.data(), seldist.data(), nullptr, left.data(), right.data())))
+            return fail(ctx, "mlp_qp_guide_tree_ex", rc);
+        for (auto& w : weights) w = std::max(w, 1e-6f);
+    } else if (rc) return fail(ctx, "mlp_qp_guide_tree_device", rc);
     const int iters = con_iters >= 0 ? con_iters : (n > 50 ? 1 : 2);
     for (int it = 0; it < iters; ++it) {
         const float cutoff = (it == iters - 1) ? 1e-5f : 0.01f;
-        if ((rc = mlp_relax(ctx, MLP_QP, weights.data(), seldist.data(), 200.0f, 3.0f, cutoff))) return fail(ctx, "mlp_relax", rc);
+        if ((rc = mlp_relax(ctx, MLP_QP, resident ? nullptr : weights.data(), resident ? nullptr : seldist.data(), 200.0f, 3.0f, cutoff))) return fail(ctx, "mlp_relax", rc);
     }
     const double t3 = now();
     char* rows = nullptr;

@@ -678,3 +678,48 @@ def test_local_model_register_band_kernels_equal_the_round1_kernels(lens, mask, 
     if mask == 4:
         dist, S, _ = O.posterior_stage(O.CPNP_P0, 4, O.hmm_tables(), O.part_tables(O.CPNP_P0), seqs)
         np.testing.assert_array_equal(got[0], dist)
+
+
+@pytest.mark.parametrize("case", ["posterior_9", "posterior_dups", "random_1000", "ties_1000", "ties_257", "two", "three"])
+def test_device_guide_tree_equals_the_host_tree(case):
+    """QuickProbs' guide tree built on the device (tree_dev.cu: single-CTA UPGMA, weights, subtree distances) against the host
+    restatement (host_tree.cpp, itself pinned on the reference's trees): parent / children, weights and selectivity distances bit
+    for bit -- on distances a posterior stage produced (with duplicated sequences: exact ties) and on injected matrices
+    quantised to a handful of values, where almost every merge has to break ties the way the reference's row-major scan does.
+    A consistency repetition fed from the resident tree equals one fed with the host arrays."""
+    rng = np.random.default_rng(len(case))
+    if case.startswith("posterior"):
+        seqs = synth.family(9, 60, seed=11)
+        if case == "posterior_dups":
+            seqs = [seqs[i % 4] if i % 3 else seqs[i] for i in range(9)] + seqs[:3]
+        eng = engine(M.QP, seqs)
+        eng.posterior_all_pairs(M.QP, 3, 0.01)
+    else:
+        n = {"random_1000": 1000, "ties_1000": 1000, "ties_257": 257, "two": 2, "three": 3}[case]
+        seqs = synth.family(n, 8, seed=5)
+        eng = engine(M.QP, seqs)
+        eng.posterior_all_pairs(M.QP, 3, 0.01)          # allocates the sets and the distance matrix
+        d = rng.random((n, n)).astype(np.float32)
+        if case.startswith("ties"):
+            d = (np.floor(d * 6) / 8 + 0.125).astype(np.float32)
+        d = np.triu(d, 1); d = d + d.T
+        eng.debug_set_distances(d)
+    n = len(seqs)
+    d = eng.distances()
+    host = M.qp_guide_tree_ex(d.copy())
+    dev = eng.qp_guide_tree_device(min_weight=0.0, want_seldist=True)
+    for k in ("parent", "left", "right", "weights", "seldist"):
+        np.testing.assert_array_equal(np.asarray(host[k]).reshape(-1), np.asarray(dev[k]).reshape(-1), err_msg=k)
+    np.testing.assert_array_equal(eng.distances(), d)   # the resident matrix is not the one the clustering consumed
+    if case.startswith("posterior"):
+        w = np.maximum(host["weights"], np.float32(1e-6))
+        eng.qp_guide_tree_device(min_weight=1e-6)
+        eng.relax(M.QP, None, None, 200.0, 3.0, 0.01)
+        got = [eng.csr(a, b) for a in range(n) for b in range(n) if a != b]
+        eng.posterior_all_pairs(M.QP, 3, 0.01)
+        eng.relax(M.QP, w, host["seldist"], 200.0, 3.0, 0.01)
+        ref = [eng.csr(a, b) for a in range(n) for b in range(n) if a != b]
+        for r, g in zip(ref, got):
+            for x, y in zip(r, g):
+                np.testing.assert_array_equal(x, y)
+    eng.close()
