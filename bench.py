@@ -139,7 +139,7 @@ def _tr(name, t0):
     return time.perf_counter()
 
 
-def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
+def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None, want_dist=False):
     """posterior stage -> [distances all-reduce] -> guide tree on the device -> [selective import] -> consistency [-> read-back of the own shard]."""
     t0 = time.perf_counter()
     if e2e:
@@ -151,6 +151,8 @@ def one_step(eng, M, n, e2e, seqs=None, world=1, host_out=None):
     t0 = _tr("posterior", t0)
     if world > 1:
         eng.exchange_distances()
+    d = eng.distances() if (e2e or want_dist) else None   # part of the result (the e2e arm reads it back every step); the tree no longer needs it on the host
+    t0 = _tr("distances", t0)
     # guide tree on the device (tree_dev.cu): weights (saturated at 1e-6, ExtendedMSA.cpp:237-238) and selectivity distances stay resident
     # for the consistency stage; only a sharded run needs the selectivity distances on the host (for its import list)
     tree = eng.qp_guide_tree_device(1e-6, want_seldist=(world > 1))
@@ -343,7 +345,7 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     dev_ms = float(np.mean(ms_dev))
     # ---- parity digest of the step's result (untimed): distances + every matrix of the relaxed set
-    _, _, d_last = one_step(eng, M, n, False, world=world)
+    _, _, d_last = one_step(eng, M, n, False, world=world, want_dist=True)
     dg = torch.from_numpy(eng.set_digest().view(np.int64)).cuda()
     if dist is not None:
         dist.all_reduce(dg)                           # int64 wrap-around sum == sum mod 2^64 of the ranks' disjoint parts
