@@ -230,6 +230,10 @@ int mlp_get_csr_packed_end(mlp_ctx* ctx);
 int mlp_alloc_pinned(int64_t bytes, void** out);
 void mlp_free_pinned(void* p);
 
+/* Developer hook (tools/loc_ab.py with MLP_LOC_SPLIT=1): candidates / firing cells of the local model's forward and backward Z
+ * chains (loc_c.cu) since the last call, out4 = {fwd candidates, fwd firing, bwd candidates, bwd firing}. */
+int mlp_debug_loc_counters(mlp_ctx* ctx, unsigned long long* out4);
+
 /* Test hook: overwrite the resident n*n distance matrix (the device guide tree is checked on tie-heavy matrices with it). */
 int mlp_debug_set_distances(mlp_ctx* ctx, const float* nxn);
 

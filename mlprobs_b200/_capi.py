@@ -25,7 +25,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
            "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end",
-           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
+           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_debug_loc_counters", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
 
 
 class HmmTables(C.Structure):

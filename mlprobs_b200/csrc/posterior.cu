@@ -1064,6 +1064,7 @@ cudaError_t posterior_set_scalars(const DevScalars& s, cudaStream_t st) {
     if (e == cudaSuccess) e = part_c_set_scalars(s, st);
     if (e == cudaSuccess) e = hmm_c_set_scalars(s, st);
     if (e == cudaSuccess) e = loc_c_set_scalars(s, st);
+    if (e == cudaSuccess) e = part_sc_set_scalars(s, st);
     return e;
 }
 
@@ -1084,18 +1085,18 @@ bool posterior_c_available(int kernel, const KArgs& a) {
         (kernel == MLP_K_HMM_BWD && (old & 8)) || (kernel == MLP_K_FINAL && (old & 16))) return false;
     if ((kernel == MLP_K_LOCAL_FWD || kernel == MLP_K_LOCAL_BWD || kernel == MLP_K_LOCAL_CAND) && (old & 32)) return false;
     switch (kernel) {
-        case MLP_K_PART_FWD: case MLP_K_PART_REV: return a.flavour == 0;
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return true;   // QuickProbs: part_c.cu (plain FP64); c_p_np_aln: part_sc.cu (rescaled FP64)
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return true;
         case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: case MLP_K_LOCAL_CAND: return a.layerLC != nullptr;
         case MLP_K_FINAL: return final_c_mode(a) >= 0;
         default: return false;
     }
 }
-size_t posterior_c_smem(int kernel) {
+size_t posterior_c_smem(int kernel, const KArgs& a) {
     const int warps = MLP_BLOCK / 32;
     switch (kernel) {
         // tables | small per-warp words (backward caps / stage counters) | per-warp edge + residue ring (sweep_c.cuh)
-        case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES + warps * MLP_SWEEP_RING_BYTES(3, 8);
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return MLP_PART_TABLE_BYTES + warps * MLP_SWEEP_RING_BYTES(a.flavour == 0 ? 3 : 4, 8);   // cpnp: + the row's scale exponent
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(5, 4);
         case MLP_K_FINAL: return MLP_FINAL_TABLE_BYTES + 64 + warps * MLP_SWEEP_RING_BYTES(2, 4);
         case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: return MLP_HMM_TABLE_BYTES + 128 + warps * MLP_SWEEP_RING_BYTES(4, 4);
@@ -1105,7 +1106,7 @@ size_t posterior_c_smem(int kernel) {
 }
 static void (*c_kernel(int kernel, int C, const KArgs& a))(KArgs) {
     switch (kernel) {
-        case MLP_K_PART_FWD: case MLP_K_PART_REV: return part_c_kernel(kernel, C);
+        case MLP_K_PART_FWD: case MLP_K_PART_REV: return a.flavour == 0 ? part_c_kernel(kernel, C) : part_sc_kernel(kernel, C);
         case MLP_K_HMM_FWD: case MLP_K_HMM_BWD: return hmm_c_kernel(kernel, C);
         case MLP_K_FINAL: return final_c_kernel(C, final_c_mode(a));
         case MLP_K_LOCAL_FWD: case MLP_K_LOCAL_BWD: case MLP_K_LOCAL_CAND: return loc_c_kernel(kernel, C);
@@ -1115,13 +1116,13 @@ static void (*c_kernel(int kernel, int C, const KArgs& a))(KArgs) {
 int posterior_c_max_blocks_per_sm(int kernel, int C, const KArgs& a) {
     void (*fn)(KArgs) = c_kernel(kernel, C, a);
     int nb = 0;
-    if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, MLP_BLOCK, posterior_c_smem(kernel)) != cudaSuccess || nb < 1) nb = 1;
+    if (!fn || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, MLP_BLOCK, posterior_c_smem(kernel, a)) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 cudaError_t posterior_c_launch(int kernel, int C, const KArgs& a, int grid, cudaStream_t st) {
     void (*fn)(KArgs) = c_kernel(kernel, C, a);
     if (!fn) return cudaErrorInvalidValue;
-    fn<<<grid, MLP_BLOCK, posterior_c_smem(kernel), st>>>(a);
+    fn<<<grid, MLP_BLOCK, posterior_c_smem(kernel, a), st>>>(a);
     return cudaGetLastError();
 }
 

@@ -80,7 +80,7 @@ cudaError_t posterior_launch(int kernel, const KArgs& a, int grid, size_t smem, 
 int posterior_max_blocks_per_sm(int kernel, size_t smem);
 // Register-band kernels, compiled per columns-per-lane value C (part_c.cu, hmm_c.cu, final_c.cu)
 bool posterior_c_available(int kernel, const KArgs& a);          // is there a C-specialised kernel for this launch?
-size_t posterior_c_smem(int kernel);
+size_t posterior_c_smem(int kernel, const KArgs& a);
 int posterior_c_max_blocks_per_sm(int kernel, int C, const KArgs& a);
 cudaError_t posterior_c_launch(int kernel, int C, const KArgs& a, int grid, cudaStream_t st);
 cudaError_t part_c_set_scalars(const DevScalars& s, cudaStream_t st);
@@ -89,6 +89,8 @@ void (*part_c_kernel(int kernel, int C))(KArgs);
 void (*hmm_c_kernel(int kernel, int C))(KArgs);
 void (*final_c_kernel(int C, int mode))(KArgs);
 cudaError_t loc_c_set_scalars(const DevScalars& s, cudaStream_t st);
+cudaError_t part_sc_set_scalars(const DevScalars& s, cudaStream_t st);
+void (*part_sc_kernel(int kernel, int C))(KArgs);
 void (*loc_c_kernel(int kernel, int C))(KArgs);
 cudaError_t loc_replay_launch(const KArgs& a, cudaStream_t st);
 cudaError_t loc_debug_counters(unsigned long long out[4]);

@@ -651,8 +651,9 @@ def test_register_band_kernels_equal_the_round1_kernels(lens, monkeypatch):
 def test_local_model_register_band_kernels_equal_the_round1_kernels(lens, mask, monkeypatch):
     """cpnp's 3-state local model on the register-band sweeps with the filtered, thread-per-pair Z chain (loc_c.cu: k_loc_fwd_c,
     k_loc_bwd_c, k_loc_cand_c, k_loc_replay) and the C-specialised merge kernel for c_p_np_aln's model mixes (final_c.cu, modes 1, 2, 4, 7)
-    against the round-1 kernels (MLP_OLD_SWEEP bits 32 and 16: warp-per-pair replay of the complete row-major layer without a
-    candidate filter; general merge kernel): distances and every matrix bit for bit, every model alone and all three merged (mask
+    and the rescaled FP64 partition sweeps on the same skeleton (part_sc.cu)
+    against the round-1 kernels (MLP_OLD_SWEEP bits 32, 16, 2 and 1: warp-per-pair replay of the complete row-major layer without a
+    candidate filter; general merge kernel; shared-memory-band partition sweeps): distances and every matrix bit for bit, every model alone and all three merged (mask
     7, where the Z terms and the candidate lists alias the partition layer); mask 4 also against the oracle."""
     rng = np.random.default_rng(sum(lens) + mask)
     al = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
@@ -670,7 +671,7 @@ def test_local_model_register_band_kernels_equal_the_round1_kernels(lens, mask, 
         eng.close()
         return out
 
-    ref, got = run(48), run(0)
+    ref, got = run(51), run(0)
     np.testing.assert_array_equal(ref[0], got[0])
     for r, g in zip(ref[1], got[1]):
         for x, y in zip(r, g):
