@@ -203,10 +203,12 @@ struct PartRevS {
         nw[0] = zm; nw[1] = h; nw[2] = v;
         row_seen = max(row_seen, exp_of(zm) + e_row);
         // MSAPartProbs.cpp:286-297: posterior = Zf * Zr / (score * Z), no threshold (the 0.001 filter is commented out there)
-        double tmp = __dmul_rn(in[0], zm);
-        tmp = __ddiv_rn(tmp, __dmul_rn(score, Ztot));
-        tmp = scalbn(tmp, fexp + e_row - zexp);
-        P[idx] = (float)tmp;
+        // The scale shift k is applied with one exact power-of-two multiply instead of scalbn: |k| > 1000 would mean a posterior
+        // below 2^-800 (the scaled operands stay within 2^+-200 of one another), where the clamped factor gives the same +0 as a
+        // float; a product in the double-denormal range rounds once either way.  (Skipping the division where the float result
+        // underflows was measured: c_p_np_aln's unfiltered posterior is non-zero almost everywhere, the test cost more than it saved.)
+        const double q = __ddiv_rn(__dmul_rn(in[0], zm), __dmul_rn(score, Ztot));
+        P[idx] = (float)__dmul_rn(q, pow2c(fexp + e_row - zexp));
     }
     __device__ __forceinline__ void end_row(int, int, const T (&)[C][NS], T (&)[NS]) { e_prev = e_row; if (row_seen != MLP_EXP_NONE) seen_exp = row_seen; }
 };
