@@ -25,6 +25,12 @@ WORKLOADS = {
     # BASELINE.json configs[2]: the config the metric is quoted on
     "A": dict(n=1000, length=300, name="synthetic 1,000 protein seqs x len 300: all-pairs posterior + consistency"),
     "small": dict(n=200, length=300, name="synthetic 200 protein seqs x len 300 (development size)"),
+    # BASELINE.json configs[4]: the sparse set (16 M matrices) does not fit HBM -> streamed two-pass flow (mlp_stream_begin / mlp_restrict_pairs)
+    "B": dict(n=4000, length=500, stream=True, scratch=24 << 30, cells=1 << 31,
+              name="synthetic 4,000 protein seqs x len 500 stress: 8.0 M pairs, all-pairs posterior + consistency, streamed"),
+    # the same streamed flow at a size where the ordinary flow also fits: the two digests are compared in the run
+    "Bs": dict(n=400, length=120, stream=True, scratch=64 << 20, cells=0, clustered=(8, 50), compare=True,
+               name="synthetic 400 protein seqs (8 sub-families) x len 120: streamed flow checked against the ordinary flow"),
 }
 FP32_ISSUE_PEAK = 148 * 128 * 1.965e9          # lane-instructions / s
 # algorithmic FP32-slot equivalents per grid cell: 5-state forward+backward+posterior, partition function
@@ -72,6 +78,8 @@ class ClockSampler(threading.Thread):
 
 def make_family(wl, rank=0):
     from mlprobs_b200 import synth
+    if wl.get("clustered"):
+        return synth.family_clustered(wl["clustered"][0], wl["clustered"][1], wl["length"], seed=20220148 + 4)
     return synth.family_fast(wl["n"], wl["length"], seed=20220148 + 2)
 
 
@@ -242,6 +250,108 @@ def cpnp_object(M, dev, seqs, total_cells, n_sub):
     return out
 
 
+def stream_step(eng, M, n, rank, world, want_digest=False):
+    """BASELINE config #5's flow: streamed stage over all owned pairs (every batch finished, digested and dropped) -> distances
+    all-reduce -> guide tree on the device -> ordinary stage over the pairs inside a <= 200-leaf subtree only -> selective import ->
+    consistency on those pairs.  Returns (per-stage stats, combined per-matrix digest of this rank or None)."""
+    st = {}
+    t0 = time.perf_counter()
+    eng.stream_begin(1)
+    eng.posterior_all_pairs(M.QP, 3, 0.01); st["streamed_stage"] = eng.stats()
+    streamed = eng.stream_end(want_digest)
+    st["t_streamed_ms"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    if world > 1:
+        eng.exchange_distances()
+    tree = eng.qp_guide_tree_device(1e-6, want_seldist=True)
+    sd = tree["seldist"].reshape(n, n)
+    st["t_tree_ms"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    eng.restrict_pairs(sd, 200.0)
+    eng.posterior_all_pairs(M.QP, 3, 0.01); st["ingroup_stage"] = eng.stats()
+    st["t_ingroup_ms"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    if world > 1:
+        eng.exchange_needed(sd, 200.0); st["exchange"] = eng.stats()
+    st["t_exchange_ms"] = (time.perf_counter() - t0) * 1e3; t0 = time.perf_counter()
+    eng.relax(M.QP, None, None, 200.0, 3.0, float(np.float32(1e-5))); st["relax"] = eng.stats()
+    st["t_relax_ms"] = (time.perf_counter() - t0) * 1e3
+    digest = None
+    if want_digest:
+        ingroup = sd <= 200.0
+        np.fill_diagonal(ingroup, False)
+        digest = np.where(ingroup, eng.set_digest().reshape(n, n), streamed.reshape(n, n))
+        st["ingroup_pairs_all_ranks"] = int(ingroup.sum() // 2)
+    eng.set_shard(rank, world)
+    return st, digest
+
+
+def run_streamed(args, wl, M, torch, dist, eng, seqs, rank, world, dev, sampler):
+    """bench line of a streamed workload (B: 4,000 x 500; Bs: the same flow next to the ordinary one)."""
+    n = len(seqs)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_digest(dg):
+        t = torch.from_numpy(np.ascontiguousarray(dg).view(np.int64).reshape(-1)).cuda()
+        if dist is not None:
+            dist.all_reduce(t)
+        return zlib.crc32(t.cpu().numpy().tobytes()) & 0xffffffff
+
+    lens = np.array([len(s) for s in seqs], np.int64) + 1
+    total_cells = int((lens.sum() ** 2 - (lens ** 2).sum()) // 2)
+    npairs = n * (n - 1) // 2
+    eng.configure(wl["scratch"], wl["cells"])
+    for _ in range(args.warmup):
+        stream_step(eng, M, n, rank, world)
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for k in range(args.steps):
+        last, dg = stream_step(eng, M, n, rank, world, want_digest=(k == args.steps - 1))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps      # the last step includes the digest read-back (n*n*8 bytes per rank)
+    crc_streamed = reduce_digest(dg)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    compare = None
+    if wl.get("compare"):
+        eng.configure(0, 0)
+        one_step(eng, M, n, False, world=world)
+        compare = reduce_digest(eng.set_digest().reshape(n, n))
+    t = torch.tensor([wall_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_ms = float(t[0])
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    eng.close()
+    if rank != 0:
+        return
+    models = 2
+    km = {k: v for k, v in last["streamed_stage"]["ms_kernel"].items() if v}
+    line = {"metric": "pair_hmm_cell_updates_per_second", "value": total_cells * models / (wall_ms * 1e-3) / 1e9, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "flavour": "quickprobs (5-state pair-HMM f32 + partition function f64, 1 consistency rep)", "models_per_cell": models,
+                       "n": n, "pairs": npairs, "cells": total_cells,
+                       "flow": "streamed two-pass: every rank's pairs go through the posterior stage in batches whose matrices are finished (re-quantisation of a repetition without third sequences), digested and dropped; distances all-reduced; guide tree on the device; the pairs inside a <= 200-leaf subtree are recomputed, exchanged within the selectivity (NCCL) and relaxed.  value counts the all-pairs cells once (the recomputed pairs are extra work inside the same wall time)",
+                       "l2_policy": "inputs larger than L2: each batch streams the dense DP layers of thousands of pairs"},
+            "stage_ms_rank0": {k: round(last[k], 1) for k in last if k.startswith("t_")},
+            "streamed_stage_kernel_ms_rank0": km,
+            "streamed_matrices_cells_rank0": int(last["streamed_stage"]["nnz"]),
+            "ingroup_pairs": last.get("ingroup_pairs_all_ranks"),
+            "exchange_ms_rank0": last["exchange"]["ms_total"] if "exchange" in last else None,
+            "hbm_used_gb_rank0": round((total_b - free_b) / 1e9, 1),
+            "e2e": None,
+            "e2e_note": "not measured for this workload: the streamed flow hands the matrices out batch by batch (digests here); a host consumer for them is the next step",
+            "parity_digest": {"value": {"set_crc32": crc_streamed}, "ordinary_flow": ({"set_crc32": compare} if compare is not None else None),
+                              "match": (crc_streamed == compare) if compare is not None else None,
+                              "what": "CRC32 of the n x n per-matrix device digests (row pointers + cells of every matrix after the consistency repetition), summed over ranks; streamed flow vs the ordinary flow where that fits"},
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "fp32_issue", "stage_frac": total_cells * SLOTS_PER_CELL["stage_qp"] / max(world, 1) / (wall_ms * 1e-3) / FP32_ISSUE_PEAK,
+                         "stage_frac_note": "430 algorithmic slots per cell x cells per GPU / wall time of the step / (148 SMs x 128 lanes x 1.965 GHz)"}}
+    print(json.dumps(line))
+
+
 def families_per_sec(seqs):
     """FASTA -> FASTA through the drop-in executables (process start, CUDA context, tail and file output included)."""
     out = {}
@@ -321,6 +431,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if wl.get("stream"):
+        sampler = ClockSampler(dev); sampler.start()
+        run_streamed(args, wl, M, torch, dist, eng, seqs, rank, world, dev, sampler)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     lens = np.array([len(s) for s in seqs], np.int64) + 1
     total_cells = int((lens.sum() ** 2 - (lens ** 2).sum()) // 2)
     npairs = n * (n - 1) // 2

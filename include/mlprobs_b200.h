@@ -107,6 +107,19 @@ int mlp_get_distances(mlp_ctx* ctx, float* nxn);
 int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seldist_nxn,
               float selectivity, float selfweight, float cutoff);
 
+/* Streamed posterior stage for families whose sparse set does not fit HBM (BASELINE config #5: 4,000 x 500, 16 M matrices; the
+ * reference's own GPU path streams relaxation sectors for the same reason, KernelAlignment/Multiple/QuickConsistencyStage.cpp:163-190).
+ * Between mlp_stream_begin and mlp_stream_end, mlp_posterior_all_pairs(MLP_QP) finishes every batch of pairs on the spot: the cells get
+ * the re-quantisation a consistency repetition applies to a matrix whose pair accepts no third sequence (ConsistencyStage.cpp:
+ * 213-258 with sumW = 1; `reps` repetitions), the per-matrix digest (format of mlp_set_digest) is accumulated, and the cell pool is
+ * reused by the next batch.  Afterwards the distances are complete and mlp_qp_guide_tree_device can run; the pairs that DO accept third
+ * sequences (subtree distance <= selectivity: a few per cent of a large family) are then recomputed by an ordinary stage restricted
+ * to them with mlp_restrict_pairs, exchanged (mlp_exchange_needed) and relaxed as usual; mlp_set_shard restores the full shard.
+ * mlp_stream_end copies the digests of the streamed matrices to per_matrix_nn (n*n, may be NULL). */
+int mlp_stream_begin(mlp_ctx* ctx, int reps);
+int mlp_stream_end(mlp_ctx* ctx, uint64_t* per_matrix_nn);
+int mlp_restrict_pairs(mlp_ctx* ctx, const float* seldist_nxn, float selectivity);
+
 /* QuickProbs' guide tree ON THE DEVICE, from the distance matrix the posterior stage left in HBM (which stays untouched):
  * UPGMA clustering (ClusterTree::build ClusterTree.cpp:17-124), normalised sequence weights (GuideTree::calculateSeqsWeights
  * GuideTree.cpp:114-154) raised to at least min_weight (ExtendedMSA.cpp:237-238 saturates them at 1e-6; pass 0 for the raw

@@ -25,7 +25,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
            "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end",
-           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_debug_loc_counters", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
+           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_debug_loc_counters", "mlp_stream_begin", "mlp_stream_end", "mlp_restrict_pairs", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
 
 
 class HmmTables(C.Structure):
@@ -84,6 +84,9 @@ def load():
         lib.mlp_exchange_distances.argtypes = [C.c_void_p]
         lib.mlp_exchange_needed.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         lib.mlp_qp_guide_tree_device.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 5
+        lib.mlp_stream_begin.argtypes = [C.c_void_p, C.c_int]
+        lib.mlp_stream_end.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mlp_restrict_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
         lib.mlp_set_digest.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_last_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.mlp_csr_layout.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -468,6 +471,19 @@ class Engine:
         sd = np.zeros((n, n), np.float32) if want_seldist else None
         self._ck(self._lib.mlp_qp_guide_tree_device(self._ctx, C.c_float(min_weight), _ptr(w), _ptr(par), _ptr(left), _ptr(right), _ptr(sd)))
         return {"weights": w, "parent": par, "left": left, "right": right, "seldist": sd}
+
+    def stream_begin(self, reps=1):
+        """Streamed posterior stage (mlp_stream_begin): batches are finished, digested and dropped."""
+        self._ck(self._lib.mlp_stream_begin(self._ctx, int(reps)))
+
+    def stream_end(self, want_digest=True):
+        out = np.zeros((self.n, self.n), np.uint64) if want_digest else None
+        self._ck(self._lib.mlp_stream_end(self._ctx, _ptr(out)))
+        return out
+
+    def restrict_pairs(self, seldist, selectivity=200.0):
+        sd = np.ascontiguousarray(seldist, np.float32)
+        self._ck(self._lib.mlp_restrict_pairs(self._ctx, _ptr(sd), C.c_float(selectivity)))
 
     def debug_set_distances(self, d):
         d = np.ascontiguousarray(d, np.float32)

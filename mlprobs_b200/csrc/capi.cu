@@ -87,7 +87,7 @@ extern "C" void mlp_destroy(mlp_ctx* ctx) {
     free_dev(ctx->d_match); free_dev(ctx->d_ins); free_dev(ctx->d_sub);
     free_dev(ctx->d_counter); free_dev(ctx->d_err);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
-    free_dev(ctx->d_tree); free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp); free_dev(ctx->d_relax_tasks);
+    free_dev(ctx->d_sdigest); free_dev(ctx->d_len); free_dev(ctx->d_tree); free_dev(ctx->d_weights); free_dev(ctx->d_seldist); free_dev(ctx->d_xq); free_dev(ctx->d_xused); free_dev(ctx->d_xcnt); free_dev(ctx->d_ximp); free_dev(ctx->d_relax_tasks);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -104,6 +104,62 @@ extern "C" int mlp_configure(mlp_ctx* ctx, int64_t scratch_bytes, int64_t cell_c
     if (!ctx || scratch_bytes < 0 || cell_capacity < 0) return MLP_E_ARG;
     ctx->scratch_budget = scratch_bytes;
     ctx->cell_capacity_req = cell_capacity;
+    return MLP_OK;
+}
+
+// Streamed posterior stage for families whose sparse set does not fit HBM (BASELINE config #5: 4,000 x 500, 16 M matrices).
+// Between _begin and _end mlp_posterior_all_pairs(MLP_QP) finishes every batch on the spot -- the re-quantisation a consistency
+// repetition applies to a matrix whose pair accepts no third sequence (`reps` of them), then the per-matrix digest -- and reuses the
+// cell pool for the next batch.  Distances are complete afterwards; the matrices of the pairs that DO accept third sequences (same
+// <= selectivity-leaf subtree) are recomputed by an ordinary stage restricted to them (mlp_restrict_pairs) and relaxed as usual.
+extern "C" int mlp_stream_begin(mlp_ctx* ctx, int reps) {
+    if (!ctx || reps < 1 || reps > 8) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    const int n = ctx->n;
+    if (n < 2) { ctx->err = "set sequences first"; return MLP_E_STATE; }
+    const long long nn = (long long)n * n;
+    if (nn > ctx->sdigest_cap) {
+        free_dev(ctx->d_sdigest); ctx->d_sdigest = nullptr; ctx->sdigest_cap = 0;
+        CK(cudaMalloc(&ctx->d_sdigest, (size_t)nn * sizeof(unsigned long long)));
+        ctx->sdigest_cap = nn;
+    }
+    if (n > ctx->len_cap) {
+        free_dev(ctx->d_len); ctx->d_len = nullptr; ctx->len_cap = 0;
+        CK(cudaMalloc(&ctx->d_len, (size_t)n * sizeof(int)));
+        ctx->len_cap = n;
+    }
+    CK(cudaMemsetAsync(ctx->d_sdigest, 0, (size_t)nn * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_len, ctx->len.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream_mode = true; ctx->stream_reps = reps;
+    return MLP_OK;
+}
+
+// Ends streamed mode; per_matrix_nn (n*n, may be NULL) receives the digests of the streamed matrices in mlp_set_digest's format.
+extern "C" int mlp_stream_end(mlp_ctx* ctx, uint64_t* per_matrix_nn) {
+    if (!ctx) return MLP_E_ARG;
+    cudaSetDevice(ctx->device);
+    ctx->stream_mode = false;
+    if (per_matrix_nn) {
+        if (!ctx->d_sdigest) return MLP_E_STATE;
+        CK(cudaMemcpyAsync(per_matrix_nn, ctx->d_sdigest, (size_t)ctx->n * ctx->n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return MLP_OK;
+}
+
+// Restricts this rank's shard to the pairs whose subtree-size distance is within the selectivity -- the only pairs that accept third
+// sequences (ConsistencyStage.cpp:181-216) and the only matrices a consistency repetition reads.  mlp_set_shard restores the shard.
+extern "C" int mlp_restrict_pairs(mlp_ctx* ctx, const float* seldist_nxn, float selectivity) {
+    if (!ctx || !seldist_nxn) return MLP_E_ARG;
+    const int n = ctx->n;
+    std::vector<PairTask> keep;
+    for (const PairTask& t : ctx->owned)
+        if (seldist_nxn[(size_t)t.a * n + t.b] <= selectivity) keep.push_back(t);
+    ctx->owned.swap(keep);
+    ctx->restricted = true;
+    ctx->relax_tasks.clear();
+    ctx->relax_tasks_on_device = false;
     return MLP_OK;
 }
 
@@ -250,6 +306,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
 extern "C" int mlp_set_shard(mlp_ctx* ctx, int rank, int world) {
     if (!ctx || world < 1 || rank < 0 || rank >= world) return MLP_E_ARG;
     ctx->rank = rank; ctx->world = world;
+    ctx->restricted = false;
     ctx->owned.clear();
     for (size_t k = 0; k < ctx->all_pairs.size(); ++k)
         if ((int)(k % world) == rank) ctx->owned.push_back(ctx->all_pairs[k]);
@@ -271,7 +328,7 @@ static int ensure_sets(mlp_ctx* ctx) {
     if (!ctx->d_rp_off || nn > ctx->nn_cap || ctx->rp_total + 8 > ctx->rp_cap) {
         // first family, or one that does not fit the pools kept from the previous families: re-allocate with head-room
         release_sets(ctx);
-        const long long nn_cap = nn + nn / 4 + 64, rp_cap = ctx->rp_total + ctx->rp_total / 4 + 64;   // rp_cap includes the 8 ints a 16-byte aligned bulk copy may read past the end
+        const long long nn_cap = nn + std::min<long long>(nn / 4, 1 << 22) + 64, rp_cap = ctx->rp_total + std::min<long long>(ctx->rp_total / 4, 1LL << 28) + 64;   // rp_cap includes the 8 ints a 16-byte aligned bulk copy may read past the end
         CK(cudaMalloc(&ctx->d_rp_off, (size_t)nn_cap * sizeof(long long)));
         for (int s = 0; s < 2; ++s) {
             CK(cudaMalloc(&ctx->set[s].rp_pool, (size_t)rp_cap * sizeof(int)));
@@ -429,6 +486,26 @@ static int launch_one(mlp_ctx* ctx, int kernel, KArgs a, int ntasks, KernelTimer
     return MLP_OK;
 }
 
+__global__ void k_set_digest(const PairTask* __restrict__ tasks, int ntasks, int n, const int* __restrict__ len, const long long* __restrict__ rp_off,
+                             const int* __restrict__ rp_pool, const long long* __restrict__ nz_off, const int* __restrict__ nz_cnt,
+                             const int2* __restrict__ cells, unsigned long long* __restrict__ out);
+
+// Streamed posterior stage: what ConsistencyStage::doRelaxation (ConsistencyStage.cpp:133-266) does to a matrix whose pair accepts no
+// third sequence -- P / sumW with sumW = 1, cutoff, store as uint16 fixed point -- i.e. one more quantisation of every cell per
+// repetition.  A cell below the cutoff would have to be dropped (and the row pointers rebuilt): flagged instead, it cannot happen
+// with the reference's cutoffs (every kept posterior is >= 0.01 quantised down, the repetition's cutoff is <= 0.01 resp. 1e-5).
+__global__ void k_stream_requant(int2* __restrict__ cells, long long count, int reps, float cutoff, int* __restrict__ err) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (long long)gridDim.x * blockDim.x) {
+        float v = __int_as_float(cells[k].y);
+        for (int r = 0; r < reps; ++r) {
+            v = __fdiv_rn(v, 1.0f);
+            if (!(v >= cutoff)) atomicOr(err, 32);
+            v = dev_quantize_u16(v);
+        }
+        cells[k].y = __float_as_int(v);
+    }
+}
+
 static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float cutoff, const std::vector<PairTask>& tasks_in,
                                float* dense, float* dense5, float* denseP, float* denseL) {
     if (tasks_in.empty()) return MLP_OK;
@@ -441,7 +518,7 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
     // Memory plan: the first batch is small and measures the sparse density; the cell pool is then grown once to the
     // extrapolated size, the same amount is left free for the relaxation output set, and the rest goes to dense scratch.
     size_t budget = (size_t)1 << 31;
-    bool planned = tasks_in.size() < 2048;
+    bool planned = tasks_in.size() < 2048 || ctx->stream_mode;   // streamed stage: the pool holds one batch at a time, nothing to extrapolate
     if (planned) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
@@ -603,11 +680,31 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
             const double done_frac = (double)(pos) / (double)tasks_in.size();
             long long want = (long long)((double)used / std::max(done_frac, 1e-3) * 1.15) + (1 << 20);
             want = std::max(want, ctx->set[ctx->cur].cap * 2);
+            if (ctx->stream_mode) want = ctx->set[ctx->cur].cap * 2;
             int rc2 = grow_cells(ctx, ctx->cur, want, cursor_before);
             if (rc2 != MLP_OK) return rc2;
         }
         CK(cudaMemcpyAsync(ctx->set[ctx->cur].cursor, &cursor_before, sizeof(cursor_before), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        }
+        if (ctx->stream_mode) {
+            // finish, digest and drop this batch's matrices: the next batch reuses the pool from the same cursor
+            unsigned long long used = 0;
+            { int rcc = read_cursor(ctx, ctx->cur, &used); if (rcc != MLP_OK) return rcc; }
+            const long long cnt = (long long)used - (long long)cursor_before;
+            const CsrSetDev& S = ctx->set[ctx->cur];
+            if (cnt > 0) {
+                k_stream_requant<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(S.cells + cursor_before, cnt, ctx->stream_reps, 1e-5f, ctx->d_err);
+                CK(cudaGetLastError());
+            }
+            k_set_digest<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d_tasks, (int)batch.size(), ctx->n, ctx->d_len, ctx->d_rp_off, S.rp_pool, S.nz_off, S.nz_cnt, S.cells, ctx->d_sdigest);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(S.cursor, &cursor_before, sizeof(cursor_before), cudaMemcpyHostToDevice, ctx->stream));
+            int err2 = 0;
+            { int rcw = read_words(ctx, ctx->cur, nullptr, &err2); if (rcw != MLP_OK) return rcw; }
+            if (err2) { ctx->err = "streamed stage: a cell fell below the consistency cutoff (not supported in streamed mode)"; return MLP_E_UNSUPPORTED; }
+            ctx->stats.launches += 2;
+            ctx->stats.nnz += cnt / 2;
         }
         if (!planned && pos < tasks_in.size()) {
             unsigned long long used = 0;
@@ -754,7 +851,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
     if (flavour == MLP_QP) model_mask = MLP_M_HMM5 | MLP_M_PART;
-    ctx->tree_resident = false;                      // a device guide tree belongs to the distance matrix it was built from
+    if (!ctx->restricted) ctx->tree_resident = false;   // a device guide tree belongs to the distance matrix it was built from (a stage over a restricted shard recomputes part of the same matrix)
     if ((model_mask & MLP_M_PART) && flavour != MLP_QP) {
         // letters J, O, U index sub_matrix[-1] in the reference: refuse instead of guessing
         for (long long k = 0; k < ctx->total_res; ++k) {
@@ -782,8 +879,8 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     ctx->stats.ms_total = ms;
     unsigned long long cur = 0;
     { int rcc = read_cursor(ctx, 0, &cur); if (rcc != MLP_OK) return rcc; }
-    ctx->stats.nnz = (int64_t)(cur / 2);
-    ctx->flavour_of_set = flavour;
+    if (!ctx->stream_mode) ctx->stats.nnz = (int64_t)(cur / 2);
+    ctx->flavour_of_set = ctx->stream_mode ? -1 : flavour;   // a streamed stage leaves distances and digests, not a set
     ctx->set_partial = ctx->dist_partial = (ctx->world > 1);
     ctx->imported = false;
     return MLP_OK;
@@ -1282,6 +1379,7 @@ extern "C" int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const 
     {   // the relaxed set can only shrink: size the output pool to what the input set holds
         unsigned long long used = 0;
         { int rcc = read_cursor(ctx, in, &used); if (rcc != MLP_OK) return rcc; }
+        if (ctx->imported && ctx->own_cells > 0) used = (unsigned long long)ctx->own_cells;   // imported matrices are read, never written
         if ((long long)used + 1024 > ctx->set[out].cap) { rc = grow_cells(ctx, out, (long long)used + 1024, 0); if (rc != MLP_OK) return rc; }
     }
     if (!ctx->relax_tasks_on_device) {

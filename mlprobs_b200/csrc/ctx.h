@@ -21,6 +21,11 @@ struct mlp_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: partition-function sweeps, overlapped with the HMM sweeps
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // streamed posterior stage (mlp_stream_begin, large families): every batch's matrices are finished (QuickProbs' re-quantisation of a
+    // consistency repetition without third sequences), digested and dropped, so the cell pool only ever holds one batch
+    bool stream_mode = false; int stream_reps = 1; unsigned long long* d_sdigest = nullptr; long long sdigest_cap = 0; int* d_len = nullptr; int len_cap = 0;
+    bool restricted = false;                             // shard cut down by mlp_restrict_pairs (a stage over it keeps the resident guide tree)
+    long long own_cells = 0;                             // cells of the set before mlp_exchange_needed appended its imports
     bool loc_old = false;                                // local model: fall back to the round-1 kernels (set when loc_c.cu's checked bound fails)
     int overlap = 0, bps_part = 0, bps_hmm = 0;          // tuning knobs (MLP_OVERLAP, MLP_BPS_PART, MLP_BPS_HMM); measured: no gain, off
     std::string err;

@@ -357,5 +357,6 @@ extern "C" int mlp_exchange_needed(mlp_ctx* ctx, const float* seldist_nxn, float
     ctx->stats.launches = 2;
     ctx->set_partial = false;                      // every matrix a relaxation of the owned pairs can read is now present
     ctx->imported = true;
+    ctx->own_cells = (long long)used_local;
     return MLP_OK;
 }

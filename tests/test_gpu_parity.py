@@ -724,3 +724,44 @@ def test_device_guide_tree_equals_the_host_tree(case):
             for x, y in zip(r, g):
                 np.testing.assert_array_equal(x, y)
     eng.close()
+
+
+def _two_pass_digest(eng, n, scratch=None):
+    """The streamed flow for families whose set does not fit HBM: streamed stage over all pairs (finished + digested + dropped batch
+    by batch), guide tree, ordinary stage + consistency restricted to the pairs that accept third sequences."""
+    if scratch:
+        eng.configure(scratch, 0)
+    eng.stream_begin(1)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    streamed = eng.stream_end().reshape(n, n)
+    tree = eng.qp_guide_tree_device(1e-6, want_seldist=True)
+    sd = tree["seldist"].reshape(n, n)
+    eng.restrict_pairs(sd, 200.0)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    eng.relax(M.QP, None, None, 200.0, 3.0, float(np.float32(1e-5)))
+    relaxed = eng.set_digest().reshape(n, n)
+    eng.set_shard(0, 1)
+    ingroup = sd <= 200.0
+    np.fill_diagonal(ingroup, False)
+    return np.where(ingroup, relaxed, streamed), ingroup
+
+
+def test_streamed_two_pass_flow_equals_the_ordinary_flow():
+    """BASELINE config #5's flow (mlp_stream_begin / mlp_restrict_pairs: cell pool recycled batch by batch, only the pairs inside a
+    <= 200-leaf subtree are kept, exchanged and relaxed) on the reference-pinned 400-sequence family where QuickProbs' selectivity
+    rejects third sequences: every matrix's digest after the consistency repetition equals the ordinary flow's (which
+    test_qp_selectivity_fixture_400_sequences pins on the reference), with the dense scratch capped so that the streamed stage
+    really runs many batches."""
+    d = load_golden("qp_syn400")
+    seqs = split_seqs(d); n = len(seqs)
+    eng = engine(M.QP, seqs)
+    eng.posterior_all_pairs(M.QP, 3, 0.01)
+    t = eng.qp_guide_tree_device(1e-6)
+    eng.relax(M.QP, None, None, 200.0, 3.0, float(np.float32(1e-5)))
+    ref = eng.set_digest().reshape(n, n)
+    eng.close()
+    eng = engine(M.QP, seqs)
+    got, ingroup = _two_pass_digest(eng, n, scratch=64 << 20)
+    eng.close()
+    assert 0.05 < ingroup.mean() < 0.6          # both kinds of pairs are present
+    np.testing.assert_array_equal(got, ref)
