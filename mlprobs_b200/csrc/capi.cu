@@ -263,6 +263,7 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     if (!same_shape) END_READBACK(ctx);              // a different family may re-allocate the pools a split read-back is copying from
     ctx->flavour_of_set = -1;
     ctx->set_partial = ctx->dist_partial = false;
+    ctx->stream_mode = false;                        // a streamed stage belongs to the family it was begun for
     ctx->n = n;
     ctx->len.assign(len, len + n);
     ctx->seq_off.resize(n);
@@ -287,7 +288,10 @@ extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const 
     CK(cudaMemcpy(ctx->d_res, codes.data(), tot + 16, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_seq_off, ctx->seq_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
     ctx->stats.h2d_bytes += tot + 16 + n * (int64_t)sizeof(long long);
-    if (same_shape) return MLP_OK;    // same lengths as the family before (a re-submitted family): pair list, shard and layout stand
+    if (same_shape) {                 // same lengths as the family before (a re-submitted family): pair list, shard and layout stand
+        if (ctx->restricted) return mlp_set_shard(ctx, ctx->rank, ctx->world);   // ... but not a shard cut down by mlp_restrict_pairs
+        return MLP_OK;
+    }
     build_sorted_pairs(n, len, ctx->all_pairs);
     // fixed row-pointer layout: ordered pair (a,b) owns len[a]+2 ints
     ctx->rp_off_h.assign((size_t)n * n, 0);
@@ -641,7 +645,8 @@ static int run_posterior_tasks(mlp_ctx* ctx, int flavour, uint32_t mask, float c
                 static const bool split = getenv("MLP_LOC_SPLIT") != nullptr;   // developer knob (local model alone): candidate pass -> slots 0 / 2, chain -> slots 1 / 3
                 for (int phase = 0; phase < 2; ++phase) {
                     const int kid = phase == 0 ? MLP_K_LOCAL_FWD : MLP_K_LOCAL_BWD;
-                    KArgs al = a; al.loc_phase = phase; al.loc_debug = split ? 1 : 0;
+                    const bool force_guard = getenv("MLP_LOC_FORCE_FALLBACK") != nullptr;   // test knob: the chain reports a failed bound check -> the batch is redone by the round-1 kernels
+                    KArgs al = a; al.loc_phase = phase; al.loc_debug = (split ? 1 : 0) | (force_guard ? 2 : 0);
                     if ((rc = launch_one(ctx, kid, al, nt, kt, kid, nullptr, 0, &cgroups)) != MLP_OK) return rc;
                     if ((rc = launch_one(ctx, MLP_K_LOCAL_CAND, al, nt, kt, split ? 2 * phase : kid, nullptr, 0, &cgroups)) != MLP_OK) return rc;
                     kt.begin(split ? 2 * phase + 1 : kid, ctx->stream);
@@ -851,6 +856,7 @@ extern "C" int mlp_posterior_all_pairs(mlp_ctx* ctx, int flavour, uint32_t model
     if (!ctx->have_tables || ctx->n < 2) { ctx->err = "set tables and sequences first"; return MLP_E_STATE; }
     if (flavour < MLP_QP || flavour > MLP_CPNP_P1 || (model_mask & 7u) == 0) return MLP_E_ARG;
     if (flavour == MLP_QP) model_mask = MLP_M_HMM5 | MLP_M_PART;
+    if (ctx->stream_mode && flavour != MLP_QP) { ctx->err = "the streamed stage finishes matrices the way QuickProbs' consistency does; c_p_np_aln reads every matrix"; return MLP_E_UNSUPPORTED; }
     if (!ctx->restricted) ctx->tree_resident = false;   // a device guide tree belongs to the distance matrix it was built from (a stage over a restricted shard recomputes part of the same matrix)
     if ((model_mask & MLP_M_PART) && flavour != MLP_QP) {
         // letters J, O, U index sub_matrix[-1] in the reference: refuse instead of guessing

@@ -348,8 +348,8 @@ __global__ void __launch_bounds__(128) k_loc_replay(KArgs a) {
         }
     }
     if (!(fabsf(sum) < 4.0e6f) && sum != MLP_LOG_ZERO) bad = true;   // the 8.5 margin of the candidate test must survive its own rounding
-    if (bad) atomicOr(a.err, 16);
-    if (a.loc_debug) { atomicAdd(&g_loc_dbg[2 * a.loc_phase], (unsigned long long)ncand); atomicAdd(&g_loc_dbg[2 * a.loc_phase + 1], (unsigned long long)nfire); }
+    if (bad || (a.loc_debug & 2)) atomicOr(a.err, 16);
+    if (a.loc_debug & 1) { atomicAdd(&g_loc_dbg[2 * a.loc_phase], (unsigned long long)ncand); atomicAdd(&g_loc_dbg[2 * a.loc_phase + 1], (unsigned long long)nfire); }
     if (a.loc_phase == 0) a.pout[ti].tFL = sum;
     else a.pout[ti].totalL = __fdiv_rn(__fadd_rn(a.pout[ti].tFL, sum), 2.0f);
 }

@@ -765,3 +765,29 @@ def test_streamed_two_pass_flow_equals_the_ordinary_flow():
     eng.close()
     assert 0.05 < ingroup.mean() < 0.6          # both kinds of pairs are present
     np.testing.assert_array_equal(got, ref)
+
+
+def test_local_model_bound_check_failure_falls_back_to_the_unfiltered_kernels(monkeypatch):
+    """loc_c.cu's filtered Z chain checks its one assumption (running sum >= bound - 0.5) at every candidate; a failed check sets bit
+    16 of the error word and the batch is redone by the round-1 kernels (no filter, no assumption).  MLP_LOC_FORCE_FALLBACK makes the
+    chain report a failure: the stage must give the same distances and matrices as an undisturbed run, on the same context twice
+    (the context stays on the round-1 kernels afterwards)."""
+    seqs = synth.family(7, 90, seed=21)
+    n = len(seqs)
+
+    def run(eng):
+        eng.posterior_all_pairs(M.CPNP_P0, 4, 0.01)
+        return eng.distances().copy(), [eng.csr(a, b) for a in range(n) for b in range(a + 1, n)]
+
+    eng = engine(M.CPNP_P0, seqs)
+    ref = run(eng)
+    eng.close()
+    monkeypatch.setenv("MLP_LOC_FORCE_FALLBACK", "1")
+    lib_eng = engine(M.CPNP_P0, seqs)
+    for _ in range(2):
+        got = run(lib_eng)
+        np.testing.assert_array_equal(ref[0], got[0])
+        for r, g in zip(ref[1], got[1]):
+            for x, y in zip(r, g):
+                np.testing.assert_array_equal(x, y)
+    lib_eng.close()
