@@ -111,7 +111,7 @@ int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seld
  * reference's own GPU path streams relaxation sectors for the same reason, KernelAlignment/Multiple/QuickConsistencyStage.cpp:163-190).
  * Between mlp_stream_begin and mlp_stream_end, mlp_posterior_all_pairs(MLP_QP) finishes every batch of pairs on the spot: the cells get
  * the re-quantisation a consistency repetition applies to a matrix whose pair accepts no third sequence (ConsistencyStage.cpp:
- * 213-258 with sumW = 1; `reps` repetitions), the per-matrix digest (format of mlp_set_digest) is accumulated, and the cell pool is
+ * 213-258 with sumW = 1; reps must be 1, QuickProbs' own count above 50 sequences), the per-matrix digest (format of mlp_set_digest) is accumulated, and the cell pool is
  * reused by the next batch.  Afterwards the distances are complete and mlp_qp_guide_tree_device can run; the pairs that DO accept third
  * sequences (subtree distance <= selectivity: a few per cent of a large family) are then recomputed by an ordinary stage restricted
  * to them with mlp_restrict_pairs, exchanged (mlp_exchange_needed) and relaxed as usual; mlp_set_shard restores the full shard.

@@ -117,6 +117,10 @@ extern "C" int mlp_stream_begin(mlp_ctx* ctx, int reps) {
     cudaSetDevice(ctx->device);
     const int n = ctx->n;
     if (n < 2) { ctx->err = "set sequences first"; return MLP_E_STATE; }
+    // Only the last repetition runs with the 1e-5 cutoff (ConsistencyStage.cpp:108-115); an earlier one uses 0.01 and would drop the
+    // cells whose quantised value fell just below it.  QuickProbs runs ONE repetition above 50 sequences (Configuration.cpp:100-103),
+    // and a family small enough for two has no pair outside a 200-leaf subtree, i.e. nothing to stream.
+    if (reps != 1) { ctx->err = "the streamed stage implements the single consistency repetition QuickProbs runs above 50 sequences"; return MLP_E_UNSUPPORTED; }
     const long long nn = (long long)n * n;
     if (nn > ctx->sdigest_cap) {
         free_dev(ctx->d_sdigest); ctx->d_sdigest = nullptr; ctx->sdigest_cap = 0;
