@@ -32,6 +32,9 @@ def run(report_path=None, suites=None, tools=None):
             if key == "cpnpG_sha" and not (tools and key in tools):
                 continue                  # the feature-line run is opt-in (added at the end of round 1, not yet run on a GPU)
             fams = [m for m in man if m["suite"] == suite and key in m and (key != "cpnpG_sha" or m.get("cpnpG_exact"))]
+            max_s = float(os.environ.get("MLP_SUITE_MAX_REF_S", "0"))      # GPU-time budget: skip families whose REFERENCE run of this tool took longer
+            if max_s > 0:
+                fams = [m for m in fams if float(m.get(key[:-4] + "_s", 0) or 0) <= max_s]
             if not fams:
                 continue
             outdir = os.path.join(tmp, "out_%s_%s" % (suite, key))
