@@ -119,6 +119,9 @@ int mlp_relax(mlp_ctx* ctx, int flavour, const float* weights, const float* seld
 int mlp_stream_begin(mlp_ctx* ctx, int reps);
 int mlp_stream_end(mlp_ctx* ctx, uint64_t* per_matrix_nn);
 int mlp_restrict_pairs(mlp_ctx* ctx, const float* seldist_nxn, float selectivity);
+/* Host utility (no GPU work): the pairs of mlp_shard_pairs(rank, world) that mlp_restrict_pairs keeps; pairs_out may be NULL (count only). */
+int mlp_shard_pairs_within(int n, const int32_t* len, int rank, int world, const float* seldist_nxn, float selectivity,
+                           int32_t* pairs_out, int64_t* count);
 
 /* QuickProbs' guide tree ON THE DEVICE, from the distance matrix the posterior stage left in HBM (which stays untouched):
  * UPGMA clustering (ClusterTree::build ClusterTree.cpp:17-124), normalised sequence weights (GuideTree::calculateSeqsWeights

@@ -25,7 +25,7 @@ EXPORTS = ["mlp_default_tables", "mlp_create", "mlp_destroy", "mlp_last_error", 
            "mlp_cpnp_g_features", "mlp_qp_guide_tree_ex", "mlp_qp_finish_alignment_host", "mlp_qp_finish_alignment",
            "mlp_free_host", "mlp_get_csr_packed", "mlp_cpnp_guide_tree", "mlp_cpnp_finish_alignment_host",
            "mlp_cpnp_finish_alignment", "mlp_debug_glibc_rand", "mlp_column_scores", "mlp_exchange_begin", "mlp_exchange_end",
-           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_debug_loc_counters", "mlp_stream_begin", "mlp_stream_end", "mlp_restrict_pairs", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
+           "mlp_exchange_distances", "mlp_exchange_needed", "mlp_qp_guide_tree_device", "mlp_debug_set_distances", "mlp_debug_loc_counters", "mlp_stream_begin", "mlp_stream_end", "mlp_restrict_pairs", "mlp_shard_pairs_within", "mlp_set_digest", "mlp_get_csr_packed_begin", "mlp_get_csr_packed_end"]
 
 
 class HmmTables(C.Structure):
@@ -305,6 +305,25 @@ def shard_pairs(lens, rank, world):
         raise MlpError(rc)
     out = np.zeros((cnt.value, 2), np.int32)
     rc = lib.mlp_shard_pairs(len(lens), lens.ctypes.data_as(C.c_void_p), rank, world, out.ctypes.data_as(C.c_void_p), C.byref(cnt))
+    if rc:
+        raise MlpError(rc)
+    return out
+
+
+def shard_pairs_within(lens, rank, world, seldist, selectivity=200.0):
+    """The pairs of shard_pairs(rank, world) whose subtree-size distance is within the selectivity -- what mlp_restrict_pairs keeps
+    (host-only, no GPU needed)."""
+    lens = np.ascontiguousarray(lens, np.int32)
+    sd = np.ascontiguousarray(seldist, np.float32)
+    lib = load()
+    lib.mlp_shard_pairs_within.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_int64)]
+    cnt = C.c_int64(0)
+    rc = lib.mlp_shard_pairs_within(len(lens), lens.ctypes.data_as(C.c_void_p), rank, world, sd.ctypes.data_as(C.c_void_p), C.c_float(selectivity), None, C.byref(cnt))
+    if rc:
+        raise MlpError(rc)
+    out = np.zeros((cnt.value, 2), np.int32)
+    rc = lib.mlp_shard_pairs_within(len(lens), lens.ctypes.data_as(C.c_void_p), rank, world, sd.ctypes.data_as(C.c_void_p), C.c_float(selectivity),
+                                    out.ctypes.data_as(C.c_void_p), C.byref(cnt))
     if rc:
         raise MlpError(rc)
     return out

@@ -248,6 +248,23 @@ extern "C" int mlp_shard_pairs(int n, const int32_t* len, int rank, int world, i
     return MLP_OK;
 }
 
+// Host utility (no GPU work): the pairs of mlp_shard_pairs(rank, world) that mlp_restrict_pairs keeps -- the multi-GPU contract of the
+// streamed flow can be checked without a device (tests/test_sharding_gloo.py).
+extern "C" int mlp_shard_pairs_within(int n, const int32_t* len, int rank, int world, const float* seldist_nxn, float selectivity,
+                                      int32_t* pairs_out, int64_t* count) {
+    if (n < 2 || !len || world < 1 || rank < 0 || rank >= world || !count || !seldist_nxn) return MLP_E_ARG;
+    std::vector<PairTask> all;
+    build_sorted_pairs(n, len, all);
+    int64_t c = 0;
+    for (size_t k = 0; k < all.size(); ++k)
+        if ((int)(k % world) == rank && seldist_nxn[(size_t)all[k].a * n + all[k].b] <= selectivity) {
+            if (pairs_out) { pairs_out[2 * c] = all[k].a; pairs_out[2 * c + 1] = all[k].b; }
+            ++c;
+        }
+    *count = c;
+    return MLP_OK;
+}
+
 extern "C" int mlp_set_sequences(mlp_ctx* ctx, int n, const int32_t* len, const uint8_t* residues) {
     if (!ctx || n < 2 || !len || !residues) return MLP_E_ARG;
     cudaSetDevice(ctx->device);
