@@ -193,3 +193,20 @@ def test_g_feature_line_host_code_on_suite_families():
                 assert abs(float(got[4]) - float(want[4])) <= 5e-3 * max(1.0, abs(float(want[4]))) and abs(float(got[5]) - float(want[5])) < 0.02
             other += 1
     assert checked >= 40 and other >= 3
+
+
+def test_float_facts_the_device_shortcuts_rest_on():
+    """Pure IEEE-754 facts behind two exact shortcuts of the CUDA path, checked in numpy float32:
+    final_c.cu mode 7 treats a merged posterior p as 0 when sq = v5^2 + vp^2 + vl^2 < 2^-122 and the MEA score it is added to is
+    >= 2^-30: then p = sqrt(sq / 3) < 2^-60 and p + s == s; part_sc.cu applies the scale shift with one multiply by a power of two,
+    which is exact for normal results."""
+    rng = np.random.default_rng(7)
+    sq = (rng.random(20000).astype(np.float32) * np.float32(2.0 ** -122)).astype(np.float32)
+    p = np.sqrt((sq / np.float32(3.0)).astype(np.float32)).astype(np.float32)
+    assert float(p.max()) < 2.0 ** -60
+    s = np.exp2(rng.uniform(-30, 8, 20000)).astype(np.float32)
+    s[:4] = np.float32(2.0 ** -30)
+    assert np.array_equal((p + s).astype(np.float32), s)
+    q = rng.random(20000) * np.exp2(rng.integers(-200, 200, 20000).astype(np.float64))
+    k = rng.integers(-300, 300, 20000)
+    assert np.array_equal(q * np.exp2(k.astype(np.float64)), np.ldexp(q, k))
