@@ -22,7 +22,7 @@ def test_ox_and_oxx_families_are_byte_identical_to_the_reference_programs():
 def test_ox_families_non_progressive_program_is_byte_identical():
     """c_p_np_aln -p 1 (alignment graph + similar-set refinement) with the clock value the reference outputs were pinned to."""
     import suite_parity
-    rep = suite_parity.run(None, suites=("ox",), tools=("cpnp1_sha",))
+    rep = suite_parity.run(None, suites=("ox",), tools=("cpnp1_sha",), gpu_verified_only=True)
     assert rep["suites"], "no -p 1 reference outputs in the manifest"
     assert rep["mismatches"] == [] and rep["failures"] == []
     for key, v in rep["suites"].items():

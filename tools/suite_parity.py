@@ -10,7 +10,7 @@ SUITES = os.path.join(ROOT, "tests", "golden", "suites")
 BIN = os.path.join(ROOT, "mlprobs_b200", "bin")
 
 
-def run(report_path=None, suites=None, tools=None):
+def run(report_path=None, suites=None, tools=None, gpu_verified_only=False):
     manifest = json.load(open(os.path.join(SUITES, "manifest.json")))
     man = manifest["families"]
     seed = str(manifest.get("p1_fixtime", 777))
@@ -35,6 +35,8 @@ def run(report_path=None, suites=None, tools=None):
             max_s = float(os.environ.get("MLP_SUITE_MAX_REF_S", "0"))      # GPU-time budget: skip families whose REFERENCE run of this tool took longer
             if max_s > 0:
                 fams = [m for m in fams if float(m.get(key[:-4] + "_s", 0) or 0) <= max_s]
+            if gpu_verified_only:         # the GPU test-suite: families pinned after the last GPU run of a round (checked on the CPU only, tools/p1_host_sweep.py) stay out
+                fams = [m for m in fams if key not in m.get("cpu_checked_only", [])]
             if not fams:
                 continue
             outdir = os.path.join(tmp, "out_%s_%s" % (suite, key))
