@@ -1,7 +1,7 @@
 """Suite-level parity of the two drop-in executables: byte-identical FASTA output on bundled benchmark families
-(tests/golden/suites, written by oracle/gen_suite_golden.py from the reference programs).  The ox and oxx suites run here
-(546 families, quickprobs and c_p_np_aln -p 0, about a minute and a half) plus c_p_np_aln -p 1 on ox; tools/suite_parity.py
-runs all four suites (1276 families)."""
+(tests/golden/suites, written by oracle/gen_suite_golden*.py from the reference programs).  The ox and oxx suites run here
+(790 families, quickprobs and c_p_np_aln -p 0, about two and a half minutes on a B200) plus c_p_np_aln -p 1 on ox, the -G line and the
+realignment regions; tools/suite_parity.py runs all four suites (1,599 families; profiles/r2b_suite_parity_all_1599.txt)."""
 import os
 import sys
 import pytest
