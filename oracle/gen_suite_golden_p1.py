@@ -4,7 +4,7 @@ Build container only.  The program is run as oracle/_ref/ref_cpnp msa --p1 --thr
 (its refinement races on the shared posterior otherwise) and the harness' pinned time() instead of the wall clock the
 program seeds every refinement sweep with.  Only families whose `-p 0` reference run took at most --max-seconds are run
 (the alignment graph of the reference copies its whole child table per candidate cell and is slow on large families).
-Usage: gen_suite_golden_p1.py [--max-seconds S] [--workers W]"""
+Usage: gen_suite_golden_p1.py [--min-seconds S] [--max-seconds S] [--workers W] [--timeout S]"""
 import os, sys, json, hashlib, subprocess, tempfile, time, argparse
 from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,6 +12,7 @@ REF = "/root/reference/TEST"
 CPNP = os.path.join(ROOT, "oracle", "_ref", "ref_cpnp")
 MAN = os.path.join(ROOT, "tests", "golden", "suites", "manifest.json")
 FIXTIME = 777
+TIMEOUT = 900
 
 
 def run_one(job):
@@ -20,7 +21,7 @@ def run_one(job):
     out = os.path.join(tmp, "%s_%s.p1" % (m["suite"], m["name"]))
     t0 = time.time()
     try:
-        c = subprocess.run([CPNP, "msa", path, out, "--p1", "--threads", "1", "--fixtime", str(FIXTIME)], capture_output=True, timeout=900)
+        c = subprocess.run([CPNP, "msa", path, out, "--p1", "--threads", "1", "--fixtime", str(FIXTIME)], capture_output=True, timeout=TIMEOUT)
         ok = c.returncode == 0 and os.path.exists(out) and os.path.getsize(out) > 0
     except subprocess.TimeoutExpired:
         ok = False
@@ -31,10 +32,13 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-seconds", type=float, default=5.0)
     ap.add_argument("--workers", type=int, default=6)
+    ap.add_argument("--min-seconds", type=float, default=0.0)
+    ap.add_argument("--timeout", type=int, default=900)
     a = ap.parse_args()
+    TIMEOUT = a.timeout
     man = json.load(open(MAN))
     tmp = tempfile.mkdtemp()
-    todo = [(m, tmp) for m in man["families"] if m.get("cpnp_s") is not None and m["cpnp_sha"] and m["cpnp_s"] <= a.max_seconds and "cpnp1_sha" not in m]
+    todo = [(m, tmp) for m in man["families"] if m.get("cpnp_s") is not None and m["cpnp_sha"] and a.min_seconds <= m["cpnp_s"] <= a.max_seconds and "cpnp1_sha" not in m]
     todo.sort(key=lambda j: -j[0]["cpnp_s"])
     print("to run:", len(todo), flush=True)
     t0 = time.time()

@@ -8,7 +8,8 @@ with its clock pinned, oracle/gen_suite_golden_p1.py / gen_suite_golden_rest.py)
 and the FASTA text -- input order, trimmed headers, 60 residues per line, as csrc/cpnp_main.cpp writes it -- must hash to the pinned value.
 This is test infrastructure (it imports the oracle); the device flow itself is compared by tools/suite_parity.py cpnp1_sha on a GPU.
 
-Usage: p1_host_sweep.py [--min-ref-s S] [--max-ref-s S] [--minutes M] [--procs P] [--log FILE] [suite ...]
+Usage: p1_host_sweep.py [--min-ref-s S] [--max-ref-s S] [--minutes M] [--procs P] [--log FILE] [--cpu-checked-only] [suite ...]
+--cpu-checked-only: just the families pinned after the last GPU run (manifest key `cpu_checked_only`).
 Families run largest reference time first, one process per family; the sweep stops handing out work after M minutes."""
 import hashlib, io, json, multiprocessing as mp, os, sys, tarfile, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -63,6 +64,9 @@ def main():
         return default
     lo = float(opt("--min-ref-s", "0")); hi = float(opt("--max-ref-s", "1e30")); minutes = float(opt("--minutes", "60"))
     procs = int(opt("--procs", str(os.cpu_count()))); log = opt("--log", os.path.join(ROOT, "gpurun_out", "p1_host_sweep.txt"))
+    only_new = "--cpu-checked-only" in args
+    if only_new:
+        args.remove("--cpu-checked-only")
     manifest = json.load(open(os.path.join(SUITES, "manifest.json")))
     seed = int(manifest.get("p1_fixtime", 777))
     tmp = tempfile.mkdtemp()
@@ -70,7 +74,8 @@ def main():
         if os.path.exists(os.path.join(SUITES, arc)):
             with tarfile.open(os.path.join(SUITES, arc)) as tar:
                 tar.extractall(tmp, filter="data")
-    fams = [m for m in manifest["families"] if m.get("cpnp1_sha") and lo <= float(m.get("cpnp1_s") or 0) <= hi and (not args or m["suite"] in args)]
+    fams = [m for m in manifest["families"] if m.get("cpnp1_sha") and lo <= float(m.get("cpnp1_s") or 0) <= hi and (not args or m["suite"] in args)
+            and (not only_new or "cpnp1_sha" in m.get("cpu_checked_only", []))]
     fams.sort(key=lambda m: -float(m.get("cpnp1_s") or 0))
     jobs = [(os.path.join(tmp, m["suite"], m["name"]), m, seed) for m in fams]
     os.makedirs(os.path.dirname(log), exist_ok=True)
