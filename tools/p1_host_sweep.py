@@ -8,7 +8,7 @@ with its clock pinned, oracle/gen_suite_golden_p1.py / gen_suite_golden_rest.py)
 and the FASTA text -- input order, trimmed headers, 60 residues per line, as csrc/cpnp_main.cpp writes it -- must hash to the pinned value.
 This is test infrastructure (it imports the oracle); the device flow itself is compared by tools/suite_parity.py cpnp1_sha on a GPU.
 
-Usage: p1_host_sweep.py [--min-ref-s S] [--max-ref-s S] [--minutes M] [--procs P] [--log FILE] [--cpu-checked-only] [suite ...]
+Usage: p1_host_sweep.py [--min-ref-s S] [--max-ref-s S] [--minutes M] [--procs P] [--log FILE] [--cpu-checked-only] [--manifest FILE] [suite ...]
 --cpu-checked-only: just the families pinned after the last GPU run (manifest key `cpu_checked_only`).
 Families run largest reference time first, one process per family; the sweep stops handing out work after M minutes."""
 import hashlib, io, json, multiprocessing as mp, os, sys, tarfile, tempfile, time
@@ -67,7 +67,7 @@ def main():
     only_new = "--cpu-checked-only" in args
     if only_new:
         args.remove("--cpu-checked-only")
-    manifest = json.load(open(os.path.join(SUITES, "manifest.json")))
+    manifest = json.load(open(opt("--manifest", os.path.join(SUITES, "manifest.json"))))
     seed = int(manifest.get("p1_fixtime", 777))
     tmp = tempfile.mkdtemp()
     for arc in ("inputs.tar.gz", "inputs_rest.tar.gz"):
